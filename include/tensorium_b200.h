@@ -1,0 +1,304 @@
+/*
+ * tensorium_b200.h — C ABI of libtensorium_b200.so
+ *
+ * A B200 (sm_100a) native replacement for the reference's CUDA backend unit
+ * `nnCuda` (reference: source/nncuda.pas, class TNNCuda<T>, lines 35-211; the
+ * global instance `cuda : TNNCuda<Single>`, source/ntensors.pas:1053-1056).
+ * Every entry point below is what a FreePascal `external 'tensorium_b200'`
+ * declaration binds; INTEGRATION.md shows the replacement unit.
+ *
+ * Conventions (same as the reference methods they replace):
+ *   - all sizes, strides and offsets are int64_t (= Pascal SizeInt on x86-64);
+ *     offsets are in ELEMENTS (floats), not bytes;
+ *   - `float*` arguments are raw device pointers obtained from
+ *     tnn_create_device_buffer (plain cudaMalloc memory: TTensor.Free calls
+ *     cudaFree on them directly, ntensors.pas:6126-6129) or any other CUDA
+ *     allocation of the same device;
+ *   - tensors are fp32, NCHW, weights [filters][C*kh*kw] (nConvolutionLayer.pas:115-119);
+ *   - calls are asynchronous on the context's stream (nncuda.pas:455) except the
+ *     host<->device copies and tnn_finish;
+ *   - every function returns 0 on success, non-zero on failure; the message is
+ *     available from tnn_last_error() (thread local).  The reference's SAFE_CALL
+ *     (nncuda.pas:237-274) asserts on the same condition.
+ *   - arithmetic follows the reference's CPU path (ntensors.pas / nactivation.pas),
+ *     not its NVRTC kernels, where the two differ: variance is
+ *     divided by N-1, normalisation clamps max(sqrt(var),1e-6), tanh = (e^x-e^-x)/(e^x+e^-x).
+ *
+ * No entry point falls back to the CPU: if no sm_100 device is present,
+ * tnn_create fails.
+ */
+#ifndef TENSORIUM_B200_H
+#define TENSORIUM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define TNN_API __declspec(dllexport)
+#else
+#define TNN_API __attribute__((visibility("default")))
+#endif
+
+typedef struct tnn_context tnn_context; /* one TNNCuda<Single> instance */
+
+/* TActivationType ordinals — source/ntypes.pas:66-71 (must match; cf. cuda_sgemm.cu:93-98) */
+typedef enum {
+  TNN_ACT_LOGISTIC = 0, TNN_ACT_RELU = 1, TNN_ACT_RELU6 = 2, TNN_ACT_RELIE = 3, TNN_ACT_LINEAR = 4,
+  TNN_ACT_RAMP = 5, TNN_ACT_TANH = 6, TNN_ACT_PLSE = 7, TNN_ACT_REVLEAKY = 8, TNN_ACT_LEAKY = 9,
+  TNN_ACT_ELU = 10, TNN_ACT_LOGGY = 11, TNN_ACT_STAIR = 12, TNN_ACT_HARDTAN = 13, TNN_ACT_LHTAN = 14,
+  TNN_ACT_SELU = 15, TNN_ACT_SOFTMAX = 16, TNN_ACT_GELU = 17, TNN_ACT_SWISH = 18, TNN_ACT_MISH = 19,
+  TNN_ACT_HARD_MISH = 20, TNN_ACT_NORM_CHAN = 21, TNN_ACT_NORM_CHAN_SOFTMAX = 22,
+  TNN_ACT_NORM_CHAN_SOFTMAX_MAXVAL = 23
+} tnn_activation;
+
+/* Contraction arithmetic of the conv / SGEMM kernels (replaces TNNCuda.useBLAS, nncuda.pas:91) */
+typedef enum {
+  TNN_MATH_FP32 = 0,   /* CUDA-core FMA, fp32 exact products (reference: cublasSgemm SIMT / sgemm1_nn) */
+  TNN_MATH_3XTF32 = 1, /* tcgen05 kind::tf32, big/small split, 3 MMAs: fp32-level accuracy (default)   */
+  TNN_MATH_TF32 = 2    /* tcgen05 kind::tf32, single MMA (optional fast mode, 5e-3 tolerance)           */
+} tnn_math_mode;
+
+/* ------------------------------------------------------------------ lifetime / device */
+/* TNNCuda.deviceCount nncuda.pas:443-446 */
+TNN_API int32_t tnn_device_count(int32_t *count);
+/* TNNCuda.Create(deviceIndex) nncuda.pas:448-467 (cudaSetDevice + stream; NVRTC/cuBLAS not needed) */
+TNN_API int32_t tnn_create(int32_t device_index, tnn_context **ctx);
+/* TNNCuda.Destroy nncuda.pas:469-476 */
+TNN_API int32_t tnn_destroy(tnn_context *ctx);
+/* message of the last failure on this thread (SAFE_CALL's assert text, nncuda.pas:237-274) */
+TNN_API const char *tnn_last_error(void);
+/* properties.name (read by CIFAR10Conv.pas:138) */
+TNN_API const char *tnn_device_name(tnn_context *ctx);
+/* properties.multiProcessorCount / major / minor */
+TNN_API int32_t tnn_device_info(tnn_context *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor);
+/* TNNCuda.stream field (nncuda.pas:78): adopt / read the CUstream all ops are enqueued on */
+TNN_API int32_t tnn_set_stream(tnn_context *ctx, void *cuda_stream);
+TNN_API void *tnn_get_stream(tnn_context *ctx);
+/* TNNCuda.useBLAS (nncuda.pas:91) becomes the math mode of the contraction kernels */
+TNN_API int32_t tnn_set_math_mode(tnn_context *ctx, int32_t mode);
+TNN_API int32_t tnn_get_math_mode(tnn_context *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+TNN_API int64_t tnn_launch_count(tnn_context *ctx);
+/* library build id string (arch, git-less) */
+TNN_API const char *tnn_version(void);
+
+/* ------------------------------------------------------------------ memory */
+/* createDeviceBuffer(N bytes) nncuda.pas:488-491 */
+TNN_API int32_t tnn_create_device_buffer(tnn_context *ctx, int64_t bytes, float **mem);
+/* freeDeviceBuffer nncuda.pas:493-497 */
+TNN_API int32_t tnn_free_device_buffer(tnn_context *ctx, float *mem);
+/* readBuffer (D2H, synchronous) nncuda.pas:499-510 */
+TNN_API int32_t tnn_read_buffer(tnn_context *ctx, const float *mem, size_t bytes, void *host);
+/* writeBuffer (H2D, synchronous) nncuda.pas:512-522 */
+TNN_API int32_t tnn_write_buffer(tnn_context *ctx, float *mem, size_t bytes, const void *host);
+/* asynchronous variants for pinned host memory (no reference counterpart; used by the harness) */
+TNN_API int32_t tnn_read_buffer_async(tnn_context *ctx, const float *mem, size_t bytes, void *host);
+TNN_API int32_t tnn_write_buffer_async(tnn_context *ctx, float *mem, size_t bytes, const void *host);
+/* finish nncuda.pas:1575-1584 */
+TNN_API int32_t tnn_finish(tnn_context *ctx);
+
+/* ------------------------------------------------------------------ activations (nncuda.pas:524-580) */
+/* ActivateArray(N, x, offset, activation): in place; no-op for acLINEAR.  CPU twin: activate_array nactivation.pas:508-621 */
+TNN_API int32_t tnn_activate_array(tnn_context *ctx, int64_t N, float *x, int64_t offset, int32_t activation);
+/* activateArraySWISH(N, x, offset, output_sigmoid, output) nncuda.pas:544-560 */
+TNN_API int32_t tnn_activate_array_swish(tnn_context *ctx, int64_t N, const float *x, int64_t offset,
+                                         float *output_sigmoid, float *output);
+/* DeriveArray(N, x(outputs), offset, activation, delta): delta *= f'(x).  CPU twin: gradient_array nactivation.pas:624-717 */
+TNN_API int32_t tnn_derive_array(tnn_context *ctx, int64_t N, const float *x, int64_t offset, int32_t activation,
+                                 float *delta);
+
+/* ------------------------------------------------------------------ bias / scale (nncuda.pas:582-622,1468-1510) */
+/* forwardBias(dstSize, dst, offset, srcSize, src, incb, batch): dst[i+offset] += src[(i/blockSize)%srcSize].  CPU twin ntensors.pas:7709-7727 */
+TNN_API int32_t tnn_forward_bias(tnn_context *ctx, int64_t dstSize, float *dst, int64_t offset, int64_t srcSize,
+                                 const float *src, int64_t incb, int64_t batch);
+/* backwardBias(dstSize, dst, srcSize, src, srcOffset, incb, batch): dst[f] += sum over batch,block.  CPU twin addSums ntensors.pas:7729-7781 */
+TNN_API int32_t tnn_backward_bias(tnn_context *ctx, int64_t dstSize, float *dst, int64_t srcSize, const float *src,
+                                  int64_t srcOffset, int64_t incb, int64_t batch);
+/* forwardScale nncuda.pas:1468-1488.  CPU twin ntensors.pas:7687-7707 */
+TNN_API int32_t tnn_forward_scale(tnn_context *ctx, int64_t dstSize, float *dst, int64_t offset, int64_t scaleSize,
+                                  const float *scale, int64_t incb, int64_t batch);
+/* forwardScaleAdd nncuda.pas:1490-1510: dst = dst*scale[f] + bias[f] */
+TNN_API int32_t tnn_forward_scale_add(tnn_context *ctx, int64_t dstSize, float *dst, int64_t offset,
+                                      int64_t scaleSize, const float *scales, const float *biases, int64_t incb,
+                                      int64_t batch);
+
+/* ------------------------------------------------------------------ SGEMM (nncuda.pas:624-895) */
+/* gemm: row-major C = beta*C + alpha*op(A)*op(B).  CPU twin cblas_sgemm ntensors.pas:2231-2286 */
+TNN_API int32_t tnn_gemm(tnn_context *ctx, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
+                         float alpha, const float *A, int64_t aOffset, int64_t lda, const float *B, int64_t bOffset,
+                         int64_t ldb, float beta, float *C, int64_t cOffset, int64_t ldc);
+/* gemmBatched (arrays of device pointers live in HOST memory, as PCUMem in nncuda.pas:727-807) */
+TNN_API int32_t tnn_gemm_batched(tnn_context *ctx, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
+                                 float alpha, const float *const *A, int64_t aOffset, int64_t lda,
+                                 const float *const *B, int64_t bOffset, int64_t ldb, float beta, float *const *C,
+                                 int64_t cOffset, int64_t ldc, int64_t batchCount);
+/* gemmStridedBatched nncuda.pas:809-895.  strideC = 0 ACCUMULATES the batch sequentially into one C
+ * (the wgrad call, nConvolutionLayer.pas:1228-1232), as the reference's non-BLAS host loop does. */
+TNN_API int32_t tnn_gemm_strided_batched(tnn_context *ctx, int32_t transA, int32_t transB, int64_t M, int64_t N,
+                                         int64_t K, float alpha, const float *A, int64_t aOffset, int64_t lda,
+                                         int64_t strideA, const float *B, int64_t bOffset, int64_t ldb,
+                                         int64_t strideB, float beta, float *C, int64_t cOffset, int64_t ldc,
+                                         int64_t strideC, int64_t batchCount);
+
+/* ------------------------------------------------------------------ BLAS-1 style (nncuda.pas:897-1054) */
+TNN_API int32_t tnn_addvv(tnn_context *ctx, int64_t N, const float *src1, int64_t src1Offset, int64_t inca,
+                          const float *src2, int64_t src2Offset, int64_t incb, float *dst, int64_t dstOffset,
+                          int64_t incc);
+TNN_API int32_t tnn_subvv(tnn_context *ctx, int64_t N, const float *src1, int64_t src1Offset, int64_t inca,
+                          const float *src2, int64_t src2Offset, int64_t incb, float *dst, int64_t dstOffset,
+                          int64_t incc);
+TNN_API int32_t tnn_mulvv(tnn_context *ctx, int64_t N, const float *src1, int64_t src1Offset, int64_t inca,
+                          const float *src2, int64_t src2Offset, int64_t incb, float *dst, int64_t dstOffset,
+                          int64_t incc);
+/* fmavv: dst = src1*src2 + src3 (the reference wrapper is an empty stub, nncuda.pas:937-943; kernel cuda_sgemm.cu:1671) */
+TNN_API int32_t tnn_fmavv(tnn_context *ctx, int64_t N, const float *src1, int64_t src1Offset, int64_t inca,
+                          const float *src2, int64_t src2Offset, int64_t incb, const float *src3,
+                          int64_t src3Offset, int64_t incc, float *dst, int64_t dstOffset, int64_t incd);
+/* axpy: y += a*x.  CPU twin ntensors.pas:7603-7671 */
+TNN_API int32_t tnn_axpy(tnn_context *ctx, int64_t N, float a, const float *x, int64_t xOffset, int64_t incx,
+                         float *y, int64_t yOffset, int64_t incy);
+TNN_API int32_t tnn_power(tnn_context *ctx, int64_t N, const float *x, int64_t xOffset, int64_t incx, float a,
+                          float *y, int64_t yOffset, int64_t incy);
+/* scale: x *= a (a = 0 zeroes deltas, nnet.pas:291) */
+TNN_API int32_t tnn_scale(tnn_context *ctx, int64_t N, float a, float *x, int64_t stride);
+TNN_API int32_t tnn_fill(tnn_context *ctx, int64_t N, float *x, int64_t offset, float val, int64_t stride);
+TNN_API int32_t tnn_copy(tnn_context *ctx, int64_t N, const float *src, int64_t srcOffset, int64_t inca, float *dst,
+                         int64_t dstOffset, int64_t incb);
+/* fmavss: dst[offset+i] = src[offset+i]*scalar + bias  nncuda.pas:1288-1300 */
+TNN_API int32_t tnn_fmavss(tnn_context *ctx, int64_t N, const float *src, int64_t offset, float scalar, float bias,
+                           float *dst);
+TNN_API int32_t tnn_clamp(tnn_context *ctx, int64_t N, float alpha, const float *src, float *dst, int64_t stride,
+                          int64_t offset);
+/* inverseSqrt: dst = 1/sqrt(max(src,1e-6)) (alpha is ignored by the reference too, nncuda.pas:1563-1573) */
+TNN_API int32_t tnn_inverse_sqrt(tnn_context *ctx, int64_t N, float alpha, const float *src, float *dst,
+                                 int64_t stride, int64_t offset);
+
+/* ------------------------------------------------------------------ losses / softmax / pooling / misc layers */
+TNN_API int32_t tnn_cross_entropy_logistic(tnn_context *ctx, int64_t N, const float *pred, const float *truth,
+                                           float *delta, float *error);
+TNN_API int32_t tnn_cross_entropy_softmax(tnn_context *ctx, int64_t N, const float *pred, const float *truth,
+                                          float *delta, float *error);
+TNN_API int32_t tnn_cost_l2(tnn_context *ctx, int64_t N, const float *pred, const float *truth, float *delta,
+                            float *error);
+/* softmaxBatch nncuda.pas:1056-1073 */
+TNN_API int32_t tnn_softmax_batch(tnn_context *ctx, int64_t N, const float *input, int64_t iOffset, int64_t batch,
+                                  int64_t batch_size, int64_t groups, int64_t group_size, int64_t stride, float temp,
+                                  float *output, int64_t oOffset);
+/* forwardMaxPool / backwardMaxPool nncuda.pas:1088-1142; indexes are 64-bit (size_t in cuda_sgemm.cu:868) */
+TNN_API int32_t tnn_forward_maxpool(tnn_context *ctx, int64_t aBatch, int64_t outC, int64_t outH, int64_t outW,
+                                    const float *input, int64_t c, int64_t h, int64_t w, int64_t stride_x,
+                                    int64_t stride_y, int64_t padding, int64_t kernelSize, uint64_t *indexes,
+                                    float *output);
+TNN_API int32_t tnn_backward_maxpool(tnn_context *ctx, int64_t aBatch, int64_t outC, int64_t outH, int64_t outW,
+                                     float *output, const uint64_t *indexes, const float *delta);
+/* upSample nncuda.pas:1267-1286 (in = low-res, out = high-res; isForward=0 accumulates into in) */
+TNN_API int32_t tnn_upsample(tnn_context *ctx, int64_t aBatch, int64_t aChannels, int64_t outHeight,
+                             int64_t outWidth, float *in, int64_t stride, int32_t isForward, float scale, float *out,
+                             int32_t zeroIn);
+/* forwardDropout / backwardDropout nncuda.pas:1512-1538; `seed` replaces the wrapper's random($10000000) */
+TNN_API int32_t tnn_forward_dropout(tnn_context *ctx, int64_t N, const float *src, float probability, float scale,
+                                    float *rnd, float *dst, uint64_t seed);
+TNN_API int32_t tnn_backward_dropout(tnn_context *ctx, int64_t N, const float *src, float probability, float scale,
+                                     const float *rnd, float *dst);
+
+/* ------------------------------------------------------------------ im2col / col2im (nncuda.pas:1144-1265) */
+/* im2col: col[c][kh][kw][oh][ow] (the CPU layout, ntensors.pas:11415-11491), one image */
+TNN_API int32_t tnn_im2col(tnn_context *ctx, int64_t aChannels, int64_t aHeight, int64_t aWidth, int64_t kernelHeight,
+                           int64_t kernelWidth, int64_t padHeight, int64_t padWidth, int64_t strideY, int64_t strideX,
+                           int64_t dilationY, int64_t dilationX, const float *im, int64_t imOffset, float *col,
+                           int64_t colOffset);
+/* col2im: scatter-ADD of col into im (ntensors.pas:11650-11763), one image */
+TNN_API int32_t tnn_col2im(tnn_context *ctx, int64_t aChannels, int64_t aHeight, int64_t aWidth, int64_t kernelHeight,
+                           int64_t kernelWidth, int64_t padHeight, int64_t padWidth, int64_t strideY, int64_t strideX,
+                           int64_t dilationY, int64_t dilationX, const float *col, int64_t colOffset, float *im,
+                           int64_t imOffset);
+
+/* ------------------------------------------------------------------ batch-norm pieces (nncuda.pas:1302-1466) */
+/* means / variances / meansAndVars(srcSize, dstSize, groups, src, offset, means[, vars]).
+ * blockSize = srcSize/(dstSize*groups); variance is UNBIASED (/(S-1)) like ntensors.pas:9102-9177 */
+TNN_API int32_t tnn_means(tnn_context *ctx, int64_t srcSize, int64_t dstSize, int64_t groups, const float *src,
+                          int64_t offset, float *means);
+TNN_API int32_t tnn_variances(tnn_context *ctx, int64_t srcSize, int64_t dstSize, int64_t groups, const float *src,
+                              int64_t offset, const float *means, float *vars);
+TNN_API int32_t tnn_means_and_vars(tnn_context *ctx, int64_t srcSize, int64_t dstSize, int64_t groups,
+                                   const float *src, int64_t offset, float *means, float *vars);
+/* normalize(srcSize(=channels), dstSize, groups, means, meansStride, vars, varsStride, dst, dstOffset):
+ * dst = (dst-mean[c]) / max(sqrt(var[c]),1e-6)  (ntensors.pas:4357-4382; sqrt(max(var,1e-6)) when blockSize=1) */
+TNN_API int32_t tnn_normalize(tnn_context *ctx, int64_t srcSize, int64_t dstSize, int64_t groups, const float *means,
+                              int64_t meansStride, const float *vars, int64_t varsStride, float *dst,
+                              int64_t dstOffset);
+/* meansAndVarsDelta nncuda.pas:1398-1419.  CPU twin sMeanAndVarianceDelta ntensors.pas:8831-8899 */
+TNN_API int32_t tnn_means_and_vars_delta(tnn_context *ctx, int64_t srcSize, int64_t dstSize, int64_t groups,
+                                         const float *delta, const float *x, int64_t offset, const float *mean,
+                                         const float *variance, float *mean_delta, float *variance_delta);
+/* normalizeDelta nncuda.pas:1421-1446.  CPU twin sNormalizeDelta ntensors.pas:8902-8951 */
+TNN_API int32_t tnn_normalize_delta(tnn_context *ctx, int64_t deltaSize, int64_t meanSize, int64_t groups,
+                                    float *delta, const float *x, int64_t offset, const float *mean,
+                                    const float *variance, const float *mean_delta, const float *variance_delta);
+/* addDots(N, dstSize, groups, src1, src2, srcOffset, dst): dst[c] += sum src1*src2.  CPU twin ntensors.pas:7783-7837 */
+TNN_API int32_t tnn_add_dots(tnn_context *ctx, int64_t N, int64_t dstSize, int64_t groups, const float *src1,
+                             const float *src2, int64_t srcOffset, float *dst);
+
+/* ------------------------------------------------------------------ coarse, fused entry points
+ * New with this backend: the bodies of TConvolutionalLayer.forwardGPU / backwardGPU / updateGPU
+ * (nConvolutionLayer.pas:1022-1330) and TBaseLayer.batchNormGPU (nbaselayer.pas:550-660) collapse into
+ * these calls (INTEGRATION.md shows the edited method bodies).  No column buffer is materialised. */
+
+typedef struct {
+  int64_t batch, c, h, w;          /* input  [batch][c][h][w]                                   */
+  int64_t filters, kh, kw;         /* weights [filters][c*kh*kw]                                */
+  int64_t pad_h, pad_w, stride_y, stride_x, dilation_y, dilation_x;
+} tnn_conv_desc;
+
+/* forwardGPU steps 2-5 (nConvolutionLayer.pas:1040-1122) in one kernel:
+ *   out = act( conv(in, weights) * scale[f] + bias[f] )
+ * `scale` may be NULL (1.0); pass scale[f] = scales[f]/max(sqrt(rolling_variance[f]),1e-6) and the matching
+ * folded bias for inference-mode batch-norm, or the fuseBatchNorm'ed weights (nConvolutionLayer.pas:102-126)
+ * with scale = NULL.  `bias` may be NULL.  activation: TNN_ACT_LINEAR/LEAKY/LOGISTIC/RELU/... (elementwise ones). */
+TNN_API int32_t tnn_conv2d_forward(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,
+                                   const float *weights, const float *scale, const float *bias,
+                                   int32_t activation, float *out, int64_t outOffset);
+/* backwardGPU wgrad (nConvolutionLayer.pas:1203-1232): weight_updates += sum_b delta_b * im2col(in_b)^T */
+TNN_API int32_t tnn_conv2d_backward_filter(tnn_context *ctx, const tnn_conv_desc *d, const float *in,
+                                           int64_t inOffset, const float *delta, int64_t deltaOffset,
+                                           float *weight_updates);
+/* backwardGPU dgrad (nConvolutionLayer.pas:1250-1275): in_delta += col2im(weights^T * delta_b) */
+TNN_API int32_t tnn_conv2d_backward_data(tnn_context *ctx, const tnn_conv_desc *d, const float *weights,
+                                         const float *delta, int64_t deltaOffset, float *in_delta,
+                                         int64_t inDeltaOffset);
+/* training-mode batchNormGPU (nbaselayer.pas:583-643) fused: statistics, rolling update
+ * (r = (1-m) r + m stat), x := out, out := normalised, x_norm := out, then out = out*scale+bias and
+ * the layer activation.  All per-channel vectors have `channels` entries. */
+TNN_API int32_t tnn_batchnorm_forward_training(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize,
+                                               float *out, float *x, float *x_norm, float *mean, float *variance,
+                                               float *rolling_mean, float *rolling_variance, float bn_momentum,
+                                               const float *scales, const float *biases, int32_t activation);
+/* inference-mode batchNormGPU (nbaselayer.pas:628-643) + activation in one pass */
+TNN_API int32_t tnn_batchnorm_forward_inference(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize,
+                                                float *out, const float *rolling_mean,
+                                                const float *rolling_variance, const float *scales,
+                                                const float *biases, int32_t activation);
+/* DeriveArray + batchNormBackGPU (nConvolutionLayer.pas:1186, nbaselayer.pas:662-714) fused:
+ * delta *= f'(out); scale_updates += sum x_norm*delta; delta *= scale; mean_delta, variance_delta; delta normalised */
+TNN_API int32_t tnn_batchnorm_backward(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize,
+                                       const float *out, int32_t activation, float *delta, const float *x,
+                                       const float *x_norm, const float *mean, const float *variance,
+                                       const float *scales, float *scale_updates, float *mean_delta,
+                                       float *variance_delta);
+/* updateGPU (nConvolutionLayer.pas:1309-1322) for one parameter tensor in one kernel:
+ *   updates += decay_term*params ; params += rate*updates ; updates *= momentum
+ * with decay_term = -decay*batch for weights, 0 for biases/scales; rate = learning_rate/batch. */
+TNN_API int32_t tnn_sgd_update(tnn_context *ctx, int64_t N, float *params, float *updates, float rate,
+                               float momentum, float decay_term);
+/* out[b][cOff..cOff+c] = in  — per-image channel concat used by route layers */
+TNN_API int32_t tnn_concat_channels(tnn_context *ctx, int64_t batch, int64_t c, int64_t blockSize, const float *in,
+                                    int64_t outChannels, int64_t cOffset, float *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TENSORIUM_B200_H */

@@ -1,0 +1,205 @@
+// api_core.cu — lifetime, memory and stream entry points of the C ABI.
+// Replaces TNNCuda<T>.Create/Destroy/createDeviceBuffer/readBuffer/writeBuffer/finish
+// (reference: source/nncuda.pas:443-522,1575-1584).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void tnn_set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+extern "C" {
+
+const char *tnn_last_error(void) { return g_err; }
+
+const char *tnn_version(void) { return "tensorium_b200 0.1 (sm_100a; tcgen05 3xTF32 implicit-GEMM conv)"; }
+
+int32_t tnn_device_count(int32_t *count) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    tnn_set_error("cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    if (count) *count = 0;
+    return 2;
+  }
+  if (count) *count = n;
+  return 0;
+}
+
+int32_t tnn_create(int32_t device_index, tnn_context **out) {
+  if (!out) {
+    tnn_set_error("tnn_create: null out pointer");
+    return 1;
+  }
+  *out = nullptr;
+  int n = 0;
+  TNN_CUDA(cudaGetDeviceCount(&n));
+  if (device_index < 0 || device_index >= n) {
+    tnn_set_error("tnn_create: device %d out of range (%d devices)", device_index, n);
+    return 1;
+  }
+  tnn_context *ctx = new tnn_context();
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->device = device_index;
+  cudaError_t e = cudaGetDeviceProperties(&ctx->prop, device_index);
+  if (e != cudaSuccess) {
+    delete ctx;
+    tnn_set_error("cudaGetDeviceProperties failed: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  if (ctx->prop.major != 10) {
+    // no fallback path: this library only carries sm_100a code
+    tnn_set_error("tnn_create: device %d (%s, sm_%d%d) is not a Blackwell sm_100 GPU", device_index,
+                  ctx->prop.name, ctx->prop.major, ctx->prop.minor);
+    delete ctx;
+    return 5;
+  }
+  e = cudaSetDevice(device_index);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    tnn_set_error("tnn_create: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  ctx->own_stream = true;
+  ctx->math_mode = TNN_MATH_3XTF32;
+  *out = ctx;
+  return 0;
+}
+
+int32_t tnn_destroy(tnn_context *ctx) {
+  if (!ctx) return 0;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->red_partials) cudaFree(ctx->red_partials);
+  if (ctx->red_counters) cudaFree(ctx->red_counters);
+  if (ctx->work) cudaFree(ctx->work);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return 0;
+}
+
+const char *tnn_device_name(tnn_context *ctx) { return ctx ? ctx->prop.name : ""; }
+
+int32_t tnn_device_info(tnn_context *ctx, int32_t *sm_count, int32_t *cc_major, int32_t *cc_minor) {
+  TNN_CHECK_CTX(ctx);
+  if (sm_count) *sm_count = ctx->prop.multiProcessorCount;
+  if (cc_major) *cc_major = ctx->prop.major;
+  if (cc_minor) *cc_minor = ctx->prop.minor;
+  return 0;
+}
+
+int32_t tnn_set_stream(tnn_context *ctx, void *cuda_stream) {
+  TNN_CHECK_CTX(ctx);
+  if (ctx->own_stream) {
+    TNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    TNN_CUDA(cudaStreamDestroy(ctx->stream));
+    ctx->own_stream = false;
+  }
+  ctx->stream = (cudaStream_t)cuda_stream;
+  return 0;
+}
+
+void *tnn_get_stream(tnn_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+int32_t tnn_set_math_mode(tnn_context *ctx, int32_t mode) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(mode >= TNN_MATH_FP32 && mode <= TNN_MATH_TF32, "unknown math mode");
+  ctx->math_mode = mode;
+  return 0;
+}
+
+int32_t tnn_get_math_mode(tnn_context *ctx) { return ctx ? ctx->math_mode : -1; }
+
+int64_t tnn_launch_count(tnn_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int32_t tnn_create_device_buffer(tnn_context *ctx, int64_t bytes, float **mem) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(mem != nullptr && bytes >= 0, "bad arguments");
+  *mem = nullptr;
+  if (bytes == 0) return 0;
+  TNN_CUDA(cudaSetDevice(ctx->device));
+  TNN_CUDA(cudaMalloc((void **)mem, (size_t)bytes));
+  return 0;
+}
+
+int32_t tnn_free_device_buffer(tnn_context *ctx, float *mem) {
+  TNN_CHECK_CTX(ctx);
+  if (mem) TNN_CUDA(cudaFree(mem));
+  return 0;
+}
+
+int32_t tnn_read_buffer(tnn_context *ctx, const float *mem, size_t bytes, void *host) {
+  TNN_CHECK_CTX(ctx);
+  TNN_CUDA(cudaMemcpyAsync(host, mem, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  TNN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t tnn_write_buffer(tnn_context *ctx, float *mem, size_t bytes, const void *host) {
+  TNN_CHECK_CTX(ctx);
+  TNN_CUDA(cudaMemcpyAsync(mem, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  TNN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int32_t tnn_read_buffer_async(tnn_context *ctx, const float *mem, size_t bytes, void *host) {
+  TNN_CHECK_CTX(ctx);
+  TNN_CUDA(cudaMemcpyAsync(host, mem, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return 0;
+}
+
+int32_t tnn_write_buffer_async(tnn_context *ctx, float *mem, size_t bytes, const void *host) {
+  TNN_CHECK_CTX(ctx);
+  TNN_CUDA(cudaMemcpyAsync(mem, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+int32_t tnn_finish(tnn_context *ctx) {
+  TNN_CHECK_CTX(ctx);
+  TNN_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+}  // extern "C"
+
+int tnn_reserve_reduction(tnn_context *ctx, size_t partial_floats, size_t counters) {
+  if (ctx->red_partials_bytes < partial_floats * sizeof(float)) {
+    // the old buffer may still be in use by kernels queued on the stream
+    TNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->red_partials) TNN_CUDA(cudaFree(ctx->red_partials));
+    ctx->red_partials = nullptr;
+    size_t bytes = partial_floats * sizeof(float) * 2;
+    TNN_CUDA(cudaMalloc((void **)&ctx->red_partials, bytes));
+    ctx->red_partials_bytes = bytes;
+  }
+  if (ctx->red_counters_n < counters) {
+    TNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->red_counters) TNN_CUDA(cudaFree(ctx->red_counters));
+    ctx->red_counters = nullptr;
+    size_t n = counters * 2;
+    TNN_CUDA(cudaMalloc((void **)&ctx->red_counters, n * sizeof(unsigned int)));
+    TNN_CUDA(cudaMemsetAsync(ctx->red_counters, 0, n * sizeof(unsigned int), ctx->stream));
+    ctx->red_counters_n = n;
+  }
+  return 0;
+}
+
+int tnn_reserve_work(tnn_context *ctx, size_t bytes) {
+  if (ctx->work_bytes < bytes) {
+    TNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->work) TNN_CUDA(cudaFree(ctx->work));
+    ctx->work = nullptr;
+    TNN_CUDA(cudaMalloc((void **)&ctx->work, bytes));
+    ctx->work_bytes = bytes;
+  }
+  return 0;
+}

@@ -1,0 +1,145 @@
+// common.cuh — context, error handling and small device helpers shared by all kernels of
+// libtensorium_b200.so (the sm_100a replacement for the reference's nncuda.pas backend).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/tensorium_b200.h"
+
+struct tnn_context {
+  int device;
+  cudaStream_t stream;
+  bool own_stream;
+  cudaDeviceProp prop;
+  int math_mode;
+  int64_t launches;
+  // scratch for two-stage reductions (partials + arrival counters), grown on demand
+  float *red_partials;
+  size_t red_partials_bytes;
+  unsigned int *red_counters;
+  size_t red_counters_n;
+  // scratch for the contraction kernels (pre-split / transposed weight copies, split-K partials)
+  float *work;
+  size_t work_bytes;
+};
+
+void tnn_set_error(const char *fmt, ...);
+
+#define TNN_CHECK_CTX(ctx)                         \
+  do {                                             \
+    if (!(ctx)) {                                  \
+      tnn_set_error("%s: null context", __func__); \
+      return 1;                                    \
+    }                                              \
+  } while (0)
+
+#define TNN_CUDA(call)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (call);                                                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      tnn_set_error("%s:%d %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      return 2;                                                                                 \
+    }                                                                                           \
+  } while (0)
+
+// after a kernel launch: count it and surface launch-configuration errors
+#define TNN_LAUNCHED(ctx)                                                                  \
+  do {                                                                                     \
+    (ctx)->launches++;                                                                     \
+    cudaError_t e__ = cudaPeekAtLastError();                                               \
+    if (e__ != cudaSuccess) {                                                              \
+      tnn_set_error("%s:%d kernel launch failed: %s", __FILE__, __LINE__,                  \
+                    cudaGetErrorString(cudaGetLastError()));                               \
+      return 3;                                                                            \
+    }                                                                                      \
+  } while (0)
+
+#define TNN_REQUIRE(cond, msg)                               \
+  do {                                                       \
+    if (!(cond)) {                                           \
+      tnn_set_error("%s: %s (%s)", __func__, msg, #cond);    \
+      return 4;                                              \
+    }                                                        \
+  } while (0)
+
+int tnn_reserve_reduction(tnn_context *ctx, size_t partial_floats, size_t counters);
+int tnn_reserve_work(tnn_context *ctx, size_t bytes);
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------- device helpers
+#define TNN_EPS 0.000001f  // sEPSILON, ntensors.pas:95
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Scalar activation, following the CPU functions of nactivation.pas:272-401 (not the NVRTC kernels
+// where they differ).  Decimal-constant multiplies are done in fp64 and rounded once, like the
+// Pascal expressions (real-typed literal * single), so the piecewise-linear ones are bit-exact.
+__device__ __forceinline__ float tnn_act(float x, int a) {
+  switch (a) {
+    case TNN_ACT_LOGISTIC: return 1.0f / (1.0f + expf(-x));
+    case TNN_ACT_RELU: return x * (float)(x > 0);
+    case TNN_ACT_RELU6: return x * (float)(x > 0) * (float)(x <= 6);  // 0 above 6: reference quirk (nactivation.pas:316)
+    case TNN_ACT_RELIE: return x > 0 ? x : (float)(0.01 * (double)x);
+    case TNN_ACT_RAMP: return (float)((double)x * (double)(x > 0) + 0.1 * (double)x);
+    case TNN_ACT_TANH: { float px = expf(x), nx = expf(-x); return (px - nx) / (px + nx); }
+    case TNN_ACT_PLSE:
+      if (x < -4) return (float)(0.01 * ((double)x + 4));
+      if (x > 4) return (float)(0.01 * ((double)x - 4) + 1);
+      return (float)(0.125 * (double)x + 0.5);
+    case TNN_ACT_REVLEAKY:
+    case TNN_ACT_LEAKY: return x < 0 ? (float)(0.1 * (double)x) : x;
+    case TNN_ACT_ELU: return (x >= 0) ? x : (expf(x) - 1.0f);
+    case TNN_ACT_LOGGY: return 2.0f / (1.0f + expf(-x)) - 1.0f;
+    case TNN_ACT_STAIR: {
+      long long n = (long long)floorf(x);
+      if (n % 2 == 0) return floorf(x / 2);
+      return (x - (float)n) + floorf(x / 2);
+    }
+    case TNN_ACT_HARDTAN: return x < -1 ? -1.0f : (x > 1 ? 1.0f : x);
+    case TNN_ACT_LHTAN:
+      if (x < 0) return (float)(0.001 * (double)x);
+      if (x > 1) return (float)(0.001 * ((double)x - 1) + 1);
+      return x;
+    case TNN_ACT_SELU: return (x >= 0) ? (float)(1.0507 * (double)x) : (float)(1.0507 * 1.6732 * ((double)expf(x) - 1.0));
+    case TNN_ACT_GELU: return (float)(0.5 * (double)x * (1.0 + tanh(0.797885 * (double)x + 0.035677 * (double)x * (double)x * (double)x)));
+    case TNN_ACT_SWISH: return x * (1.0f / (1.0f + expf(-x)));
+    default: return x;  // LINEAR and the non-elementwise types
+  }
+}
+
+// Gradient as a function of the layer OUTPUT (nactivation.pas:403-501)
+__device__ __forceinline__ float tnn_grad(float x, int a) {
+  switch (a) {
+    case TNN_ACT_LOGISTIC: return (1 - x) * x;
+    case TNN_ACT_RELU: return (float)(x > 0);
+    case TNN_ACT_RELU6: return (float)((x > 0) && (x < 6));
+    case TNN_ACT_RELIE: return x > 0 ? 1.0f : 0.01f;
+    case TNN_ACT_RAMP: return (float)((double)(x > 0) + 0.1);
+    case TNN_ACT_TANH: return 1 - x * x;
+    case TNN_ACT_PLSE: return (x < 0 || x > 1) ? 0.01f : 0.125f;
+    case TNN_ACT_REVLEAKY:
+    case TNN_ACT_LEAKY: return x > 0 ? 1.0f : 0.1f;
+    case TNN_ACT_ELU: return (x >= 0) ? 1.0f : (x + 1);
+    case TNN_ACT_LOGGY: { float y = (x + 1.0f) / 2.0f; return 2 * (1 - y) * y; }
+    case TNN_ACT_STAIR: return floorf(x) == x ? 0.0f : 1.0f;
+    case TNN_ACT_HARDTAN: return (x > -1 && x < 1) ? 1.0f : 0.0f;
+    case TNN_ACT_LHTAN: return (x > 0 && x < 1) ? 1.0f : 0.001f;
+    case TNN_ACT_SELU: return (x >= 0) ? 1.0507f : (float)((double)x + 1.0507 * 1.6732);
+    case TNN_ACT_GELU: {
+      double xd = x, x3 = xd * xd * xd, t = 0.0356774 * x3 + 0.797885 * xd;
+      double sech = 2.0 / (exp(t) + exp(-t));
+      return (float)(0.5 * tanh(t) + (0.0535161 * x3 + 0.398942 * xd) * sech * sech + 0.5);
+    }
+    default: return 1.0f;
+  }
+}
+
+static inline bool tnn_act_is_elementwise(int a) {
+  return a >= 0 && a <= TNN_ACT_SWISH && a != TNN_ACT_SOFTMAX;
+}

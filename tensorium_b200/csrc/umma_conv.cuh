@@ -1,0 +1,556 @@
+// umma_conv.cuh — tcgen05 (5th-gen tensor core) contraction kernel for sm_100a.
+//
+// One kernel template serves the implicit-GEMM convolution forward and plain SGEMM:
+//   D[m][n] (TMEM, fp32, 128 lanes x BN columns) = sum_k A(m,k) * B(n,k)
+// * Operands are staged in shared memory in the UMMA canonical SWIZZLE_128B layouts by 8 producer
+//   warps that read global memory directly (im2col is done on the fly — no column buffer exists),
+//   then consumed by `tcgen05.mma.cta_group::1.kind::tf32` issued by one thread of a dedicated warp.
+// * 3xTF32: every fp32 operand is split in registers on its way to shared memory into
+//   hi = x with the low 13 mantissa bits cleared (exactly a TF32 number) and lo = x - hi (exact in fp32);
+//   D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi gives fp32-level accuracy (the dropped A_lo*B_lo term is
+//   ~2^-22 relative).  TF32 mode stores only the raw value (hardware ignores the low mantissa bits).
+// * mbarrier ring: producers -> full[s] -> MMA warp -> tcgen05.commit -> empty[s] -> producers;
+//   final tcgen05.commit -> accum barrier -> all 8 producer warps turn into the epilogue:
+//   tcgen05.ld (32 lanes x 32 columns per instruction) -> scale/bias/activation -> coalesced stores.
+//
+// Shared-memory operand layouts (bytes; every tile is 1024B aligned):
+//   K-major  (rows = M or N index, 32 floats = 128B per row):   row*128 + ((chunk16 ^ (row&7))<<4)
+//            descriptor: SWIZZLE_128B, SBO = 1024 (8 rows), advance 32B per UMMA_K=8 step
+//   MN-major (32 consecutive M/N elements = 128B per k row, 8 k rows per 1024B atom):
+//            ((k>>3)*(R/32) + (mn>>5))*1024 + (k&7)*128 + ((((mn&31)>>2) ^ (k&7))<<4) + (mn&3)*4
+//            descriptor: SWIZZLE_128B, LBO = 1024 (next 32-element atom along M/N),
+//            SBO = (R/32)*1024 (next 8-row k group), advance one SBO per UMMA_K=8 step
+#pragma once
+#include "common.cuh"
+#include "gemm_simt.cuh"
+
+namespace umma {
+
+constexpr int kNotTaken = -100;
+constexpr int BM = 128;
+constexpr int BK = 32;
+constexpr int kProducerWarps = 8;
+constexpr int kProducerThreads = kProducerWarps * 32;
+constexpr int kThreads = kProducerThreads + 32;  // + MMA warp
+constexpr int kMaxStages = 4;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(addr), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier when all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void mma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, M=128, N=n
+__host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) |
+         ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// store one element of an MN-major tile with R rows (R % 32 == 0)
+template <bool SPLIT>
+__device__ __forceinline__ void sts_mn(uint8_t *hi, uint8_t *lo, int R, int mn, int k, float v) {
+  const int off = (((k >> 3) * (R >> 5) + (mn >> 5)) << 10) + ((k & 7) << 7) + (((((mn & 31) >> 2) ^ (k & 7))) << 4) +
+                  ((mn & 3) << 2);
+  if (SPLIT) {
+    const float h = tf32_hi(v);
+    *reinterpret_cast<float *>(hi + off) = h;
+    *reinterpret_cast<float *>(lo + off) = v - h;
+  } else {
+    *reinterpret_cast<float *>(hi + off) = v;
+  }
+}
+// store one 16-byte chunk (4 consecutive k) of a K-major tile
+template <bool SPLIT>
+__device__ __forceinline__ void sts_k(uint8_t *hi, uint8_t *lo, int row, int chunk, float4 v) {
+  const int off = (row << 7) + ((chunk ^ (row & 7)) << 4);
+  if (SPLIT) {
+    float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+    *reinterpret_cast<float4 *>(hi + off) = h;
+    *reinterpret_cast<float4 *>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+  } else {
+    *reinterpret_cast<float4 *>(hi + off) = v;
+  }
+}
+
+// ------------------------------------------------------------------ operand loaders
+// Every loader fills one [R rows][32 k] tile for k-block kb with the 256 producer threads.
+//   kMnMajor     layout it writes (decides the descriptor)
+//   fill<SPLIT>(hi, lo, R, mn0, kb, tid)   mn0 = first row of the tile
+
+// matrix whose k index is contiguous: elem(mn,k) = p[mn*ld + k]   (A of NN/NT, B of NT, conv weights)
+struct KContigLoader {
+  static constexpr bool kMnMajor = false;
+  const float *p;
+  int64_t ld;
+  int64_t rows, K;   // valid extent
+  int64_t K1, zfold; // fold-batch-into-k: k = b*K1 + kk -> p + b*zfold (K1 % 32 == 0), else K1 = K
+  bool vec_ok;       // rows 16B aligned and K1 % 4 == 0
+  template <bool SPLIT>
+  __device__ __forceinline__ void fill(uint8_t *hi, uint8_t *lo, int R, int64_t mn0, int64_t kb, int tid) const {
+    const int64_t k0 = kb * BK;
+    const int64_t b = k0 / K1;
+    const int64_t kk0 = k0 - b * K1;
+    const float *base = p + b * zfold;
+    for (int e = tid; e < R * 8; e += kProducerThreads) {
+      const int row = e >> 3, chunk = e & 7;
+      const int64_t mn = mn0 + row;
+      const int64_t kk = kk0 + chunk * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (mn < rows) {
+        const float *q = base + mn * ld + kk;
+        if (vec_ok && kk + 3 < K1) {
+          v = __ldg(reinterpret_cast<const float4 *>(q));
+        } else {
+          if (kk + 0 < K1) v.x = __ldg(q + 0);
+          if (kk + 1 < K1) v.y = __ldg(q + 1);
+          if (kk + 2 < K1) v.z = __ldg(q + 2);
+          if (kk + 3 < K1) v.w = __ldg(q + 3);
+        }
+      }
+      sts_k<SPLIT>(hi, lo, row, chunk, v);
+    }
+  }
+};
+
+// matrix whose mn index is contiguous: elem(mn,k) = p[k*ld + mn]   (A of TN, B of NN/TN)
+struct MnContigLoader {
+  static constexpr bool kMnMajor = true;
+  const float *p;
+  int64_t ld;
+  int64_t rows, K;
+  int64_t K1, zfold;
+  template <bool SPLIT>
+  __device__ __forceinline__ void fill(uint8_t *hi, uint8_t *lo, int R, int64_t mn0, int64_t kb, int tid) const {
+    const int64_t k0 = kb * BK;
+    const int64_t b = k0 / K1;
+    const int64_t kk0 = k0 - b * K1;
+    const float *base = p + b * zfold;
+    const int sh = 31 - __clz(R);  // R is a power of two >= 32: a warp covers 32 consecutive rows of one k
+    for (int e = tid; e < R * BK; e += kProducerThreads) {
+      const int row = e & (R - 1), k = e >> sh;
+      const int64_t mn = mn0 + row;
+      float v = 0.f;
+      if (mn < rows && kk0 + k < K1) v = __ldg(base + (kk0 + k) * ld + mn);
+      sts_mn<SPLIT>(hi, lo, R, row, k, v);
+    }
+  }
+};
+
+// implicit im2col: row = output pixel (b, oh, ow) folded over the batch, k = (c, kr, kc)
+// elem = in[b][c][oh*sy - ph + kr*dy][ow*sx - pw + kc*dx] or 0     (sim2Col ntensors.pas:11415-11491)
+struct Im2colPixelLoader {
+  static constexpr bool kMnMajor = true;
+  const float *in;
+  simt::ConvGeom g;
+  int64_t rows;  // batch*OH*OW
+  int64_t K;     // C*kh*kw
+  template <bool SPLIT>
+  __device__ __forceinline__ void fill(uint8_t *hi, uint8_t *lo, int R, int64_t mn0, int64_t kb, int tid) const {
+    // R == 128: thread -> (pixel row = tid & 127, k half = tid >> 7), 16 consecutive k each
+    const int row = tid & 127;
+    const int64_t mn = mn0 + row;
+    const bool valid = mn < rows;
+    const int P = g.OH * g.OW;
+    const int pix = valid ? (int)mn : 0;
+    const int b = pix / P, p = pix - b * P;
+    const int oh = p / g.OW, ow = p - oh * g.OW;
+    const int ih0 = oh * g.sy - g.ph, iw0 = ow * g.sx - g.pw;
+    const float *base = in + (int64_t)b * g.inImg + (int64_t)ih0 * g.W + iw0;
+    const int kk = g.kh * g.kw;
+    int k = (int)(kb * BK) + (tid >> 7) * 16;
+    int c = k / kk;
+    int rem = k - c * kk;
+    int kr = rem / g.kw, kc = rem - kr * g.kw;
+    const int kl0 = (tid >> 7) * 16;
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j, ++k) {
+      float v = 0.f;
+      if (valid && k < K) {
+        const int dh = kr * g.dy, dw = kc * g.dx;
+        if ((unsigned)(ih0 + dh) < (unsigned)g.H && (unsigned)(iw0 + dw) < (unsigned)g.W)
+          v = __ldg(base + ((int64_t)c * g.H + dh) * g.W + dw);
+      }
+      sts_mn<SPLIT>(hi, lo, R, row, kl0 + j, v);
+      if (++kc == g.kw) { kc = 0; if (++kr == g.kh) { kr = 0; ++c; } }
+    }
+  }
+};
+
+// ------------------------------------------------------------------ epilogues
+// Row context per thread (its TMEM lane = row m), then one call per column.
+struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
+  float *out;
+  const float *scale, *bias;
+  int P;
+  int64_t outImg;
+  int act;
+  int64_t rows, cols;
+  struct Row { float *q; };
+  __device__ __forceinline__ Row row(int64_t m) const {
+    const int b = (int)(m / P), p = (int)(m - (int64_t)b * P);
+    return Row{out + (int64_t)b * outImg + p};
+  }
+  __device__ __forceinline__ void store(const Row &r, int64_t n, float acc) const {
+    float v = acc;
+    if (scale) v = __fmul_rn(v, __ldg(scale + n));
+    if (bias) v = __fadd_rn(v, __ldg(bias + n));
+    r.q[n * P] = tnn_act(v, act);
+  }
+};
+struct GemmEpilogue {  // C[z][m][n] = alpha*acc + beta*C
+  float *C;
+  int64_t ldc;
+  float alpha, beta;
+  int64_t rows, cols;
+  struct Row { float *q; };
+  __device__ __forceinline__ Row row(int64_t m) const { return Row{C + m * ldc}; }
+  __device__ __forceinline__ void store(const Row &r, int64_t n, float acc) const {
+    r.q[n] = (beta == 0.f) ? alpha * acc : fmaf(alpha, acc, beta * r.q[n]);
+  }
+};
+struct GemmAtomicEpilogue {  // split-k: C += alpha*acc
+  float *C;
+  int64_t ldc;
+  float alpha, beta;
+  int64_t rows, cols;
+  struct Row { float *q; };
+  __device__ __forceinline__ Row row(int64_t m) const { return Row{C + m * ldc}; }
+  __device__ __forceinline__ void store(const Row &r, int64_t n, float acc) const { atomicAdd(r.q + n, alpha * acc); }
+};
+
+// ------------------------------------------------------------------ the kernel
+struct SharedCtl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t accum;
+  uint32_t tmem_base;
+};
+
+// grid: x = M tiles, y = N tiles, z = k splits.  BN = runtime tile width (multiple of 16, <= 256; multiple of 32
+// when B is MN-major).  SPLIT = 3xTF32.
+template <bool SPLIT, typename LA, typename LB, typename EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t kBlocksPerSplit, uint32_t tmemCols) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ SharedCtl ctl;
+  // 1024B-aligned operand ring
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const int aBytes = BM * BK * 4;
+  const int bBytes = BN * BK * 4;
+  const int stageBytes = (aBytes + bBytes) * (SPLIT ? 2 : 1);
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&ctl.full[s], kProducerWarps);
+      mbar_init(&ctl.empty[s], 1);
+    }
+    mbar_init(&ctl.accum, 1);
+    fence_barrier_init();
+  }
+  if (warp == kProducerWarps) tmem_alloc(&ctl.tmem_base, tmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = ctl.tmem_base;
+
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int64_t n0 = (int64_t)blockIdx.y * BN;
+  const int64_t kbBegin = (int64_t)blockIdx.z * kBlocksPerSplit;
+  const int64_t kbEnd = min(kBlocksTotal, kbBegin + kBlocksPerSplit);
+  const int64_t nkb = kbEnd - kbBegin;
+
+  if (warp < kProducerWarps) {
+    // ===================== producers: global -> (split) -> swizzled smem =====================
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t kb = kbBegin; kb < kbEnd; ++kb) {
+      mbar_wait(&ctl.empty[stage], phase ^ 1);
+      uint8_t *sa = smem + (size_t)stage * stageBytes;
+      uint8_t *sa_lo = sa + aBytes;
+      uint8_t *sb = sa + (SPLIT ? 2 : 1) * aBytes;
+      uint8_t *sb_lo = sb + bBytes;
+      la.template fill<SPLIT>(sa, sa_lo, BM, m0, kb, threadIdx.x);
+      lb.template fill<SPLIT>(sb, sb_lo, BN, n0, kb, threadIdx.x);
+      fence_proxy_async();  // make generic-proxy smem writes visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl.full[stage]);
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+    // ===================== epilogue: TMEM -> registers -> global =====================
+    if (nkb > 0) {
+      mbar_wait(&ctl.accum, 0);
+      tc_fence_after();
+      const int quad = warp & 3;           // TMEM lane quadrant this warp may read
+      const int half = warp >> 2;          // column half
+      const int64_t m = m0 + quad * 32 + lane;
+      const bool mvalid = m < epi.rows;
+      typename EPI::Row rc = epi.row(mvalid ? m : 0);
+      const int nChunks = (BN + 31) >> 5;  // 32-column chunks; chunk i starts at column 32*i (< tmemCols)
+      for (int ci = half; ci < nChunks; ci += 2) {
+        const int c0 = ci * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
+        if (mvalid) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int64_t n = n0 + c0 + j;
+            if (c0 + j < BN && n < epi.cols) epi.store(rc, n, __uint_as_float(r[j]));
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== MMA issuer (one elected thread) =====================
+    const uint32_t idesc = make_idesc(BN, LA::kMnMajor, LB::kMnMajor);
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t kb = kbBegin; kb < kbEnd; ++kb) {
+      mbar_wait(&ctl.full[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
+        const uint32_t sa_lo = sa + aBytes;
+        const uint32_t sb = sa + (SPLIT ? 2 : 1) * aBytes;
+        const uint32_t sb_lo = sb + bBytes;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          // A: 128 rows.  MN-major: LBO 1024, SBO 4*1024, next k group = +SBO.  K-major: SBO 1024, next k = +32B.
+          const uint32_t aoff = LA::kMnMajor ? ks * (BM / 32) * 1024 : ks * 32;
+          const uint32_t boff = LB::kMnMajor ? ks * (BN / 32) * 1024 : ks * 32;
+          const uint32_t a_lbo = LA::kMnMajor ? 1024 : 16, a_sbo = LA::kMnMajor ? (BM / 32) * 1024 : 1024;
+          const uint32_t b_lbo = LB::kMnMajor ? 1024 : 16, b_sbo = LB::kMnMajor ? (BN / 32) * 1024 : 1024;
+          const uint64_t ah = make_desc(sa + aoff, a_lbo, a_sbo);
+          const uint64_t bh = make_desc(sb + boff, b_lbo, b_sbo);
+          const uint32_t first = (kb != kbBegin || ks != 0) ? 1u : 0u;
+          if (SPLIT) {
+            const uint64_t al = make_desc(sa_lo + aoff, a_lbo, a_sbo);
+            const uint64_t bl = make_desc(sb_lo + boff, b_lbo, b_sbo);
+            mma_tf32(tmem_d, al, bh, idesc, first);  // small terms first
+            mma_tf32(tmem_d, ah, bl, idesc, 1u);
+            mma_tf32(tmem_d, ah, bh, idesc, 1u);
+          } else {
+            mma_tf32(tmem_d, ah, bh, idesc, first);
+          }
+        }
+        mma_commit(&ctl.empty[stage]);            // frees the smem slot when the MMAs have read it
+        if (kb == kbEnd - 1) mma_commit(&ctl.accum);  // accumulator complete
+      }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kProducerWarps) tmem_dealloc(tmem_d, tmemCols);
+}
+
+// ------------------------------------------------------------------ host side
+struct Plan {
+  int BN, stages, kSplits;
+  uint32_t tmemCols;
+  size_t smemBytes;
+  int64_t kBlocks, kBlocksPerSplit;
+  dim3 grid;
+};
+
+inline uint32_t pow2_cols(int bn) {
+  uint32_t c = 32;
+  while ((int)c < bn) c <<= 1;
+  return c;
+}
+
+inline Plan make_plan(tnn_context *ctx, int64_t M, int64_t N, int64_t K, bool split, bool bMnMajor, bool allowSplitK) {
+  Plan p;
+  int bn;
+  if (N >= 256) bn = 256;
+  else bn = (int)(((N + 15) / 16) * 16);
+  if (bMnMajor) {  // MN-major B tiles need whole 32-element atoms
+    bn = (bn <= 32) ? 32 : (bn <= 64) ? 64 : (bn <= 128) ? 128 : 256;
+  }
+  if (bn < 16) bn = 16;
+  p.BN = bn;
+  p.tmemCols = pow2_cols(bn);
+  const size_t stageBytes = (size_t)(BM + bn) * BK * 4 * (split ? 2 : 1);
+  const size_t budget = 200 * 1024;
+  int st = (int)(budget / stageBytes);
+  if (st > kMaxStages) st = kMaxStages;
+  if (st < 2) st = 2;
+  p.kBlocks = cdiv64(K, BK);
+  if (p.kBlocks < 1) p.kBlocks = 1;
+  if ((int64_t)st > p.kBlocks) st = (int)(p.kBlocks < 2 ? 2 : p.kBlocks);
+  p.stages = st;
+  p.smemBytes = stageBytes * st + 1024;
+  const int64_t tiles = cdiv64(M, BM) * cdiv64(N, bn);
+  int ks = 1;
+  if (allowSplitK) {
+    const int64_t sms = ctx->prop.multiProcessorCount;
+    if (tiles < sms && p.kBlocks >= 16) {
+      ks = (int)(sms / tiles);
+      const int64_t maxs = p.kBlocks / 8;
+      if (ks > maxs) ks = (int)maxs;
+      if (ks < 1) ks = 1;
+    }
+  }
+  p.kBlocksPerSplit = cdiv64(p.kBlocks, ks);
+  p.kSplits = (int)cdiv64(p.kBlocks, p.kBlocksPerSplit);
+  p.grid = dim3((unsigned)cdiv64(M, BM), (unsigned)cdiv64(N, bn), (unsigned)p.kSplits);
+  return p;
+}
+
+template <bool SPLIT, typename LA, typename LB, typename EPI>
+int launch(tnn_context *ctx, const Plan &p, LA la, LB lb, EPI epi) {
+  auto kern = k_umma<SPLIT, LA, LB, EPI>;
+  TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
+  TNN_REQUIRE(p.grid.y <= 65535 && p.grid.z <= 65535, "grid too large");
+  kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(la, lb, epi, p.BN, p.stages, p.kBlocks, p.kBlocksPerSplit,
+                                                       p.tmemCols);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
+inline bool gemm_supported(tnn_context *, int64_t M, int64_t N, int64_t K) {
+  // tiny problems are latency bound: leave them to the CUDA-core kernel
+  return M * N * K >= (1ll << 18) && K >= 8;
+}
+
+template <typename LA, typename LB>
+int gemm_launch(tnn_context *ctx, LA la, LB lb, int64_t M, int64_t N, int64_t Ktot, float alpha, float beta, float *C,
+                int64_t ldc, bool allowSplitK) {
+  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  Plan p = make_plan(ctx, M, N, Ktot, split, LB::kMnMajor, allowSplitK && beta == 1.0f);
+  if (p.kSplits > 1) {
+    GemmAtomicEpilogue epi{C, ldc, alpha, beta, M, N};
+    return split ? launch<true>(ctx, p, la, lb, epi) : launch<false>(ctx, p, la, lb, epi);
+  }
+  GemmEpilogue epi{C, ldc, alpha, beta, M, N};
+  return split ? launch<true>(ctx, p, la, lb, epi) : launch<false>(ctx, p, la, lb, epi);
+}
+
+// C = beta*C + alpha*op(A)op(B); batch > 1 either loops (strideC != 0) or is folded into k (strideC == 0, beta == 1)
+inline int gemm(tnn_context *ctx, bool tA, bool tB, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                int64_t lda, int64_t sA, const float *B, int64_t ldb, int64_t sB, float beta, float *C, int64_t ldc,
+                int64_t sC, int batch, bool foldBatchIntoK) {
+  if (foldBatchIntoK && batch > 1 && (K % BK) != 0) return kNotTaken;  // k-blocks would straddle images
+  const int nz = foldBatchIntoK ? 1 : batch;
+  for (int z = 0; z < nz; ++z) {
+    const float *Az = A + (foldBatchIntoK ? 0 : z * sA);
+    const float *Bz = B + (foldBatchIntoK ? 0 : z * sB);
+    float *Cz = C + (foldBatchIntoK ? 0 : z * sC);
+    const int64_t Ktot = foldBatchIntoK ? K * batch : K;
+    const int64_t K1 = K;
+    int rc;
+    auto vec_ok = [&](const float *p, int64_t ld, int64_t zs) {
+      return (((uintptr_t)p) & 15) == 0 && (ld % 4) == 0 && (zs % 4) == 0 && (K1 % 4) == 0;
+    };
+    if (!tA && tB) {  // A k-contig, B k-contig
+      KContigLoader la{Az, lda, M, Ktot, K1, foldBatchIntoK ? sA : 0, vec_ok(Az, lda, sA)};
+      KContigLoader lb{Bz, ldb, N, Ktot, K1, foldBatchIntoK ? sB : 0, vec_ok(Bz, ldb, sB)};
+      rc = gemm_launch(ctx, la, lb, M, N, Ktot, alpha, beta, Cz, ldc, true);
+    } else if (!tA && !tB) {  // A k-contig, B n-contig
+      KContigLoader la{Az, lda, M, Ktot, K1, foldBatchIntoK ? sA : 0, vec_ok(Az, lda, sA)};
+      MnContigLoader lb{Bz, ldb, N, Ktot, K1, foldBatchIntoK ? sB : 0};
+      rc = gemm_launch(ctx, la, lb, M, N, Ktot, alpha, beta, Cz, ldc, true);
+    } else if (tA && !tB) {  // A m-contig, B n-contig
+      MnContigLoader la{Az, lda, M, Ktot, K1, foldBatchIntoK ? sA : 0};
+      MnContigLoader lb{Bz, ldb, N, Ktot, K1, foldBatchIntoK ? sB : 0};
+      rc = gemm_launch(ctx, la, lb, M, N, Ktot, alpha, beta, Cz, ldc, true);
+    } else {  // A m-contig, B k-contig
+      MnContigLoader la{Az, lda, M, Ktot, K1, foldBatchIntoK ? sA : 0};
+      KContigLoader lb{Bz, ldb, N, Ktot, K1, foldBatchIntoK ? sB : 0, vec_ok(Bz, ldb, sB)};
+      rc = gemm_launch(ctx, la, lb, M, N, Ktot, alpha, beta, Cz, ldc, true);
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+// conv forward: D[pixel][filter]; A = im2col gather (MN-major), B = weights [F][C*kh*kw] (K-major)
+inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
+                        const float *scale, const float *bias, int act, float *out) {
+  const int64_t M = (int64_t)batch * g.OH * g.OW;
+  const int64_t N = g.F;
+  const int64_t K = (int64_t)g.C * g.kh * g.kw;
+  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  Plan p = make_plan(ctx, M, N, K, split, false, false);
+  Im2colPixelLoader la{in, g, M, K};
+  const bool vec = ((((uintptr_t)weights) & 15) == 0) && (K % 4 == 0);
+  KContigLoader lb{weights, K, N, K, K, 0, vec};
+  ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N};
+  return split ? launch<true>(ctx, p, la, lb, epi) : launch<false>(ctx, p, la, lb, epi);
+}
+
+}  // namespace umma

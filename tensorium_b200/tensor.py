@@ -1,0 +1,94 @@
+"""TSingleTensor — minimal host-side twin of the reference's TTensor<Single> record
+(source/ntensors.pas:226-902): host storage `Data`, device twin `devData`, `Groups` (= batch) and the
+`lastOP` residency flag with pushToDevice / pullFromDevice (ntensors.pas:6153-6315).
+
+Only what crosses the backend boundary is mirrored; the tensor utility methods of the
+reference (printing, plotting, image I/O, ...) are out of scope.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+cdCPU, cdCUDA = 0, 1
+
+_cuda = None  # the global `cuda : TNNCuda<Single>` (ntensors.pas:1053-1056)
+
+
+def initCUDART(deviceIndex: int = 0):
+    """ntensors.pas:6191-6209: create the global backend instance."""
+    global _cuda
+    from .nncuda import TNNCuda
+    if _cuda is None or _cuda.deviceIndex != deviceIndex:
+        _cuda = TNNCuda(deviceIndex)
+    return _cuda
+
+
+def cuda():
+    if _cuda is None:
+        raise RuntimeError("initCUDART() has not been called")
+    return _cuda
+
+
+class TSingleTensor:
+    def __init__(self, shape, groups: int | None = None, data=None, device: bool = True):
+        self.FShape = tuple(int(s) for s in shape)
+        self.Groups = int(groups) if groups is not None else (self.FShape[0] if len(self.FShape) > 1 else 1)
+        if data is not None:
+            self.Data = np.ascontiguousarray(data, dtype=np.float32).reshape(self.FShape).copy()
+        else:
+            self.Data = np.zeros(self.FShape, dtype=np.float32)
+        self.devData = 0
+        self.lastOP = cdCPU
+        if device and self.Data.size:
+            self.devData = cuda().createDeviceBuffer(self.Data.nbytes)  # ntensors.pas:6103-6109
+
+    # shape helpers (ntensors.pas: Size/Volume/Area/c/h/w)
+    def Size(self) -> int:
+        return int(self.Data.size)
+
+    size = Size
+
+    def volume(self) -> int:
+        return self.Size() // self.Groups if self.Groups else self.Size()
+
+    def area(self) -> int:
+        return self.FShape[-1] * self.FShape[-2] if len(self.FShape) >= 2 else self.Size()
+
+    def c(self):
+        return self.FShape[-3]
+
+    def h(self):
+        return self.FShape[-2]
+
+    def w(self):
+        return self.FShape[-1]
+
+    # residency (ntensors.pas:6153-6229)
+    def wasGPU(self) -> bool:
+        return self.lastOP == cdCUDA
+
+    def setCUDA(self):
+        self.lastOP = cdCUDA
+
+    def setCPU(self):
+        self.lastOP = cdCPU
+
+    def pushToDevice(self):  # ntensors.pas:6231-6262
+        cuda().writeBuffer(self.devData, self.Data.nbytes, self.Data)
+        self.lastOP = cdCUDA
+
+    def pullFromDevice(self):  # ntensors.pas:6264-6315
+        cuda().readBuffer(self.devData, self.Data.nbytes, self.Data)
+        self.lastOP = cdCPU
+        return self.Data
+
+    def Free(self):  # ntensors.pas:6126-6129
+        if self.devData:
+            cuda().freeDeviceBuffer(self.devData)
+            self.devData = 0
+
+    def __del__(self):
+        try:
+            self.Free()
+        except Exception:
+            pass
