@@ -99,7 +99,7 @@ __device__ __forceinline__ float tnn_act(float x, int a) {
     case TNN_ACT_STAIR: {
       long long n = (long long)floorf(x);
       if (n % 2 == 0) return floorf(x / 2);
-      return (x - (float)n) + floorf(x / 2);
+      return (float)(((double)x - (double)n) + floor((double)x / 2));
     }
     case TNN_ACT_HARDTAN: return x < -1 ? -1.0f : (x > 1 ? 1.0f : x);
     case TNN_ACT_LHTAN:
@@ -116,17 +116,17 @@ __device__ __forceinline__ float tnn_act(float x, int a) {
 // Gradient as a function of the layer OUTPUT (nactivation.pas:403-501)
 __device__ __forceinline__ float tnn_grad(float x, int a) {
   switch (a) {
-    case TNN_ACT_LOGISTIC: return (1 - x) * x;
+    case TNN_ACT_LOGISTIC: return (float)((1.0 - (double)x) * (double)x);
     case TNN_ACT_RELU: return (float)(x > 0);
     case TNN_ACT_RELU6: return (float)((x > 0) && (x < 6));
     case TNN_ACT_RELIE: return x > 0 ? 1.0f : 0.01f;
     case TNN_ACT_RAMP: return (float)((double)(x > 0) + 0.1);
-    case TNN_ACT_TANH: return 1 - x * x;
+    case TNN_ACT_TANH: return (float)(1.0 - (double)x * (double)x);
     case TNN_ACT_PLSE: return (x < 0 || x > 1) ? 0.01f : 0.125f;
     case TNN_ACT_REVLEAKY:
     case TNN_ACT_LEAKY: return x > 0 ? 1.0f : 0.1f;
     case TNN_ACT_ELU: return (x >= 0) ? 1.0f : (x + 1);
-    case TNN_ACT_LOGGY: { float y = (x + 1.0f) / 2.0f; return 2 * (1 - y) * y; }
+    case TNN_ACT_LOGGY: { double y = ((double)x + 1.0) / 2.0; return (float)(2 * (1 - y) * y); }
     case TNN_ACT_STAIR: return floorf(x) == x ? 0.0f : 1.0f;
     case TNN_ACT_HARDTAN: return (x > -1 && x < 1) ? 1.0f : 0.0f;
     case TNN_ACT_LHTAN: return (x > 0 && x < 1) ? 1.0f : 0.001f;

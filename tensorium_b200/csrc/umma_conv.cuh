@@ -16,10 +16,12 @@
 // Shared-memory operand layouts (bytes; every tile is 1024B aligned):
 //   K-major  (rows = M or N index, 32 floats = 128B per row):   row*128 + ((chunk16 ^ (row&7))<<4)
 //            descriptor: SWIZZLE_128B, SBO = 1024 (8 rows), advance 32B per UMMA_K=8 step
-//   MN-major (32 consecutive M/N elements = 128B per k row, 8 k rows per 1024B atom):
-//            ((k>>3)*(R/32) + (mn>>5))*1024 + (k&7)*128 + ((((mn&31)>>2) ^ (k&7))<<4) + (mn&3)*4
-//            descriptor: SWIZZLE_128B, LBO = 1024 (next 32-element atom along M/N),
-//            SBO = (R/32)*1024 (next 8-row k group), advance one SBO per UMMA_K=8 step
+//   MN-major (32 consecutive M/N elements = 128B per k row, 4 k rows per 512B atom; the only MN-major layout
+//            the hardware takes for 32-bit operands is SWIZZLE_128B_BASE32B = Swizzle<2,5,2>: 32-byte chunks of a
+//            row XOR (k&3); measured on B200: plain SWIZZLE_128B MN-major tf32 yields zeros):
+//            ((k>>2)*(R/32) + (mn>>5))*512 + (k&3)*128 + ((((mn&31)>>3) ^ (k&3))<<5) + (mn&7)*4
+//            descriptor: SWIZZLE_128B_BASE32B, LBO = 512 (next 32-element atom along M/N),
+//            SBO = (R/32)*512 (next 4-row k group), advance two SBO per UMMA_K=8 step
 #pragma once
 #include "common.cuh"
 #include "gemm_simt.cuh"
@@ -98,14 +100,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), SWIZZLE_128B, version 1
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout), version 1;
+// layout_type: 2 = SWIZZLE_128B (K-major tiles), 1 = SWIZZLE_128B_BASE32B (MN-major 32-bit tiles)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                              uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): D=F32, A=B=TF32, M=128, N=n
@@ -119,8 +123,8 @@ __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__flo
 // store one element of an MN-major tile with R rows (R % 32 == 0)
 template <bool SPLIT>
 __device__ __forceinline__ void sts_mn(uint8_t *hi, uint8_t *lo, int R, int mn, int k, float v) {
-  const int off = (((k >> 3) * (R >> 5) + (mn >> 5)) << 10) + ((k & 7) << 7) + (((((mn & 31) >> 2) ^ (k & 7))) << 4) +
-                  ((mn & 3) << 2);
+  const int off = (((k >> 2) * (R >> 5) + (mn >> 5)) << 9) + ((k & 3) << 7) + (((((mn & 31) >> 3) ^ (k & 3))) << 5) +
+                  ((mn & 7) << 2);
   if (SPLIT) {
     const float h = tf32_hi(v);
     *reinterpret_cast<float *>(hi + off) = h;
@@ -387,17 +391,18 @@ k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t 
         const uint32_t sb_lo = sb + bBytes;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
-          // A: 128 rows.  MN-major: LBO 1024, SBO 4*1024, next k group = +SBO.  K-major: SBO 1024, next k = +32B.
-          const uint32_t aoff = LA::kMnMajor ? ks * (BM / 32) * 1024 : ks * 32;
-          const uint32_t boff = LB::kMnMajor ? ks * (BN / 32) * 1024 : ks * 32;
-          const uint32_t a_lbo = LA::kMnMajor ? 1024 : 16, a_sbo = LA::kMnMajor ? (BM / 32) * 1024 : 1024;
-          const uint32_t b_lbo = LB::kMnMajor ? 1024 : 16, b_sbo = LB::kMnMajor ? (BN / 32) * 1024 : 1024;
-          const uint64_t ah = make_desc(sa + aoff, a_lbo, a_sbo);
-          const uint64_t bh = make_desc(sb + boff, b_lbo, b_sbo);
+          // MN-major: LBO 512, SBO (R/32)*512, one UMMA_K=8 step = two 4-row k groups.  K-major: SBO 1024, +32B.
+          const uint32_t aoff = LA::kMnMajor ? ks * 2 * (BM / 32) * 512 : ks * 32;
+          const uint32_t boff = LB::kMnMajor ? ks * 2 * (BN / 32) * 512 : ks * 32;
+          const uint32_t a_lbo = LA::kMnMajor ? 512 : 16, a_sbo = LA::kMnMajor ? (BM / 32) * 512 : 1024;
+          const uint32_t b_lbo = LB::kMnMajor ? 512 : 16, b_sbo = LB::kMnMajor ? (BN / 32) * 512 : 1024;
+          const uint32_t a_lt = LA::kMnMajor ? 1u : 2u, b_lt = LB::kMnMajor ? 1u : 2u;
+          const uint64_t ah = make_desc(sa + aoff, a_lbo, a_sbo, a_lt);
+          const uint64_t bh = make_desc(sb + boff, b_lbo, b_sbo, b_lt);
           const uint32_t first = (kb != kbBegin || ks != 0) ? 1u : 0u;
           if (SPLIT) {
-            const uint64_t al = make_desc(sa_lo + aoff, a_lbo, a_sbo);
-            const uint64_t bl = make_desc(sb_lo + boff, b_lbo, b_sbo);
+            const uint64_t al = make_desc(sa_lo + aoff, a_lbo, a_sbo, a_lt);
+            const uint64_t bl = make_desc(sb_lo + boff, b_lbo, b_sbo, b_lt);
             mma_tf32(tmem_d, al, bh, idesc, first);  // small terms first
             mma_tf32(tmem_d, ah, bl, idesc, 1u);
             mma_tf32(tmem_d, ah, bh, idesc, 1u);

@@ -152,6 +152,7 @@ class TConvolutionalLayer:
                                         self.biases.devData, self.ActivationType)
             for t in (self.x, self.x_norm, self.mean, self.variance, self.rolling_mean, self.rolling_variance):
                 t.setCUDA()
+            self._bn_fold = None  # rolling statistics changed
         else:
             # inference batch-norm folded into the conv epilogue: out = act(conv*s + b'),
             # s = scale/max(sqrt(var),eps), b' = bias - mean*s

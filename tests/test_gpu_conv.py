@@ -1,0 +1,221 @@
+"""GPU parity of the convolution path: im2col/col2im index mapping (bit-exact), implicit-GEMM forward /
+backward-filter / backward-data (tolerance of BASELINE.json's north_star), and the layer-level sequences."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from util import TOL_3XTF32, TOL_TF32, Dev, rel_elem, rel_max
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FP32, X3, TF32 = 0, 1, 2
+
+GEOMS = [  # (B, C, H, W, F, k, pad, stride)
+    (2, 3, 16, 16, 32, 3, 1, 1),      # YOLO/CIFAR first layer shape (K = 27)
+    (2, 32, 16, 16, 64, 3, 1, 2),     # stride-2 downsampler
+    (3, 64, 13, 13, 32, 1, 0, 1),     # 1x1 bottleneck on a 13x13 map
+    (2, 32, 13, 13, 255, 1, 0, 1),    # YOLO head: 255 filters
+    (1, 128, 26, 26, 256, 3, 1, 1),   # deep 3x3
+    (2, 5, 9, 8, 6, 3, 1, 2),         # ragged everything
+    (1, 16, 7, 7, 300, 3, 1, 1),      # more than one filter tile
+    (4, 8, 5, 5, 16, 5, 2, 1),        # 5x5 kernel (LeNet-like)
+]
+
+
+def test_im2col_bit_exact(cuda_backend, oracle):
+    cu = cuda_backend
+    for cs in json.load(open(os.path.join(GOLD, "hand_im2col.json"))):
+        im = np.array(cs["im"], dtype=np.float32)
+        want = np.array(cs["col"], dtype=np.float32)
+        dim, dcol = Dev(cu, im, pad_front=3), Dev(cu, n=want.size, pad_front=5)
+        c, h, w = im.shape
+        cu.im2col(c, h, w, cs["kh"], cs["kw"], cs["ph"], cs["pw"], cs["sy"], cs["sx"], cs["dy"], cs["dx"], dim._base, 3,
+                  dcol._base, 5)
+        assert np.array_equal(dcol.read(want.shape), want)
+    rng = np.random.default_rng(0)
+    for (c, h, w, k, p, s, d) in [(3, 17, 13, 3, 1, 1, 1), (4, 16, 16, 3, 1, 2, 1), (2, 9, 9, 3, 2, 1, 2), (5, 8, 6, 1, 0, 1, 1)]:
+        x = rng.uniform(-1, 1, (c, h, w)).astype(np.float32)
+        want = oracle.im2col(x, k, k, p, p, s, s, d, d)
+        dim, dcol = Dev(cu, x), Dev(cu, n=want.size)
+        cu.im2col(c, h, w, k, k, p, p, s, s, d, d, dim.ptr, 0, dcol.ptr, 0)
+        assert np.array_equal(dcol.read(want.shape), want)  # pure gather: bytes must match
+
+
+def test_col2im_bit_exact(cuda_backend, oracle):
+    cu = cuda_backend
+    rng = np.random.default_rng(1)
+    for (c, h, w, k, p, s, d) in [(3, 17, 13, 3, 1, 1, 1), (4, 16, 16, 3, 1, 2, 1), (2, 9, 9, 3, 2, 1, 2), (5, 8, 6, 1, 0, 1, 1),
+                                  (2, 7, 7, 2, 0, 2, 1)]:
+        oh, ow = oracle.out_dim(h, p, k, s, d), oracle.out_dim(w, p, k, s, d)
+        # (a) small integers: exact sums regardless of order
+        col = rng.integers(-4, 5, (c * k * k, oh * ow)).astype(np.float32)
+        im0 = rng.integers(-4, 5, (c, h, w)).astype(np.float32)
+        want = oracle.col2im(col, c, h, w, k, k, p, p, s, s, d, d, im=im0.copy())
+        dcol, dim = Dev(cu, col), Dev(cu, im0)
+        cu.col2im(c, h, w, k, k, p, p, s, s, d, d, dcol.ptr, 0, dim.ptr, 0)
+        assert np.array_equal(dim.read(im0.shape), want)
+        # (b) real values: the gather adds in the CPU scatter's (kernel_row, kernel_col) order -> same bits
+        col = rng.uniform(-1, 1, col.shape).astype(np.float32)
+        want = oracle.col2im(col, c, h, w, k, k, p, p, s, s, d, d, im=im0.copy())
+        dcol.write(col)
+        dim.write(im0)
+        cu.col2im(c, h, w, k, k, p, p, s, s, d, d, dcol.ptr, 0, dim.ptr, 0)
+        assert np.array_equal(dim.read(im0.shape), want)
+
+
+def conv_case(rng, B, C, H, W, F, k):
+    x = rng.uniform(0, 1, (B, C, H, W)).astype(np.float32)
+    s = np.sqrt(2.0 / (k * k * C))
+    w = rng.uniform(-s, s, (F, C * k * k)).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, F).astype(np.float32)
+    return x, w, b
+
+
+@pytest.mark.parametrize("mode,tol", [(FP32, 2e-6), (X3, TOL_3XTF32), (TF32, TOL_TF32)])
+@pytest.mark.parametrize("geom", GEOMS)
+def test_conv_forward(cuda_backend, oracle, mode, tol, geom):
+    cu = cuda_backend
+    B, C, H, W, F, k, p, s = geom
+    rng = np.random.default_rng(sum(geom))
+    x, w, b = conv_case(rng, B, C, H, W, F, k)
+    want = oracle.conv2d(x, w, p, s, s, 1, k, k)
+    oracle.forward_bias(want, b, B)
+    oracle.activate_array(want, oracle.ACT["LEAKY"])
+    dx, dw, db = Dev(cu, x, pad_front=2), Dev(cu, w), Dev(cu, b)
+    dout = Dev(cu, n=want.size, pad_front=1)
+    desc = cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s)
+    cu.set_math_mode(mode)
+    cu.conv2dForward(desc, dx._base, 2, dw.ptr, None, db.ptr, oracle.ACT["LEAKY"], dout._base, 1)
+    cu.set_math_mode(X3)
+    got = dout.read(want.shape)
+    e1, e2 = rel_max(got, want), rel_elem(got, want, floor=1.0)
+    assert e1 < tol and e2 < tol, (e1, e2)
+
+
+def test_conv_forward_fp32_bit_exact_with_fma_oracle(cuda_backend, oracle):
+    cu = cuda_backend
+    oracle.set_mode(oracle.MODE_FMA)
+    try:
+        B, C, H, W, F, k, p, s = 2, 5, 9, 8, 6, 3, 1, 2
+        x, w, b = conv_case(np.random.default_rng(3), B, C, H, W, F, k)
+        want = oracle.conv2d(x, w, p, s, s, 1, k, k)
+        dx, dw, dout = Dev(cu, x), Dev(cu, w), Dev(cu, n=want.size)
+        cu.set_math_mode(FP32)
+        cu.conv2dForward(cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s), dx.ptr, 0, dw.ptr, None, None, 4, dout.ptr, 0)
+        assert np.array_equal(dout.read(want.shape), want)
+    finally:
+        oracle.set_mode(oracle.MODE_PAS)
+        cu.set_math_mode(X3)
+
+
+@pytest.mark.parametrize("act", ["LINEAR", "LOGISTIC", "RELU"])
+def test_conv_forward_scale_bias_activation_epilogue(cuda_backend, oracle, act):
+    cu = cuda_backend
+    B, C, H, W, F, k, p, s = 2, 16, 12, 12, 48, 3, 1, 1
+    rng = np.random.default_rng(9)
+    x, w, b = conv_case(rng, B, C, H, W, F, k)
+    sc = rng.uniform(0.5, 1.5, F).astype(np.float32)
+    want = oracle.conv2d(x, w, p, s, s, 1, k, k)
+    oracle.forward_scale(want, sc, B)
+    oracle.forward_bias(want, b, B)
+    oracle.activate_array(want, oracle.ACT[act])
+    dx, dw, db, ds, dout = Dev(cu, x), Dev(cu, w), Dev(cu, b), Dev(cu, sc), Dev(cu, n=want.size)
+    cu.conv2dForward(cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s), dx.ptr, 0, dw.ptr, ds.ptr, db.ptr, oracle.ACT[act],
+                     dout.ptr, 0)
+    assert rel_max(dout.read(want.shape), want) < TOL_3XTF32
+
+
+@pytest.mark.parametrize("geom", GEOMS[:6])
+def test_conv_backward(cuda_backend, oracle, geom):
+    cu = cuda_backend
+    B, C, H, W, F, k, p, s = geom
+    rng = np.random.default_rng(sum(geom) + 1)
+    x, w, _ = conv_case(rng, B, C, H, W, F, k)
+    oh, ow = oracle.out_dim(H, p, k, s), oracle.out_dim(W, p, k, s)
+    delta = rng.uniform(-1, 1, (B, F, oh, ow)).astype(np.float32)
+    wu0 = rng.uniform(-1, 1, w.shape).astype(np.float32)
+    dx0 = rng.uniform(-1, 1, x.shape).astype(np.float32)
+    # oracle: nConvolutionLayer.pas:628-653
+    col = oracle.im2col_batched(x, k, k, p, p, s, s)
+    wu = wu0.copy()
+    for b in range(B):
+        oracle.sgemm(False, True, F, C * k * k, oh * ow, 1.0, delta[b], oh * ow, col[b], oh * ow, 1.0, wu, C * k * k)
+    ws = np.zeros_like(col)
+    oracle.sgemm_strided_batched(True, False, C * k * k, oh * ow, F, 1.0, w, C * k * k, 0, delta, oh * ow, F * oh * ow, 0.0,
+                                 ws, oh * ow, ws[0].size, B)
+    dxw = oracle.col2im_batched(ws, B, C, H, W, k, k, p, p, s, s, im=dx0.copy())
+    desc = cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s)
+    din, dw, dd, dwu, ddx = Dev(cu, x), Dev(cu, w), Dev(cu, delta), Dev(cu, wu0), Dev(cu, dx0)
+    cu.conv2dBackwardFilter(desc, din.ptr, 0, dd.ptr, 0, dwu.ptr)
+    cu.conv2dBackwardData(desc, dw.ptr, dd.ptr, 0, ddx.ptr, 0)
+    assert rel_max(dwu.read(w.shape), wu) < TOL_3XTF32
+    assert rel_max(ddx.read(x.shape), dxw) < TOL_3XTF32
+
+
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("bn", [0, 1])
+def test_layer_forward_backward_update_against_golden(cuda_backend, oracle, fused, bn):
+    """TConvolutionalLayer.forwardGPU/backwardGPU/updateGPU (fused entry points and the reference's own call
+    sequence) against the frozen fixtures of tests/golden/ (oracle, pure-Pascal mode)."""
+    from tensorium_b200 import layers as L
+    from tensorium_b200.tensor import TSingleTensor
+    f = np.load(os.path.join(GOLD, "oracle_fixtures.npz"))
+    p = f"pas_conv_bn{bn}_"
+    lay = L.TConvolutionalLayer(3, 9, 8, 5, 6, 3, 2, 1, oracle.ACT["LEAKY"], bn, train=True, fused=fused)
+    lay.weights.Data[...] = f[p + "w"]
+    lay.biases.Data[...] = f[p + "bias"]
+    if bn:
+        lay.scales.Data[...] = f[p + "scales"]
+        lay.rolling_mean.Data[...] = f[p + "rm"]
+        lay.rolling_variance.Data[...] = f[p + "rv"]
+    x = TSingleTensor(f[p + "x"].shape, 3, f[p + "x"])
+    ws = TSingleTensor((lay.getWorkspaceSize(),), 1)
+    st = L.TNNetState(input=x, workspace=ws, isTraining=False)
+    lay.forwardGPU(st)
+    assert rel_max(lay.output.pullFromDevice(), f[p + "y_inf"]) < TOL_3XTF32
+    st.isTraining = True
+    lay.forwardGPU(st)
+    assert rel_max(lay.output.pullFromDevice(), f[p + "y_tr"]) < TOL_3XTF32
+    lay.output.setCUDA()
+    if bn:
+        assert rel_max(lay.rolling_mean.pullFromDevice(), f[p + "rm_after"]) < 1e-5
+        assert rel_max(lay.mean.pullFromDevice(), f[p + "mean"]) < 1e-5
+        for t in (lay.rolling_mean, lay.mean):
+            t.setCUDA()
+    lay.delta.Data[...] = f[p + "g"]
+    lay.delta.setCPU()
+    st.delta = TSingleTensor(f[p + "x"].shape, 3)
+    st.delta.pushToDevice()
+    lay.backwardGPU(st)
+    assert rel_max(st.delta.pullFromDevice(), f[p + "dx"]) < TOL_3XTF32
+    assert rel_max(lay.weight_updates.pullFromDevice(), f[p + "dw"]) < TOL_3XTF32
+    lay.weight_updates.setCUDA()
+    if bn:
+        assert rel_max(lay.scale_updates.pullFromDevice(), f[p + "dscale"]) < TOL_3XTF32
+        lay.scale_updates.setCUDA()
+    else:
+        assert rel_max(lay.bias_updates.pullFromDevice(), f[p + "db"]) < 1e-5
+        lay.bias_updates.setCUDA()
+    lay.updateGPU(L.TUpdateArgs(batch=3, learningRate=0.001, momentum=0.9, decay=0.0001))
+    assert rel_max(lay.weights.pullFromDevice(), f[p + "w_after"]) < 1e-6
+    assert rel_max(lay.weight_updates.pullFromDevice(), f[p + "wu_after"]) < TOL_3XTF32
+
+
+def test_conv_roundtrip_linearity_large(cuda_backend):
+    """Size-independent property at a bench-sized layer: conv(a*x1 + x2) == a*conv(x1) + conv(x2)."""
+    cu = cuda_backend
+    B, C, H, W, F, k, p, s = 4, 64, 104, 104, 128, 3, 1, 1
+    rng = np.random.default_rng(12)
+    x1 = rng.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    x2 = rng.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    w = rng.uniform(-0.05, 0.05, (F, C * k * k)).astype(np.float32)
+    desc = cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s)
+    dw = Dev(cu, w)
+    outs = []
+    for x in (x1, x2, (np.float32(0.5) * x1 + x2).astype(np.float32)):
+        dx, do = Dev(cu, x), Dev(cu, n=B * F * H * W)
+        cu.conv2dForward(desc, dx.ptr, 0, dw.ptr, None, None, 4, do.ptr, 0)
+        outs.append(do.read())
+    assert rel_max(outs[2], 0.5 * outs[0].astype(np.float64) + outs[1]) < 1e-5
