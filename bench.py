@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — YOLOv3-416 inference images/s on B200 through the Tensorium drop-in backend.
+
+Workload = BASELINE.json configs[3]: YOLOv3 416x416 inference, batch 64 per GPU, random-init weights
+(BN folded like MSCOCOYolo.pas:327-340), synthetic U[0,1) images; batch-sharded across GPUs with no collective
+(weak scaling: every rank runs its own batch of 64).  One "step" = one forward pass of the 107-layer net.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math 3xtf32|tf32|fp32]
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` includes the pinned-host H2D copy of
+the batch and the D2H read of the three yolo outputs every step.  `roofline` is for the dominant kernel (the
+tcgen05 implicit-GEMM conv): algorithmic FLOPs (2*B*F*OH*OW*C*k*k summed over the 75 convs) / summed CUDA-event
+durations of those launches.  `cpu_baseline` / `--impl reference` time the reference's CPU algorithm (oracle/, the
+C restatement — FreePascal is not available to build the reference itself) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 64
+SIZE = 416
+METRIC = "YOLOv3-416 inference images/sec"
+MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [r.split(", ") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        busy = [s for s in sm if s > 0]
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(rows)}
+
+
+def synthetic_images(batch, seed=1234):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.random((batch, 3, SIZE, SIZE), dtype=np.float32)
+
+
+# ------------------------------------------------------------------------------------------ CPU (reference) arm
+def cpu_forward_rate(n_images, reps=1, seed=1234):
+    """images/s of the reference's CPU algorithm (oracle restatement, AVX2/FMA build flavour of the YOLO sample,
+    MSCOCO_Yolo/Makefile:8) on all host threads.  Returns (images_per_s, seconds, threads)."""
+    from oracle import oracle as orc
+    from oracle import ref_net
+    from tensorium_b200.nnet import init_yolov3_params, yolov3_spec
+    orc.build()
+    orc.set_mode(orc.MODE_FMA)
+    orc.set_threads(os.cpu_count() or 1)
+    spec = yolov3_spec()
+    params = init_yolov3_params(spec, seed=seed)
+    x = synthetic_images(n_images, seed)
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        ref_net.forward(spec, params, x)
+    dt = time.perf_counter() - t0
+    orc.set_mode(orc.MODE_PAS)
+    return n_images * reps / dt, dt, orc.max_threads()
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    rates = []
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_forward_rate(1)
+    t_all = 0.0
+    for _ in range(args.steps):
+        r, dt, threads = cpu_forward_rate(1)
+        rates.append(r); t_all += dt
+    value = args.steps / t_all
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * t_all / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"YOLOv3-{SIZE} inference (107 layers, BN fused), reference CPU algorithm "
+                               f"(C restatement of ntensors.pas cblas_sgemm+sim2Col), 1 image per step",
+                   "global_batch": 1, "image": SIZE},
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{args.steps} x 1 image full forward ({cpu_model()})"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from tensorium_b200 import tensor
+    from tensorium_b200.layers import TConvolutionalLayer, TNNetState
+    from tensorium_b200.nnet import build_yolov3
+
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    cu = tensor.initCUDART(local_rank)  # raises if libtensorium_b200.so / a B200 is missing: no fallback
+    cu.set_stream(stream.cuda_stream)
+    cu.set_math_mode(MATH[args.math])
+    net = build_yolov3(BATCH, SIZE, seed=1234)
+    x_host = torch.from_numpy(synthetic_images(BATCH, 1234 + rank)).pin_memory()
+    nbytes_in = x_host.numel() * 4
+    cu.writeBuffer(net.input.devData, nbytes_in, x_host.numpy())
+    yolos = net.yolo_layers()
+    out_host = [torch.empty(l.output.FShape, dtype=torch.float32).pin_memory() for l in yolos]
+    nbytes_out = sum(t.numel() * 4 for t in out_host)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    def step_resident():
+        net.predict()
+
+    def step_e2e():
+        cu.writeBufferAsync(net.input.devData, nbytes_in, x_host.data_ptr())
+        net.predict()
+        for l, t in zip(yolos, out_host):
+            cu.readBufferAsync(l.output.devData, t.numel() * 4, t.data_ptr())
+        cu.finish()
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    l0 = cu.launch_count()
+    ms = timed(step_resident, args.steps)
+    launches = cu.launch_count() - l0
+    clocks = sampler.stop() if sampler else None
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    total_images = BATCH * world * args.steps
+    value = total_images / (ms / 1000.0)
+    e2e_value = total_images / (ms_e2e / 1000.0)
+
+    # ---- roofline of the dominant kernel: the tcgen05 implicit-GEMM conv, all 75 launches of one step
+    convs = [(i, l) for i, l in enumerate(net.layers) if isinstance(l, TConvolutionalLayer)]
+    per_layer = []
+    reps = 3
+    for i, l in convs:
+        src = net.input if i == 0 else net.layers[i - 1].output
+        st = TNNetState(input=src)
+        l.forwardGPU(st)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            l.forwardGPU(st)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t = e0.elapsed_time(e1) / reps
+        fl = 2.0 * l.batch * l.filters * l.outH * l.outW * l.c * l.kernelSize ** 2
+        per_layer.append(dict(layer=i, c=l.c, f=l.filters, k=l.kernelSize, s=l.stride_x, hw=l.outH, ms=t,
+                              tflops=fl / t / 1e9))
+    conv_ms = sum(p["ms"] for p in per_layer)
+    conv_flops = float(net.conv_flops())
+    achieved = conv_flops / (conv_ms / 1000.0) / 1e12
+    peaks, which = load_peaks()
+    tf32_peak = float(peaks.get("tf32_tflops_sustained", peaks["bf16_tflops_sustained"] / 2.0))
+
+    if rank == 0:
+        if args.layers_out:
+            os.makedirs(os.path.dirname(args.layers_out) or ".", exist_ok=True)
+            json.dump(dict(math=args.math, conv_ms=conv_ms, step_ms=ms / args.steps, per_layer=per_layer),
+                      open(args.layers_out, "w"), indent=1)
+        cpu = None
+        if world == 1 and not args.no_cpu:
+            r, dt, threads = cpu_forward_rate(args.cpu_images)
+            cpu = {"value": r, "unit": "images/s", "cores": threads, "kind": "port",
+                   "sample": f"{args.cpu_images} image(s) full YOLOv3-416 forward in {dt:.1f}s, oracle (C restatement of "
+                             f"the reference CPU path, FMA flavour), {cpu_model()}"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.math != "tf32" else "tf32",
+            "data": "synthetic",
+            "config": {"workload": f"YOLOv3-{SIZE} inference, 107 layers (75 conv), BN folded, random-init weights",
+                       "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": SIZE,
+                       "math": args.math, "parallelism": f"batch-sharded x{world}, no collective",
+                       "l2": "activations streamed per step = 14.6 GB per GPU, far larger than the 126 MB L2 (no flush needed)"},
+            "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes_in,
+                    "d2h_bytes_per_step": nbytes_out, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
+                         "frac": achieved / tf32_peak, "traffic": None,
+                         "kernel": "umma::k_umma (tcgen05 kind::tf32 implicit-GEMM conv, 75 launches/step)",
+                         "peak_source": f"TF32 dense = bf16_tflops_sustained/2 of {which} MEASURED_PEAKS.json",
+                         "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / (ms / args.steps),
+                         "mma_issue_factor": 3 if args.math == "3xtf32" else 1},
+            "cpu_baseline": cpu,
+            "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--math", default="3xtf32", choices=list(MATH))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-images", type=int, default=2)
+    ap.add_argument("--layers-out", default="", help="write the per-conv-layer timing table (JSON) here")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -294,6 +294,11 @@ TNN_API int32_t tnn_batchnorm_backward(tnn_context *ctx, int64_t batch, int64_t 
  * with decay_term = -decay*batch for weights, 0 for biases/scales; rate = learning_rate/batch. */
 TNN_API int32_t tnn_sgd_update(tnn_context *ctx, int64_t N, float *params, float *updates, float rate,
                                float momentum, float decay_term);
+/* TYoloLayer.forwardGPU's per-(image, anchor) ActivateArray / fmavss loop (nyololayer.pas:1081-1099) in one
+ * launch: logistic on the x, y, objectness and class planes of out[batch][n*(5+classes)][wh]; x,y are then
+ * mapped v*scale_xy + 0.5*(1-scale_xy) when scale_xy != 1. */
+TNN_API int32_t tnn_yolo_activate(tnn_context *ctx, int64_t batch, int64_t n, int64_t classes, int64_t wh,
+                                  float *out, float scale_xy);
 /* out[b][cOff..cOff+c] = in  — per-image channel concat used by route layers */
 TNN_API int32_t tnn_concat_channels(tnn_context *ctx, int64_t batch, int64_t c, int64_t blockSize, const float *in,
                                     int64_t outChannels, int64_t cOffset, float *out);

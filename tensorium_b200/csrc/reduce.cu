@@ -251,6 +251,22 @@ int32_t tnn_batchnorm_forward_inference(tnn_context *ctx, int64_t batch, int64_t
       });
 }
 
+// TYoloLayer.forwardGPU activation loop (nyololayer.pas:1081-1099) as one plane map
+int32_t tnn_yolo_activate(tnn_context *ctx, int64_t batch, int64_t n, int64_t classes, int64_t wh, float *out,
+                          float scale_xy) {
+  TNN_CHECK_CTX(ctx);
+  const int entries = (int)(classes + 5);
+  const float a = scale_xy, b = 0.5f * (1.0f - scale_xy);
+  return planemap::launch<0, 0>(ctx, out, nullptr, nullptr, nullptr, nullptr, batch * n * entries * wh, n * entries,
+                                batch, [entries, a, b] __device__(float &v, float, float, float &, float &, int c) {
+                                  const int e = c % entries;
+                                  if (e == 2 || e == 3) return;
+                                  float t = 1.0f / (1.0f + expf(-v));
+                                  if (e < 2 && a != 1.0f) t = __fadd_rn(__fmul_rn(t, a), b);
+                                  v = t;
+                                });
+}
+
 // rolling = (1-m)*rolling + m*stat  (nbaselayer.pas:590-608: scale then axpy, separately rounded)
 __global__ void k_rolling(int64_t n, float *rm, const float *mean, float *rv, const float *var, float m) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -23,8 +23,11 @@
 //            descriptor: SWIZZLE_128B_BASE32B, LBO = 512 (next 32-element atom along M/N),
 //            SBO = (R/32)*512 (next 4-row k group), advance two SBO per UMMA_K=8 step
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+
 #include "common.cuh"
 #include "gemm_simt.cuh"
+#include <string.h>
 
 namespace umma {
 
@@ -33,7 +36,9 @@ constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int kProducerWarps = 8;
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kThreads = kProducerThreads + 32;  // + MMA warp
+constexpr int kMmaWarp = kProducerWarps;         // warp 8: tcgen05.mma issuer (+ TMEM alloc/dealloc)
+constexpr int kTmaWarp = kProducerWarps + 1;     // warp 9: TMA producer of the weight operand
+constexpr int kThreads = kProducerThreads + 64;
 constexpr int kMaxStages = 4;
 
 // ------------------------------------------------------------------ PTX wrappers
@@ -44,6 +49,19 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// TMA: global (tensor map, coords {c0 = k, c1 = row}) -> swizzled smem tile, completion on an mbarrier
+__device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
+          "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(tmap)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -119,6 +137,12 @@ __host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn
 }
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+// TF32 mode: round to nearest (the tensor core itself would truncate, which biases every product toward zero)
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 
 // store one element of an MN-major tile with R rows (R % 32 == 0)
 template <bool SPLIT>
@@ -130,7 +154,7 @@ __device__ __forceinline__ void sts_mn(uint8_t *hi, uint8_t *lo, int R, int mn, 
     *reinterpret_cast<float *>(hi + off) = h;
     *reinterpret_cast<float *>(lo + off) = v - h;
   } else {
-    *reinterpret_cast<float *>(hi + off) = v;
+    *reinterpret_cast<float *>(hi + off) = tf32_rna(v);
   }
 }
 // store one 16-byte chunk (4 consecutive k) of a K-major tile
@@ -142,46 +166,64 @@ __device__ __forceinline__ void sts_k(uint8_t *hi, uint8_t *lo, int row, int chu
     *reinterpret_cast<float4 *>(hi + off) = h;
     *reinterpret_cast<float4 *>(lo + off) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
   } else {
-    *reinterpret_cast<float4 *>(hi + off) = v;
+    *reinterpret_cast<float4 *>(hi + off) = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
   }
 }
 
 // ------------------------------------------------------------------ operand loaders
-// Every loader fills one [R rows][32 k] tile for k-block kb with the 256 producer threads.
-//   kMnMajor     layout it writes (decides the descriptor)
-//   fill<SPLIT>(hi, lo, R, mn0, kb, tid)   mn0 = first row of the tile
+// A loader stages one [R rows][32 k] operand tile per k-block with the 256 producer threads, in two phases so
+// that global-memory latency overlaps the pipeline wait:
+//   Ctx  init(R, mn0, tid)                 per-thread constants (row decode etc.)
+//   void load(ctx, regs, kb)               issue ALL global loads of k-block kb into registers
+//   void store<SPLIT>(ctx, regs, hi, lo)   split (3xTF32) and write the swizzled smem tile
+//   kMnMajor   smem layout it writes (decides the descriptor);  kTma: tile is written by the TMA warp instead
 
 // matrix whose k index is contiguous: elem(mn,k) = p[mn*ld + k]   (A of NN/NT, B of NT, conv weights)
 struct KContigLoader {
   static constexpr bool kMnMajor = false;
+  static constexpr bool kTma = false;
   const float *p;
   int64_t ld;
   int64_t rows, K;   // valid extent
   int64_t K1, zfold; // fold-batch-into-k: k = b*K1 + kk -> p + b*zfold (K1 % 32 == 0), else K1 = K
   bool vec_ok;       // rows 16B aligned and K1 % 4 == 0
-  template <bool SPLIT>
-  __device__ __forceinline__ void fill(uint8_t *hi, uint8_t *lo, int R, int64_t mn0, int64_t kb, int tid) const {
+  struct Ctx { int R; int64_t mn0; int tid; };
+  struct Regs { float4 v[8]; };
+  __device__ __forceinline__ Ctx init(int R, int64_t mn0, int tid) const { return Ctx{R, mn0, tid}; }
+  __device__ __forceinline__ void load(const Ctx &c, Regs &r, int64_t kb) const {
     const int64_t k0 = kb * BK;
     const int64_t b = k0 / K1;
     const int64_t kk0 = k0 - b * K1;
     const float *base = p + b * zfold;
-    for (int e = tid; e < R * 8; e += kProducerThreads) {
-      const int row = e >> 3, chunk = e & 7;
-      const int64_t mn = mn0 + row;
-      const int64_t kk = kk0 + chunk * 4;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = c.tid + i * kProducerThreads;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (mn < rows) {
-        const float *q = base + mn * ld + kk;
-        if (vec_ok && kk + 3 < K1) {
-          v = __ldg(reinterpret_cast<const float4 *>(q));
-        } else {
-          if (kk + 0 < K1) v.x = __ldg(q + 0);
-          if (kk + 1 < K1) v.y = __ldg(q + 1);
-          if (kk + 2 < K1) v.z = __ldg(q + 2);
-          if (kk + 3 < K1) v.w = __ldg(q + 3);
+      if (e < c.R * 8) {
+        const int row = e >> 3, chunk = e & 7;
+        const int64_t mn = c.mn0 + row;
+        const int64_t kk = kk0 + chunk * 4;
+        if (mn < rows) {
+          const float *q = base + mn * ld + kk;
+          if (vec_ok && kk + 3 < K1) {
+            v = __ldg(reinterpret_cast<const float4 *>(q));
+          } else {
+            if (kk + 0 < K1) v.x = __ldg(q + 0);
+            if (kk + 1 < K1) v.y = __ldg(q + 1);
+            if (kk + 2 < K1) v.z = __ldg(q + 2);
+            if (kk + 3 < K1) v.w = __ldg(q + 3);
+          }
         }
       }
-      sts_k<SPLIT>(hi, lo, row, chunk, v);
+      r.v[i] = v;
+    }
+  }
+  template <bool SPLIT>
+  __device__ __forceinline__ void store(const Ctx &c, const Regs &r, uint8_t *hi, uint8_t *lo) const {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int e = c.tid + i * kProducerThreads;
+      if (e < c.R * 8) sts_k<SPLIT>(hi, lo, e >> 3, e & 7, r.v[i]);
     }
   }
 };
@@ -189,39 +231,64 @@ struct KContigLoader {
 // matrix whose mn index is contiguous: elem(mn,k) = p[k*ld + mn]   (A of TN, B of NN/TN)
 struct MnContigLoader {
   static constexpr bool kMnMajor = true;
+  static constexpr bool kTma = false;
   const float *p;
   int64_t ld;
   int64_t rows, K;
   int64_t K1, zfold;
-  template <bool SPLIT>
-  __device__ __forceinline__ void fill(uint8_t *hi, uint8_t *lo, int R, int64_t mn0, int64_t kb, int tid) const {
+  struct Ctx { int R, sh; int64_t mn0; int tid; };
+  struct Regs { float v[32]; };
+  __device__ __forceinline__ Ctx init(int R, int64_t mn0, int tid) const { return Ctx{R, 31 - __clz(R), mn0, tid}; }
+  __device__ __forceinline__ void load(const Ctx &c, Regs &r, int64_t kb) const {
     const int64_t k0 = kb * BK;
     const int64_t b = k0 / K1;
     const int64_t kk0 = k0 - b * K1;
     const float *base = p + b * zfold;
-    const int sh = 31 - __clz(R);  // R is a power of two >= 32: a warp covers 32 consecutive rows of one k
-    for (int e = tid; e < R * BK; e += kProducerThreads) {
-      const int row = e & (R - 1), k = e >> sh;
-      const int64_t mn = mn0 + row;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int e = c.tid + i * kProducerThreads;  // R is a power of two >= 32: a warp covers 32 rows of one k
       float v = 0.f;
-      if (mn < rows && kk0 + k < K1) v = __ldg(base + (kk0 + k) * ld + mn);
-      sts_mn<SPLIT>(hi, lo, R, row, k, v);
+      if (e < c.R * BK) {
+        const int row = e & (c.R - 1), k = e >> c.sh;
+        const int64_t mn = c.mn0 + row;
+        if (mn < rows && kk0 + k < K1) v = __ldg(base + (kk0 + k) * ld + mn);
+      }
+      r.v[i] = v;
+    }
+  }
+  template <bool SPLIT>
+  __device__ __forceinline__ void store(const Ctx &c, const Regs &r, uint8_t *hi, uint8_t *lo) const {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int e = c.tid + i * kProducerThreads;
+      if (e < c.R * BK) sts_mn<SPLIT>(hi, lo, c.R, e & (c.R - 1), e >> c.sh, r.v[i]);
     }
   }
 };
 
 // implicit im2col: row = output pixel (b, oh, ow) folded over the batch, k = (c, kr, kc)
 // elem = in[b][c][oh*sy - ph + kr*dy][ow*sx - pw + kc*dx] or 0     (sim2Col ntensors.pas:11415-11491)
+// Per thread: one pixel row and 16 consecutive k per k-block.  The in-bounds test of every kernel tap is folded
+// into a per-thread bit mask once per tile (kh*kw <= 64), the (c, kr, kc) walk and the global offset are
+// warp-uniform, and the swizzled smem address is a per-thread base plus compile-time constants.
 struct Im2colPixelLoader {
   static constexpr bool kMnMajor = true;
+  static constexpr bool kTma = false;
   const float *in;
   simt::ConvGeom g;
   int64_t rows;  // batch*OH*OW
   int64_t K;     // C*kh*kw
-  template <bool SPLIT>
-  __device__ __forceinline__ void fill(uint8_t *hi, uint8_t *lo, int R, int64_t mn0, int64_t kb, int tid) const {
-    // R == 128: thread -> (pixel row = tid & 127, k half = tid >> 7), 16 consecutive k each
+  struct Ctx {
+    const float *base;      // &in[b][0][ih0][iw0]
+    unsigned long long tapmask;  // bit (kr*kw+kc): tap inside the image for this pixel (0 if the row is padding)
+    uint32_t soff[4];       // smem byte offset of (row, k&3 = q), without the k-group term
+    int khalf;
+  };
+  struct Regs { float v[16]; };
+  __device__ __forceinline__ Ctx init(int, int64_t mn0, int tid) const {
+    Ctx c;
     const int row = tid & 127;
+    c.khalf = tid >> 7;
     const int64_t mn = mn0 + row;
     const bool valid = mn < rows;
     const int P = g.OH * g.OW;
@@ -229,25 +296,68 @@ struct Im2colPixelLoader {
     const int b = pix / P, p = pix - b * P;
     const int oh = p / g.OW, ow = p - oh * g.OW;
     const int ih0 = oh * g.sy - g.ph, iw0 = ow * g.sx - g.pw;
-    const float *base = in + (int64_t)b * g.inImg + (int64_t)ih0 * g.W + iw0;
+    c.base = in + (int64_t)b * g.inImg + (int64_t)ih0 * g.W + iw0;
+    unsigned long long m = 0;
+    if (valid) {
+      int t = 0;
+      for (int kr = 0; kr < g.kh; ++kr)
+        for (int kc = 0; kc < g.kw; ++kc, ++t)
+          if ((unsigned)(ih0 + kr * g.dy) < (unsigned)g.H && (unsigned)(iw0 + kc * g.dx) < (unsigned)g.W) m |= 1ull << t;
+    }
+    c.tapmask = m;
+    // sts_mn offset for R = 128: ((k>>2)*4 + (row>>5))*512 + (k&3)*128 + ((((row&31)>>3) ^ (k&3))<<5) + (row&7)*4
+    const uint32_t rowpart = (uint32_t)((row >> 5) << 9) + (uint32_t)((row & 7) << 2) + (uint32_t)c.khalf * 4u * 2048u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) c.soff[q] = rowpart + (uint32_t)(q << 7) + (uint32_t)(((((row & 31) >> 3) ^ q)) << 5);
+    return c;
+  }
+  __device__ __forceinline__ void load(const Ctx &cx, Regs &r, int64_t kb) const {
     const int kk = g.kh * g.kw;
-    int k = (int)(kb * BK) + (tid >> 7) * 16;
+    int k = (int)(kb * BK) + cx.khalf * 16;   // warp-uniform walk over (c, kr, kc)
     int c = k / kk;
-    int rem = k - c * kk;
-    int kr = rem / g.kw, kc = rem - kr * g.kw;
-    const int kl0 = (tid >> 7) * 16;
-#pragma unroll 4
-    for (int j = 0; j < 16; ++j, ++k) {
+    int t = k - c * kk;
+    int kr = t / g.kw, kc = t - kr * g.kw;
+    int off = c * (g.H * g.W) + kr * g.dy * g.W + kc * g.dx;
+    const int rowstep = g.dy * g.W - g.kw * g.dx;           // kc wraps: next kernel row
+    const int chanstep = g.H * g.W - g.kh * g.dy * g.W;     // kr wraps: next channel
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
       float v = 0.f;
-      if (valid && k < K) {
-        const int dh = kr * g.dy, dw = kc * g.dx;
-        if ((unsigned)(ih0 + dh) < (unsigned)g.H && (unsigned)(iw0 + dw) < (unsigned)g.W)
-          v = __ldg(base + ((int64_t)c * g.H + dh) * g.W + dw);
+      if (((cx.tapmask >> t) & 1ull) && k < K) v = __ldg(cx.base + off);
+      r.v[j] = v;
+      ++k; ++t; ++kc; off += g.dx;
+      if (kc == g.kw) {
+        kc = 0; off += rowstep;
+        if (t == kk) { t = 0; off += chanstep; }
       }
-      sts_mn<SPLIT>(hi, lo, R, row, kl0 + j, v);
-      if (++kc == g.kw) { kc = 0; if (++kr == g.kh) { kr = 0; ++c; } }
     }
   }
+  template <bool SPLIT>
+  __device__ __forceinline__ void store(const Ctx &cx, const Regs &r, uint8_t *hi, uint8_t *lo) const {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const uint32_t off = cx.soff[j & 3] + (uint32_t)((j >> 2) * 2048);
+      if (SPLIT) {
+        const float h = tf32_hi(r.v[j]);
+        *reinterpret_cast<float *>(hi + off) = h;
+        *reinterpret_cast<float *>(lo + off) = r.v[j] - h;
+      } else {
+        *reinterpret_cast<float *>(hi + off) = tf32_rna(r.v[j]);
+      }
+    }
+  }
+};
+
+// weights pre-split into a zero-padded K-major copy [F][Kpad] (hi and lo planes) and fetched by TMA
+struct TmaWeightsLoader {
+  static constexpr bool kMnMajor = false;
+  static constexpr bool kTma = true;
+  struct Ctx {};
+  struct Regs {};
+  __device__ __forceinline__ Ctx init(int, int64_t, int) const { return Ctx{}; }
+  __device__ __forceinline__ void load(const Ctx &, Regs &, int64_t) const {}
+  template <bool SPLIT>
+  __device__ __forceinline__ void store(const Ctx &, const Regs &, uint8_t *, uint8_t *) const {}
 };
 
 // ------------------------------------------------------------------ epilogues
@@ -300,11 +410,12 @@ struct SharedCtl {
   uint32_t tmem_base;
 };
 
-// grid: x = M tiles, y = N tiles, z = k splits.  BN = runtime tile width (multiple of 16, <= 256; multiple of 32
-// when B is MN-major).  SPLIT = 3xTF32.
+// grid: x = M tiles, y = N tiles, z = k splits.  BN = runtime tile width (multiple of 16, <= 256; a power of two
+// >= 32 when B is MN-major).  SPLIT = 3xTF32.  tmBhi/tmBlo: tensor maps of the pre-split weights (LB::kTma only).
 template <bool SPLIT, typename LA, typename LB, typename EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t kBlocksPerSplit, uint32_t tmemCols) {
+k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t kBlocksPerSplit, uint32_t tmemCols,
+       const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ SharedCtl ctl;
   // 1024B-aligned operand ring
@@ -317,13 +428,17 @@ k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t 
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&ctl.full[s], kProducerWarps);
+      mbar_init(&ctl.full[s], kProducerWarps + (LB::kTma ? 1 : 0));
       mbar_init(&ctl.empty[s], 1);
     }
     mbar_init(&ctl.accum, 1);
     fence_barrier_init();
   }
-  if (warp == kProducerWarps) tmem_alloc(&ctl.tmem_base, tmemCols);
+  if (warp == kMmaWarp) tmem_alloc(&ctl.tmem_base, tmemCols);
+  if (LB::kTma && warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmBhi);
+    if (SPLIT) tma_prefetch_desc(&tmBlo);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -336,7 +451,15 @@ k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t 
   const int64_t nkb = kbEnd - kbBegin;
 
   if (warp < kProducerWarps) {
-    // ===================== producers: global -> (split) -> swizzled smem =====================
+    // ===================== producers: global -> registers -> (split) -> swizzled smem =====================
+    const typename LA::Ctx ca = la.init(BM, m0, threadIdx.x);
+    const typename LB::Ctx cb = lb.init(BN, n0, threadIdx.x);
+    typename LA::Regs ra;
+    typename LB::Regs rb;
+    if (nkb > 0) {
+      la.load(ca, ra, kbBegin);
+      if (!LB::kTma) lb.load(cb, rb, kbBegin);
+    }
     int stage = 0;
     uint32_t phase = 0;
     for (int64_t kb = kbBegin; kb < kbEnd; ++kb) {
@@ -345,11 +468,15 @@ k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t 
       uint8_t *sa_lo = sa + aBytes;
       uint8_t *sb = sa + (SPLIT ? 2 : 1) * aBytes;
       uint8_t *sb_lo = sb + bBytes;
-      la.template fill<SPLIT>(sa, sa_lo, BM, m0, kb, threadIdx.x);
-      lb.template fill<SPLIT>(sb, sb_lo, BN, n0, kb, threadIdx.x);
+      la.template store<SPLIT>(ca, ra, sa, sa_lo);
+      if (!LB::kTma) lb.template store<SPLIT>(cb, rb, sb, sb_lo);
       fence_proxy_async();  // make generic-proxy smem writes visible to the tensor core (async proxy)
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl.full[stage]);
+      if (kb + 1 < kbEnd) {  // the next k-block's loads fly while we wait for its smem slot
+        la.load(ca, ra, kb + 1);
+        if (!LB::kTma) lb.load(cb, rb, kb + 1);
+      }
       if (++stage == stages) { stage = 0; phase ^= 1; }
     }
     // ===================== epilogue: TMEM -> registers -> global =====================
@@ -357,7 +484,7 @@ k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t 
       mbar_wait(&ctl.accum, 0);
       tc_fence_after();
       const int quad = warp & 3;           // TMEM lane quadrant this warp may read
-      const int half = warp >> 2;          // column half
+      const int half = warp >> 2;          // even / odd 32-column chunks
       const int64_t m = m0 + quad * 32 + lane;
       const bool mvalid = m < epi.rows;
       typename EPI::Row rc = epi.row(mvalid ? m : 0);
@@ -375,7 +502,7 @@ k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t 
         }
       }
     }
-  } else {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one elected thread) =====================
     const uint32_t idesc = make_idesc(BN, LA::kMnMajor, LB::kMnMajor);
     const uint32_t smem_base = smem_u32(smem);
@@ -416,11 +543,43 @@ k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t 
       __syncwarp();
       if (++stage == stages) { stage = 0; phase ^= 1; }
     }
+  } else if (LB::kTma && lane == 0) {
+    // ===================== TMA producer of the weight tiles (one thread) =====================
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int64_t kb = kbBegin; kb < kbEnd; ++kb) {
+      mbar_wait(&ctl.empty[stage], phase ^ 1);
+      const uint32_t sb = smem_base + (uint32_t)stage * stageBytes + (SPLIT ? 2 : 1) * aBytes;
+      mbar_arrive_expect_tx(&ctl.full[stage], (uint32_t)bBytes * (SPLIT ? 2 : 1));
+      tma_load_2d(sb, &tmBhi, (int)(kb * BK), (int)n0, &ctl.full[stage]);
+      if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, (int)(kb * BK), (int)n0, &ctl.full[stage]);
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kProducerWarps) tmem_dealloc(tmem_d, tmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_d, tmemCols);
+}
+
+// ------------------------------------------------------------------ weight preparation (TMA path)
+// hi/lo (3xTF32) or rna-rounded (TF32) zero-padded copy of W[F][K] -> [F][Kpad]
+__global__ void __launch_bounds__(256) k_prepare_weights(const float *__restrict__ w, int64_t F, int64_t K, int64_t Kpad,
+                                                         float *__restrict__ hi, float *__restrict__ lo, int split) {
+  const int64_t total = F * Kpad;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const int64_t f = i / Kpad, k = i - f * Kpad;
+    const float v = (k < K) ? __ldg(w + f * K + k) : 0.f;
+    if (split) {
+      const float h = tf32_hi(v);
+      hi[i] = h;
+      lo[i] = v - h;
+    } else {
+      hi[i] = tf32_rna(v);
+    }
+  }
 }
 
 // ------------------------------------------------------------------ host side
@@ -477,12 +636,15 @@ inline Plan make_plan(tnn_context *ctx, int64_t M, int64_t N, int64_t K, bool sp
 }
 
 template <bool SPLIT, typename LA, typename LB, typename EPI>
-int launch(tnn_context *ctx, const Plan &p, LA la, LB lb, EPI epi) {
+int launch(tnn_context *ctx, const Plan &p, LA la, LB lb, EPI epi, const CUtensorMap *tmHi = nullptr,
+           const CUtensorMap *tmLo = nullptr) {
   auto kern = k_umma<SPLIT, LA, LB, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
   TNN_REQUIRE(p.grid.y <= 65535 && p.grid.z <= 65535, "grid too large");
+  alignas(64) CUtensorMap dummy;
+  memset(&dummy, 0, sizeof(dummy));
   kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(la, lb, epi, p.BN, p.stages, p.kBlocks, p.kBlocksPerSplit,
-                                                       p.tmemCols);
+                                                       p.tmemCols, tmHi ? *tmHi : dummy, tmLo ? *tmLo : dummy);
   TNN_LAUNCHED(ctx);
   return 0;
 }
@@ -543,19 +705,70 @@ inline int gemm(tnn_context *ctx, bool tA, bool tB, int64_t M, int64_t N, int64_
   return 0;
 }
 
-// conv forward: D[pixel][filter]; A = im2col gather (MN-major), B = weights [F][C*kh*kw] (K-major)
+// cuTensorMapEncodeTiled, fetched once through the runtime (no link-time dependency on libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// K-major fp32 matrix [rows][Kpad] -> SWIZZLE_128B tiles of 32 k x boxRows rows (OOB rows read as zero)
+inline int encode_weights_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t Kpad, int boxRows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kpad * 4};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)boxRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tnn_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return 6;
+  }
+  return 0;
+}
+
+// conv forward: D[pixel][filter]; A = im2col gather (MN-major, producer warps), B = weights via TMA (K-major)
 inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
                         const float *scale, const float *bias, int act, float *out) {
   const int64_t M = (int64_t)batch * g.OH * g.OW;
   const int64_t N = g.F;
   const int64_t K = (int64_t)g.C * g.kh * g.kw;
+  if (g.kh * g.kw > 64 || g.inImg >= (1ll << 31)) return kNotTaken;  // tap mask is 64 bits, offsets 32 bits
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
+  const int64_t Kpad = p.kBlocks * BK;
+  const size_t plane = (size_t)N * Kpad * sizeof(float);
+  int rc = tnn_reserve_work(ctx, plane * 2);
+  if (rc) return rc;
+  float *whi = ctx->work;
+  float *wlo = ctx->work + (size_t)N * Kpad;
+  {
+    int64_t blocks = cdiv64(N * Kpad, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_prepare_weights<<<(int)blocks, 256, 0, ctx->stream>>>(weights, N, K, Kpad, whi, wlo, split ? 1 : 0);
+    TNN_LAUNCHED(ctx);
+  }
+  alignas(64) CUtensorMap tmHi, tmLo;
+  rc = encode_weights_map(&tmHi, whi, N, Kpad, p.BN);
+  if (rc) return rc;
+  rc = encode_weights_map(&tmLo, split ? wlo : whi, N, Kpad, p.BN);
+  if (rc) return rc;
   Im2colPixelLoader la{in, g, M, K};
-  const bool vec = ((((uintptr_t)weights) & 15) == 0) && (K % 4 == 0);
-  KContigLoader lb{weights, K, N, K, K, 0, vec};
+  TmaWeightsLoader lb{};
   ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N};
-  return split ? launch<true>(ctx, p, la, lb, epi) : launch<false>(ctx, p, la, lb, epi);
+  return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
 }
 
 }  // namespace umma

@@ -55,7 +55,7 @@ class TConvolutionalLayer:
     layerType = ltCONVOLUTIONAL
 
     def __init__(self, batch, h, w, c, filters, kernelSize, stride=1, padding=0, activation=nn.acLEAKY,
-                 batch_normalize=False, dilation=1, train=False, fused=True, rng=None):
+                 batch_normalize=False, dilation=1, train=False, fused=True, rng=None, host_output=True):
         self.batch, self.h, self.w, self.c = batch, h, w, c
         self.filters = self.n = filters
         self.kernelSize, self.stride_x, self.stride_y = kernelSize, stride, stride
@@ -78,7 +78,7 @@ class TConvolutionalLayer:
                                      data=rng.uniform(-scale, scale, (filters, c * kernelSize * kernelSize)))
         self.biases = TSingleTensor((filters,), groups=1)
         shape = (batch, filters, self.outH, self.outW)
-        self.output = TSingleTensor(shape, groups=batch)
+        self.output = TSingleTensor(shape, groups=batch, host=host_output)
         if train:
             self.weight_updates = TSingleTensor(self.weights.FShape, groups=1)
             self.bias_updates = TSingleTensor((filters,), groups=1)

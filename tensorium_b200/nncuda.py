@@ -327,6 +327,9 @@ class TNNCuda:
     def sgdUpdate(self, N, params, updates, rate, momentum, decay_term):
         self._ck(self._l.tnn_sgd_update(self._h, N, _addr(params), _addr(updates), rate, momentum, decay_term))
 
+    def yoloActivate(self, batch, n, classes, wh, out, scale_xy=1.0):
+        self._ck(self._l.tnn_yolo_activate(self._h, batch, n, classes, wh, _addr(out), scale_xy))
+
     def concatChannels(self, batch, c, blockSize, in_, outChannels, cOffset, out):
         self._ck(self._l.tnn_concat_channels(self._h, batch, c, blockSize, _addr(in_), outChannels, cOffset,
                                              _addr(out)))

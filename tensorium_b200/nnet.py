@@ -1,0 +1,319 @@
+"""TNNet and the YOLOv3 graph layers — host-side mirror of the callers either side of the conv hot path
+(SURVEY.md §8f rank 2): shortcut (source/naddlayer.pas:885-910), route (source/nconcatlayer.pas:205-222),
+upsample (source/nupsamplelayer.pas:190-206), yolo (source/nyololayer.pas:97-122,399-498,1068-1112), the
+sequential net driver (source/nnet.py:275-317, 452-472) and NMS (source/ntypes.pas:1059-1108,1612-1646).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import nncuda as nn
+from .layers import TConvolutionalLayer, TNNetState
+from .tensor import TSingleTensor, cuda
+
+
+class TShortcutLayer:
+    """TAddLayer.forwardGPU (naddlayer.pas:885-910): output = input + layers[from].output, then activation."""
+    layerType = "shortcut"
+
+    def __init__(self, batch, index_from, c, h, w, activation=nn.acLINEAR):
+        self.batch, self.c, self.h, self.w = batch, c, h, w
+        self.outC, self.outH, self.outW = c, h, w
+        self.inputLayers = [index_from]
+        self.ActivationType = activation
+        self.output = TSingleTensor((batch, c, h, w), groups=batch, host=False)
+
+    def forwardGPU(self, state: TNNetState, net: "TNNet"):
+        cu = cuda()
+        self.output.setCUDA()
+        other = net.layers[self.inputLayers[0]].output
+        # copy + addvv of the reference collapse into one out-of-place add (same arithmetic: a single fp32 add)
+        cu.addvv(self.output.Size(), state.input.devData, 0, 1, other.devData, 0, 1, self.output.devData, 0, 1)
+        cu.ActivateArray(self.output.Size(), self.output.devData, 0, self.ActivationType)
+
+
+class TConcatLayer:
+    """Route.  The reference copies whole tensors back to back (nconcatlayer.pas:214-220), which equals a
+    per-image channel concat only for batch=1; here every image is concatenated along C."""
+    layerType = "route"
+
+    def __init__(self, batch, input_layers, shapes):
+        self.batch = batch
+        self.inputLayers = list(input_layers)
+        self.h, self.w = shapes[0][1], shapes[0][2]
+        self.outC = sum(s[0] for s in shapes)
+        self.outH, self.outW = self.h, self.w
+        self._cs = [s[0] for s in shapes]
+        self.output = TSingleTensor((batch, self.outC, self.h, self.w), groups=batch, host=False)
+
+    def forwardGPU(self, state: TNNetState, net: "TNNet"):
+        cu = cuda()
+        self.output.setCUDA()
+        off = 0
+        for li, c in zip(self.inputLayers, self._cs):
+            src = net.layers[li].output
+            if self.batch == 1 or len(self.inputLayers) == 1:
+                cu.copy(src.Size(), src.devData, 0, 1, self.output.devData, off * self.h * self.w, 1)
+            else:
+                cu.concatChannels(self.batch, c, self.h * self.w, src.devData, self.outC, off, self.output.devData)
+            off += c
+
+
+class TUpsampleLayer:
+    """nupsamplelayer.pas:190-206 (forward, non-reverse)."""
+    layerType = "upsample"
+
+    def __init__(self, batch, c, h, w, stride=2, scale=1.0):
+        self.batch, self.c, self.h, self.w, self.stride, self.scale = batch, c, h, w, stride, scale
+        self.outC, self.outH, self.outW = c, h * stride, w * stride
+        self.output = TSingleTensor((batch, c, self.outH, self.outW), groups=batch, host=False)
+
+    def forwardGPU(self, state: TNNetState, net: "TNNet"):
+        self.output.setCUDA()
+        cuda().upSample(self.batch, self.c, self.h, self.w, state.input.devData, self.stride, 1, self.scale,
+                        self.output.devData)
+
+
+class TYoloLayer:
+    """nyololayer.pas: forwardGPU :1068-1112, entryIndex :97-103, getBox :105-122, getDetections :399-441."""
+    layerType = "yolo"
+
+    def __init__(self, batch, c, h, w, mask, anchors, classes=80, scale_xy=1.0, fused=True):
+        self.batch, self.c, self.h, self.w = batch, c, h, w
+        self.outC, self.outH, self.outW = c, h, w
+        self.mask, self.n, self.classes = list(mask), len(mask), classes
+        self.biases = np.asarray(anchors, dtype=np.float32)
+        self.scaleXY = scale_xy
+        self.outputs = h * w * self.n * (classes + 4 + 1)
+        assert c == self.n * (classes + 5)
+        self.fused = fused
+        self.output = TSingleTensor((batch, c, h, w), groups=batch, host=False)
+
+    def entryIndex(self, abatch, location, entry):
+        wh = self.w * self.h
+        _n, loc = divmod(location, wh)
+        return abatch * self.outputs + _n * (self.classes + 5) * wh + entry * wh + loc
+
+    def forwardGPU(self, state: TNNetState, net: "TNNet"):
+        cu = cuda()
+        self.output.setCUDA()
+        wh = self.w * self.h
+        cu.copy(state.input.Size(), state.input.devData, 0, 1, self.output.devData, 0, 1)
+        if self.fused:
+            cu.yoloActivate(self.batch, self.n, self.classes, wh, self.output.devData, self.scaleXY)
+            return
+        for b in range(self.batch):  # the reference's 2 launches per (image, anchor)
+            for _n in range(self.n):
+                bbox_index = self.entryIndex(b, _n * wh, 0)
+                cu.ActivateArray(2 * wh, self.output.devData, bbox_index, nn.acLOGISTIC)
+                obj_index = self.entryIndex(b, _n * wh, 4)
+                cu.ActivateArray((1 + self.classes) * wh, self.output.devData, obj_index, nn.acLOGISTIC)
+                if self.scaleXY != 1:
+                    cu.fmavss(2 * wh, self.output.devData, bbox_index, self.scaleXY, 0.5 * (1 - self.scaleXY),
+                              self.output.devData)
+
+    def getDetections(self, pred: np.ndarray, netw, neth, thresh, abatch=0):
+        """pred: host copy of this layer's output [batch, c, h, w].  Returns (boxes[n,4] xywh relative, objectness[n],
+        prob[n,classes]) following nyololayer.pas:399-441 with relative=True, letter=False."""
+        wh = self.w * self.h
+        p = pred[abatch].reshape(self.n, self.classes + 5, wh)
+        boxes, objs, probs = [], [], []
+        for i in range(wh):
+            row, col = divmod(i, self.w)
+            for _n in range(self.n):
+                objectness = p[_n, 4, i]
+                if objectness > thresh:
+                    a = self.mask[_n]
+                    bx = (col + p[_n, 0, i]) / self.w
+                    by = (row + p[_n, 1, i]) / self.h
+                    bw = np.exp(p[_n, 2, i]) * self.biases[2 * a] / netw
+                    bh = np.exp(p[_n, 3, i]) * self.biases[2 * a + 1] / neth
+                    pr = objectness * p[_n, 5:, i]
+                    pr = np.where(pr > thresh, pr, 0).astype(np.float32)
+                    boxes.append((bx, by, bw, bh))
+                    objs.append(objectness)
+                    probs.append(pr)
+        if not boxes:
+            return np.zeros((0, 4), np.float32), np.zeros(0, np.float32), np.zeros((0, self.classes), np.float32)
+        return np.asarray(boxes, np.float32), np.asarray(objs, np.float32), np.stack(probs)
+
+
+def box_iou(a, b):
+    """ntypes.pas:1059-1108 (xywh boxes)."""
+    def overlap(x1, w1, x2, w2):
+        return min(x1 + w1 / 2, x2 + w2 / 2) - max(x1 - w1 / 2, x2 - w2 / 2)
+    w, h = overlap(a[0], a[2], b[0], b[2]), overlap(a[1], a[3], b[1], b[3])
+    if w < 0 or h < 0:
+        return 0.0
+    i = w * h
+    u = a[2] * a[3] + b[2] * b[3] - i
+    return 0.0 if i == 0 or u == 0 else float(i / u)
+
+
+def doNMSSort(boxes, objs, probs, thresh):
+    """TDetectionsHelper.doNMSSort ntypes.pas:1612-1646: per class, sort by class probability, suppress IoU > thresh."""
+    keep = objs != 0
+    boxes, objs, probs = boxes[keep], objs[keep], probs[keep].copy()
+    for k in range(probs.shape[1] if probs.size else 0):
+        order = np.argsort(-probs[:, k], kind="stable")
+        for ii, i in enumerate(order):
+            if probs[i, k] == 0:
+                continue
+            for j in order[ii + 1:]:
+                if probs[j, k] != 0 and box_iou(boxes[i], boxes[j]) > thresh:
+                    probs[j, k] = 0
+    return boxes, objs, probs
+
+
+class TNNet:
+    """Sequential driver: TNNet.forward (nnet.pas:275-317) / predict (nnet.pas:452-472), GPU path."""
+
+    def __init__(self, layers, batch, c, h, w):
+        self.layers = layers
+        self.batch, self.c, self.h, self.w = batch, c, h, w
+        self.input = TSingleTensor((batch, c, h, w), groups=batch, host=False)
+        # state.workspace (im2col columns) is only needed by the reference's unfused call sequence
+        ws = max([l.getWorkspaceSize() for l in layers if isinstance(l, TConvolutionalLayer) and not l.fused] + [0])
+        self.workspace = TSingleTensor((ws,), groups=1, host=False) if ws else None
+
+    def forward(self, state: TNNetState):
+        state.workspace = self.workspace
+        for i, l in enumerate(self.layers):
+            state.index = i
+            if isinstance(l, TConvolutionalLayer):
+                l.forwardGPU(state)
+            else:
+                l.forwardGPU(state, self)
+            state.input = l.output
+        return state.input
+
+    def predict(self, x_dev_tensor: TSingleTensor | None = None):
+        st = TNNetState(input=x_dev_tensor or self.input, isTraining=False)
+        return self.forward(st)
+
+    def yolo_layers(self):
+        return [l for l in self.layers if isinstance(l, TYoloLayer)]
+
+    def conv_flops(self) -> int:
+        """Algorithmic FLOPs of one forward pass over the whole batch: 2*B*F*OH*OW*C*kh*kw per conv."""
+        return sum(2 * l.batch * l.filters * l.outH * l.outW * l.c * l.kernelSize ** 2 for l in self.layers
+                   if isinstance(l, TConvolutionalLayer))
+
+    def Detections(self, thresh=0.45, nms=0.45, abatch=0, host_outputs=None):
+        """nnet.pas:584-677 + MSCOCOYolo.pas:252-253: gather yolo detections of one image, then NMS."""
+        bs, os_, ps = [], [], []
+        for li, l in enumerate(self.yolo_layers()):
+            pred = host_outputs[li] if host_outputs is not None else l.output.pullFromDevice()
+            b, o, p = l.getDetections(pred, self.w, self.h, thresh, abatch)
+            bs.append(b), os_.append(o), ps.append(p)
+        boxes, objs, probs = np.concatenate(bs), np.concatenate(os_), np.concatenate(ps)
+        return doNMSSort(boxes, objs, probs, nms)
+
+
+YOLOV3_ANCHORS = [10, 13, 16, 30, 33, 23, 30, 61, 62, 45, 59, 119, 116, 90, 156, 198, 373, 326]
+
+
+def yolov3_spec():
+    """The standard Darknet-53 / YOLOv3 layer list (the .cfg is not in the reference tree: MSCOCOYolo.pas:31 points
+    outside it).  107 layers: 75 conv, 23 shortcut, 4 route, 2 upsample, 3 yolo."""
+    L = []
+    conv = lambda f, k, s=1, bn=1, act="leaky": L.append(("conv", f, k, s, bn, act))
+
+    def res(n, f):
+        for _ in range(n):
+            conv(f // 2, 1)
+            conv(f, 3)
+            L.append(("shortcut", -3))
+
+    conv(32, 3)
+    conv(64, 3, 2); res(1, 64)
+    conv(128, 3, 2); res(2, 128)
+    conv(256, 3, 2); res(8, 256)
+    conv(512, 3, 2); res(8, 512)
+    conv(1024, 3, 2); res(4, 1024)
+    for _ in range(3):
+        conv(512, 1); conv(1024, 3)
+    conv(255, 1, 1, 0, "linear"); L.append(("yolo", [6, 7, 8]))
+    L.append(("route", [-4])); conv(256, 1); L.append(("upsample", 2)); L.append(("route", [-1, 61]))
+    for _ in range(3):
+        conv(256, 1); conv(512, 3)
+    conv(255, 1, 1, 0, "linear"); L.append(("yolo", [3, 4, 5]))
+    L.append(("route", [-4])); conv(128, 1); L.append(("upsample", 2)); L.append(("route", [-1, 36]))
+    for _ in range(3):
+        conv(128, 1); conv(256, 3)
+    conv(255, 1, 1, 0, "linear"); L.append(("yolo", [0, 1, 2]))
+    assert len(L) == 107
+    return L
+
+
+def layer_channels(spec, c_in=3):
+    """Output channel count of every layer of a spec (routes sum their sources)."""
+    outc, c = [], c_in
+    for i, item in enumerate(spec):
+        if item[0] == "conv":
+            c = item[1]
+        elif item[0] == "route":
+            c = sum(outc[(i + j) if j < 0 else j] for j in item[1])
+        outc.append(c)
+    return outc
+
+
+def init_yolov3_params(spec, c_in=3, seed=1234, objectness_bias=-4.0):
+    """Random-init parameters of BASELINE config 4: weights U(-s,s), s=sqrt(2/(k*k*C))
+    (nConvolutionLayer.pas:216-220); BN scales=1, rolling_mean U(-0.1,0.1), rolling_variance U(0.5,1.5); the
+    objectness biases of the three head convs = -4 so that only a few hundred boxes pass the 0.45 threshold."""
+    rng = np.random.default_rng(seed)
+    outc = layer_channels(spec, c_in)
+    params = []
+    for i, item in enumerate(spec):
+        if item[0] != "conv":
+            params.append(None)
+            continue
+        _, f, k, s, bn, act = item
+        c = outc[i - 1] if i else c_in
+        sc = np.sqrt(2.0 / (k * k * c))
+        p = dict(w=rng.uniform(-sc, sc, (f, c * k * k)).astype(np.float32), b=np.zeros(f, np.float32))
+        if bn:
+            p.update(scales=np.ones(f, np.float32), rm=rng.uniform(-0.1, 0.1, f).astype(np.float32),
+                     rv=rng.uniform(0.5, 1.5, f).astype(np.float32))
+        else:  # head conv: 3 anchors x (4 box + 1 obj + 80 classes)
+            p["b"].reshape(3, 85)[:, 4] = objectness_bias
+        params.append(p)
+    return params
+
+
+def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=1234):
+    """Builds the 107-layer net on the current `cuda` backend.  fuse_bn=True mirrors MSCOCOYolo.pas:327-340
+    (Neural.fuseBatchNorm before predict)."""
+    spec = yolov3_spec()
+    params = params or init_yolov3_params(spec, seed=seed)
+    act = {"leaky": nn.acLEAKY, "linear": nn.acLINEAR}
+    layers = []
+    c, h, w = 3, size, size
+    for i, item in enumerate(spec):
+        kind = item[0]
+        if kind == "conv":
+            _, f, k, s, bn, a = item
+            l = TConvolutionalLayer(batch, h, w, c, f, k, s, k // 2, act[a], bn, fused=fused, host_output=False)
+            p = params[i]
+            l.weights.Data[...] = p["w"]
+            l.biases.Data[...] = p["b"]
+            if bn:
+                l.scales.Data[...] = p["scales"]
+                l.rolling_mean.Data[...] = p["rm"]
+                l.rolling_variance.Data[...] = p["rv"]
+                if fuse_bn:
+                    l.fuseBatchNorm()
+        elif kind == "shortcut":
+            src = layers[i + item[1]]
+            l = TShortcutLayer(batch, i + item[1], src.outC, src.outH, src.outW)
+        elif kind == "route":
+            idx = [(i + j) if j < 0 else j for j in item[1]]
+            l = TConcatLayer(batch, idx, [(layers[j].outC, layers[j].outH, layers[j].outW) for j in idx])
+        elif kind == "upsample":
+            l = TUpsampleLayer(batch, c, h, w, item[1])
+        elif kind == "yolo":
+            l = TYoloLayer(batch, c, h, w, item[1], YOLOV3_ANCHORS, 80, fused=fused)
+        layers.append(l)
+        c, h, w = l.outC, l.outH, l.outW
+    return TNNet(layers, batch, 3, size, size)

@@ -30,21 +30,29 @@ def cuda():
 
 
 class TSingleTensor:
-    def __init__(self, shape, groups: int | None = None, data=None, device: bool = True):
+    def __init__(self, shape, groups: int | None = None, data=None, device: bool = True, host: bool = True):
         self.FShape = tuple(int(s) for s in shape)
         self.Groups = int(groups) if groups is not None else (self.FShape[0] if len(self.FShape) > 1 else 1)
+        self._n = int(np.prod(self.FShape)) if len(self.FShape) else 1
         if data is not None:
-            self.Data = np.ascontiguousarray(data, dtype=np.float32).reshape(self.FShape).copy()
+            self._data = np.ascontiguousarray(data, dtype=np.float32).reshape(self.FShape).copy()
         else:
-            self.Data = np.zeros(self.FShape, dtype=np.float32)
+            # host=False: activation tensors that only ever live on the device get their host twin lazily
+            self._data = np.zeros(self.FShape, dtype=np.float32) if host else None
         self.devData = 0
-        self.lastOP = cdCPU
-        if device and self.Data.size:
-            self.devData = cuda().createDeviceBuffer(self.Data.nbytes)  # ntensors.pas:6103-6109
+        self.lastOP = cdCPU if host or data is not None else cdCUDA
+        if device and self._n:
+            self.devData = cuda().createDeviceBuffer(self._n * 4)  # ntensors.pas:6103-6109
+
+    @property
+    def Data(self) -> np.ndarray:
+        if self._data is None:
+            self._data = np.zeros(self.FShape, dtype=np.float32)
+        return self._data
 
     # shape helpers (ntensors.pas: Size/Volume/Area/c/h/w)
     def Size(self) -> int:
-        return int(self.Data.size)
+        return self._n
 
     size = Size
 

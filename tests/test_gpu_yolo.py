@@ -1,0 +1,76 @@
+"""End-to-end YOLOv3 graph on the GPU backend vs the CPU oracle: per-layer outputs and post-NMS boxes
+(BASELINE.json: same count, same class, IoU >= 0.99)."""
+import numpy as np
+import pytest
+
+from util import TOL_3XTF32, rel_max
+
+pytestmark = pytest.mark.gpu
+
+
+def run_net(cu, size, batch, fused, params, x):
+    from tensorium_b200.nnet import build_yolov3
+    net = build_yolov3(batch, size, params=params, fused=fused)
+    cu.writeBuffer(net.input.devData, x.nbytes, x)
+    net.predict()
+    return net
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_yolov3_small_against_oracle(cuda_backend, oracle, fused):
+    from oracle import ref_net
+    from tensorium_b200.nnet import box_iou, doNMSSort, init_yolov3_params, yolov3_spec
+    cu = cuda_backend
+    size, batch = 96, 2
+    spec = yolov3_spec()
+    params = init_yolov3_params(spec, seed=5, objectness_bias=-1.5)
+    x = np.random.default_rng(6).random((batch, 3, size, size), dtype=np.float32)
+    probe = {i: None for i in range(len(spec))}
+    oracle.set_mode(oracle.MODE_FMA)
+    try:
+        want = ref_net.forward(spec, params, x, collect=probe)
+    finally:
+        oracle.set_mode(oracle.MODE_PAS)
+    net = run_net(cu, size, batch, fused, params, x)
+    # (1) per-layer parity: every conv layer is fed the ORACLE's input of that layer and must reproduce the
+    #     oracle's output within the north-star tolerance (no accumulated drift in this comparison)
+    from tensorium_b200.layers import TConvolutionalLayer, TNNetState
+    from tensorium_b200.tensor import TSingleTensor
+    worst = 0.0
+    for i, l in enumerate(net.layers):
+        if not isinstance(l, TConvolutionalLayer):
+            continue
+        src = x if i == 0 else probe[i - 1]
+        t = TSingleTensor(src.shape, batch, src)
+        st = TNNetState(input=t, workspace=net.workspace)
+        l.forwardGPU(st)
+        e = rel_max(l.output.pullFromDevice(), probe[i])
+        worst = max(worst, e)
+        assert e < TOL_3XTF32, (i, e)
+    print("worst per-layer rel err", worst)
+    # (2) end to end: 75 convolutions of drift stay well inside the detection tolerance
+    net.predict()
+    for i in (4, 36, 61, 79, 98, 105):
+        got = net.layers[i].output.pullFromDevice()
+        assert got.shape == probe[i].shape and rel_max(got, probe[i]) < 2e-3, (i, rel_max(got, probe[i]))
+    outs = [l.output.pullFromDevice() for l in net.yolo_layers()]
+    for g, r in zip(outs, want):
+        assert rel_max(g, r) < 2e-3
+    # detections + NMS on both sides (getDetections nyololayer.pas:399-441, doNMSSort ntypes.pas:1612-1646).
+    # The threshold is placed in a gap of the oracle's objectness values near their 90% quantile so that a few dozen
+    # boxes pass and none sits within the arithmetic tolerance of the threshold.
+    objs = np.sort(np.concatenate([w.reshape(batch, 3, 85, -1)[:, :, 4, :].ravel() for w in want]))
+    idx = int(0.9 * objs.size)
+    while objs[idx] - objs[idx - 1] < 1e-3:
+        idx += 1
+    thresh = float((objs[idx] + objs[idx - 1]) / 2)
+    total = 0
+    for b in range(batch):
+        db, do, dp = net.Detections(thresh, 0.45, b, host_outputs=outs)
+        rb, ro, rp = net.Detections(thresh, 0.45, b, host_outputs=want)
+        assert len(db) == len(rb)
+        total += len(db)
+        for i in range(len(db)):
+            assert np.array_equal(dp[i] > 0, rp[i] > 0)  # same surviving classes
+            assert box_iou(db[i], rb[i]) >= 0.99
+    assert total > 0  # the comparison is not vacuous

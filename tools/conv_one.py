@@ -1,0 +1,34 @@
+"""Run single conv configurations through tnn_conv2d_forward (for ncu / timing).  usage: conv_one.py [math] [cfg ...]
+cfg = B,C,H,F,k,s"""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from tensorium_b200 import tensor
+from util import Dev
+
+MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+math = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
+cfgs = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]] or [(64, 256, 26, 512, 3, 1)]
+cu = tensor.initCUDART(0)
+cu.set_math_mode(MATH[math])
+rng = np.random.default_rng(0)
+for (B, C, H, F, k, s) in cfgs:
+    p = k // 2
+    oh = (H + 2 * p - k) // s + 1
+    x = rng.random((B, C, H, H), dtype=np.float32)
+    w = rng.uniform(-0.05, 0.05, (F, C * k * k)).astype(np.float32)
+    b = np.zeros(F, np.float32)
+    dx, dw, db, do = Dev(cu, x), Dev(cu, w), Dev(cu, b), Dev(cu, n=B * F * oh * oh)
+    desc = cu.conv_desc(B, C, H, H, F, k, k, p, p, s, s)
+    for _ in range(2):
+        cu.conv2dForward(desc, dx.ptr, 0, dw.ptr, None, db.ptr, 9, do.ptr, 0)
+    cu.finish()
+    t0 = time.perf_counter()
+    n = 5
+    for _ in range(n):
+        cu.conv2dForward(desc, dx.ptr, 0, dw.ptr, None, db.ptr, 9, do.ptr, 0)
+    cu.finish()
+    dt = (time.perf_counter() - t0) / n
+    fl = 2.0 * B * F * oh * oh * C * k * k
+    print(f"B{B} C{C} H{H} F{F} k{k} s{s}: {dt*1e3:.3f} ms  {fl/dt/1e12:.1f} TFLOP/s ({math})", flush=True)
