@@ -113,6 +113,19 @@ __device__ __forceinline__ float tnn_act(float x, int a) {
   }
 }
 
+// Epilogue variant for the fused conv kernels: no fp64 (F2F/DMUL run at a small fraction of the fp32 rate and
+// stalled the tcgen05 epilogue warps); differs from tnn_act by at most 1 ulp on the decimal-constant branches.
+__device__ __forceinline__ float tnn_act_fast(float x, int a) {
+  switch (a) {
+    case TNN_ACT_LINEAR: return x;
+    case TNN_ACT_REVLEAKY:
+    case TNN_ACT_LEAKY: return x < 0 ? 0.1f * x : x;
+    case TNN_ACT_RELU: return x > 0 ? x : 0.f * x;
+    case TNN_ACT_LOGISTIC: return 1.0f / (1.0f + __expf(-x));
+    default: return tnn_act(x, a);
+  }
+}
+
 // Gradient as a function of the layer OUTPUT (nactivation.pas:403-501)
 __device__ __forceinline__ float tnn_grad(float x, int a) {
   switch (a) {

@@ -1,17 +1,22 @@
 // umma_conv.cuh — tcgen05 (5th-gen tensor core) contraction kernel for sm_100a.
 //
-// One kernel template serves the implicit-GEMM convolution forward and plain SGEMM:
-//   D[m][n] (TMEM, fp32, 128 lanes x BN columns) = sum_k A(m,k) * B(n,k)
-// * Operands are staged in shared memory in the UMMA canonical SWIZZLE_128B layouts by 8 producer
-//   warps that read global memory directly (im2col is done on the fly — no column buffer exists),
-//   then consumed by `tcgen05.mma.cta_group::1.kind::tf32` issued by one thread of a dedicated warp.
-// * 3xTF32: every fp32 operand is split in registers on its way to shared memory into
-//   hi = x with the low 13 mantissa bits cleared (exactly a TF32 number) and lo = x - hi (exact in fp32);
-//   D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi gives fp32-level accuracy (the dropped A_lo*B_lo term is
-//   ~2^-22 relative).  TF32 mode stores only the raw value (hardware ignores the low mantissa bits).
-// * mbarrier ring: producers -> full[s] -> MMA warp -> tcgen05.commit -> empty[s] -> producers;
-//   final tcgen05.commit -> accum barrier -> all 8 producer warps turn into the epilogue:
-//   tcgen05.ld (32 lanes x 32 columns per instruction) -> scale/bias/activation -> coalesced stores.
+// One persistent, warp-specialised kernel template serves the implicit-GEMM convolution forward and plain SGEMM:
+//   D[m][n] (TMEM, fp32, 128 lanes x BN columns, double buffered) = sum_k A(m,k) * B(n,k)
+//
+//   warps 0-3   epilogue   tcgen05.ld (32 lanes x 32 columns) -> scale/bias/activation -> coalesced stores;
+//                          overlaps the next tile's main loop through the second TMEM accumulator
+//   warps 4-11  producers  read global memory directly (im2col on the fly — no column buffer exists), keep
+//                          kPrefetch k-blocks of loads in flight in registers, split fp32 into TF32 hi/lo and
+//                          write the UMMA canonical swizzled shared-memory tiles
+//   warp 12     MMA        one thread issues tcgen05.mma.cta_group::1.kind::tf32 (3 per k-step in 3xTF32)
+//   warp 13     TMA        one thread streams the pre-split weight tiles (cp.async.bulk.tensor, SWIZZLE_128B)
+//
+// Every CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (m fastest, so co-resident CTAs share weights
+// in L2); the smem ring and its mbarrier phases run continuously across tiles.
+//
+// 3xTF32: hi = x with the low 13 mantissa bits cleared (exactly a TF32 number), lo = x - hi (exact in fp32);
+// D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi.  TF32 mode stores cvt.rna.tf32 of the operand (the tensor core itself
+// would truncate, which biases every product toward zero).
 //
 // Shared-memory operand layouts (bytes; every tile is 1024B aligned):
 //   K-major  (rows = M or N index, 32 floats = 128B per row):   row*128 + ((chunk16 ^ (row&7))<<4)
@@ -24,22 +29,24 @@
 //            SBO = (R/32)*512 (next 4-row k group), advance two SBO per UMMA_K=8 step
 #pragma once
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include <string.h>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
-#include <string.h>
 
 namespace umma {
 
 constexpr int kNotTaken = -100;
 constexpr int BM = 128;
 constexpr int BK = 32;
-constexpr int kProducerWarps = 8;
+constexpr int kEpilogueWarps = 4;                      // warps 0-3 (warp % 4 = TMEM lane quadrant)
+constexpr int kProducerWarps = 8;                      // warps 4-11
 constexpr int kProducerThreads = kProducerWarps * 32;
-constexpr int kMmaWarp = kProducerWarps;         // warp 8: tcgen05.mma issuer (+ TMEM alloc/dealloc)
-constexpr int kTmaWarp = kProducerWarps + 1;     // warp 9: TMA producer of the weight operand
-constexpr int kThreads = kProducerThreads + 64;
-constexpr int kMaxStages = 4;
+constexpr int kFirstProducerWarp = kEpilogueWarps;
+constexpr int kMmaWarp = kEpilogueWarps + kProducerWarps;  // 12 (+ TMEM alloc/dealloc)
+constexpr int kTmaWarp = kMmaWarp + 1;                     // 13
+constexpr int kThreads = (kTmaWarp + 1) * 32;              // 448
+constexpr int kMaxStages = 6;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -137,18 +144,13 @@ __host__ __device__ inline uint32_t make_idesc(int n, bool a_mn_major, bool b_mn
 }
 
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
-// TF32 mode: round to nearest (the tensor core itself would truncate, which biases every product toward zero)
 __device__ __forceinline__ float tf32_rna(float x) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
   return __uint_as_float(u);
 }
-
-// store one element of an MN-major tile with R rows (R % 32 == 0)
 template <bool SPLIT>
-__device__ __forceinline__ void sts_mn(uint8_t *hi, uint8_t *lo, int R, int mn, int k, float v) {
-  const int off = (((k >> 2) * (R >> 5) + (mn >> 5)) << 9) + ((k & 3) << 7) + (((((mn & 31) >> 3) ^ (k & 3))) << 5) +
-                  ((mn & 7) << 2);
+__device__ __forceinline__ void sts_elem(uint8_t *hi, uint8_t *lo, uint32_t off, float v) {
   if (SPLIT) {
     const float h = tf32_hi(v);
     *reinterpret_cast<float *>(hi + off) = h;
@@ -156,6 +158,11 @@ __device__ __forceinline__ void sts_mn(uint8_t *hi, uint8_t *lo, int R, int mn, 
   } else {
     *reinterpret_cast<float *>(hi + off) = tf32_rna(v);
   }
+}
+// byte offset of element (mn, k) in an MN-major tile with R rows (R % 32 == 0)
+__device__ __forceinline__ uint32_t mn_off(int R, int mn, int k) {
+  return (uint32_t)((((k >> 2) * (R >> 5) + (mn >> 5)) << 9) + ((k & 3) << 7) + (((((mn & 31) >> 3) ^ (k & 3))) << 5) +
+                    ((mn & 7) << 2));
 }
 // store one 16-byte chunk (4 consecutive k) of a K-major tile
 template <bool SPLIT>
@@ -171,33 +178,34 @@ __device__ __forceinline__ void sts_k(uint8_t *hi, uint8_t *lo, int row, int chu
 }
 
 // ------------------------------------------------------------------ operand loaders
-// A loader stages one [R rows][32 k] operand tile per k-block with the 256 producer threads, in two phases so
-// that global-memory latency overlaps the pipeline wait:
-//   Ctx  init(R, mn0, tid)                 per-thread constants (row decode etc.)
-//   void load(ctx, regs, kb)               issue ALL global loads of k-block kb into registers
-//   void store<SPLIT>(ctx, regs, hi, lo)   split (3xTF32) and write the swizzled smem tile
+// A loader stages one [R rows][32 k] operand tile per k-block with the 256 producer threads in two phases, so
+// global-memory latency overlaps the pipeline (kPrefetch k-blocks of loads are in flight per thread):
+//   TileCtx tile_ctx(R, mn0, tid)              per-thread constants of one output tile (row decode etc.)
+//   void    load(tctx, regs, kb, tid)          issue ALL global loads of k-block kb into registers
+//   void    store<SPLIT>(regs, hi, lo, R, tid) split (3xTF32) and write the swizzled smem tile
 //   kMnMajor   smem layout it writes (decides the descriptor);  kTma: tile is written by the TMA warp instead
 
-// matrix whose k index is contiguous: elem(mn,k) = p[mn*ld + k]   (A of NN/NT, B of NT, conv weights)
+// matrix whose k index is contiguous: elem(mn,k) = p[mn*ld + k]   (A of NN/NT, B of NT)
 struct KContigLoader {
   static constexpr bool kMnMajor = false;
   static constexpr bool kTma = false;
+  static constexpr int kPrefetch = 1;
   const float *p;
   int64_t ld;
   int64_t rows, K;   // valid extent
   int64_t K1, zfold; // fold-batch-into-k: k = b*K1 + kk -> p + b*zfold (K1 % 32 == 0), else K1 = K
   bool vec_ok;       // rows 16B aligned and K1 % 4 == 0
-  struct Ctx { int R; int64_t mn0; int tid; };
+  struct TileCtx { int R; int64_t mn0; };
   struct Regs { float4 v[8]; };
-  __device__ __forceinline__ Ctx init(int R, int64_t mn0, int tid) const { return Ctx{R, mn0, tid}; }
-  __device__ __forceinline__ void load(const Ctx &c, Regs &r, int64_t kb) const {
+  __device__ __forceinline__ TileCtx tile_ctx(int R, int64_t mn0, int) const { return TileCtx{R, mn0}; }
+  __device__ __forceinline__ void load(const TileCtx &c, Regs &r, int64_t kb, int tid) const {
     const int64_t k0 = kb * BK;
     const int64_t b = k0 / K1;
     const int64_t kk0 = k0 - b * K1;
     const float *base = p + b * zfold;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int e = c.tid + i * kProducerThreads;
+      const int e = tid + i * kProducerThreads;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (e < c.R * 8) {
         const int row = e >> 3, chunk = e & 7;
@@ -219,11 +227,11 @@ struct KContigLoader {
     }
   }
   template <bool SPLIT>
-  __device__ __forceinline__ void store(const Ctx &c, const Regs &r, uint8_t *hi, uint8_t *lo) const {
+  __device__ __forceinline__ void store(const Regs &r, uint8_t *hi, uint8_t *lo, int R, int tid) const {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int e = c.tid + i * kProducerThreads;
-      if (e < c.R * 8) sts_k<SPLIT>(hi, lo, e >> 3, e & 7, r.v[i]);
+      const int e = tid + i * kProducerThreads;
+      if (e < R * 8) sts_k<SPLIT>(hi, lo, e >> 3, e & 7, r.v[i]);
     }
   }
 };
@@ -232,21 +240,22 @@ struct KContigLoader {
 struct MnContigLoader {
   static constexpr bool kMnMajor = true;
   static constexpr bool kTma = false;
+  static constexpr int kPrefetch = 1;
   const float *p;
   int64_t ld;
   int64_t rows, K;
   int64_t K1, zfold;
-  struct Ctx { int R, sh; int64_t mn0; int tid; };
+  struct TileCtx { int R, sh; int64_t mn0; };
   struct Regs { float v[32]; };
-  __device__ __forceinline__ Ctx init(int R, int64_t mn0, int tid) const { return Ctx{R, 31 - __clz(R), mn0, tid}; }
-  __device__ __forceinline__ void load(const Ctx &c, Regs &r, int64_t kb) const {
+  __device__ __forceinline__ TileCtx tile_ctx(int R, int64_t mn0, int) const { return TileCtx{R, 31 - __clz(R), mn0}; }
+  __device__ __forceinline__ void load(const TileCtx &c, Regs &r, int64_t kb, int tid) const {
     const int64_t k0 = kb * BK;
     const int64_t b = k0 / K1;
     const int64_t kk0 = k0 - b * K1;
     const float *base = p + b * zfold;
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const int e = c.tid + i * kProducerThreads;  // R is a power of two >= 32: a warp covers 32 rows of one k
+      const int e = tid + i * kProducerThreads;  // R is a power of two >= 32: a warp covers 32 rows of one k
       float v = 0.f;
       if (e < c.R * BK) {
         const int row = e & (c.R - 1), k = e >> c.sh;
@@ -257,38 +266,39 @@ struct MnContigLoader {
     }
   }
   template <bool SPLIT>
-  __device__ __forceinline__ void store(const Ctx &c, const Regs &r, uint8_t *hi, uint8_t *lo) const {
+  __device__ __forceinline__ void store(const Regs &r, uint8_t *hi, uint8_t *lo, int R, int tid) const {
+    const int sh = 31 - __clz(R);
 #pragma unroll
     for (int i = 0; i < 32; ++i) {
-      const int e = c.tid + i * kProducerThreads;
-      if (e < c.R * BK) sts_mn<SPLIT>(hi, lo, c.R, e & (c.R - 1), e >> c.sh, r.v[i]);
+      const int e = tid + i * kProducerThreads;
+      if (e < R * BK) sts_elem<SPLIT>(hi, lo, mn_off(R, e & (R - 1), e >> sh), r.v[i]);
     }
   }
 };
 
-// implicit im2col: row = output pixel (b, oh, ow) folded over the batch, k = (c, kr, kc)
+// implicit im2col: row = output pixel (b, oh, ow) folded over the batch.
 // elem = in[b][c][oh*sy - ph + kr*dy][ow*sx - pw + kc*dx] or 0     (sim2Col ntensors.pas:11415-11491)
-// Per thread: one pixel row and 16 consecutive k per k-block.  The in-bounds test of every kernel tap is folded
-// into a per-thread bit mask once per tile (kh*kw <= 64), the (c, kr, kc) walk and the global offset are
-// warp-uniform, and the swizzled smem address is a per-thread base plus compile-time constants.
+// The contraction index is re-ordered (the weight copy is ours, see k_prepare_weights) as
+//     k = ((cg*kh*kw + tap)*16 + ci),   c = cg*16 + ci,   tap = kr*kw + kc
+// so the 16 consecutive k one thread stages per k-block share ONE kernel tap and walk 16 channels: the
+// in-bounds test is one bit of a per-tile tap mask, and each load is `pointer += H*W; predicated LDG`.
+// Channels are padded to a multiple of 16 (zero weights, loads predicated off).
 struct Im2colPixelLoader {
   static constexpr bool kMnMajor = true;
   static constexpr bool kTma = false;
+  static constexpr int kPrefetch = 3;
   const float *in;
   simt::ConvGeom g;
   int64_t rows;  // batch*OH*OW
-  int64_t K;     // C*kh*kw
-  struct Ctx {
-    const float *base;      // &in[b][0][ih0][iw0]
+  int HW, kk;    // H*W, kh*kw
+  struct TileCtx {
+    const float *base;           // &in[b][0][ih0][iw0]
     unsigned long long tapmask;  // bit (kr*kw+kc): tap inside the image for this pixel (0 if the row is padding)
-    uint32_t soff[4];       // smem byte offset of (row, k&3 = q), without the k-group term
-    int khalf;
   };
   struct Regs { float v[16]; };
-  __device__ __forceinline__ Ctx init(int, int64_t mn0, int tid) const {
-    Ctx c;
+  __device__ __noinline__ TileCtx tile_ctx(int, int64_t mn0, int tid) const {
+    TileCtx c;
     const int row = tid & 127;
-    c.khalf = tid >> 7;
     const int64_t mn = mn0 + row;
     const bool valid = mn < rows;
     const int P = g.OH * g.OW;
@@ -305,46 +315,42 @@ struct Im2colPixelLoader {
           if ((unsigned)(ih0 + kr * g.dy) < (unsigned)g.H && (unsigned)(iw0 + kc * g.dx) < (unsigned)g.W) m |= 1ull << t;
     }
     c.tapmask = m;
-    // sts_mn offset for R = 128: ((k>>2)*4 + (row>>5))*512 + (k&3)*128 + ((((row&31)>>3) ^ (k&3))<<5) + (row&7)*4
-    const uint32_t rowpart = (uint32_t)((row >> 5) << 9) + (uint32_t)((row & 7) << 2) + (uint32_t)c.khalf * 4u * 2048u;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) c.soff[q] = rowpart + (uint32_t)(q << 7) + (uint32_t)(((((row & 31) >> 3) ^ q)) << 5);
     return c;
   }
-  __device__ __forceinline__ void load(const Ctx &cx, Regs &r, int64_t kb) const {
-    const int kk = g.kh * g.kw;
-    int k = (int)(kb * BK) + cx.khalf * 16;   // warp-uniform walk over (c, kr, kc)
-    int c = k / kk;
-    int t = k - c * kk;
-    int kr = t / g.kw, kc = t - kr * g.kw;
-    int off = c * (g.H * g.W) + kr * g.dy * g.W + kc * g.dx;
-    const int rowstep = g.dy * g.W - g.kw * g.dx;           // kc wraps: next kernel row
-    const int chanstep = g.H * g.W - g.kh * g.dy * g.W;     // kr wraps: next channel
+  struct Src { const float *q; int nc; };
+  // address of the first of this thread's 16 elements in k-block kb and how many of them exist (kept out of line:
+  // two integer divisions that would otherwise be replicated in every unrolled prefetch slot)
+  __device__ __noinline__ Src source(const TileCtx &cx, int kb, int tid) const {
+    const int gi = kb * 2 + (tid >> 7);  // 16-wide k group of this thread
+    const int cg = gi / kk, tap = gi - cg * kk;
+    const int kr = tap / g.kw, kc = tap - kr * g.kw;
+    const int c0 = cg * 16;
+    const bool on = (cx.tapmask >> tap) & 1ull;
+    Src s;
+    s.q = cx.base + (int64_t)c0 * HW + (kr * g.dy * g.W + kc * g.dx);
+    s.nc = on ? g.C - c0 : 0;  // channels of this group that exist (may exceed 16, may be <= 0)
+    return s;
+  }
+  __device__ __forceinline__ void load(const TileCtx &cx, Regs &r, int64_t kb, int tid) const {
+    const Src s = source(cx, (int)kb, tid);
+    const uint32_t hw = (uint32_t)HW;
+    uint32_t off = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      float v = 0.f;
-      if (((cx.tapmask >> t) & 1ull) && k < K) v = __ldg(cx.base + off);
-      r.v[j] = v;
-      ++k; ++t; ++kc; off += g.dx;
-      if (kc == g.kw) {
-        kc = 0; off += rowstep;
-        if (t == kk) { t = 0; off += chanstep; }
-      }
+      r.v[j] = (j < s.nc) ? __ldg(s.q + off) : 0.f;
+      off += hw;
     }
   }
   template <bool SPLIT>
-  __device__ __forceinline__ void store(const Ctx &cx, const Regs &r, uint8_t *hi, uint8_t *lo) const {
+  __device__ __forceinline__ void store(const Regs &r, uint8_t *hi, uint8_t *lo, int, int tid) const {
+    const int row = tid & 127, khalf = tid >> 7;
+    // mn_off for R = 128 and k = khalf*16 + j: per-thread base + compile-time terms
+    const uint32_t rowpart = (uint32_t)((row >> 5) << 9) + (uint32_t)((row & 7) << 2) + (uint32_t)khalf * 4u * 2048u;
+    uint32_t soff[4];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const uint32_t off = cx.soff[j & 3] + (uint32_t)((j >> 2) * 2048);
-      if (SPLIT) {
-        const float h = tf32_hi(r.v[j]);
-        *reinterpret_cast<float *>(hi + off) = h;
-        *reinterpret_cast<float *>(lo + off) = r.v[j] - h;
-      } else {
-        *reinterpret_cast<float *>(hi + off) = tf32_rna(r.v[j]);
-      }
-    }
+    for (int q = 0; q < 4; ++q) soff[q] = rowpart + (uint32_t)(q << 7) + (uint32_t)(((((row & 31) >> 3) ^ q)) << 5);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) sts_elem<SPLIT>(hi, lo, soff[j & 3] + (uint32_t)((j >> 2) * 2048), r.v[j]);
   }
 };
 
@@ -352,12 +358,13 @@ struct Im2colPixelLoader {
 struct TmaWeightsLoader {
   static constexpr bool kMnMajor = false;
   static constexpr bool kTma = true;
-  struct Ctx {};
+  static constexpr int kPrefetch = 3;
+  struct TileCtx {};
   struct Regs {};
-  __device__ __forceinline__ Ctx init(int, int64_t, int) const { return Ctx{}; }
-  __device__ __forceinline__ void load(const Ctx &, Regs &, int64_t) const {}
+  __device__ __forceinline__ TileCtx tile_ctx(int, int64_t, int) const { return TileCtx{}; }
+  __device__ __forceinline__ void load(const TileCtx &, Regs &, int64_t, int) const {}
   template <bool SPLIT>
-  __device__ __forceinline__ void store(const Ctx &, const Regs &, uint8_t *, uint8_t *) const {}
+  __device__ __forceinline__ void store(const Regs &, uint8_t *, uint8_t *, int, int) const {}
 };
 
 // ------------------------------------------------------------------ epilogues
@@ -374,22 +381,49 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
     const int b = (int)(m / P), p = (int)(m - (int64_t)b * P);
     return Row{out + (int64_t)b * outImg + p};
   }
-  __device__ __forceinline__ void store(const Row &r, int64_t n, float acc) const {
+  __device__ __forceinline__ float affine(int64_t n, float acc) const {
     float v = acc;
     if (scale) v = __fmul_rn(v, __ldg(scale + n));
     if (bias) v = __fadd_rn(v, __ldg(bias + n));
-    r.q[n * P] = tnn_act(v, act);
+    return v;
+  }
+  // 32 consecutive columns starting at n; `cnt` of them are valid.  The activation switch stays outside the
+  // unrolled loops (instruction-cache footprint).
+  __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt) const {
+    float *q = r.q + n * P;
+    if (act == TNN_ACT_LEAKY || act == TNN_ACT_REVLEAKY) {
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j)
+        if (j < cnt) { const float v = affine(n + j, __uint_as_float(acc[j])); q[(int64_t)j * P] = v < 0 ? 0.1f * v : v; }
+    } else if (act == TNN_ACT_LINEAR) {
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j)
+        if (j < cnt) q[(int64_t)j * P] = affine(n + j, __uint_as_float(acc[j]));
+    } else {
+#pragma unroll 1
+      for (int j = 0; j < 32; ++j)
+        if (j < cnt) q[(int64_t)j * P] = tnn_act(affine(n + j, __uint_as_float(acc[j])), act);
+    }
   }
 };
-struct GemmEpilogue {  // C[z][m][n] = alpha*acc + beta*C
+struct GemmEpilogue {  // C[m][n] = alpha*acc + beta*C
   float *C;
   int64_t ldc;
   float alpha, beta;
   int64_t rows, cols;
   struct Row { float *q; };
   __device__ __forceinline__ Row row(int64_t m) const { return Row{C + m * ldc}; }
-  __device__ __forceinline__ void store(const Row &r, int64_t n, float acc) const {
-    r.q[n] = (beta == 0.f) ? alpha * acc : fmaf(alpha, acc, beta * r.q[n]);
+  __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt) const {
+    float *q = r.q + n;
+    if (beta == 0.f) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < cnt) q[j] = alpha * __uint_as_float(acc[j]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (j < cnt) q[j] = fmaf(alpha, __uint_as_float(acc[j]), beta * q[j]);
+    }
   }
 };
 struct GemmAtomicEpilogue {  // split-k: C += alpha*acc
@@ -399,22 +433,40 @@ struct GemmAtomicEpilogue {  // split-k: C += alpha*acc
   int64_t rows, cols;
   struct Row { float *q; };
   __device__ __forceinline__ Row row(int64_t m) const { return Row{C + m * ldc}; }
-  __device__ __forceinline__ void store(const Row &r, int64_t n, float acc) const { atomicAdd(r.q + n, alpha * acc); }
+  __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt) const {
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j)
+      if (j < cnt) atomicAdd(r.q + n + j, alpha * __uint_as_float(acc[j]));
+  }
 };
 
 // ------------------------------------------------------------------ the kernel
 struct SharedCtl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
-  uint64_t accum;
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
   uint32_t tmem_base;
 };
 
-// grid: x = M tiles, y = N tiles, z = k splits.  BN = runtime tile width (multiple of 16, <= 256; a power of two
-// >= 32 when B is MN-major).  SPLIT = 3xTF32.  tmBhi/tmBlo: tensor maps of the pre-split weights (LB::kTma only).
+struct TileSched {  // tiles are numbered m fastest, then n, then k-split (32-bit: divisions stay cheap and small)
+  int mTiles, nTiles, kSplits, kBlocks, kBlocksPerSplit, numTiles;
+  __device__ __noinline__ void decode(int t, int &mt, int &nt, int &kb0, int &kb1) const {
+    const unsigned r = (unsigned)t / (unsigned)mTiles;
+    mt = t - (int)r * mTiles;
+    const unsigned ks = r / (unsigned)nTiles;
+    nt = (int)r - (int)ks * nTiles;
+    kb0 = (int)ks * kBlocksPerSplit;
+    kb1 = min(kBlocks, kb0 + kBlocksPerSplit);
+  }
+};
+
+// BN = runtime tile width (multiple of 16, <= 256; a power of two >= 32 when B is MN-major).  SPLIT = 3xTF32.
+// accCols = TMEM columns per accumulator buffer (2 buffers are allocated).  tmBhi/tmBlo: tensor maps of the
+// pre-split weights (LB::kTma only).
 template <bool SPLIT, typename LA, typename LB, typename EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t kBlocksPerSplit, uint32_t tmemCols,
+k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accCols,
        const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ SharedCtl ctl;
@@ -431,10 +483,13 @@ k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t 
       mbar_init(&ctl.full[s], kProducerWarps + (LB::kTma ? 1 : 0));
       mbar_init(&ctl.empty[s], 1);
     }
-    mbar_init(&ctl.accum, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl.tmem_full[s], 1);
+      mbar_init(&ctl.tmem_empty[s], kEpilogueWarps);
+    }
     fence_barrier_init();
   }
-  if (warp == kMmaWarp) tmem_alloc(&ctl.tmem_base, tmemCols);
+  if (warp == kMmaWarp) tmem_alloc(&ctl.tmem_base, accCols * 2);
   if (LB::kTma && warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmBhi);
     if (SPLIT) tma_prefetch_desc(&tmBlo);
@@ -442,63 +497,69 @@ k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_d = ctl.tmem_base;
+  const uint32_t tmem_base = ctl.tmem_base;
 
-  const int64_t m0 = (int64_t)blockIdx.x * BM;
-  const int64_t n0 = (int64_t)blockIdx.y * BN;
-  const int64_t kbBegin = (int64_t)blockIdx.z * kBlocksPerSplit;
-  const int64_t kbEnd = min(kBlocksTotal, kbBegin + kBlocksPerSplit);
-  const int64_t nkb = kbEnd - kbBegin;
-
-  if (warp < kProducerWarps) {
+  if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
     // ===================== producers: global -> registers -> (split) -> swizzled smem =====================
-    const typename LA::Ctx ca = la.init(BM, m0, threadIdx.x);
-    const typename LB::Ctx cb = lb.init(BN, n0, threadIdx.x);
-    typename LA::Regs ra;
-    typename LB::Regs rb;
-    if (nkb > 0) {
-      la.load(ca, ra, kbBegin);
-      if (!LB::kTma) lb.load(cb, rb, kbBegin);
+    constexpr int D = LA::kPrefetch;
+    const int tid = threadIdx.x - kFirstProducerWarp * 32;
+    typename LA::Regs ra[D];
+    typename LB::Regs rb[D];
+    // load cursor (runs D k-blocks ahead of the store cursor)
+    int ltile = blockIdx.x, lkb = 0, lkb1 = 0, lmt = 0, lnt = 0;
+    typename LA::TileCtx ca;
+    typename LB::TileCtx cb;
+    bool lvalid = ltile < sched.numTiles;
+    if (lvalid) {
+      sched.decode(ltile, lmt, lnt, lkb, lkb1);
+      ca = la.tile_ctx(BM, (int64_t)lmt * BM, tid);
+      cb = lb.tile_ctx(BN, (int64_t)lnt * BN, tid);
+    }
+    auto issue_load = [&](typename LA::Regs &xa, typename LB::Regs &xb) {
+      if (!lvalid) return;
+      la.load(ca, xa, lkb, tid);
+      if (!LB::kTma) lb.load(cb, xb, lkb, tid);
+      if (++lkb == lkb1) {
+        ltile += gridDim.x;
+        lvalid = ltile < sched.numTiles;
+        if (lvalid) {
+          sched.decode(ltile, lmt, lnt, lkb, lkb1);
+          ca = la.tile_ctx(BM, (int64_t)lmt * BM, tid);
+          cb = lb.tile_ctx(BN, (int64_t)lnt * BN, tid);
+        }
+      }
+    };
+    // store cursor
+    int64_t remaining = 0;  // k-blocks this CTA stages in total
+    for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x) {
+      int mt, nt, k0, k1;
+      sched.decode(t, mt, nt, k0, k1);
+      remaining += k1 - k0;
     }
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t kb = kbBegin; kb < kbEnd; ++kb) {
-      mbar_wait(&ctl.empty[stage], phase ^ 1);
-      uint8_t *sa = smem + (size_t)stage * stageBytes;
-      uint8_t *sa_lo = sa + aBytes;
-      uint8_t *sb = sa + (SPLIT ? 2 : 1) * aBytes;
-      uint8_t *sb_lo = sb + bBytes;
-      la.template store<SPLIT>(ca, ra, sa, sa_lo);
-      if (!LB::kTma) lb.template store<SPLIT>(cb, rb, sb, sb_lo);
-      fence_proxy_async();  // make generic-proxy smem writes visible to the tensor core (async proxy)
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ctl.full[stage]);
-      if (kb + 1 < kbEnd) {  // the next k-block's loads fly while we wait for its smem slot
-        la.load(ca, ra, kb + 1);
-        if (!LB::kTma) lb.load(cb, rb, kb + 1);
-      }
-      if (++stage == stages) { stage = 0; phase ^= 1; }
-    }
-    // ===================== epilogue: TMEM -> registers -> global =====================
-    if (nkb > 0) {
-      mbar_wait(&ctl.accum, 0);
-      tc_fence_after();
-      const int quad = warp & 3;           // TMEM lane quadrant this warp may read
-      const int half = warp >> 2;          // even / odd 32-column chunks
-      const int64_t m = m0 + quad * 32 + lane;
-      const bool mvalid = m < epi.rows;
-      typename EPI::Row rc = epi.row(mvalid ? m : 0);
-      const int nChunks = (BN + 31) >> 5;  // 32-column chunks; chunk i starts at column 32*i (< tmemCols)
-      for (int ci = half; ci < nChunks; ci += 2) {
-        const int c0 = ci * 32;
-        uint32_t r[32];
-        tmem_ld32(tmem_d + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, r);
-        if (mvalid) {
+    int prime = D;  // the first D passes only issue loads (fills the register slots)
+    while (remaining > 0) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int64_t n = n0 + c0 + j;
-            if (c0 + j < BN && n < epi.cols) epi.store(rc, n, __uint_as_float(r[j]));
+      for (int d = 0; d < D; ++d) {
+        if (remaining > 0) {
+          if (prime == 0) {
+            mbar_wait(&ctl.empty[stage], phase ^ 1);
+            uint8_t *sa = smem + (size_t)stage * stageBytes;
+            uint8_t *sa_lo = sa + aBytes;
+            uint8_t *sb = sa + (SPLIT ? 2 : 1) * aBytes;
+            uint8_t *sb_lo = sb + bBytes;
+            la.template store<SPLIT>(ra[d], sa, sa_lo, BM, tid);
+            if (!LB::kTma) lb.template store<SPLIT>(rb[d], sb, sb_lo, BN, tid);
+            fence_proxy_async();  // make generic-proxy smem writes visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl.full[stage]);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+            --remaining;
+          } else {
+            --prime;
           }
+          issue_load(ra[d], rb[d]);  // (re)fill this register slot: D k-blocks of loads stay in flight
         }
       }
     }
@@ -508,70 +569,125 @@ k_umma(LA la, LB lb, EPI epi, int BN, int stages, int64_t kBlocksTotal, int64_t 
     const uint32_t smem_base = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;
-    for (int64_t kb = kbBegin; kb < kbEnd; ++kb) {
-      mbar_wait(&ctl.full[stage], phase);
+    int it = 0;
+    for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x, ++it) {
+      int mt, nt, kb0, kb1;
+      sched.decode(t, mt, nt, kb0, kb1);
+      const int as = (int)(it & 1);
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait(&ctl.tmem_empty[as], (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
-        const uint32_t sa_lo = sa + aBytes;
-        const uint32_t sb = sa + (SPLIT ? 2 : 1) * aBytes;
-        const uint32_t sb_lo = sb + bBytes;
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait(&ctl.full[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
+          const uint32_t sa_lo = sa + aBytes;
+          const uint32_t sb = sa + (SPLIT ? 2 : 1) * aBytes;
+          const uint32_t sb_lo = sb + bBytes;
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          // MN-major: LBO 512, SBO (R/32)*512, one UMMA_K=8 step = two 4-row k groups.  K-major: SBO 1024, +32B.
-          const uint32_t aoff = LA::kMnMajor ? ks * 2 * (BM / 32) * 512 : ks * 32;
-          const uint32_t boff = LB::kMnMajor ? ks * 2 * (BN / 32) * 512 : ks * 32;
-          const uint32_t a_lbo = LA::kMnMajor ? 512 : 16, a_sbo = LA::kMnMajor ? (BM / 32) * 512 : 1024;
-          const uint32_t b_lbo = LB::kMnMajor ? 512 : 16, b_sbo = LB::kMnMajor ? (BN / 32) * 512 : 1024;
-          const uint32_t a_lt = LA::kMnMajor ? 1u : 2u, b_lt = LB::kMnMajor ? 1u : 2u;
-          const uint64_t ah = make_desc(sa + aoff, a_lbo, a_sbo, a_lt);
-          const uint64_t bh = make_desc(sb + boff, b_lbo, b_sbo, b_lt);
-          const uint32_t first = (kb != kbBegin || ks != 0) ? 1u : 0u;
-          if (SPLIT) {
-            const uint64_t al = make_desc(sa_lo + aoff, a_lbo, a_sbo, a_lt);
-            const uint64_t bl = make_desc(sb_lo + boff, b_lbo, b_sbo, b_lt);
-            mma_tf32(tmem_d, al, bh, idesc, first);  // small terms first
-            mma_tf32(tmem_d, ah, bl, idesc, 1u);
-            mma_tf32(tmem_d, ah, bh, idesc, 1u);
-          } else {
-            mma_tf32(tmem_d, ah, bh, idesc, first);
+          for (int ks = 0; ks < BK / 8; ++ks) {
+            // MN-major: LBO 512, SBO (R/32)*512, one UMMA_K=8 step = two 4-row k groups.  K-major: SBO 1024, +32B.
+            const uint32_t aoff = LA::kMnMajor ? ks * 2 * (BM / 32) * 512 : ks * 32;
+            const uint32_t boff = LB::kMnMajor ? ks * 2 * (BN / 32) * 512 : ks * 32;
+            const uint32_t a_lbo = LA::kMnMajor ? 512 : 16, a_sbo = LA::kMnMajor ? (BM / 32) * 512 : 1024;
+            const uint32_t b_lbo = LB::kMnMajor ? 512 : 16, b_sbo = LB::kMnMajor ? (BN / 32) * 512 : 1024;
+            const uint32_t a_lt = LA::kMnMajor ? 1u : 2u, b_lt = LB::kMnMajor ? 1u : 2u;
+            const uint64_t ah = make_desc(sa + aoff, a_lbo, a_sbo, a_lt);
+            const uint64_t bh = make_desc(sb + boff, b_lbo, b_sbo, b_lt);
+            const uint32_t acc = (kb != kb0 || ks != 0) ? 1u : 0u;
+            if (SPLIT) {
+              const uint64_t al = make_desc(sa_lo + aoff, a_lbo, a_sbo, a_lt);
+              const uint64_t bl = make_desc(sb_lo + boff, b_lbo, b_sbo, b_lt);
+              mma_tf32(tmem_d, al, bh, idesc, acc);  // small terms first
+              mma_tf32(tmem_d, ah, bl, idesc, 1u);
+              mma_tf32(tmem_d, ah, bh, idesc, 1u);
+            } else {
+              mma_tf32(tmem_d, ah, bh, idesc, acc);
+            }
           }
+          mma_commit(&ctl.empty[stage]);                     // frees the smem slot when the MMAs have read it
+          if (kb == kb1 - 1) mma_commit(&ctl.tmem_full[as]);  // accumulator complete
         }
-        mma_commit(&ctl.empty[stage]);            // frees the smem slot when the MMAs have read it
-        if (kb == kbEnd - 1) mma_commit(&ctl.accum);  // accumulator complete
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-      __syncwarp();
-      if (++stage == stages) { stage = 0; phase ^= 1; }
     }
-  } else if (LB::kTma && lane == 0) {
+  } else if (warp == kTmaWarp) {
     // ===================== TMA producer of the weight tiles (one thread) =====================
-    const uint32_t smem_base = smem_u32(smem);
-    int stage = 0;
-    uint32_t phase = 0;
-    for (int64_t kb = kbBegin; kb < kbEnd; ++kb) {
-      mbar_wait(&ctl.empty[stage], phase ^ 1);
-      const uint32_t sb = smem_base + (uint32_t)stage * stageBytes + (SPLIT ? 2 : 1) * aBytes;
-      mbar_arrive_expect_tx(&ctl.full[stage], (uint32_t)bBytes * (SPLIT ? 2 : 1));
-      tma_load_2d(sb, &tmBhi, (int)(kb * BK), (int)n0, &ctl.full[stage]);
-      if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, (int)(kb * BK), (int)n0, &ctl.full[stage]);
-      if (++stage == stages) { stage = 0; phase ^= 1; }
+    if (LB::kTma && lane == 0) {
+      const uint32_t smem_base = smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x) {
+        int mt, nt, kb0, kb1;
+        sched.decode(t, mt, nt, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&ctl.empty[stage], phase ^ 1);
+          const uint32_t sb = smem_base + (uint32_t)stage * stageBytes + (SPLIT ? 2 : 1) * aBytes;
+          mbar_arrive_expect_tx(&ctl.full[stage], (uint32_t)bBytes * (SPLIT ? 2 : 1));
+          tma_load_2d(sb, &tmBhi, (int)(kb * BK), (int)(nt * BN), &ctl.full[stage]);
+          if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, (int)(kb * BK), (int)(nt * BN), &ctl.full[stage]);
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps 0-3: TMEM -> registers -> global =====================
+    const int quad = warp;  // == warp % 4: the TMEM lane quadrant this warp may read
+    int it = 0;
+    for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x, ++it) {
+      int mt, nt, kb0, kb1;
+      sched.decode(t, mt, nt, kb0, kb1);
+      const int as = (int)(it & 1);
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int64_t m = (int64_t)mt * BM + quad * 32 + lane;
+      const int64_t n0 = (int64_t)nt * BN;
+      const bool mvalid = m < epi.rows;
+      typename EPI::Row rc = epi.row(mvalid ? m : 0);
+      mbar_wait(&ctl.tmem_full[as], use & 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
+      const int nChunks = (BN + 31) >> 5;  // 32-column chunks; chunk i starts at column 32*i (< accCols)
+      for (int ci = 0; ci < nChunks; ++ci) {
+        const int c0 = ci * 32;
+        uint32_t r[32];
+        tmem_ld32(tmem_d + (uint32_t)c0, r);
+        if (ci == nChunks - 1) {  // all TMEM reads of this warp are done: hand the buffer back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&ctl.tmem_empty[as]);
+        }
+        if (mvalid) {
+          int64_t cnt = min((int64_t)(BN - c0), epi.cols - (n0 + c0));
+          if (cnt > 32) cnt = 32;
+          if (cnt > 0) epi.store_chunk(rc, n0 + c0, r, (int)cnt);
+        }
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_d, tmemCols);
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, accCols * 2);
 }
 
 // ------------------------------------------------------------------ weight preparation (TMA path)
-// hi/lo (3xTF32) or rna-rounded (TF32) zero-padded copy of W[F][K] -> [F][Kpad]
-__global__ void __launch_bounds__(256) k_prepare_weights(const float *__restrict__ w, int64_t F, int64_t K, int64_t Kpad,
-                                                         float *__restrict__ hi, float *__restrict__ lo, int split) {
+// hi/lo (3xTF32) or rna-rounded (TF32) zero-padded copy of W[F][C*kk] -> [F][Kpad] in the loader's k order:
+// k = (cg*kk + tap)*16 + ci  <-  W[f][(cg*16+ci)*kk + tap]
+__global__ void __launch_bounds__(256) k_prepare_weights(const float *__restrict__ w, int64_t F, int C, int kk,
+                                                         int64_t Kpad, float *__restrict__ hi, float *__restrict__ lo,
+                                                         int split) {
   const int64_t total = F * Kpad;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
-    const int64_t f = i / Kpad, k = i - f * Kpad;
-    const float v = (k < K) ? __ldg(w + f * K + k) : 0.f;
+    const int64_t f = i / Kpad;
+    const int k = (int)(i - f * Kpad);
+    const int ci = k & 15, gt = k >> 4;
+    const int cg = gt / kk, tap = gt - cg * kk;
+    const int c = cg * 16 + ci;
+    const float v = (c < C) ? __ldg(w + (f * C + c) * kk + tap) : 0.f;
     if (split) {
       const float h = tf32_hi(v);
       hi[i] = h;
@@ -584,11 +700,11 @@ __global__ void __launch_bounds__(256) k_prepare_weights(const float *__restrict
 
 // ------------------------------------------------------------------ host side
 struct Plan {
-  int BN, stages, kSplits;
-  uint32_t tmemCols;
+  int BN, stages;
+  uint32_t accCols;
   size_t smemBytes;
-  int64_t kBlocks, kBlocksPerSplit;
-  dim3 grid;
+  TileSched sched;
+  int grid;
 };
 
 inline uint32_t pow2_cols(int bn) {
@@ -607,31 +723,34 @@ inline Plan make_plan(tnn_context *ctx, int64_t M, int64_t N, int64_t K, bool sp
   }
   if (bn < 16) bn = 16;
   p.BN = bn;
-  p.tmemCols = pow2_cols(bn);
+  p.accCols = pow2_cols(bn);
   const size_t stageBytes = (size_t)(BM + bn) * BK * 4 * (split ? 2 : 1);
   const size_t budget = 200 * 1024;
   int st = (int)(budget / stageBytes);
   if (st > kMaxStages) st = kMaxStages;
   if (st < 2) st = 2;
-  p.kBlocks = cdiv64(K, BK);
-  if (p.kBlocks < 1) p.kBlocks = 1;
-  if ((int64_t)st > p.kBlocks) st = (int)(p.kBlocks < 2 ? 2 : p.kBlocks);
   p.stages = st;
   p.smemBytes = stageBytes * st + 1024;
-  const int64_t tiles = cdiv64(M, BM) * cdiv64(N, bn);
-  int ks = 1;
+  TileSched &s = p.sched;
+  s.kBlocks = (int)cdiv64(K, BK);
+  if (s.kBlocks < 1) s.kBlocks = 1;
+  s.mTiles = (int)cdiv64(M, BM);
+  s.nTiles = (int)cdiv64(N, bn);
+  const int64_t sms = ctx->prop.multiProcessorCount;
+  int64_t ks = 1;
   if (allowSplitK) {
-    const int64_t sms = ctx->prop.multiProcessorCount;
-    if (tiles < sms && p.kBlocks >= 16) {
-      ks = (int)(sms / tiles);
-      const int64_t maxs = p.kBlocks / 8;
-      if (ks > maxs) ks = (int)maxs;
+    const int64_t tiles = (int64_t)s.mTiles * s.nTiles;
+    if (tiles < sms && s.kBlocks >= 16) {
+      ks = sms / tiles;
+      const int64_t maxs = s.kBlocks / 8;
+      if (ks > maxs) ks = maxs;
       if (ks < 1) ks = 1;
     }
   }
-  p.kBlocksPerSplit = cdiv64(p.kBlocks, ks);
-  p.kSplits = (int)cdiv64(p.kBlocks, p.kBlocksPerSplit);
-  p.grid = dim3((unsigned)cdiv64(M, BM), (unsigned)cdiv64(N, bn), (unsigned)p.kSplits);
+  s.kBlocksPerSplit = (int)cdiv64(s.kBlocks, ks);
+  s.kSplits = (int)cdiv64(s.kBlocks, s.kBlocksPerSplit);
+  s.numTiles = s.mTiles * s.nTiles * s.kSplits;
+  p.grid = (int)(s.numTiles < sms ? s.numTiles : sms);
   return p;
 }
 
@@ -640,11 +759,10 @@ int launch(tnn_context *ctx, const Plan &p, LA la, LB lb, EPI epi, const CUtenso
            const CUtensorMap *tmLo = nullptr) {
   auto kern = k_umma<SPLIT, LA, LB, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
-  TNN_REQUIRE(p.grid.y <= 65535 && p.grid.z <= 65535, "grid too large");
   alignas(64) CUtensorMap dummy;
   memset(&dummy, 0, sizeof(dummy));
-  kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(la, lb, epi, p.BN, p.stages, p.kBlocks, p.kBlocksPerSplit,
-                                                       p.tmemCols, tmHi ? *tmHi : dummy, tmLo ? *tmLo : dummy);
+  kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(la, lb, epi, p.sched, p.BN, p.stages, p.accCols,
+                                                       tmHi ? *tmHi : dummy, tmLo ? *tmLo : dummy);
   TNN_LAUNCHED(ctx);
   return 0;
 }
@@ -659,7 +777,7 @@ int gemm_launch(tnn_context *ctx, LA la, LB lb, int64_t M, int64_t N, int64_t Kt
                 int64_t ldc, bool allowSplitK) {
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   Plan p = make_plan(ctx, M, N, Ktot, split, LB::kMnMajor, allowSplitK && beta == 1.0f);
-  if (p.kSplits > 1) {
+  if (p.sched.kSplits > 1) {
     GemmAtomicEpilogue epi{C, ldc, alpha, beta, M, N};
     return split ? launch<true>(ctx, p, la, lb, epi) : launch<false>(ctx, p, la, lb, epi);
   }
@@ -744,11 +862,12 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
                         const float *scale, const float *bias, int act, float *out) {
   const int64_t M = (int64_t)batch * g.OH * g.OW;
   const int64_t N = g.F;
-  const int64_t K = (int64_t)g.C * g.kh * g.kw;
-  if (g.kh * g.kw > 64 || g.inImg >= (1ll << 31)) return kNotTaken;  // tap mask is 64 bits, offsets 32 bits
+  const int kk = g.kh * g.kw;
+  const int64_t K = (int64_t)((g.C + 15) / 16) * kk * 16;  // contraction length in the (cg, tap, ci) order
+  if (kk > 64 || g.inImg >= (1ll << 31)) return kNotTaken;  // tap mask is 64 bits, offsets 32 bits
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
-  const int64_t Kpad = p.kBlocks * BK;
+  const int64_t Kpad = (int64_t)p.sched.kBlocks * BK;
   const size_t plane = (size_t)N * Kpad * sizeof(float);
   int rc = tnn_reserve_work(ctx, plane * 2);
   if (rc) return rc;
@@ -757,7 +876,7 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   {
     int64_t blocks = cdiv64(N * Kpad, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_prepare_weights<<<(int)blocks, 256, 0, ctx->stream>>>(weights, N, K, Kpad, whi, wlo, split ? 1 : 0);
+    k_prepare_weights<<<(int)blocks, 256, 0, ctx->stream>>>(weights, N, g.C, kk, Kpad, whi, wlo, split ? 1 : 0);
     TNN_LAUNCHED(ctx);
   }
   alignas(64) CUtensorMap tmHi, tmLo;
@@ -765,7 +884,7 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   if (rc) return rc;
   rc = encode_weights_map(&tmLo, split ? wlo : whi, N, Kpad, p.BN);
   if (rc) return rc;
-  Im2colPixelLoader la{in, g, M, K};
+  Im2colPixelLoader la{in, g, M, g.H * g.W, kk};
   TmaWeightsLoader lb{};
   ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
