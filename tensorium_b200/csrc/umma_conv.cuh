@@ -83,6 +83,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
       "}\n" ::"r"(addr), "r"(parity)
       : "memory");
 }
+// one lane polls the mbarrier, the other 31 park at the warp barrier (no issue slots burnt on spinning)
+__device__ __forceinline__ void mbar_wait_warp(uint64_t *bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+// same, for waits that are normally long (epilogue waiting for a whole tile, producers waiting for a free slot):
+// back off between polls so the polling lane does not steal issue slots from the producer warps of its scheduler
+__device__ __forceinline__ void mbar_wait_warp_relaxed(uint64_t *bar, uint32_t parity, unsigned ns) {
+  if ((threadIdx.x & 31) == 0) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done = 0;
+    while (true) {
+      asm volatile(
+          "{\n.reg .pred p;\n"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+          "selp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(done)
+          : "r"(addr), "r"(parity)
+          : "memory");
+      if (done) break;
+      __nanosleep(ns);
+    }
+  }
+  __syncwarp();
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -197,8 +222,9 @@ struct KContigLoader {
   bool vec_ok;       // rows 16B aligned and K1 % 4 == 0
   struct TileCtx { int R; int64_t mn0; };
   struct Regs { float4 v[8]; };
-  __device__ __forceinline__ TileCtx tile_ctx(int R, int64_t mn0, int) const { return TileCtx{R, mn0}; }
-  __device__ __forceinline__ void load(const TileCtx &c, Regs &r, int64_t kb, int tid) const {
+  __device__ __forceinline__ void fill_lut(int *, int) const {}
+  __device__ __forceinline__ TileCtx tile_ctx(int R, int64_t mn0, int, int) const { return TileCtx{R, mn0}; }
+  __device__ __forceinline__ void load(TileCtx &c, Regs &r, int64_t kb, int tid, const int *) const {
     const int64_t k0 = kb * BK;
     const int64_t b = k0 / K1;
     const int64_t kk0 = k0 - b * K1;
@@ -247,8 +273,9 @@ struct MnContigLoader {
   int64_t K1, zfold;
   struct TileCtx { int R, sh; int64_t mn0; };
   struct Regs { float v[32]; };
-  __device__ __forceinline__ TileCtx tile_ctx(int R, int64_t mn0, int) const { return TileCtx{R, 31 - __clz(R), mn0}; }
-  __device__ __forceinline__ void load(const TileCtx &c, Regs &r, int64_t kb, int tid) const {
+  __device__ __forceinline__ void fill_lut(int *, int) const {}
+  __device__ __forceinline__ TileCtx tile_ctx(int R, int64_t mn0, int, int) const { return TileCtx{R, 31 - __clz(R), mn0}; }
+  __device__ __forceinline__ void load(TileCtx &c, Regs &r, int64_t kb, int tid, const int *) const {
     const int64_t k0 = kb * BK;
     const int64_t b = k0 / K1;
     const int64_t kk0 = k0 - b * K1;
@@ -294,10 +321,23 @@ struct Im2colPixelLoader {
   struct TileCtx {
     const float *base;           // &in[b][0][ih0][iw0]
     unsigned long long tapmask;  // bit (kr*kw+kc): tap inside the image for this pixel (0 if the row is padding)
+    int cg, tap;                 // (channel group, tap) of the NEXT k-block this thread loads (walks forward)
   };
   struct Regs { float v[16]; };
-  __device__ __noinline__ TileCtx tile_ctx(int, int64_t mn0, int tid) const {
+  // lut[t] = element offset of kernel tap t inside a channel plane
+  __device__ __forceinline__ void fill_lut(int *lut, int tid_all) const {
+    if (tid_all < kk) {
+      const int kr = tid_all / g.kw, kc = tid_all - kr * g.kw;
+      lut[tid_all] = kr * g.dy * g.W + kc * g.dx;
+    }
+  }
+  __device__ __noinline__ TileCtx tile_ctx(int, int64_t mn0, int tid, int kb0) const {
     TileCtx c;
+    {
+      const int gi = kb0 * 2 + (tid >> 7);
+      c.cg = gi / kk;
+      c.tap = gi - c.cg * kk;
+    }
     const int row = tid & 127;
     const int64_t mn = mn0 + row;
     const bool valid = mn < rows;
@@ -317,29 +357,21 @@ struct Im2colPixelLoader {
     c.tapmask = m;
     return c;
   }
-  struct Src { const float *q; int nc; };
-  // address of the first of this thread's 16 elements in k-block kb and how many of them exist (kept out of line:
-  // two integer divisions that would otherwise be replicated in every unrolled prefetch slot)
-  __device__ __noinline__ Src source(const TileCtx &cx, int kb, int tid) const {
-    const int gi = kb * 2 + (tid >> 7);  // 16-wide k group of this thread
-    const int cg = gi / kk, tap = gi - cg * kk;
-    const int kr = tap / g.kw, kc = tap - kr * g.kw;
-    const int c0 = cg * 16;
-    const bool on = (cx.tapmask >> tap) & 1ull;
-    Src s;
-    s.q = cx.base + (int64_t)c0 * HW + (kr * g.dy * g.W + kc * g.dx);
-    s.nc = on ? g.C - c0 : 0;  // channels of this group that exist (may exceed 16, may be <= 0)
-    return s;
-  }
-  __device__ __forceinline__ void load(const TileCtx &cx, Regs &r, int64_t kb, int tid) const {
-    const Src s = source(cx, (int)kb, tid);
+  // loads the thread's 16 channels of the current (cg, tap) and advances the walk by one k-block (two groups)
+  __device__ __forceinline__ void load(TileCtx &cx, Regs &r, int64_t, int, const int *lut) const {
+    const int c0 = cx.cg * 16;
+    const bool on = (cx.tapmask >> cx.tap) & 1ull;
+    const float *q = cx.base + (int64_t)c0 * HW + lut[cx.tap];
+    const int nc = on ? g.C - c0 : 0;  // channels of this group that exist (may exceed 16, may be <= 0)
     const uint32_t hw = (uint32_t)HW;
     uint32_t off = 0;
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
-      r.v[j] = (j < s.nc) ? __ldg(s.q + off) : 0.f;
+      r.v[j] = (j < nc) ? __ldg(q + off) : 0.f;
       off += hw;
     }
+    cx.tap += 2;
+    if (cx.tap >= kk) { cx.tap -= kk; ++cx.cg; if (cx.tap >= kk) { cx.tap -= kk; ++cx.cg; } }
   }
   template <bool SPLIT>
   __device__ __forceinline__ void store(const Regs &r, uint8_t *hi, uint8_t *lo, int, int tid) const {
@@ -361,13 +393,18 @@ struct TmaWeightsLoader {
   static constexpr int kPrefetch = 3;
   struct TileCtx {};
   struct Regs {};
-  __device__ __forceinline__ TileCtx tile_ctx(int, int64_t, int) const { return TileCtx{}; }
-  __device__ __forceinline__ void load(const TileCtx &, Regs &, int64_t, int) const {}
+  __device__ __forceinline__ void fill_lut(int *, int) const {}
+  __device__ __forceinline__ TileCtx tile_ctx(int, int64_t, int, int) const { return TileCtx{}; }
+  __device__ __forceinline__ void load(TileCtx &, Regs &, int64_t, int, const int *) const {}
   template <bool SPLIT>
   __device__ __forceinline__ void store(const Regs &, uint8_t *, uint8_t *, int, int) const {}
 };
 
 // ------------------------------------------------------------------ epilogues
+// activations other than linear / leaky: one out-of-line copy (the switch is large; inlining it into the unrolled
+// epilogue blew the kernel up to 300 KB of SASS)
+__device__ __noinline__ float act_out_of_line(float v, int a) { return tnn_act(v, a); }
+
 // Row context per thread (its TMEM lane = row m), then one call per column.
 struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
   float *out;
@@ -381,28 +418,31 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
     const int b = (int)(m / P), p = (int)(m - (int64_t)b * P);
     return Row{out + (int64_t)b * outImg + p};
   }
-  __device__ __forceinline__ float affine(int64_t n, float acc) const {
-    float v = acc;
-    if (scale) v = __fmul_rn(v, __ldg(scale + n));
-    if (bias) v = __fadd_rn(v, __ldg(bias + n));
-    return v;
-  }
-  // 32 consecutive columns starting at n; `cnt` of them are valid.  The activation switch stays outside the
-  // unrolled loops (instruction-cache footprint).
-  __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt) const {
+  // 32 consecutive columns starting at n; `cnt` of them are valid.  Each lane fetches the scale/bias of ONE column
+  // (coalesced) and the unrolled loop broadcasts them with shuffles.  The activation switch stays outside the loops.
+  __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt,
+                                              bool rowvalid) const {
+    const int lane = threadIdx.x & 31;
+    const float sc = (scale && lane < cnt) ? __ldg(scale + n + lane) : 1.0f;
+    const float bi = (bias && lane < cnt) ? __ldg(bias + n + lane) : 0.0f;
     float *q = r.q + n * P;
-    if (act == TNN_ACT_LEAKY || act == TNN_ACT_REVLEAKY) {
-#pragma unroll 8
-      for (int j = 0; j < 32; ++j)
-        if (j < cnt) { const float v = affine(n + j, __uint_as_float(acc[j])); q[(int64_t)j * P] = v < 0 ? 0.1f * v : v; }
-    } else if (act == TNN_ACT_LINEAR) {
-#pragma unroll 8
-      for (int j = 0; j < 32; ++j)
-        if (j < cnt) q[(int64_t)j * P] = affine(n + j, __uint_as_float(acc[j]));
+    const bool leaky = act == TNN_ACT_LEAKY || act == TNN_ACT_REVLEAKY;
+    if (leaky || act == TNN_ACT_LINEAR) {
+      const float neg = leaky ? 0.1f : 1.0f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = __shfl_sync(0xffffffffu, sc, j), b = __shfl_sync(0xffffffffu, bi, j);
+        float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s), b);
+        v = v < 0 ? neg * v : v;
+        if (rowvalid && j < cnt) q[(int64_t)j * P] = v;
+      }
     } else {
-#pragma unroll 1
-      for (int j = 0; j < 32; ++j)
-        if (j < cnt) q[(int64_t)j * P] = tnn_act(affine(n + j, __uint_as_float(acc[j])), act);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const float s = __shfl_sync(0xffffffffu, sc, j), b = __shfl_sync(0xffffffffu, bi, j);
+        const float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s), b);
+        if (rowvalid && j < cnt) q[(int64_t)j * P] = act_out_of_line(v, act);
+      }
     }
   }
 };
@@ -413,7 +453,9 @@ struct GemmEpilogue {  // C[m][n] = alpha*acc + beta*C
   int64_t rows, cols;
   struct Row { float *q; };
   __device__ __forceinline__ Row row(int64_t m) const { return Row{C + m * ldc}; }
-  __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt) const {
+  __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt,
+                                              bool rowvalid) const {
+    if (!rowvalid) return;
     float *q = r.q + n;
     if (beta == 0.f) {
 #pragma unroll
@@ -433,8 +475,10 @@ struct GemmAtomicEpilogue {  // split-k: C += alpha*acc
   int64_t rows, cols;
   struct Row { float *q; };
   __device__ __forceinline__ Row row(int64_t m) const { return Row{C + m * ldc}; }
-  __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt) const {
-#pragma unroll 4
+  __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt,
+                                              bool rowvalid) const {
+    if (!rowvalid) return;
+#pragma unroll
     for (int j = 0; j < 32; ++j)
       if (j < cnt) atomicAdd(r.q + n + j, alpha * __uint_as_float(acc[j]));
   }
@@ -447,6 +491,7 @@ struct SharedCtl {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  int lut[64];  // loader scratch (per-tap offsets of the im2col gather)
 };
 
 struct TileSched {  // tiles are numbered m fastest, then n, then k-split (32-bit: divisions stay cheap and small)
@@ -490,6 +535,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
     fence_barrier_init();
   }
   if (warp == kMmaWarp) tmem_alloc(&ctl.tmem_base, accCols * 2);
+  la.fill_lut(ctl.lut, threadIdx.x);
   if (LB::kTma && warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmBhi);
     if (SPLIT) tma_prefetch_desc(&tmBlo);
@@ -512,20 +558,20 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
     bool lvalid = ltile < sched.numTiles;
     if (lvalid) {
       sched.decode(ltile, lmt, lnt, lkb, lkb1);
-      ca = la.tile_ctx(BM, (int64_t)lmt * BM, tid);
-      cb = lb.tile_ctx(BN, (int64_t)lnt * BN, tid);
+      ca = la.tile_ctx(BM, (int64_t)lmt * BM, tid, lkb);
+      cb = lb.tile_ctx(BN, (int64_t)lnt * BN, tid, lkb);
     }
     auto issue_load = [&](typename LA::Regs &xa, typename LB::Regs &xb) {
       if (!lvalid) return;
-      la.load(ca, xa, lkb, tid);
-      if (!LB::kTma) lb.load(cb, xb, lkb, tid);
+      la.load(ca, xa, lkb, tid, ctl.lut);
+      if (!LB::kTma) lb.load(cb, xb, lkb, tid, ctl.lut);
       if (++lkb == lkb1) {
         ltile += gridDim.x;
         lvalid = ltile < sched.numTiles;
         if (lvalid) {
           sched.decode(ltile, lmt, lnt, lkb, lkb1);
-          ca = la.tile_ctx(BM, (int64_t)lmt * BM, tid);
-          cb = lb.tile_ctx(BN, (int64_t)lnt * BN, tid);
+          ca = la.tile_ctx(BM, (int64_t)lmt * BM, tid, lkb);
+          cb = lb.tile_ctx(BN, (int64_t)lnt * BN, tid, lkb);
         }
       }
     };
@@ -544,7 +590,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
       for (int d = 0; d < D; ++d) {
         if (remaining > 0) {
           if (prime == 0) {
-            mbar_wait(&ctl.empty[stage], phase ^ 1);
+            mbar_wait_warp(&ctl.empty[stage], phase ^ 1);
             uint8_t *sa = smem + (size_t)stage * stageBytes;
             uint8_t *sa_lo = sa + aBytes;
             uint8_t *sb = sa + (SPLIT ? 2 : 1) * aBytes;
@@ -575,11 +621,11 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
       sched.decode(t, mt, nt, kb0, kb1);
       const int as = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait(&ctl.tmem_empty[as], (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
+      mbar_wait_warp(&ctl.tmem_empty[as], (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait(&ctl.full[stage], phase);
+        mbar_wait_warp(&ctl.full[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
@@ -646,7 +692,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
       const int64_t n0 = (int64_t)nt * BN;
       const bool mvalid = m < epi.rows;
       typename EPI::Row rc = epi.row(mvalid ? m : 0);
-      mbar_wait(&ctl.tmem_full[as], use & 1);
+      mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
       const int nChunks = (BN + 31) >> 5;  // 32-column chunks; chunk i starts at column 32*i (< accCols)
@@ -659,10 +705,10 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl.tmem_empty[as]);
         }
-        if (mvalid) {
-          int64_t cnt = min((int64_t)(BN - c0), epi.cols - (n0 + c0));
+        {
+          int64_t cnt = min((int64_t)(BN - c0), epi.cols - (n0 + c0));  // warp-uniform
           if (cnt > 32) cnt = 32;
-          if (cnt > 0) epi.store_chunk(rc, n0 + c0, r, (int)cnt);
+          if (cnt > 0) epi.store_chunk(rc, n0 + c0, r, (int)cnt, mvalid);
         }
       }
     }
