@@ -83,6 +83,27 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(rows)}
 
 
+def rank_seed(rank: int) -> int:
+    """Every rank draws its own batch (batch sharding: independent images per GPU, no data-path collective)."""
+    return 1234 + rank
+
+
+def reduce_max_ms(ms: float, world: int, device="cuda") -> float:
+    """Timing contract: the step time of the job is the MAX over ranks."""
+    if world <= 1:
+        return ms
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([ms], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def aggregate_images_per_s(world: int, steps: int, ms_total: float, per_gpu_batch: int = BATCH) -> float:
+    """Whole-job throughput: all ranks' images divided by the max-over-ranks time."""
+    return per_gpu_batch * world * steps / (ms_total / 1000.0)
+
+
 def synthetic_images(batch, seed=1234):
     rng = np.random.Generator(np.random.PCG64(seed))
     return rng.random((batch, 3, SIZE, SIZE), dtype=np.float32)
@@ -162,7 +183,7 @@ def run_ours(args, rank, world, local_rank):
     cu.set_stream(stream.cuda_stream)
     cu.set_math_mode(MATH[args.math])
     net = build_yolov3(BATCH, SIZE, seed=1234)
-    x_host = torch.from_numpy(synthetic_images(BATCH, 1234 + rank)).pin_memory()
+    x_host = torch.from_numpy(synthetic_images(BATCH, rank_seed(rank))).pin_memory()
     nbytes_in = x_host.numel() * 4
     cu.writeBuffer(net.input.devData, nbytes_in, x_host.numpy())
     yolos = net.yolo_layers()
@@ -182,12 +203,7 @@ def run_ours(args, rank, world, local_rank):
             fn()
         e1.record(stream)
         barrier()
-        ms = e0.elapsed_time(e1)
-        if world > 1:
-            t = torch.tensor([ms], device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        return reduce_max_ms(e0.elapsed_time(e1), world)
 
     def step_resident():
         net.predict()
@@ -210,9 +226,8 @@ def run_ours(args, rank, world, local_rank):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
-    total_images = BATCH * world * args.steps
-    value = total_images / (ms / 1000.0)
-    e2e_value = total_images / (ms_e2e / 1000.0)
+    value = aggregate_images_per_s(world, args.steps, ms)
+    e2e_value = aggregate_images_per_s(world, args.steps, ms_e2e)
 
     # ---- roofline of the dominant kernel: the tcgen05 implicit-GEMM conv, all 75 launches of one step
     convs = [(i, l) for i, l in enumerate(net.layers) if isinstance(l, TConvolutionalLayer)]
