@@ -176,6 +176,9 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # keep stdout to the single JSON line (NCCL prints its version banner there at VERSION/INFO level)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)

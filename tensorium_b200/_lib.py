@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libtensorium_b200.so")
+LIB_PATH = os.environ.get("TNN_LIB", os.path.join(HERE, "libtensorium_b200.so"))  # TNN_LIB: A/B experiments only
 
 i32, i64, f32, u64 = C.c_int32, C.c_int64, C.c_float, C.c_uint64
 vp, cp, sz = C.c_void_p, C.c_char_p, C.c_size_t

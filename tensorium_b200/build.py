@@ -20,7 +20,7 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--extended-lambda", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden", "-DTNN_BUILDING",
-]
+] + os.environ.get("TNN_EXTRA_NVCC_FLAGS", "").split()  # experiments only, e.g. -DTNN_PIXEL_PREFETCH=5
 
 
 def _deps_digest() -> str:

@@ -5,6 +5,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "umma_conv.cuh"
+#include "conv_direct.cuh"
 
 namespace {
 
@@ -197,6 +198,8 @@ int32_t tnn_conv2d_forward(tnn_context *ctx, const tnn_conv_desc *d, const float
   out += outOffset;
   const int64_t K = (int64_t)g.C * g.kh * g.kw;
   const int64_t Npix = d->batch * g.OH * g.OW;
+  // tiny contractions (first layer, C*kh*kw <= 64): exact-fp32 direct convolution in registers, any math mode
+  if (direct::supported(g)) return direct::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out);
   if (ctx->math_mode != TNN_MATH_FP32) {
     rc = umma::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out);
     if (rc != umma::kNotTaken) return rc;
