@@ -100,6 +100,13 @@ TNN_API int32_t tnn_read_buffer_async(tnn_context *ctx, const float *mem, size_t
 TNN_API int32_t tnn_write_buffer_async(tnn_context *ctx, float *mem, size_t bytes, const void *host);
 /* finish nncuda.pas:1575-1584 */
 TNN_API int32_t tnn_finish(tnn_context *ctx);
+/* stream-to-stream ordering between two contexts of one device (no reference counterpart: the reference has a single
+ * stream; used to overlap host<->device copies on a second TNNCuda instance with compute) */
+typedef struct tnn_event tnn_event;
+TNN_API int32_t tnn_event_create(tnn_context *ctx, tnn_event **ev);
+TNN_API int32_t tnn_event_record(tnn_context *ctx, tnn_event *ev);       /* after all work queued on ctx so far */
+TNN_API int32_t tnn_stream_wait_event(tnn_context *ctx, tnn_event *ev);  /* later work on ctx waits for ev    */
+TNN_API int32_t tnn_event_destroy(tnn_event *ev);
 
 /* ------------------------------------------------------------------ activations (nncuda.pas:524-580) */
 /* ActivateArray(N, x, offset, activation): in place; no-op for acLINEAR.  CPU twin: activate_array nactivation.pas:508-621 */

@@ -44,6 +44,10 @@ SIGNATURES = {
     "tnn_read_buffer_async": (i32, [ctxp, fptr, sz, vp]),
     "tnn_write_buffer_async": (i32, [ctxp, fptr, sz, vp]),
     "tnn_finish": (i32, [ctxp]),
+    "tnn_event_create": (i32, [ctxp, C.POINTER(vp)]),
+    "tnn_event_record": (i32, [ctxp, vp]),
+    "tnn_stream_wait_event": (i32, [ctxp, vp]),
+    "tnn_event_destroy": (i32, [vp]),
     "tnn_activate_array": (i32, [ctxp, i64, fptr, i64, i32]),
     "tnn_activate_array_swish": (i32, [ctxp, i64, fptr, i64, fptr, fptr]),
     "tnn_derive_array": (i32, [ctxp, i64, fptr, i64, i32, fptr]),

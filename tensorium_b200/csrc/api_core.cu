@@ -163,6 +163,46 @@ int32_t tnn_write_buffer_async(tnn_context *ctx, float *mem, size_t bytes, const
   return 0;
 }
 
+struct tnn_event {
+  cudaEvent_t ev;
+};
+
+int32_t tnn_event_create(tnn_context *ctx, tnn_event **ev) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(ev != nullptr, "null out pointer");
+  tnn_event *e = new tnn_event();
+  cudaError_t r = cudaEventCreateWithFlags(&e->ev, cudaEventDisableTiming);
+  if (r != cudaSuccess) {
+    delete e;
+    tnn_set_error("cudaEventCreate failed: %s", cudaGetErrorString(r));
+    return 2;
+  }
+  *ev = e;
+  return 0;
+}
+
+int32_t tnn_event_record(tnn_context *ctx, tnn_event *ev) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(ev != nullptr, "null event");
+  TNN_CUDA(cudaEventRecord(ev->ev, ctx->stream));
+  return 0;
+}
+
+int32_t tnn_stream_wait_event(tnn_context *ctx, tnn_event *ev) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(ev != nullptr, "null event");
+  TNN_CUDA(cudaStreamWaitEvent(ctx->stream, ev->ev, 0));
+  return 0;
+}
+
+int32_t tnn_event_destroy(tnn_event *ev) {
+  if (ev) {
+    cudaEventDestroy(ev->ev);
+    delete ev;
+  }
+  return 0;
+}
+
 int32_t tnn_finish(tnn_context *ctx) {
   TNN_CHECK_CTX(ctx);
   TNN_CUDA(cudaStreamSynchronize(ctx->stream));

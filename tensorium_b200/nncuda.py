@@ -128,6 +128,21 @@ class TNNCuda:
     def finish(self):
         self._ck(self._l.tnn_finish(self._h))
 
+    # ---- events (stream-to-stream ordering between two TNNCuda instances of one device)
+    def createEvent(self) -> int:
+        e = C.c_void_p()
+        self._ck(self._l.tnn_event_create(self._h, C.byref(e)))
+        return int(e.value)
+
+    def recordEvent(self, ev: int):
+        self._ck(self._l.tnn_event_record(self._h, C.c_void_p(ev)))
+
+    def waitEvent(self, ev: int):
+        self._ck(self._l.tnn_stream_wait_event(self._h, C.c_void_p(ev)))
+
+    def destroyEvent(self, ev: int):
+        self._l.tnn_event_destroy(C.c_void_p(ev))
+
     # ---- activations (nncuda.pas:524-580)
     def ActivateArray(self, N, x, offset, activation):
         self._ck(self._l.tnn_activate_array(self._h, N, _addr(x), offset, int(activation)))
