@@ -220,6 +220,10 @@ int32_t tnn_conv2d_backward_filter(tnn_context *ctx, const tnn_conv_desc *d, con
   delta += deltaOffset;
   const int64_t N = (int64_t)g.C * g.kh * g.kw;
   const int64_t Kt = d->batch * (int64_t)g.OH * g.OW;
+  if (ctx->math_mode != TNN_MATH_FP32) {
+    rc = umma::conv_backward_filter(ctx, g, (int)d->batch, in, delta, weight_updates);
+    if (rc != umma::kNotTaken) return rc;
+  }
   simt::DeltaRowsFoldK la{delta, g};
   simt::Im2colRowsFoldK lb{in, g};
   const int splits = pick_splits(ctx, g.F, N, Kt);
@@ -237,6 +241,10 @@ int32_t tnn_conv2d_backward_data(tnn_context *ctx, const tnn_conv_desc *d, const
   in_delta += inDeltaOffset;
   const int64_t K = (int64_t)g.F * g.kh * g.kw;
   const int64_t Npix = d->batch * (int64_t)g.H * g.W;
+  if (ctx->math_mode != TNN_MATH_FP32) {
+    rc = umma::conv_backward_data(ctx, g, (int)d->batch, weights, delta, in_delta);
+    if (rc != umma::kNotTaken) return rc;
+  }
   simt::WeightsByChannel la{weights, g};
   simt::DeltaGatherCols lb{delta, g};
   DgradEpi epi{in_delta, g.H * g.W, g.inImg};

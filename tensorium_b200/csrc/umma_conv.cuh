@@ -34,6 +34,10 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 
+#ifndef TNN_PIXEL_PREFETCH
+#define TNN_PIXEL_PREFETCH 3  // k-blocks of im2col loads kept in flight per producer thread
+#endif
+
 namespace umma {
 
 constexpr int kNotTaken = -100;
@@ -313,7 +317,7 @@ struct MnContigLoader {
 struct Im2colPixelLoader {
   static constexpr bool kMnMajor = true;
   static constexpr bool kTma = false;
-  static constexpr int kPrefetch = 3;
+  static constexpr int kPrefetch = TNN_PIXEL_PREFETCH;
   const float *in;
   simt::ConvGeom g;
   int64_t rows;  // batch*OH*OW
@@ -413,6 +417,7 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
   int64_t outImg;
   int act;
   int64_t rows, cols;
+  bool accumulate;  // out += value (dgrad adds into the upstream delta, like the reference's col2im)
   struct Row { float *q; };
   __device__ __forceinline__ Row row(int64_t m) const {
     const int b = (int)(m / P), p = (int)(m - (int64_t)b * P);
@@ -434,7 +439,7 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
         const float s = __shfl_sync(0xffffffffu, sc, j), b = __shfl_sync(0xffffffffu, bi, j);
         float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s), b);
         v = v < 0 ? neg * v : v;
-        if (rowvalid && j < cnt) q[(int64_t)j * P] = v;
+        if (rowvalid && j < cnt) q[(int64_t)j * P] = accumulate ? q[(int64_t)j * P] + v : v;
       }
     } else {
 #pragma unroll
@@ -491,7 +496,8 @@ struct SharedCtl {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
-  int lut[64];  // loader scratch (per-tap offsets of the im2col gather)
+  int lut[64];     // A-loader scratch (per-tap offsets of the im2col gather)
+  int lut_b[192];  // B-loader scratch (wgrad: per-tap {offset, dh, dw})
 };
 
 struct TileSched {  // tiles are numbered m fastest, then n, then k-split (32-bit: divisions stay cheap and small)
@@ -536,6 +542,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
   }
   if (warp == kMmaWarp) tmem_alloc(&ctl.tmem_base, accCols * 2);
   la.fill_lut(ctl.lut, threadIdx.x);
+  lb.fill_lut(ctl.lut_b, threadIdx.x);
   if (LB::kTma && warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmBhi);
     if (SPLIT) tma_prefetch_desc(&tmBlo);
@@ -564,7 +571,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
     auto issue_load = [&](typename LA::Regs &xa, typename LB::Regs &xb) {
       if (!lvalid) return;
       la.load(ca, xa, lkb, tid, ctl.lut);
-      if (!LB::kTma) lb.load(cb, xb, lkb, tid, ctl.lut);
+      if (!LB::kTma) lb.load(cb, xb, lkb, tid, ctl.lut_b);
       if (++lkb == lkb1) {
         ltile += gridDim.x;
         lvalid = ltile < sched.numTiles;
@@ -743,6 +750,88 @@ __global__ void __launch_bounds__(256) k_prepare_weights(const float *__restrict
     }
   }
 }
+
+// dgrad as a forward convolution of delta: rows = input channel c, contraction over (filter group, flipped tap, f16)
+// out[c][(fg*kk + tapv)*16 + fi] = W[fg*16+fi][c][kk-1-tapv]      (W is [F][C*kk])
+__global__ void __launch_bounds__(256) k_prepare_weights_dgrad(const float *__restrict__ w, int F, int C, int kk,
+                                                               int64_t Kpad, float *__restrict__ hi,
+                                                               float *__restrict__ lo, int split) {
+  const int64_t total = (int64_t)C * Kpad;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const int64_t c = i / Kpad;
+    const int k = (int)(i - c * Kpad);
+    const int fi = k & 15, gt = k >> 4;
+    const int fg = gt / kk, tapv = gt - fg * kk;
+    const int f = fg * 16 + fi;
+    const float v = (f < F) ? __ldg(w + ((int64_t)f * C + c) * kk + (kk - 1 - tapv)) : 0.f;
+    if (split) {
+      const float h = tf32_hi(v);
+      hi[i] = h;
+      lo[i] = v - h;
+    } else {
+      hi[i] = tf32_rna(v);
+    }
+  }
+}
+
+// wgrad B operand: rows n = (c, tap) of im2col(in)^T, k = (image b, output pixel p); K-major tile (32 pixels of one
+// image per k-block; requires OH*OW % 32 == 0).  lane = pixel, warp w stages rows w, w+8, ...
+struct Im2colRowsLoader {
+  static constexpr bool kMnMajor = false;
+  static constexpr bool kTma = false;
+  static constexpr int kPrefetch = 1;
+  const float *in;
+  simt::ConvGeom g;
+  int64_t rows;  // C*kh*kw
+  int HW, kk, P;
+  struct TileCtx { int R; int n0; };
+  struct Regs { float v[32]; };
+  // lut[3t..3t+2] = {offset inside a channel plane, dh, dw} of tap t  (kk <= 64)
+  __device__ __forceinline__ void fill_lut(int *lut, int tid_all) const {
+    if (tid_all < kk) {
+      const int kr = tid_all / g.kw, kc = tid_all - kr * g.kw;
+      lut[3 * tid_all + 0] = (kr * g.dy - g.ph) * g.W + (kc * g.dx - g.pw);
+      lut[3 * tid_all + 1] = kr * g.dy - g.ph;
+      lut[3 * tid_all + 2] = kc * g.dx - g.pw;
+    }
+  }
+  __device__ __forceinline__ TileCtx tile_ctx(int R, int64_t mn0, int, int) const { return TileCtx{R, (int)mn0}; }
+  __device__ __forceinline__ void load(TileCtx &cx, Regs &r, int64_t kb, int tid, const int *lut) const {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int64_t k0 = kb * BK;
+    const int b = (int)(k0 / P);
+    const int p = (int)(k0 - (int64_t)b * P) + lane;
+    const int oh = p / g.OW, ow = p - oh * g.OW;
+    const int ih0 = oh * g.sy, iw0 = ow * g.sx;
+    const float *base = in + (int64_t)b * g.inImg + (int64_t)ih0 * g.W + iw0;
+    int n = cx.n0 + warp;
+    int c = n / kk, tap = n - c * kk;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      float v = 0.f;
+      if (warp + 8 * i < cx.R && n < rows) {
+        const int dh = lut[3 * tap + 1], dw = lut[3 * tap + 2];
+        if ((unsigned)(ih0 + dh) < (unsigned)g.H && (unsigned)(iw0 + dw) < (unsigned)g.W)
+          v = __ldg(base + (int64_t)c * HW + lut[3 * tap]);
+      }
+      r.v[i] = v;
+      n += 8;
+      tap += 8;
+      while (tap >= kk) { tap -= kk; ++c; }
+    }
+  }
+  template <bool SPLIT>
+  __device__ __forceinline__ void store(const Regs &r, uint8_t *hi, uint8_t *lo, int R, int tid) const {
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      const int row = warp + 8 * i;
+      if (row < R)
+        sts_elem<SPLIT>(hi, lo, (uint32_t)((row << 7) + ((((lane >> 2) ^ (row & 7))) << 4) + ((lane & 3) << 2)), r.v[i]);
+    }
+  }
+};
 
 // ------------------------------------------------------------------ host side
 struct Plan {
@@ -932,8 +1021,63 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   if (rc) return rc;
   Im2colPixelLoader la{in, g, M, g.H * g.W, kk};
   TmaWeightsLoader lb{};
-  ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N};
+  ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
+}
+
+// dgrad (nConvolutionLayer.pas:1250-1275: TN gemm + col2im) for stride 1 / dilation 1:
+//   in_delta[b][c][ih][iw] += sum_{f,kr,kc} W[f][c][kr][kc] * delta[b][f][ih + ph - kr][iw + pw - kc]
+// = a forward convolution of delta (F channels, OHxOW) with the flipped, transposed weights and padding
+// (kh-1-ph, kw-1-pw), accumulated into in_delta by the epilogue.
+inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *weights,
+                              const float *delta, float *in_delta) {
+  const int kk = g.kh * g.kw;
+  if (g.sy != 1 || g.sx != 1 || g.dy != 1 || g.dx != 1 || kk > 64) return kNotTaken;
+  if (g.kh - 1 - g.ph < 0 || g.kw - 1 - g.pw < 0 || g.outImg >= (1ll << 31)) return kNotTaken;
+  simt::ConvGeom v = g;  // the virtual forward problem
+  v.C = g.F; v.H = g.OH; v.W = g.OW; v.F = g.C;
+  v.ph = g.kh - 1 - g.ph; v.pw = g.kw - 1 - g.pw;
+  v.OH = g.H; v.OW = g.W;
+  v.inImg = g.outImg; v.outImg = g.inImg;
+  const int64_t M = (int64_t)batch * v.OH * v.OW;
+  const int64_t N = v.F;
+  const int64_t K = (int64_t)((v.C + 15) / 16) * kk * 16;
+  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  Plan p = make_plan(ctx, M, N, K, split, false, false);
+  const int64_t Kpad = (int64_t)p.sched.kBlocks * BK;
+  int rc = tnn_reserve_work(ctx, (size_t)N * Kpad * sizeof(float) * 2);
+  if (rc) return rc;
+  float *whi = ctx->work, *wlo = ctx->work + (size_t)N * Kpad;
+  {
+    int64_t blocks = cdiv64(N * Kpad, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_prepare_weights_dgrad<<<(int)blocks, 256, 0, ctx->stream>>>(weights, g.F, g.C, kk, Kpad, whi, wlo, split ? 1 : 0);
+    TNN_LAUNCHED(ctx);
+  }
+  alignas(64) CUtensorMap tmHi, tmLo;
+  rc = encode_weights_map(&tmHi, whi, N, Kpad, p.BN);
+  if (rc) return rc;
+  rc = encode_weights_map(&tmLo, split ? wlo : whi, N, Kpad, p.BN);
+  if (rc) return rc;
+  Im2colPixelLoader la{delta, v, M, v.H * v.W, kk};
+  TmaWeightsLoader lb{};
+  ConvEpilogue epi{in_delta, nullptr, nullptr, v.OH * v.OW, v.outImg, TNN_ACT_LINEAR, M, N, true};
+  return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
+}
+
+// wgrad (nConvolutionLayer.pas:1203-1232: im2col + NT gemm, beta = 1, batch accumulated):
+//   weight_updates[f][(c,kr,kc)] += sum_{b,p} delta[b][f][p] * im2col(in_b)[(c,kr,kc)][p]
+// M = F (rows of delta, K-major), N = C*kh*kw (gathered, K-major), K = batch*OH*OW split across CTAs (atomic adds).
+inline int conv_backward_filter(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in,
+                                const float *delta, float *weight_updates) {
+  const int kk = g.kh * g.kw;
+  const int P = g.OH * g.OW;
+  if ((P % BK) != 0 || kk > 64) return kNotTaken;  // a k-block must not straddle two images
+  const int64_t M = g.F, N = (int64_t)g.C * kk, Ktot = (int64_t)batch * P;
+  const bool vec = ((((uintptr_t)delta) & 15) == 0) && (P % 4 == 0);
+  KContigLoader la{delta, P, M, Ktot, P, g.outImg, vec};
+  Im2colRowsLoader lb{in, g, N, g.H * g.W, kk, P};
+  return gemm_launch(ctx, la, lb, M, N, Ktot, 1.0f, 1.0f, weight_updates, N, true);
 }
 
 }  // namespace umma

@@ -127,8 +127,17 @@ def test_conv_forward_scale_bias_activation_epilogue(cuda_backend, oracle, act):
     assert rel_max(dout.read(want.shape), want) < TOL_3XTF32
 
 
-@pytest.mark.parametrize("geom", GEOMS[:6])
-def test_conv_backward(cuda_backend, oracle, geom):
+BWD_GEOMS = GEOMS[:6] + [
+    (8, 32, 32, 32, 64, 3, 1, 1),    # deepCIFAR10 c3 shape (P = 1024: tcgen05 wgrad with split-K, tcgen05 dgrad)
+    (4, 64, 16, 16, 64, 3, 1, 1),    # deepCIFAR10 c4 shape
+    (2, 128, 8, 8, 128, 3, 1, 1),    # deepCIFAR10 c6 shape (P = 64)
+    (4, 16, 12, 12, 40, 1, 0, 1),    # 1x1, P = 144 (not a multiple of 32: CUDA-core wgrad)
+]
+
+
+@pytest.mark.parametrize("mode,tol", [(FP32, 5e-6), (X3, TOL_3XTF32)])
+@pytest.mark.parametrize("geom", BWD_GEOMS)
+def test_conv_backward(cuda_backend, oracle, geom, mode, tol):
     cu = cuda_backend
     B, C, H, W, F, k, p, s = geom
     rng = np.random.default_rng(sum(geom) + 1)
@@ -148,10 +157,14 @@ def test_conv_backward(cuda_backend, oracle, geom):
     dxw = oracle.col2im_batched(ws, B, C, H, W, k, k, p, p, s, s, im=dx0.copy())
     desc = cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s)
     din, dw, dd, dwu, ddx = Dev(cu, x), Dev(cu, w), Dev(cu, delta), Dev(cu, wu0), Dev(cu, dx0)
-    cu.conv2dBackwardFilter(desc, din.ptr, 0, dd.ptr, 0, dwu.ptr)
-    cu.conv2dBackwardData(desc, dw.ptr, dd.ptr, 0, ddx.ptr, 0)
-    assert rel_max(dwu.read(w.shape), wu) < TOL_3XTF32
-    assert rel_max(ddx.read(x.shape), dxw) < TOL_3XTF32
+    cu.set_math_mode(mode)
+    try:
+        cu.conv2dBackwardFilter(desc, din.ptr, 0, dd.ptr, 0, dwu.ptr)
+        cu.conv2dBackwardData(desc, dw.ptr, dd.ptr, 0, ddx.ptr, 0)
+    finally:
+        cu.set_math_mode(X3)
+    assert rel_max(dwu.read(w.shape), wu) < tol
+    assert rel_max(ddx.read(x.shape), dxw) < tol
 
 
 @pytest.mark.parametrize("fused", [True, False])

@@ -32,3 +32,14 @@ for (B, C, H, F, k, s) in cfgs:
     dt = (time.perf_counter() - t0) / n
     fl = 2.0 * B * F * oh * oh * C * k * k
     print(f"B{B} C{C} H{H} F{F} k{k} s{s}: {dt*1e3:.3f} ms  {fl/dt/1e12:.1f} TFLOP/s ({math})", flush=True)
+    if os.environ.get("TNN_BWD"):
+        dd, dwu, ddx = Dev(cu, rng.uniform(-1, 1, (B, F, oh, oh)).astype(np.float32)), Dev(cu, n=w.size), Dev(cu, n=x.size)
+        for name, fn in (("wgrad", lambda: cu.conv2dBackwardFilter(desc, dx.ptr, 0, dd.ptr, 0, dwu.ptr)),
+                         ("dgrad", lambda: cu.conv2dBackwardData(desc, dw.ptr, dd.ptr, 0, ddx.ptr, 0))):
+            fn(); cu.finish()
+            t0 = time.perf_counter()
+            for _ in range(n):
+                fn()
+            cu.finish()
+            dt = (time.perf_counter() - t0) / n
+            print(f"    {name}: {dt*1e3:.3f} ms  {fl/dt/1e12:.1f} TFLOP/s", flush=True)
