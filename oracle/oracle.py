@@ -236,3 +236,59 @@ def fuse_batchnorm(weights, biases, scales, rmean, rvar):
     lib().orc_fuse_batchnorm(_p(weights.reshape(-1)), _p(biases), _p(scales), _p(rmean), _p(rvar), i64(f),
                              i64(weights.size // f))
     return weights, biases
+
+
+# ---------------------------------------------------------------- CIFAR-10 training path neighbours
+
+def clamp(x, lo, hi):
+    lib().orc_clamp(i64(x.size), f32(lo), f32(hi), _p(x.reshape(-1)))
+    return x
+
+
+def maxpool_forward(x, ksize, stride_x, stride_y, padding=0, want_indexes=True):
+    b, c, h, w = x.shape
+    outH = (h + padding - ksize) // stride_y + 1  # nMaxPoolLayer.pas:106-107
+    outW = (w + padding - ksize) // stride_x + 1
+    out = np.empty((b, c, outH, outW), dtype=np.float32)
+    idx = np.empty(out.shape, dtype=np.int64) if want_indexes else None
+    lib().orc_maxpool_forward(i64(b), i64(c), i64(h), i64(w), i64(outH), i64(outW), i64(ksize), i64(stride_x),
+                              i64(stride_y), i64(padding), _p(x.reshape(-1)), _p(out.reshape(-1)),
+                              idx.ctypes.data_as(C.c_void_p) if want_indexes else None)
+    return out, idx
+
+
+def maxpool_backward(indexes, delta, upstream):
+    lib().orc_maxpool_backward(i64(delta.size), indexes.ctypes.data_as(C.c_void_p), _p(delta.reshape(-1)),
+                               _p(upstream.reshape(-1)))
+    return upstream
+
+
+def softmax_batch(x, groups=1, temp=1.0):
+    b, n = x.shape
+    out = np.empty_like(x)
+    lib().orc_softmax_batch(_p(x.reshape(-1)), i64(n // groups), i64(b), i64(n), i64(groups), i64(n // groups),
+                            i64(1), f32(temp), _p(out.reshape(-1)))
+    return out
+
+
+def softmax_cross_entropy(pred, truth):
+    delta = np.empty_like(pred)
+    err = np.empty_like(pred)
+    lib().orc_softmax_cross_entropy(i64(pred.size), _p(pred.reshape(-1)), _p(truth.reshape(-1)),
+                                    _p(delta.reshape(-1)), _p(err.reshape(-1)))
+    return delta, err
+
+
+def dropout_rand(n, seed):
+    r = np.empty(n, dtype=np.float32)
+    lib().orc_dropout_rand(i64(n), C.c_uint64(seed), _p(r))
+    return r
+
+
+def dropout_apply(x, rnd, probability, scale):
+    lib().orc_dropout_apply(i64(x.size), _p(rnd.reshape(-1)), f32(probability), f32(scale), _p(x.reshape(-1)))
+    return x
+
+
+def vsum(x):
+    return float(lib().orc_sum(i64(x.size), _p(x.reshape(-1)), i64(1)))

@@ -110,7 +110,9 @@ class RefConvLayer:
         return upstream_delta
 
     # TConvolutionalLayer.update nConvolutionLayer.pas:673-710 (SGD + momentum + L2)
-    def update(self, learning_rate, momentum, decay, batch):
+    def update(self, learning_rate, momentum, decay, batch, replicas=1):
+        # replicas > 1: data-parallel bookkeeping of tensorium_b200/dataparallel.py (not in the reference)
+        momentum = momentum / replicas
         f32 = np.float32
         lr_b = f32(f32(learning_rate) / f32(batch))
         orc.axpy(f32(f32(-decay) * f32(batch)), self.weights, self.weight_updates)

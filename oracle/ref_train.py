@@ -1,0 +1,204 @@
+"""CPU training step of the reference's CIFAR-10 sample net, built on the oracle primitives.
+
+TEST INFRASTRUCTURE ONLY (see oracle/tensorium_oracle.c header; parity unpinned).
+Layers follow the reference's CPU bodies call for call:
+  TMaxPoolLayer   nMaxPoolLayer.pas:363-513      TDropoutLayer  ndropoutlayer.pas:82-133
+  TConnectedLayer nconnectedlayer.pas:157-360    TSoftmaxLayer  nsoftmaxlayer.pas:139-182
+and the driver follows TNNet.forward/backward/update/Propagate (nnet.pas:275-432).
+The model is deepCIFAR10 (nmodels.pas:82-111).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import oracle as orc
+from .ref_layers import RefConvLayer
+
+f32 = np.float32
+
+
+class RefMaxPool:
+    trainable = False
+
+    def __init__(self, batch, c, h, w, ksize, stride=0, padding=0):
+        stride = stride or ksize  # nMaxPoolLayer.pas:78-81
+        self.batch, self.c, self.h, self.w = batch, c, h, w
+        self.ksize, self.stride, self.padding = ksize, stride, padding
+        self.outH = (h + padding - ksize) // stride + 1
+        self.outW = (w + padding - ksize) // stride + 1
+        self.output = np.zeros((batch, c, self.outH, self.outW), f32)
+        self.delta = np.zeros_like(self.output)
+
+    def forward(self, x, training=False):
+        self.output, self.indexes = orc.maxpool_forward(np.ascontiguousarray(x, f32), self.ksize, self.stride,
+                                                        self.stride, self.padding)
+        return self.output
+
+    def backward(self, upstream_delta=None):
+        if upstream_delta is not None:
+            orc.maxpool_backward(self.indexes, self.delta, upstream_delta)
+
+
+class RefDropout:
+    """In place on the previous layer's output / delta (ndropoutlayer.pas:90 `output := state.input^`)."""
+    trainable = False
+
+    def __init__(self, batch, inputs, probability):
+        self.batch, self.inputs = batch, inputs
+        self.probability = f32(probability)
+        self.scale = f32(1.0 / (1.0 - probability))
+        self.seed = 0
+        self.delta = None
+
+    def forward(self, x, training=False):
+        self.output = x  # alias
+        if training:
+            self.rand = orc.dropout_rand(x.size, self.seed)
+            orc.dropout_apply(x, self.rand, self.probability, self.scale)
+        return self.output
+
+    def backward(self, upstream_delta=None):
+        if upstream_delta is None:
+            return
+        orc.dropout_apply(upstream_delta, self.rand, self.probability, self.scale)
+        self.delta = upstream_delta  # alias (ndropoutlayer.pas:130)
+
+
+class RefConnected:
+    trainable = True
+
+    def __init__(self, batch, inputs, outputs, activation, weights, biases):
+        self.batch, self.inputs, self.outputs, self.activation = batch, inputs, outputs, activation
+        self.weights = np.ascontiguousarray(weights, f32).reshape(outputs, inputs).copy()
+        self.biases = np.ascontiguousarray(biases, f32).copy()
+        self.weight_updates = np.zeros_like(self.weights)
+        self.bias_updates = np.zeros_like(self.biases)
+        self.output = np.zeros((batch, outputs), f32)
+        self.delta = np.zeros((batch, outputs), f32)
+
+    def forward(self, x, training=False):  # nconnectedlayer.pas:157-242
+        self.input = np.ascontiguousarray(x, f32).reshape(self.batch, self.inputs)
+        orc.sgemm(False, True, self.batch, self.outputs, self.inputs, 1.0, self.input, self.inputs, self.weights,
+                  self.inputs, 0.0, self.output, self.outputs)
+        orc.forward_bias(self.output, self.biases, self.batch)
+        orc.activate_array(self.output, self.activation)
+        return self.output
+
+    def backward(self, upstream_delta=None):  # nconnectedlayer.pas:244-322
+        orc.clamp(self.delta, -1.0, 1.0)
+        orc.gradient_array(self.output, self.activation, self.delta)
+        orc.add_sums(self.bias_updates, self.delta, self.batch)
+        orc.sgemm(True, False, self.outputs, self.inputs, self.batch, 1.0, self.delta, self.outputs, self.input,
+                  self.inputs, 1.0, self.weight_updates, self.inputs)
+        if upstream_delta is not None:
+            orc.sgemm(False, False, self.batch, self.inputs, self.outputs, 1.0, self.delta, self.outputs,
+                      self.weights, self.inputs, 1.0, upstream_delta.reshape(self.batch, self.inputs), self.inputs)
+
+    def update(self, learning_rate, momentum, decay, batch, replicas=1):  # nconnectedlayer.pas:324-359
+        momentum = momentum / replicas  # data-parallel bookkeeping (tensorium_b200/dataparallel.py)
+        lr_b = f32(f32(learning_rate) / f32(batch))
+        orc.axpy(lr_b, self.bias_updates, self.biases)
+        orc.scal(momentum, self.bias_updates)
+        orc.axpy(f32(f32(-decay) * f32(batch)), self.weights, self.weight_updates)
+        orc.axpy(lr_b, self.weight_updates, self.weights)
+        orc.scal(momentum, self.weight_updates)
+
+
+class RefSoftmax:
+    trainable = False
+
+    def __init__(self, batch, inputs, groups=1):
+        self.batch, self.inputs, self.groups = batch, inputs, groups
+        self.output = np.zeros((batch, inputs), f32)
+        self.delta = np.zeros((batch, inputs), f32)
+        self.cost = 0.0
+
+    def forward(self, x, training=False, truth=None):  # nsoftmaxlayer.pas:139-167
+        self.output = orc.softmax_batch(np.ascontiguousarray(x, f32).reshape(self.batch, self.inputs), self.groups)
+        if truth is not None:
+            self.delta, self.loss = orc.softmax_cross_entropy(self.output, np.ascontiguousarray(truth, f32))
+            self.cost = orc.vsum(self.loss)
+        return self.output
+
+    def backward(self, upstream_delta=None):  # nsoftmaxlayer.pas:169-182
+        if upstream_delta is not None:
+            upstream_delta += self.delta.reshape(upstream_delta.shape)
+
+
+class RefConvTrain(RefConvLayer):
+    trainable = True
+
+
+class RefNet:
+    """TNNet with lrpCONSTANT policy (nnet.pas:210-273 returns learningRate unchanged for it)."""
+
+    def __init__(self, layers, batch, learning_rate=0.001, momentum=0.9, decay=0.0001, replicas=1):
+        self.layers, self.batch, self.replicas = layers, batch, replicas
+        self.learning_rate, self.momentum, self.decay = learning_rate, momentum, decay
+
+    def forward(self, x, truth=None, training=True):  # nnet.pas:275-317
+        for l in self.layers:
+            if training and l.delta is not None:
+                l.delta[...] = 0
+            x = l.forward(x, training, truth) if isinstance(l, RefSoftmax) else l.forward(x, training)
+        return x
+
+    def backward(self):  # nnet.pas:319-376 (state.delta = nil for layer 0)
+        for i in range(len(self.layers) - 1, -1, -1):
+            self.layers[i].backward(self.layers[i - 1].delta if i else None)
+
+    def update(self):  # nnet.pas:378-403: every layer but the last
+        for l in self.layers[:-1]:
+            if l.trainable:
+                l.update(self.learning_rate, self.momentum, self.decay, self.batch * self.replicas, self.replicas)
+
+    def propagate(self, x, truth):  # nnet.pas:404-432
+        self.forward(x, truth, True)
+        self.backward()
+        return self.layers[-1].cost
+
+    def cost(self):
+        return self.layers[-1].cost
+
+
+def deepcifar10_params(seed=7, c_in=3, size=32, classes=10):
+    """Random-init parameters of deepCIFAR10 (nmodels.pas:82-111), shapes only depend on the spec."""
+    rng = np.random.default_rng(seed)
+    P = []
+    c = c_in
+    for f in (32, 32, 64, 64, 128, 128):
+        s = np.sqrt(2.0 / (9 * c))
+        P.append(dict(w=rng.uniform(-s, s, (f, c * 9)).astype(f32), b=np.zeros(f, f32), scales=np.ones(f, f32),
+                      rm=np.zeros(f, f32), rv=np.zeros(f, f32)))
+        c = f
+    n_in = 128 * (size // 8) ** 2
+    for n_out in (1024, classes):
+        s = np.sqrt(2.0 / n_in)
+        P.append(dict(w=rng.uniform(-s, s, (n_out, n_in)).astype(f32), b=np.zeros(n_out, f32)))
+        n_in = n_out
+    return P
+
+
+def build_deepcifar10(batch, params, size=32, c_in=3, classes=10, dropout=0.2, **hyper):
+    A = orc.ACT
+    L = []
+    c, h = c_in, size
+    pi = 0
+    for stage in range(3):
+        for _ in range(2):
+            p = params[pi]
+            pi += 1
+            f = p["b"].size
+            L.append(RefConvTrain(batch, c, h, h, f, 3, 1, 1, A["RELU"], True, p["w"], p["b"], p["scales"], p["rm"],
+                                  p["rv"]))
+            c = f
+        L.append(RefMaxPool(batch, c, h, h, 2))
+        h //= 2
+    L.append(RefDropout(batch, c * h * h, dropout))
+    p = params[pi]
+    L.append(RefConnected(batch, c * h * h, 1024, A["RELU"], p["w"], p["b"]))
+    L.append(RefDropout(batch, 1024, dropout))
+    p = params[pi + 1]
+    L.append(RefConnected(batch, 1024, classes, A["LINEAR"], p["w"], p["b"]))
+    L.append(RefSoftmax(batch, classes))
+    return RefNet(L, batch, **hyper)

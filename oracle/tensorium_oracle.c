@@ -602,3 +602,96 @@ void orc_fuse_batchnorm(float *weights, float *biases, const float *scales, cons
 /* misc elementwise used by the callers either side of the path */
 void orc_addvv(sz N, const float *a, const float *b, float *c) { for (sz i = 0; i < N; ++i) c[i] = a[i] + b[i]; }
 void orc_fill(sz N, float *x, float v) { for (sz i = 0; i < N; ++i) x[i] = v; }
+
+/* ---------------------------------------------------------------------------------------------
+ * Callers either side of the convolution on the CIFAR-10 training path.
+ * ------------------------------------------------------------------------------------------- */
+
+/* TTensor.Clamp ntensors.pas:10077-10100 (used by TConnectedLayer.backward nconnectedlayer.pas:261) */
+void orc_clamp(sz N, float lo, float hi, float *x) {
+  for (sz i = 0; i < N; ++i) {
+    if (x[i] < lo) x[i] = lo;
+    else if (x[i] > hi) x[i] = hi;
+  }
+}
+
+/* TMaxPoolLayer.forwardMaxPool nMaxPoolLayer.pas:404-451 (training branch; the inference helper
+ * maxpoolMP :265-320 walks the same window in the same order).  indexes may be NULL. */
+void orc_maxpool_forward(sz batch, sz c, sz h, sz w, sz outH, sz outW, sz ksize, sz stride_x, sz stride_y,
+                         sz padding, const float *in, float *out, sz *indexes) {
+  const sz w_offset = -(padding / 2), h_offset = -(padding / 2);
+  for (sz b = 0; b < batch; ++b)
+    for (sz k = 0; k < c; ++k)
+      for (sz i = 0; i < outH; ++i)
+        for (sz j = 0; j < outW; ++j) {
+          sz out_index = j + outW * (i + outH * (k + c * b));
+          float max = -3.402823466e+38F;
+          sz max_i = -1;
+          for (sz n = 0; n < ksize; ++n)
+            for (sz m = 0; m < ksize; ++m) {
+              sz cur_h = h_offset + i * stride_y + n;
+              sz cur_w = w_offset + j * stride_x + m;
+              sz index = cur_w + w * (cur_h + h * (k + b * c));
+              float val = (cur_h >= 0 && cur_h < h && cur_w >= 0 && cur_w < w) ? in[index] : -3.402823466e+38F;
+              if (val > max) {
+                max_i = index;
+                max = val;
+              }
+            }
+          out[out_index] = max;
+          if (indexes) indexes[out_index] = max_i;
+        }
+}
+
+/* TMaxPoolLayer.backwardMaxPool nMaxPoolLayer.pas:501-513 */
+void orc_maxpool_backward(sz total, const sz *indexes, const float *delta, float *upstream) {
+  for (sz i = 0; i < total; ++i) upstream[indexes[i]] = upstream[indexes[i]] + delta[i];
+}
+
+/* softmax nsoftmaxlayer.pas:83-105 and TSoftmaxLayer.softmaxBatch :108-121.  exp is the single-precision
+ * libm expf (FPC's exp(single) evaluates in extended and rounds; the two agree to 1 ulp). */
+static void softmax_one(sz n, const float *input, float temp, sz stride, float *output) {
+  if (n == 0) return;
+  float sum = 0, largest = input[0];
+  for (sz i = 1; i < n; ++i)
+    if (input[i * stride] > largest) largest = input[i * stride];
+  for (sz i = 0; i < n; ++i) {
+    float e = expf((input[i * stride] - largest) / temp);
+    sum = sum + e;
+    output[i * stride] = e;
+  }
+  for (sz i = 0; i < n; ++i) output[i * stride] = output[i * stride] / sum;
+}
+void orc_softmax_batch(const float *input, sz n, sz batch, sz batch_size, sz groups, sz group_size, sz stride,
+                       float temp, float *output) {
+  for (sz b = 0; b < batch; ++b)
+    for (sz g = 0; g < groups; ++g)
+      softmax_one(n, input + b * batch_size + g * group_size, temp, stride, output + b * batch_size + g * group_size);
+}
+
+/* TSoftmaxLayer.softmaxCrossEntropy nsoftmaxlayer.pas:123-137 */
+void orc_softmax_cross_entropy(sz N, const float *pred, const float *truth, float *delta, float *error) {
+  for (sz i = 0; i < N; ++i) {
+    float t = truth[i], p = pred[i];
+    error[i] = t != 0 ? -logf(p > sEPSILON ? p : sEPSILON) : 0.f;
+    delta[i] = t - p;
+  }
+}
+
+/* TDropoutLayer.forward / backward ndropoutlayer.pas:82-133.  The CPU path draws r from FPC's random();
+ * the CUDA path (cuda_sgemm.cu:1620-1653 via nncuda.pas:1512-1538) hashes seed+i with xorshift64* and keeps
+ * 28 bits.  The oracle takes the hashed form so both sides see the same mask for a given seed. */
+void orc_dropout_rand(sz N, uint64_t seed, float *rnd) {
+  for (sz i = 0; i < N; ++i) {
+    uint64_t x = seed + (uint64_t)i;
+    x ^= x >> 12;
+    x ^= x << 25;
+    x ^= x >> 27;
+    x *= 0x2545F4914F6CDD1DULL;
+    float r = (float)(x % 0x10000000ull);
+    rnd[i] = r / (float)0x10000000ull;
+  }
+}
+void orc_dropout_apply(sz N, const float *rnd, float probability, float scale, float *x) {
+  for (sz i = 0; i < N; ++i) x[i] = rnd[i] < probability ? 0.f : x[i] * scale;
+}

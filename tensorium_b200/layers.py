@@ -30,6 +30,7 @@ class TNNetState:  # source/ntypes.pas:46-63 (fields used on this path)
     adversarial: bool = False
     step: int = 0
     index: int = 0
+    truth: TSingleTensor | None = None
 
 
 @dataclass
@@ -43,6 +44,10 @@ class TUpdateArgs:  # source/ntypes.pas:77-87
     B2: float = 0.999
     eps: float = 1e-8
     t: int = 0
+    # data-parallel replicas whose summed updates the buffers hold (1 = the reference's single device):
+    # the momentum carried in each replica's buffer is kept as momentum/replicas so that the next
+    # all-reduce SUM restores momentum * (previous summed update)
+    replicas: int = 1
 
 
 def conv_out(n, pad, k, stride, dil=1):
@@ -53,6 +58,7 @@ class TConvolutionalLayer:
     """source/nConvolutionLayer.pas:140-321 (constructor fields) and :1022-1330 (CUDA path)."""
 
     layerType = ltCONVOLUTIONAL
+    trainable = True
 
     def __init__(self, batch, h, w, c, filters, kernelSize, stride=1, padding=0, activation=nn.acLEAKY,
                  batch_normalize=False, dilation=1, train=False, fused=True, rng=None, host_output=True):
@@ -119,7 +125,7 @@ class TConvolutionalLayer:
         self.biases.setCPU()
 
     # ---------------------------------------------------------------- forward
-    def forwardGPU(self, state: TNNetState):
+    def forwardGPU(self, state: TNNetState, net=None):
         cu = cuda()
         if not state.input.wasGPU():
             state.input.pushToDevice()
@@ -323,13 +329,14 @@ class TConvolutionalLayer:
         rate = float(f32(learning_rate / f32(args.batch)))
         decay_term = float(f32(f32(-args.decay) * f32(args.batch)))
         if self.fused:
-            cu.sgdUpdate(self.biases.Size(), self.biases.devData, self.bias_updates.devData, rate, args.momentum, 0.0)
-            cu.sgdUpdate(self.weights.Size(), self.weights.devData, self.weight_updates.devData, rate, args.momentum,
+            keep = args.momentum / args.replicas
+            cu.sgdUpdate(self.biases.Size(), self.biases.devData, self.bias_updates.devData, rate, keep, 0.0)
+            cu.sgdUpdate(self.weights.Size(), self.weights.devData, self.weight_updates.devData, rate, keep,
                          decay_term)
             if self.isBatchNormalized:
-                cu.sgdUpdate(self.scales.Size(), self.scales.devData, self.scale_updates.devData, rate,
-                             args.momentum, 0.0)
+                cu.sgdUpdate(self.scales.Size(), self.scales.devData, self.scale_updates.devData, rate, keep, 0.0)
         else:
+            assert args.replicas == 1, "the reference call sequence is single-device"
             cu.axpy(self.biases.Size(), rate, self.bias_updates.devData, 0, 1, self.biases.devData, 0, 1)
             cu.scale(self.bias_updates.Size(), args.momentum, self.bias_updates.devData, 1)
             cu.axpy(self.weight_updates.Size(), decay_term, self.weights.devData, 0, 1, self.weight_updates.devData,
@@ -341,3 +348,10 @@ class TConvolutionalLayer:
                 cu.scale(self.scale_updates.Size(), args.momentum, self.scale_updates.devData, 1)
         for t in (self.biases, self.bias_updates, self.weights, self.weight_updates):
             t.setCUDA()
+
+    def gradients(self):
+        """The update buffers a data-parallel run sums across replicas before updateGPU."""
+        g = [self.weight_updates, self.bias_updates]
+        if self.isBatchNormalized:
+            g.append(self.scale_updates)
+        return g

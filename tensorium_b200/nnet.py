@@ -1,14 +1,14 @@
 """TNNet and the YOLOv3 graph layers — host-side mirror of the callers either side of the conv hot path
 (SURVEY.md §8f rank 2): shortcut (source/naddlayer.pas:885-910), route (source/nconcatlayer.pas:205-222),
 upsample (source/nupsamplelayer.pas:190-206), yolo (source/nyololayer.pas:97-122,399-498,1068-1112), the
-sequential net driver (source/nnet.py:275-317, 452-472) and NMS (source/ntypes.pas:1059-1108,1612-1646).
+sequential net driver (source/nnet.pas:275-472) and NMS (source/ntypes.pas:1059-1108,1612-1646).
 """
 from __future__ import annotations
 
 import numpy as np
 
 from . import nncuda as nn
-from .layers import TConvolutionalLayer, TNNetState
+from .layers import TConvolutionalLayer, TNNetState, TUpdateArgs
 from .tensor import TSingleTensor, cuda
 
 
@@ -166,26 +166,92 @@ def doNMSSort(boxes, objs, probs, thresh):
 
 
 class TNNet:
-    """Sequential driver: TNNet.forward (nnet.pas:275-317) / predict (nnet.pas:452-472), GPU path."""
+    """Sequential driver, GPU path: TNNet.forward (nnet.pas:275-317), backward (:319-376), update (:378-403),
+    Propagate (:404-432), predict (:452-472).  Learning-rate policy is lrpCONSTANT (the CIFAR sample's,
+    CIFAR10Conv.pas:150-160), for which computeCurrentLearningRate returns learningRate unchanged."""
 
-    def __init__(self, layers, batch, c, h, w):
+    def __init__(self, layers, batch, c, h, w, learningRate=0.001, momentum=0.9, decay=0.0001, subdivisions=1):
         self.layers = layers
         self.batch, self.c, self.h, self.w = batch, c, h, w
+        self.learningRate, self.momentum, self.decay, self.subdivisions = learningRate, momentum, decay, subdivisions
+        self.seen = 0
+        self.replicas = 1  # set by dataparallel.GradientBucket
+        self.bucket = None
         self.input = TSingleTensor((batch, c, h, w), groups=batch, host=False)
+        self.truth = None
         # state.workspace (im2col columns) is only needed by the reference's unfused call sequence
         ws = max([l.getWorkspaceSize() for l in layers if isinstance(l, TConvolutionalLayer) and not l.fused] + [0])
         self.workspace = TSingleTensor((ws,), groups=1, host=False) if ws else None
 
     def forward(self, state: TNNetState):
         state.workspace = self.workspace
+        cu = cuda()
         for i, l in enumerate(self.layers):
             state.index = i
-            if isinstance(l, TConvolutionalLayer):
-                l.forwardGPU(state)
-            else:
-                l.forwardGPU(state, self)
+            delta = getattr(l, "delta", None)
+            if state.isTraining and delta is not None and getattr(l, "train", False):
+                cu.scale(delta.Size(), 0.0, delta.devData, 1)  # nnet.pas:288-293
+                delta.setCUDA()
+            l.forwardGPU(state, self)
             state.input = l.output
         return state.input
+
+    def backward(self, state: TNNetState):
+        original_input, original_delta = self.input, state.delta
+        state.workspace = self.workspace
+        for i in range(len(self.layers) - 1, -1, -1):
+            state.index = i
+            if i == 0:
+                state.input, state.delta = original_input, original_delta
+            else:
+                prev = self.layers[i - 1]
+                state.input, state.delta = prev.output, prev.delta
+            self.layers[i].backwardGPU(state)
+        self.seen += self.batch
+
+    def update(self):
+        """nnet.pas:378-403: every layer but the last; a data-parallel run first sums the update buffers."""
+        if self.bucket is not None:
+            self.bucket.all_reduce()
+        arg = TUpdateArgs(batch=self.batch * self.subdivisions * self.replicas, learningRate=self.learningRate,
+                          momentum=self.momentum, decay=self.decay, replicas=self.replicas)
+        for l in self.layers[:-1]:
+            if getattr(l, "trainable", False) and l.train:
+                l.updateGPU(arg)
+
+    def Propagate(self):
+        """nnet.pas:404-432; `input` and `truth` must already hold the batch (host or device side)."""
+        state = TNNetState(input=self.input, isTraining=True, truth=self.truth)
+        self.forward(state)
+        state.delta = None
+        self.backward(state)
+
+    def trainBatch(self, x: np.ndarray | None = None, truth: np.ndarray | None = None):
+        """One iteration of trainEpoch's loop body (nnet.pas:497-520): load, Propagate, update when due."""
+        if self.truth is None:
+            out = self.layers[-1].output
+            self.truth = TSingleTensor(out.FShape, groups=self.batch)
+        if x is not None:
+            self.input.Data[...] = x.reshape(self.input.FShape)
+            self.input.setCPU()
+        if truth is not None:
+            self.truth.Data[...] = truth.reshape(self.truth.FShape)
+            self.truth.setCPU()
+        self.Propagate()
+        if self.seen % (self.batch * self.subdivisions) == 0:
+            self.update()
+
+    def cost(self) -> float:
+        """nnet.pas:551-563: mean of the layers' cost[0]."""
+        cs = [l.cost for l in self.layers if hasattr(l, "cost")]
+        return float(sum(cs) / len(cs)) if cs else 0.0
+
+    def gradients(self):
+        out = []
+        for l in self.layers[:-1]:
+            if getattr(l, "trainable", False) and l.train:
+                out += l.gradients()
+        return out
 
     def predict(self, x_dev_tensor: TSingleTensor | None = None):
         st = TNNetState(input=x_dev_tensor or self.input, isTraining=False)

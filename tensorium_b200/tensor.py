@@ -30,24 +30,30 @@ def cuda():
 
 
 class TSingleTensor:
-    def __init__(self, shape, groups: int | None = None, data=None, device: bool = True, host: bool = True):
+    def __init__(self, shape, groups: int | None = None, data=None, device: bool = True, host: bool = True,
+                 devptr: int = 0, dtype=np.float32):
         self.FShape = tuple(int(s) for s in shape)
         self.Groups = int(groups) if groups is not None else (self.FShape[0] if len(self.FShape) > 1 else 1)
         self._n = int(np.prod(self.FShape)) if len(self.FShape) else 1
+        self._dtype = np.dtype(dtype)  # float32, or int64 for TSizeIntTensor (max-pool indexes)
         if data is not None:
-            self._data = np.ascontiguousarray(data, dtype=np.float32).reshape(self.FShape).copy()
+            self._data = np.ascontiguousarray(data, dtype=self._dtype).reshape(self.FShape).copy()
         else:
             # host=False: activation tensors that only ever live on the device get their host twin lazily
-            self._data = np.zeros(self.FShape, dtype=np.float32) if host else None
+            self._data = np.zeros(self.FShape, dtype=self._dtype) if host else None
         self.devData = 0
+        self._owns_dev = True
         self.lastOP = cdCPU if host or data is not None else cdCUDA
-        if device and self._n:
-            self.devData = cuda().createDeviceBuffer(self._n * 4)  # ntensors.pas:6103-6109
+        if devptr:
+            # non-owning view of device memory someone else allocated (a slice of the gradient bucket)
+            self.devData, self._owns_dev = int(devptr), False
+        elif device and self._n:
+            self.devData = cuda().createDeviceBuffer(self._n * self._dtype.itemsize)  # ntensors.pas:6103-6109
 
     @property
     def Data(self) -> np.ndarray:
         if self._data is None:
-            self._data = np.zeros(self.FShape, dtype=np.float32)
+            self._data = np.zeros(self.FShape, dtype=self._dtype)
         return self._data
 
     # shape helpers (ntensors.pas: Size/Volume/Area/c/h/w)
@@ -91,9 +97,17 @@ class TSingleTensor:
         return self.Data
 
     def Free(self):  # ntensors.pas:6126-6129
-        if self.devData:
+        if self.devData and self._owns_dev:
             cuda().freeDeviceBuffer(self.devData)
-            self.devData = 0
+        self.devData = 0
+
+    def rebind(self, devptr: int):
+        """Move the device twin into memory owned by someone else (keeps the current device contents)."""
+        if self.devData and devptr != self.devData:
+            cuda().copy(self._n, self.devData, 0, 1, devptr, 0, 1)
+            cuda().finish()
+        self.Free()
+        self.devData, self._owns_dev = int(devptr), False
 
     def __del__(self):
         try:

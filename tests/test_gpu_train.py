@@ -1,0 +1,197 @@
+"""GPU parity of one CIFAR-10 training iteration (BASELINE config 3): deepCIFAR10
+(nmodels.pas:82-111) forward + backward + SGD update through the C ABI against the CPU oracle, on the same
+seeded inputs, parameters and dropout masks — for the fused entry points and for the reference's own
+`cuda.<op>` call sequence."""
+import numpy as np
+import pytest
+
+from util import rel_max
+
+pytestmark = pytest.mark.gpu
+FP32, X3, TF32 = 0, 1, 2
+
+
+def _batch(B, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, (B, 3, 32, 32)).astype(np.float32)
+    t = np.zeros((B, 10), np.float32)
+    t[np.arange(B), rng.integers(0, 10, B)] = 1
+    return x, t
+
+
+def _pin_seeds(gnet, rnet, it):
+    from oracle import ref_train as rt
+    for i, (g, r) in enumerate(zip(gnet.layers, rnet.layers)):
+        if isinstance(r, rt.RefDropout):
+            g.seed = r.seed = 7919 * it + i + 1
+
+
+def _trainables(net):
+    return [l for l in net.layers if getattr(l, "trainable", False)]
+
+
+FORCED = ("output", "x", "x_norm", "mean", "variance", "indexes")
+
+
+def _force_forward_state(gnet, rnet):
+    """Overwrite the GPU layers' saved forward state with the oracle's.  ReLU masks and max-pool arg-max routes
+    are discontinuous: an activation that is +1e-8 on one side and 0 on the other flips a whole gradient
+    element, and the batch-norm backward sums turn that into a percent-level difference.  Forcing the state
+    makes the backward comparison test the backward ARITHMETIC (same masks, same routes) at a tight tolerance;
+    the forward outputs themselves are compared before they are overwritten."""
+    from oracle import ref_train as rt
+    for g, r in zip(gnet.layers, rnet.layers):
+        if isinstance(r, rt.RefDropout):
+            continue  # in place on the neighbour's tensors
+        for name in FORCED:
+            if hasattr(r, name) and getattr(g, name, None) is not None:
+                t = getattr(g, name)
+                t.Data[...] = np.asarray(getattr(r, name)).reshape(t.FShape)
+                t.pushToDevice()
+
+
+@pytest.mark.parametrize("fused,mode,tol", [(True, X3, 1e-4), (False, X3, 1e-4), (True, FP32, 2e-5), (True, TF32, 5e-3)])
+def test_deepcifar10_training_steps(cuda_backend, oracle, fused, mode, tol):
+    from oracle import ref_train as rt
+    from tensorium_b200 import models
+    from tensorium_b200.layers import TNNetState
+    from tensorium_b200.tensor import TSingleTensor
+    cu = cuda_backend
+    cu.set_math_mode(mode)
+    try:
+        B, steps = 8, 3
+        hyper = dict(momentum=0.9, decay=0.0001)
+        P = rt.deepcifar10_params(seed=11)
+        rnet = rt.build_deepcifar10(B, P, learning_rate=0.01, **hyper)
+        gnet = models.deepCIFAR10(B, fused=fused, params=P, learningRate=0.01, **hyper)
+        gnet.truth = TSingleTensor((B, 10), groups=B)
+        for it in range(steps):
+            x, t = _batch(B, 100 + it)
+            _pin_seeds(gnet, rnet, it)
+            rcost = rnet.propagate(x.copy(), t)
+            gnet.input.Data[...] = x
+            gnet.input.setCPU()
+            gnet.truth.Data[...] = t
+            gnet.truth.setCPU()
+            state = TNNetState(input=gnet.input, isTraining=True, truth=gnet.truth)
+            gnet.forward(state)
+            # ---- forward parity, layer by layer (the nets share weights up to the previous updates' rounding)
+            for li, (g, r) in enumerate(zip(gnet.layers, rnet.layers)):
+                if isinstance(r, rt.RefDropout):
+                    assert np.array_equal(g.rand.pullFromDevice().reshape(-1), r.rand)  # same mask bits
+                    continue
+                e = rel_max(g.output.pullFromDevice(), r.output)
+                g.output.setCUDA()
+                assert e <= tol * (1 + li), (it, li, "output", e)
+            assert abs(gnet.cost() - rcost) <= 10 * tol * max(1.0, abs(rcost)), (it, gnet.cost(), rcost)
+            # ---- backward parity on the same forward state
+            _force_forward_state(gnet, rnet)
+            state.delta = None
+            gnet.backward(state)
+            for li, (g, r) in enumerate(zip(gnet.layers, rnet.layers)):
+                for name in ("delta", "weight_updates", "bias_updates", "scale_updates", "mean_delta",
+                             "variance_delta"):
+                    if getattr(r, name, None) is None or getattr(g, name, None) is None:
+                        continue
+                    t_ = getattr(g, name)
+                    e = rel_max(t_.pullFromDevice().reshape(-1), np.asarray(getattr(r, name)).reshape(-1))
+                    t_.setCUDA()
+                    assert e <= 5 * tol, (it, li, name, e)
+            gnet.update()
+            rnet.update()
+            for li, (g, r) in enumerate(zip(_trainables(gnet), _trainables(rnet))):
+                for name in ("weights", "biases", "scales", "rolling_mean", "rolling_variance"):
+                    if not hasattr(r, name):
+                        continue
+                    e = rel_max(getattr(g, name).pullFromDevice().reshape(-1), getattr(r, name).reshape(-1))
+                    assert e <= tol, (it, li, name, e)
+        # the reference's first-iteration quirk is mirrored: a layer above a dropout sees an unassigned
+        # state.delta on the very first backward (ndropoutlayer.pas:172 wires it afterwards), so the conv
+        # stack only starts learning at iteration 2; by now every conv layer has non-zero updates
+        for g in _trainables(gnet)[:6]:
+            assert np.abs(g.weight_updates.pullFromDevice()).max() > 0
+    finally:
+        cu.set_math_mode(X3)
+
+
+def test_unforced_training_follows_the_oracle(cuda_backend, oracle):
+    """No teacher forcing: the loss trajectories (a smooth functional of the state) stay together."""
+    from oracle import ref_train as rt
+    from tensorium_b200 import models
+    B = 16
+    P = rt.deepcifar10_params(seed=3)
+    rnet = rt.build_deepcifar10(B, P, learning_rate=0.01)
+    gnet = models.deepCIFAR10(B, params=P, learningRate=0.01)
+    x, t = _batch(B, 9)
+    for it in range(5):
+        _pin_seeds(gnet, rnet, it)
+        rcost = rnet.propagate(x.copy(), t)
+        rnet.update()
+        gnet.trainBatch(x, t)
+        assert abs(gnet.cost() - rcost) <= 2e-3 * abs(rcost), (it, gnet.cost(), rcost)
+
+
+def test_training_reduces_loss(cuda_backend):
+    """Size-independent property: repeatedly fitting one batch drives the cross-entropy down."""
+    from tensorium_b200 import models
+    B = 64
+    net = models.deepCIFAR10(B, seed=3, learningRate=0.01)
+    x, t = _batch(B, 5)
+    costs = []
+    for it in range(12):
+        net.trainBatch(x, t)
+        costs.append(net.cost() / B)
+    assert costs[-1] < 0.25 * costs[0], costs
+
+
+def test_maxpool_softmax_dropout_layers(cuda_backend, oracle):
+    from tensorium_b200.layers import TNNetState
+    from tensorium_b200.tensor import TSingleTensor
+    from tensorium_b200.train_layers import TDropoutLayer, TMaxPoolLayer, TSoftmaxLayer
+    rng = np.random.default_rng(0)
+    for (b, c, h, w, k, s, p) in [(2, 3, 8, 8, 2, 0, 0), (1, 4, 9, 7, 3, 2, 1), (2, 2, 6, 6, 2, 1, 1)]:
+        x = rng.standard_normal((b, c, h, w)).astype(np.float32)
+        l = TMaxPoolLayer(b, h, w, c, k, s, s, p)
+        st = TNNetState(input=TSingleTensor(x.shape, b, data=x), isTraining=True)
+        l.forwardGPU(st)
+        want, widx = oracle.maxpool_forward(x, k, s or k, s or k, p)
+        assert np.array_equal(l.output.pullFromDevice(), want)
+        assert np.array_equal(l.indexes.pullFromDevice(), widx)
+        d = rng.standard_normal(want.shape).astype(np.float32)
+        l.delta.Data[...] = d
+        l.delta.pushToDevice()
+        up = rng.integers(-3, 4, x.shape).astype(np.float32)
+        st.delta = TSingleTensor(x.shape, b, data=up)
+        st.delta.pushToDevice()
+        l.backwardGPU(st)
+        wantup = oracle.maxpool_backward(widx, d, up.copy())
+        got = st.delta.pullFromDevice()
+        if (s or k) >= k:
+            assert np.array_equal(got, wantup)  # disjoint windows: one add per element
+        else:
+            assert rel_max(got, wantup) <= 1e-6  # overlapping windows: atomic adds in any order
+    # softmax + cross entropy
+    B, n = 5, 10
+    z = rng.standard_normal((B, n)).astype(np.float32) * 3
+    t = np.zeros((B, n), np.float32)
+    t[np.arange(B), rng.integers(0, n, B)] = 1
+    sm = TSoftmaxLayer(B, n)
+    st = TNNetState(input=TSingleTensor(z.shape, B, data=z), isTraining=True, truth=TSingleTensor(t.shape, B, data=t))
+    st.input.pushToDevice()
+    sm.forwardGPU(st)
+    want = oracle.softmax_batch(z)
+    wd, wl = oracle.softmax_cross_entropy(want, t)
+    assert rel_max(sm.output.pullFromDevice(), want) <= 1e-6
+    assert rel_max(sm.delta.pullFromDevice(), wd) <= 1e-6
+    assert abs(sm.cost - oracle.vsum(wl)) <= 1e-5 * oracle.vsum(wl)
+    # dropout: same hash -> same mask, in place
+    y = rng.standard_normal((4, 33)).astype(np.float32)
+    dl = TDropoutLayer(4, 0.3, 33)
+    dl.seed = 424242
+    st = TNNetState(input=TSingleTensor(y.shape, 4, data=y), isTraining=True)
+    dl.forwardGPU(st)
+    r = oracle.dropout_rand(y.size, 424242)
+    want = oracle.dropout_apply(y.copy(), r, np.float32(0.3), np.float32(1 / 0.7))
+    assert dl.output is st.input
+    assert np.array_equal(st.input.pullFromDevice(), want)
+    assert 0.15 < (want == 0).mean() < 0.45
