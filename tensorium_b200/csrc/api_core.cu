@@ -2,6 +2,7 @@
 // Replaces TNNCuda<T>.Create/Destroy/createDeviceBuffer/readBuffer/writeBuffer/finish
 // (reference: source/nncuda.pas:443-522,1575-1584).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -71,6 +72,11 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
   }
   ctx->own_stream = true;
   ctx->math_mode = TNN_MATH_3XTF32;
+  {
+    // kernel-selection switch for A/B measurements: TNN_TMA_ACT=0 keeps the gathering producer everywhere
+    const char *e = getenv("TNN_TMA_ACT");
+    ctx->tma_activations = (e && e[0] == '0') ? 0 : 1;
+  }
   *out = ctx;
   return 0;
 }

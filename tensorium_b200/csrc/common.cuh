@@ -13,6 +13,7 @@ struct tnn_context {
   bool own_stream;
   cudaDeviceProp prop;
   int math_mode;
+  int tma_activations;  // 1: stride-1 convolutions fetch activations by TMA when the geometry allows (default)
   int64_t launches;
   // scratch for two-stage reductions (partials + arrival counters), grown on demand
   float *red_partials;

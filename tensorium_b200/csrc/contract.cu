@@ -198,8 +198,9 @@ int32_t tnn_conv2d_forward(tnn_context *ctx, const tnn_conv_desc *d, const float
   out += outOffset;
   const int64_t K = (int64_t)g.C * g.kh * g.kw;
   const int64_t Npix = d->batch * g.OH * g.OW;
-  // tiny contractions (first layer, C*kh*kw <= 64): exact-fp32 direct convolution in registers, any math mode
-  if (direct::supported(g)) return direct::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out);
+  // tiny contractions (C*kh*kw <= 64) with few channels (the first layer), or any tiny contraction in FP32 mode:
+  // exact-fp32 direct convolution in registers
+  if (direct::supported(g) && (g.C < 16 || ctx->math_mode == TNN_MATH_FP32)) return direct::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out);
   if (ctx->math_mode != TNN_MATH_FP32) {
     rc = umma::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out);
     if (rc != umma::kNotTaken) return rc;

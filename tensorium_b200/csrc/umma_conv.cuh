@@ -29,6 +29,7 @@
 //            SBO = (R/32)*512 (next 4-row k group), advance two SBO per UMMA_K=8 step
 #pragma once
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -69,6 +70,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::
           "r"(dst_smem), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst_smem, const CUtensorMap *tmap, int c0, int c1, int c2, int c3,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+      "[%6];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
       : "memory");
 }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *tmap) {
@@ -216,6 +225,7 @@ __device__ __forceinline__ void sts_k(uint8_t *hi, uint8_t *lo, int row, int chu
 
 // matrix whose k index is contiguous: elem(mn,k) = p[mn*ld + k]   (A of NN/NT, B of NT)
 struct KContigLoader {
+  static constexpr bool kTmaA = false;
   static constexpr bool kMnMajor = false;
   static constexpr bool kTma = false;
   static constexpr int kPrefetch = 1;
@@ -268,6 +278,7 @@ struct KContigLoader {
 
 // matrix whose mn index is contiguous: elem(mn,k) = p[k*ld + mn]   (A of TN, B of NN/TN)
 struct MnContigLoader {
+  static constexpr bool kTmaA = false;
   static constexpr bool kMnMajor = true;
   static constexpr bool kTma = false;
   static constexpr int kPrefetch = 1;
@@ -315,6 +326,7 @@ struct MnContigLoader {
 // in-bounds test is one bit of a per-tile tap mask, and each load is `pointer += H*W; predicated LDG`.
 // Channels are padded to a multiple of 16 (zero weights, loads predicated off).
 struct Im2colPixelLoader {
+  static constexpr bool kTmaA = false;
   static constexpr bool kMnMajor = true;
   static constexpr bool kTma = false;
   static constexpr int kPrefetch = TNN_PIXEL_PREFETCH;
@@ -392,6 +404,7 @@ struct Im2colPixelLoader {
 
 // weights pre-split into a zero-padded K-major copy [F][Kpad] (hi and lo planes) and fetched by TMA
 struct TmaWeightsLoader {
+  static constexpr bool kTmaA = false;
   static constexpr bool kMnMajor = false;
   static constexpr bool kTma = true;
   static constexpr int kPrefetch = 3;
@@ -402,6 +415,45 @@ struct TmaWeightsLoader {
   __device__ __forceinline__ void load(TileCtx &, Regs &, int64_t, int, const int *) const {}
   template <bool SPLIT>
   __device__ __forceinline__ void store(const Regs &, uint8_t *, uint8_t *, int, int) const {}
+};
+
+// Activations fetched by TMA (stride-1 convolutions whose rows are 16-byte aligned and whose kernel columns
+// shift by multiples of 4 pixels — in practice the 1x1 convolutions; see conv_patch for the measured reason).  The 128 rows of a tile are
+// four independent "atoms" of 32 output pixels, each a TH x TW patch (TH*TW = 32) of one image; for kernel tap
+// (kr,kc) the im2col rows of an atom are the same patch of the INPUT shifted by (kr*dy - ph, kc*dx - pw), which
+// one cp.async.bulk.tensor.4d box {TW, TH, 32, 1} of the NCHW tensor {W, H, C, N} delivers — padding comes for
+// free as the TMA's out-of-bounds zero fill, and the box lands as [channel k][pixel], i.e. a run of the 512-byte
+// (4 k rows x 32 pixels) MN-major atoms (SWIZZLE_128B_ATOM_32B == the UMMA SWIZZLE_128B_BASE32B pattern).  A k-block is
+// 32 channels of ONE tap:  k = (tap*CB + cb)*32 + ci,  c = cb*32 + ci.  The atoms of a tile are 4 KB apart, so
+// the descriptor uses LBO = 4096 (next atom along M) and SBO = 512 (next 4-row k group).
+// The producer warps no longer gather: they only derive the 3xTF32 low part (or round to TF32) in shared memory.
+struct TmaPatchLoader {
+  static constexpr bool kTmaA = true;
+  static constexpr bool kMnMajor = true;
+  static constexpr bool kTma = false;
+  static constexpr int kPrefetch = 1;
+  int TW, TH, WT, HT;   // patch shape; patches per image row / column
+  int atomsPerImg;      // WT*HT
+  int numAtoms;         // batch*atomsPerImg
+  int batch;
+  int ph, pw, kw, dy, dx;
+  int CB;               // 32-channel blocks per tap
+  struct TileCtx {};
+  struct Regs {};
+  __device__ __forceinline__ void fill_lut(int *, int) const {}
+  __device__ __forceinline__ TileCtx tile_ctx(int, int64_t, int, int) const { return TileCtx{}; }
+  __device__ __forceinline__ void load(TileCtx &, Regs &, int64_t, int, const int *) const {}
+  template <bool SPLIT>
+  __device__ __forceinline__ void store(const Regs &, uint8_t *, uint8_t *, int, int) const {}
+  // image and top-left output pixel of an atom (atoms past the end map to image `batch`: the TMA zero-fills)
+  __device__ __forceinline__ void atom_origin(int atom, int &n, int &oh0, int &ow0) const {
+    n = atom / atomsPerImg;
+    const int r = atom - n * atomsPerImg;
+    const int hy = r / WT;
+    oh0 = hy * TH;
+    ow0 = (r - hy * WT) * TW;
+    if (atom >= numAtoms) n = batch;
+  }
 };
 
 // ------------------------------------------------------------------ epilogues
@@ -418,35 +470,65 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
   int act;
   int64_t rows, cols;
   bool accumulate;  // out += value (dgrad adds into the upstream delta, like the reference's col2im)
+  // TW != 0: rows are TmaPatchLoader atoms (TH x TW patches), else row m = pixel m of the batch-folded image list
+  int TW, TH, WT, atomsPerImg, OH, OW, batch;
   struct Row { float *q; };
-  __device__ __forceinline__ Row row(int64_t m) const {
-    const int b = (int)(m / P), p = (int)(m - (int64_t)b * P);
+  __device__ __forceinline__ Row row(int64_t m, bool &valid) const {
+    if (TW != 0) {
+      const int atom = (int)(m >> 5), j = (int)(m & 31);
+      const int n = atom / atomsPerImg;
+      const int r = atom - n * atomsPerImg;
+      const int hy = r / WT;
+      const int jh = j / TW;
+      const int oh = hy * TH + jh, ow = (r - hy * WT) * TW + (j - jh * TW);
+      valid = n < batch && oh < OH && ow < OW;
+      return Row{valid ? out + (int64_t)n * outImg + oh * OW + ow : out};
+    }
+    valid = m < rows;
+    const int64_t mm = valid ? m : 0;
+    const int b = (int)(mm / P), p = (int)(mm - (int64_t)b * P);
     return Row{out + (int64_t)b * outImg + p};
   }
   // 32 consecutive columns starting at n; `cnt` of them are valid.  Each lane fetches the scale/bias of ONE column
-  // (coalesced) and the unrolled loop broadcasts them with shuffles.  The activation switch stays outside the loops.
+  // (coalesced) into the warp's 64-float shared scratch; the unrolled loop reads them back four at a time as
+  // broadcast LDS.128 (shuffles cost two MIO slots per column, the pipe the stores need).  The activation switch
+  // stays outside the loops.
   __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt,
-                                              bool rowvalid) const {
+                                              bool rowvalid, float *scratch) const {
     const int lane = threadIdx.x & 31;
-    const float sc = (scale && lane < cnt) ? __ldg(scale + n + lane) : 1.0f;
-    const float bi = (bias && lane < cnt) ? __ldg(bias + n + lane) : 0.0f;
+    __syncwarp();  // the previous chunk's reads of the scratch are done
+    scratch[lane] = (scale && lane < cnt) ? __ldg(scale + n + lane) : 1.0f;
+    scratch[32 + lane] = (bias && lane < cnt) ? __ldg(bias + n + lane) : 0.0f;
+    __syncwarp();
     float *q = r.q + n * P;
     const bool leaky = act == TNN_ACT_LEAKY || act == TNN_ACT_REVLEAKY;
     if (leaky || act == TNN_ACT_LINEAR) {
       const float neg = leaky ? 0.1f : 1.0f;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float s = __shfl_sync(0xffffffffu, sc, j), b = __shfl_sync(0xffffffffu, bi, j);
-        float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s), b);
-        v = v < 0 ? neg * v : v;
-        if (rowvalid && j < cnt) q[(int64_t)j * P] = accumulate ? q[(int64_t)j * P] + v : v;
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 s4 = *reinterpret_cast<const float4 *>(scratch + j4);
+        const float4 b4 = *reinterpret_cast<const float4 *>(scratch + 32 + j4);
+        const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j4 + u;
+          float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s[u]), b[u]);
+          v = v < 0 ? neg * v : v;
+          if (rowvalid && j < cnt) q[(int64_t)j * P] = accumulate ? q[(int64_t)j * P] + v : v;
+        }
       }
     } else {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const float s = __shfl_sync(0xffffffffu, sc, j), b = __shfl_sync(0xffffffffu, bi, j);
-        const float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s), b);
-        if (rowvalid && j < cnt) q[(int64_t)j * P] = act_out_of_line(v, act);
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 s4 = *reinterpret_cast<const float4 *>(scratch + j4);
+        const float4 b4 = *reinterpret_cast<const float4 *>(scratch + 32 + j4);
+        const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j4 + u;
+          const float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s[u]), b[u]);
+          if (rowvalid && j < cnt) q[(int64_t)j * P] = act_out_of_line(v, act);
+        }
       }
     }
   }
@@ -457,9 +539,12 @@ struct GemmEpilogue {  // C[m][n] = alpha*acc + beta*C
   float alpha, beta;
   int64_t rows, cols;
   struct Row { float *q; };
-  __device__ __forceinline__ Row row(int64_t m) const { return Row{C + m * ldc}; }
+  __device__ __forceinline__ Row row(int64_t m, bool &valid) const {
+    valid = m < rows;
+    return Row{C + (valid ? m : 0) * ldc};
+  }
   __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt,
-                                              bool rowvalid) const {
+                                              bool rowvalid, float *) const {
     if (!rowvalid) return;
     float *q = r.q + n;
     if (beta == 0.f) {
@@ -479,9 +564,12 @@ struct GemmAtomicEpilogue {  // split-k: C += alpha*acc
   float alpha, beta;
   int64_t rows, cols;
   struct Row { float *q; };
-  __device__ __forceinline__ Row row(int64_t m) const { return Row{C + m * ldc}; }
+  __device__ __forceinline__ Row row(int64_t m, bool &valid) const {
+    valid = m < rows;
+    return Row{C + (valid ? m : 0) * ldc};
+  }
   __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt,
-                                              bool rowvalid) const {
+                                              bool rowvalid, float *) const {
     if (!rowvalid) return;
 #pragma unroll
     for (int j = 0; j < 32; ++j)
@@ -493,11 +581,13 @@ struct GemmAtomicEpilogue {  // split-k: C += alpha*acc
 struct SharedCtl {
   uint64_t full[kMaxStages];
   uint64_t empty[kMaxStages];
+  uint64_t araw[kMaxStages];  // TmaPatchLoader: the raw fp32 A tile of the stage has landed
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
   int lut[64];     // A-loader scratch (per-tap offsets of the im2col gather)
   int lut_b[192];  // B-loader scratch (wgrad: per-tap {offset, dh, dw})
+  alignas(16) float epi_sb[kEpilogueWarps][64];  // per epilogue warp: scale[32] | bias[32] of the current chunk
 };
 
 struct TileSched {  // tiles are numbered m fastest, then n, then k-split (32-bit: divisions stay cheap and small)
@@ -518,7 +608,9 @@ struct TileSched {  // tiles are numbered m fastest, then n, then k-split (32-bi
 template <bool SPLIT, typename LA, typename LB, typename EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accCols,
-       const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo) {
+       const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+       const __grid_constant__ CUtensorMap tmA) {
+  static_assert(!LA::kTmaA || LB::kTma, "TMA activations are paired with TMA weights");
   extern __shared__ uint8_t smem_raw[];
   __shared__ SharedCtl ctl;
   // 1024B-aligned operand ring
@@ -533,6 +625,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
     for (int s = 0; s < stages; ++s) {
       mbar_init(&ctl.full[s], kProducerWarps + (LB::kTma ? 1 : 0));
       mbar_init(&ctl.empty[s], 1);
+      mbar_init(&ctl.araw[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl.tmem_full[s], 1);
@@ -546,13 +639,47 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
   if (LB::kTma && warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmBhi);
     if (SPLIT) tma_prefetch_desc(&tmBlo);
+    if (LA::kTmaA) tma_prefetch_desc(&tmA);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = ctl.tmem_base;
 
-  if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
+  if (LA::kTmaA && warp >= kFirstProducerWarp && warp < kMmaWarp) {
+    // ===================== TMA-fed A: derive the operand the tensor core needs, in shared memory ===========
+    // 3xTF32: the raw fp32 tile IS the high operand (kind::tf32 reads the top 19 bits); write lo = x - trunc(x).
+    // TF32: round the tile in place (cvt.rna) so products are not biased toward zero.
+    const int tid = threadIdx.x - kFirstProducerWarp * 32;
+    int64_t remaining = 0;
+    for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x) {
+      int mt, nt, k0, k1;
+      sched.decode(t, mt, nt, k0, k1);
+      remaining += k1 - k0;
+    }
+    int stage = 0;
+    uint32_t phase = 0;
+    for (; remaining > 0; --remaining) {
+      mbar_wait_warp(&ctl.araw[stage], phase);
+      uint8_t *sa = smem + (size_t)stage * stageBytes;
+      uint8_t *sa_lo = sa + aBytes;
+#pragma unroll
+      for (int i = 0; i < aBytes / (16 * kProducerThreads); ++i) {
+        const int off = (i * kProducerThreads + tid) * 16;
+        const float4 v = *reinterpret_cast<const float4 *>(sa + off);
+        if (SPLIT) {
+          *reinterpret_cast<float4 *>(sa_lo + off) =
+              make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+        } else {
+          *reinterpret_cast<float4 *>(sa + off) = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl.full[stage]);
+      if (++stage == stages) { stage = 0; phase ^= 1; }
+    }
+  } else if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
     // ===================== producers: global -> registers -> (split) -> swizzled smem =====================
     constexpr int D = LA::kPrefetch;
     const int tid = threadIdx.x - kFirstProducerWarp * 32;
@@ -642,9 +769,10 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ++ks) {
             // MN-major: LBO 512, SBO (R/32)*512, one UMMA_K=8 step = two 4-row k groups.  K-major: SBO 1024, +32B.
-            const uint32_t aoff = LA::kMnMajor ? ks * 2 * (BM / 32) * 512 : ks * 32;
+            const uint32_t aoff = LA::kTmaA ? ks * 1024 : LA::kMnMajor ? ks * 2 * (BM / 32) * 512 : ks * 32;
             const uint32_t boff = LB::kMnMajor ? ks * 2 * (BN / 32) * 512 : ks * 32;
-            const uint32_t a_lbo = LA::kMnMajor ? 512 : 16, a_sbo = LA::kMnMajor ? (BM / 32) * 512 : 1024;
+            const uint32_t a_lbo = LA::kTmaA ? 4096 : LA::kMnMajor ? 512 : 16;
+            const uint32_t a_sbo = LA::kTmaA ? 512 : LA::kMnMajor ? (BM / 32) * 512 : 1024;
             const uint32_t b_lbo = LB::kMnMajor ? 512 : 16, b_sbo = LB::kMnMajor ? (BN / 32) * 512 : 1024;
             const uint32_t a_lt = LA::kMnMajor ? 1u : 2u, b_lt = LB::kMnMajor ? 1u : 2u;
             const uint64_t ah = make_desc(sa + aoff, a_lbo, a_sbo, a_lt);
@@ -676,8 +804,33 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
       for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x) {
         int mt, nt, kb0, kb1;
         sched.decode(t, mt, nt, kb0, kb1);
+        int an[4], ah[4], aw[4];  // TmaPatchLoader: image and input origin (tap 0) of the tile's four atoms
+        int tap = 0, cb = 0, kr = 0, kc = 0;
+        if constexpr (LA::kTmaA) {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            la.atom_origin(mt * 4 + a, an[a], ah[a], aw[a]);
+            ah[a] -= la.ph;
+            aw[a] -= la.pw;
+          }
+          tap = kb0 / la.CB;
+          cb = kb0 - tap * la.CB;
+          kr = tap / la.kw;
+          kc = tap - kr * la.kw;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&ctl.empty[stage], phase ^ 1);
+          if constexpr (LA::kTmaA) {
+            const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
+            mbar_arrive_expect_tx(&ctl.araw[stage], (uint32_t)aBytes);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+              tma_load_4d(sa + a * 4096, &tmA, aw[a] + kc * la.dx, ah[a] + kr * la.dy, cb * 32, an[a], &ctl.araw[stage]);
+            if (++cb == la.CB) {
+              cb = 0;
+              if (++kc == la.kw) { kc = 0; ++kr; }
+            }
+          }
           const uint32_t sb = smem_base + (uint32_t)stage * stageBytes + (SPLIT ? 2 : 1) * aBytes;
           mbar_arrive_expect_tx(&ctl.full[stage], (uint32_t)bBytes * (SPLIT ? 2 : 1));
           tma_load_2d(sb, &tmBhi, (int)(kb * BK), (int)(nt * BN), &ctl.full[stage]);
@@ -697,8 +850,8 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
       const uint32_t use = (uint32_t)(it >> 1);
       const int64_t m = (int64_t)mt * BM + quad * 32 + lane;
       const int64_t n0 = (int64_t)nt * BN;
-      const bool mvalid = m < epi.rows;
-      typename EPI::Row rc = epi.row(mvalid ? m : 0);
+      bool mvalid;
+      typename EPI::Row rc = epi.row(m, mvalid);
       mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
@@ -715,7 +868,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
         {
           int64_t cnt = min((int64_t)(BN - c0), epi.cols - (n0 + c0));  // warp-uniform
           if (cnt > 32) cnt = 32;
-          if (cnt > 0) epi.store_chunk(rc, n0 + c0, r, (int)cnt, mvalid);
+          if (cnt > 0) epi.store_chunk(rc, n0 + c0, r, (int)cnt, mvalid, ctl.epi_sb[quad]);
         }
       }
     }
@@ -775,9 +928,38 @@ __global__ void __launch_bounds__(256) k_prepare_weights_dgrad(const float *__re
   }
 }
 
+// TmaPatchLoader k order, forward and dgrad in one kernel:  k = (tap*CB + cb)*32 + ci,  channel = cb*32 + ci
+//   forward: out[f][k] = W[f][channel][tap]                         (rows = F, channels = C)
+//   dgrad:   out[c][k] = W[channel][c][kk-1-tap]                    (rows = C, channels = F; flipped taps)
+__global__ void __launch_bounds__(256) k_prepare_weights_patch(const float *__restrict__ w, int rows, int chans, int kk,
+                                                               int CB, int dgrad, float *__restrict__ hi,
+                                                               float *__restrict__ lo, int split) {
+  const int Kpad = kk * CB * 32;
+  const int64_t total = (int64_t)rows * Kpad;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const int r = (int)(i / Kpad);
+    const int k = (int)(i - (int64_t)r * Kpad);
+    const int ci = k & 31, g = k >> 5;
+    const int tap = g / CB, cb = g - tap * CB;
+    const int ch = cb * 32 + ci;
+    float v = 0.f;
+    if (ch < chans)
+      v = dgrad ? __ldg(w + ((int64_t)ch * rows + r) * kk + (kk - 1 - tap)) : __ldg(w + ((int64_t)r * chans + ch) * kk + tap);
+    if (split) {
+      const float h = tf32_hi(v);
+      hi[i] = h;
+      lo[i] = v - h;
+    } else {
+      hi[i] = tf32_rna(v);
+    }
+  }
+}
+
 // wgrad B operand: rows n = (c, tap) of im2col(in)^T, k = (image b, output pixel p); K-major tile (32 pixels of one
 // image per k-block; requires OH*OW % 32 == 0).  lane = pixel, warp w stages rows w, w+8, ...
 struct Im2colRowsLoader {
+  static constexpr bool kTmaA = false;
   static constexpr bool kMnMajor = false;
   static constexpr bool kTma = false;
   static constexpr int kPrefetch = 1;
@@ -891,13 +1073,13 @@ inline Plan make_plan(tnn_context *ctx, int64_t M, int64_t N, int64_t K, bool sp
 
 template <bool SPLIT, typename LA, typename LB, typename EPI>
 int launch(tnn_context *ctx, const Plan &p, LA la, LB lb, EPI epi, const CUtensorMap *tmHi = nullptr,
-           const CUtensorMap *tmLo = nullptr) {
+           const CUtensorMap *tmLo = nullptr, const CUtensorMap *tmA = nullptr) {
   auto kern = k_umma<SPLIT, LA, LB, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
   alignas(64) CUtensorMap dummy;
   memset(&dummy, 0, sizeof(dummy));
   kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(la, lb, epi, p.sched, p.BN, p.stages, p.accCols,
-                                                       tmHi ? *tmHi : dummy, tmLo ? *tmLo : dummy);
+                                                       tmHi ? *tmHi : dummy, tmLo ? *tmLo : dummy, tmA ? *tmA : dummy);
   TNN_LAUNCHED(ctx);
   return 0;
 }
@@ -992,9 +1174,96 @@ inline int encode_weights_map(CUtensorMap *tm, const float *base, int64_t rows, 
   return 0;
 }
 
+// NCHW activations {W, H, C, N}; box = one atom of one k-block: {TW, TH, 32, 1} = 4 KB
+inline int encode_patch_map(CUtensorMap *tm, const float *base, int64_t W, int64_t H, int64_t C, int64_t N, int TW,
+                            int TH) {
+  EncodeTiledFn enc = get_encode_tiled();
+  TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * C * 4};
+  cuuint32_t box[4] = {(cuuint32_t)TW, (cuuint32_t)TH, 32, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tnn_set_error("cuTensorMapEncodeTiled (activations) failed with CUresult %d", (int)r);
+    return 6;
+  }
+  return 0;
+}
+
+// Stride-1 convolution (forward, or dgrad posed as one) with TMA-fed activations; kNotTaken when the geometry
+// does not fit (caller falls back to the gathering producer).  `v` is the forward problem actually computed:
+// in = [batch][v.C][v.H][v.W], out = [batch][v.F][v.OH][v.OW].
+inline int conv_patch(tnn_context *ctx, const simt::ConvGeom &v, int batch, const float *in, const float *weights,
+                      bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate) {
+  if (v.sy != 1 || v.sx != 1) return kNotTaken;
+  const int kk = v.kh * v.kw;
+  // a 1x1 / no-padding convolution has no 2-D structure: view every image as one row of H*W pixels
+  const bool flat = kk == 1 && v.ph == 0 && v.pw == 0;
+  const int64_t We = flat ? (int64_t)v.H * v.W : v.W, He = flat ? 1 : v.H;
+  const int64_t OWe = flat ? We : v.OW, OHe = flat ? 1 : v.OH;
+  if ((We % 4) != 0 || v.C < 16 || (((uintptr_t)in) & 15) != 0) return kNotTaken;
+  // Measured on B200 (tools/probe/tma_probe.cu): a tiled TMA load whose innermost start coordinate is not a
+  // multiple of 16 bytes raises "illegal instruction", in or out of bounds.  Patch columns start at multiples of
+  // TW >= 8, so every kernel column must shift by a multiple of 4 pixels: true for 1-wide kernels (all 1x1
+  // convolutions), not for the +-1 column taps of a 3x3 kernel — those stay on the gathering producer.
+  if (!flat)
+    for (int kc = 0; kc < v.kw; ++kc)
+      if (((kc * v.dx - v.pw) % 4) != 0) return kNotTaken;
+  if (We >= (1ll << 31) || (int64_t)batch * v.C * v.H * v.W >= (1ll << 40)) return kNotTaken;
+  // patch shape: the TW in {32,16,8} that wastes the fewest rows
+  int TW = 0;
+  double best = 0;
+  for (int tw = 32; tw >= 8; tw >>= 1) {
+    const int th = 32 / tw;
+    const double u = (double)OWe / (double)(cdiv64(OWe, tw) * tw) * (double)OHe / (double)(cdiv64(OHe, th) * th);
+    if (u > best + 1e-9) { best = u; TW = tw; }
+  }
+  if (best < 0.75) return kNotTaken;
+  const int TH = 32 / TW;
+  const int WT = (int)cdiv64(OWe, TW), HT = (int)cdiv64(OHe, TH);
+  const int64_t numAtoms = (int64_t)batch * WT * HT;
+  if (numAtoms >= (1ll << 29)) return kNotTaken;
+  const int CB = (v.C + 31) / 32;
+  const int64_t M = cdiv64(numAtoms, 4) * BM;  // rows incl. patch padding
+  const int64_t N = v.F;
+  const int64_t K = (int64_t)kk * CB * 32;
+  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  Plan p = make_plan(ctx, M, N, K, split, false, false);
+  const size_t plane = (size_t)N * K * sizeof(float);
+  int rc = tnn_reserve_work(ctx, plane * 2);
+  if (rc) return rc;
+  float *whi = ctx->work, *wlo = ctx->work + (size_t)N * K;
+  {
+    int64_t blocks = cdiv64(N * K, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_prepare_weights_patch<<<(int)blocks, 256, 0, ctx->stream>>>(weights, (int)N, v.C, kk, CB, dgradWeights ? 1 : 0, whi,
+                                                                 wlo, split ? 1 : 0);
+    TNN_LAUNCHED(ctx);
+  }
+  alignas(64) CUtensorMap tmHi, tmLo, tmA;
+  rc = encode_weights_map(&tmHi, whi, N, K, p.BN);
+  if (rc) return rc;
+  rc = encode_weights_map(&tmLo, split ? wlo : whi, N, K, p.BN);
+  if (rc) return rc;
+  rc = encode_patch_map(&tmA, in, We, He, v.C, batch, TW, TH);
+  if (rc) return rc;
+  TmaPatchLoader la{TW, TH, WT, HT, WT * HT, (int)numAtoms, batch, flat ? 0 : v.ph, flat ? 0 : v.pw, v.kw, v.dy, v.dx, CB};
+  TmaWeightsLoader lb{};
+  ConvEpilogue epi{out, scale, bias, v.OH * v.OW, v.outImg, act, M, N, accumulate,
+                   TW, TH, WT, WT * HT, (int)OHe, (int)OWe, batch};
+  return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo, &tmA) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo, &tmA);
+}
+
 // conv forward: D[pixel][filter]; A = im2col gather (MN-major, producer warps), B = weights via TMA (K-major)
 inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
                         const float *scale, const float *bias, int act, float *out) {
+  if (ctx->tma_activations) {
+    int rc = conv_patch(ctx, g, batch, in, weights, false, scale, bias, act, out, false);
+    if (rc != kNotTaken) return rc;
+  }
   const int64_t M = (int64_t)batch * g.OH * g.OW;
   const int64_t N = g.F;
   const int kk = g.kh * g.kw;
@@ -1021,7 +1290,7 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   if (rc) return rc;
   Im2colPixelLoader la{in, g, M, g.H * g.W, kk};
   TmaWeightsLoader lb{};
-  ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false};
+  ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
 }
 
@@ -1039,6 +1308,10 @@ inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int bat
   v.ph = g.kh - 1 - g.ph; v.pw = g.kw - 1 - g.pw;
   v.OH = g.H; v.OW = g.W;
   v.inImg = g.outImg; v.outImg = g.inImg;
+  if (ctx->tma_activations) {
+    int rc = conv_patch(ctx, v, batch, delta, weights, true, nullptr, nullptr, TNN_ACT_LINEAR, in_delta, true);
+    if (rc != kNotTaken) return rc;
+  }
   const int64_t M = (int64_t)batch * v.OH * v.OW;
   const int64_t N = v.F;
   const int64_t K = (int64_t)((v.C + 15) / 16) * kk * 16;
@@ -1061,7 +1334,7 @@ inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int bat
   if (rc) return rc;
   Im2colPixelLoader la{delta, v, M, v.H * v.W, kk};
   TmaWeightsLoader lb{};
-  ConvEpilogue epi{in_delta, nullptr, nullptr, v.OH * v.OW, v.outImg, TNN_ACT_LINEAR, M, N, true};
+  ConvEpilogue epi{in_delta, nullptr, nullptr, v.OH * v.OW, v.outImg, TNN_ACT_LINEAR, M, N, true, 0, 0, 0, 0, 0, 0, 0};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
 }
 

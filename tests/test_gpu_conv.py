@@ -127,6 +127,61 @@ def test_conv_forward_scale_bias_activation_epilogue(cuda_backend, oracle, act):
     assert rel_max(dout.read(want.shape), want) < TOL_3XTF32
 
 
+TMA_GEOMS = [  # stride-1 geometries whose rows are 16-byte aligned: activations arrive by TMA (patch atoms)
+    (2, 32, 32, 32, 32, 3, 1, 1),    # deepCIFAR10 c2: 4x... 32-wide rows, one row per atom
+    (2, 64, 16, 16, 64, 3, 1, 1),    # 16-wide: 2x16 patches
+    (3, 128, 8, 8, 128, 3, 1, 1),    # 8-wide: 4x8 patches, atoms straddle nothing; 3 images = 6 atoms (ragged tile)
+    (1, 64, 52, 52, 32, 1, 0, 1),    # YOLO 1x1 bottleneck: flattened 2704-pixel rows, last atom ragged
+    (2, 32, 20, 24, 48, 3, 1, 1),    # W=24: 8-wide patches, H=20 = 5 patch rows
+    (1, 48, 12, 16, 40, 5, 2, 1),    # 5x5 kernel, C=48 (second channel block half empty)
+    (2, 36, 8, 8, 16, 3, 1, 1),      # C=36: channel quads past the end are zero-filled
+    (1, 16, 40, 36, 24, 3, 0, 1),    # no padding: output 38x34, patches overhang the right/bottom edge
+    (2, 512, 4, 4, 64, 1, 0, 1),     # tiny maps, deep: flattened 16-pixel rows (atom half empty)
+]
+
+
+@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32)])
+@pytest.mark.parametrize("geom", TMA_GEOMS)
+def test_conv_forward_tma_activations(cuda_backend, oracle, mode, tol, geom):
+    cu = cuda_backend
+    B, C, H, W, F, k, p, s = geom
+    rng = np.random.default_rng(sum(geom) + 7)
+    x, w, b = conv_case(rng, B, C, H, W, F, k)
+    want = oracle.conv2d(x, w, p, s, s, 1, k, k)
+    oracle.forward_bias(want, b, B)
+    oracle.activate_array(want, oracle.ACT["LEAKY"])
+    dx, dw, db, dout = Dev(cu, x), Dev(cu, w), Dev(cu, b), Dev(cu, n=want.size)
+    cu.fill(want.size, dout.ptr, 0, 777.0, 1)  # rows the kernel must not skip
+    cu.set_math_mode(mode)
+    try:
+        cu.conv2dForward(cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s), dx.ptr, 0, dw.ptr, None, db.ptr,
+                         oracle.ACT["LEAKY"], dout.ptr, 0)
+    finally:
+        cu.set_math_mode(X3)
+    got = dout.read(want.shape)
+    e1, e2 = rel_max(got, want), rel_elem(got, want, floor=1.0)
+    assert e1 < tol and e2 < tol, (e1, e2)
+
+
+def test_conv_tma_activations_index_exact(cuda_backend):
+    """Index-encoded input against one-hot filters: every output must be EXACTLY the input element the im2col
+    mapping names (small integers are exact in 3xTF32), so a misplaced shared-memory atom, a wrong tap shift or a
+    missing zero fill shows up as a wrong integer rather than a tolerance miss."""
+    cu = cuda_backend
+    B, C, H, W, k, p = 2, 32, 16, 24, 3, 1
+    x = (np.arange(B * C * H * W) % 4093).astype(np.float32).reshape(B, C, H, W)
+    taps = [(c, kr, kc) for c in (0, 5, 31) for kr in range(k) for kc in range(k)]
+    F = len(taps)
+    w = np.zeros((F, C, k, k), np.float32)
+    for f, (c, kr, kc) in enumerate(taps):
+        w[f, c, kr, kc] = 1
+    xp = np.pad(x, ((0, 0), (0, 0), (p, p), (p, p)))
+    want = np.stack([xp[:, c, kr:kr + H, kc:kc + W] for (c, kr, kc) in taps], axis=1)
+    dx, dw, dout = Dev(cu, x), Dev(cu, w), Dev(cu, n=want.size)
+    cu.conv2dForward(cu.conv_desc(B, C, H, W, F, k, k, p, p, 1, 1), dx.ptr, 0, dw.ptr, None, None, 4, dout.ptr, 0)
+    assert np.array_equal(dout.read(want.shape), want)
+
+
 BWD_GEOMS = GEOMS[:6] + [
     (8, 32, 32, 32, 64, 3, 1, 1),    # deepCIFAR10 c3 shape (P = 1024: tcgen05 wgrad with split-K, tcgen05 dgrad)
     (4, 64, 16, 16, 64, 3, 1, 1),    # deepCIFAR10 c4 shape
