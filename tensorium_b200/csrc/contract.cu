@@ -6,6 +6,7 @@
 #include "gemm_simt.cuh"
 #include "umma_conv.cuh"
 #include "conv_direct.cuh"
+#include "umma_halo.cuh"
 
 namespace {
 

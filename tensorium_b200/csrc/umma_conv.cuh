@@ -39,6 +39,9 @@
 #define TNN_PIXEL_PREFETCH 3  // k-blocks of im2col loads kept in flight per producer thread
 #endif
 
+#ifndef TNN_MMA_ELECT
+#define TNN_MMA_ELECT (lane == 0)
+#endif
 namespace umma {
 
 constexpr int kNotTaken = -100;
@@ -120,6 +123,17 @@ __device__ __forceinline__ void mbar_wait_warp_relaxed(uint64_t *bar, uint32_t p
     }
   }
   __syncwarp();
+}
+// one lane of a CONVERGED warp; unlike `lane == 0` the compiler knows a single thread runs the guarded block, so
+// the uniform-datapath operands of UTCMMA / UTMALDG need no per-value "waterfall" loop
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n.reg .pred P1;\n"
+      "elect.sync _|P1, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P1;\n}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -470,12 +484,13 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
   int act;
   int64_t rows, cols;
   bool accumulate;  // out += value (dgrad adds into the upstream delta, like the reference's col2im)
-  // TW != 0: rows are TmaPatchLoader atoms (TH x TW patches), else row m = pixel m of the batch-folded image list
-  int TW, TH, WT, atomsPerImg, OH, OW, batch;
+  // TW != 0: rows are patches of TH x TW output pixels (1 << ashift rows each: 32-row TmaPatchLoader atoms or the
+  // 128-row patches of the halo kernel), else row m = pixel m of the batch-folded image list
+  int TW, TH, WT, atomsPerImg, OH, OW, batch, ashift;
   struct Row { float *q; };
   __device__ __forceinline__ Row row(int64_t m, bool &valid) const {
     if (TW != 0) {
-      const int atom = (int)(m >> 5), j = (int)(m & 31);
+      const int atom = (int)(m >> ashift), j = (int)(m & ((1 << ashift) - 1));
       const int n = atom / atomsPerImg;
       const int r = atom - n * atomsPerImg;
       const int hy = r / WT;
@@ -761,7 +776,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
       for (int kb = kb0; kb < kb1; ++kb) {
         mbar_wait_warp(&ctl.full[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (TNN_MMA_ELECT) {
           const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
           const uint32_t sa_lo = sa + aBytes;
           const uint32_t sb = sa + (SPLIT ? 2 : 1) * aBytes;
@@ -1253,15 +1268,21 @@ inline int conv_patch(tnn_context *ctx, const simt::ConvGeom &v, int batch, cons
   TmaPatchLoader la{TW, TH, WT, HT, WT * HT, (int)numAtoms, batch, flat ? 0 : v.ph, flat ? 0 : v.pw, v.kw, v.dy, v.dx, CB};
   TmaWeightsLoader lb{};
   ConvEpilogue epi{out, scale, bias, v.OH * v.OW, v.outImg, act, M, N, accumulate,
-                   TW, TH, WT, WT * HT, (int)OHe, (int)OWe, batch};
+                   TW, TH, WT, WT * HT, (int)OHe, (int)OWe, batch, 5};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo, &tmA) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo, &tmA);
 }
+
+// umma_halo.cuh
+int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const float *in, const float *weights,
+              bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate);
 
 // conv forward: D[pixel][filter]; A = im2col gather (MN-major, producer warps), B = weights via TMA (K-major)
 inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
                         const float *scale, const float *bias, int act, float *out) {
   if (ctx->tma_activations) {
     int rc = conv_patch(ctx, g, batch, in, weights, false, scale, bias, act, out, false);
+    if (rc != kNotTaken) return rc;
+    rc = conv_halo(ctx, g, batch, in, weights, false, scale, bias, act, out, false);
     if (rc != kNotTaken) return rc;
   }
   const int64_t M = (int64_t)batch * g.OH * g.OW;
@@ -1290,7 +1311,7 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   if (rc) return rc;
   Im2colPixelLoader la{in, g, M, g.H * g.W, kk};
   TmaWeightsLoader lb{};
-  ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0};
+  ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
 }
 
@@ -1310,6 +1331,8 @@ inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int bat
   v.inImg = g.outImg; v.outImg = g.inImg;
   if (ctx->tma_activations) {
     int rc = conv_patch(ctx, v, batch, delta, weights, true, nullptr, nullptr, TNN_ACT_LINEAR, in_delta, true);
+    if (rc != kNotTaken) return rc;
+    rc = conv_halo(ctx, v, batch, delta, weights, true, nullptr, nullptr, TNN_ACT_LINEAR, in_delta, true);
     if (rc != kNotTaken) return rc;
   }
   const int64_t M = (int64_t)batch * v.OH * v.OW;
@@ -1334,7 +1357,7 @@ inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int bat
   if (rc) return rc;
   Im2colPixelLoader la{delta, v, M, v.H * v.W, kk};
   TmaWeightsLoader lb{};
-  ConvEpilogue epi{in_delta, nullptr, nullptr, v.OH * v.OW, v.outImg, TNN_ACT_LINEAR, M, N, true, 0, 0, 0, 0, 0, 0, 0};
+  ConvEpilogue epi{in_delta, nullptr, nullptr, v.OH * v.OW, v.outImg, TNN_ACT_LINEAR, M, N, true, 0, 0, 0, 0, 0, 0, 0, 0};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
 }
 
