@@ -269,6 +269,13 @@ typedef struct {
 TNN_API int32_t tnn_conv2d_forward(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,
                                    const float *weights, const float *scale, const float *bias,
                                    int32_t activation, float *out, int64_t outOffset);
+/* The same with the following shortcut layer folded in (TAddLayer.forwardGPU naddlayer.pas:885-910 with a linear
+ * activation: output = conv_output + layers[from].output):
+ *   out = act( conv(in, weights) * scale[f] + bias[f] ) + residual        (residual has the shape of out) */
+TNN_API int32_t tnn_conv2d_forward_residual(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,
+                                            const float *weights, const float *scale, const float *bias,
+                                            int32_t activation, const float *residual, int64_t residualOffset,
+                                            float *out, int64_t outOffset);
 /* backwardGPU wgrad (nConvolutionLayer.pas:1203-1232): weight_updates += sum_b delta_b * im2col(in_b)^T */
 TNN_API int32_t tnn_conv2d_backward_filter(tnn_context *ctx, const tnn_conv_desc *d, const float *in,
                                            int64_t inOffset, const float *delta, int64_t deltaOffset,

@@ -187,9 +187,9 @@ int32_t tnn_gemm_batched(tnn_context *ctx, int32_t transA, int32_t transB, int64
   return 0;
 }
 
-int32_t tnn_conv2d_forward(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,
-                           const float *weights, const float *scale, const float *bias, int32_t activation,
-                           float *out, int64_t outOffset) {
+int32_t tnn_conv2d_forward_residual(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,
+                                    const float *weights, const float *scale, const float *bias, int32_t activation,
+                                    const float *residual, int64_t residualOffset, float *out, int64_t outOffset) {
   TNN_CHECK_CTX(ctx);
   simt::ConvGeom g;
   int rc = fill_geom(d, g);
@@ -197,19 +197,32 @@ int32_t tnn_conv2d_forward(tnn_context *ctx, const tnn_conv_desc *d, const float
   TNN_REQUIRE(activation == TNN_ACT_LINEAR || tnn_act_is_elementwise(activation), "activation not elementwise");
   in += inOffset;
   out += outOffset;
+  if (residual) residual += residualOffset;
   const int64_t K = (int64_t)g.C * g.kh * g.kw;
   const int64_t Npix = d->batch * g.OH * g.OW;
   // tiny contractions (C*kh*kw <= 64) with few channels (the first layer), or any tiny contraction in FP32 mode:
   // exact-fp32 direct convolution in registers
-  if (direct::supported(g) && (g.C < 16 || ctx->math_mode == TNN_MATH_FP32)) return direct::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out);
-  if (ctx->math_mode != TNN_MATH_FP32) {
-    rc = umma::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out);
-    if (rc != umma::kNotTaken) return rc;
+  if (direct::supported(g) && (g.C < 16 || ctx->math_mode == TNN_MATH_FP32)) {
+    rc = direct::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out);
+  } else {
+    rc = umma::kNotTaken;
+    if (ctx->math_mode != TNN_MATH_FP32) {
+      rc = umma::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out, residual);
+      if (rc != umma::kNotTaken) return rc;  // the tensor-core epilogues add the residual themselves
+    }
+    simt::MatLoader la{weights, K, 0, true};
+    simt::Im2colCols lb{in, g};
+    ConvFwdEpi epi{out, scale, bias, g.OH * g.OW, g.outImg, activation};
+    rc = simt::launch<true, false>(ctx, g.F, Npix, K, 1, 1, la, lb, epi);
   }
-  simt::MatLoader la{weights, K, 0, true};
-  simt::Im2colCols lb{in, g};
-  ConvFwdEpi epi{out, scale, bias, g.OH * g.OW, g.outImg, activation};
-  return simt::launch<true, false>(ctx, g.F, Npix, K, 1, 1, la, lb, epi);
+  if (rc || !residual) return rc;
+  return tnn_addvv(ctx, d->batch * g.outImg, out, 0, 1, residual, 0, 1, out, 0, 1);
+}
+
+int32_t tnn_conv2d_forward(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,
+                           const float *weights, const float *scale, const float *bias, int32_t activation,
+                           float *out, int64_t outOffset) {
+  return tnn_conv2d_forward_residual(ctx, d, in, inOffset, weights, scale, bias, activation, nullptr, 0, out, outOffset);
 }
 
 int32_t tnn_conv2d_backward_filter(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,

@@ -487,6 +487,7 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
   // TW != 0: rows are patches of TH x TW output pixels (1 << ashift rows each: 32-row TmaPatchLoader atoms or the
   // 128-row patches of the halo kernel), else row m = pixel m of the batch-folded image list
   int TW, TH, WT, atomsPerImg, OH, OW, batch, ashift;
+  const float *residual;  // optional: added after the activation (the shortcut layer that follows), same shape as out
   struct Row { float *q; };
   __device__ __forceinline__ Row row(int64_t m, bool &valid) const {
     if (TW != 0) {
@@ -516,6 +517,7 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
     scratch[32 + lane] = (bias && lane < cnt) ? __ldg(bias + n + lane) : 0.0f;
     __syncwarp();
     float *q = r.q + n * P;
+    const float *rq = residual ? residual + (q - out) : nullptr;
     const bool leaky = act == TNN_ACT_LEAKY || act == TNN_ACT_REVLEAKY;
     if (leaky || act == TNN_ACT_LINEAR) {
       const float neg = leaky ? 0.1f : 1.0f;
@@ -529,7 +531,10 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
           const int j = j4 + u;
           float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s[u]), b[u]);
           v = v < 0 ? neg * v : v;
-          if (rowvalid && j < cnt) q[(int64_t)j * P] = accumulate ? q[(int64_t)j * P] + v : v;
+          if (rowvalid && j < cnt) {
+            if (rq) v = __fadd_rn(v, __ldg(rq + (int64_t)j * P));
+            q[(int64_t)j * P] = accumulate ? q[(int64_t)j * P] + v : v;
+          }
         }
       }
     } else {
@@ -542,7 +547,11 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
         for (int u = 0; u < 4; ++u) {
           const int j = j4 + u;
           const float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s[u]), b[u]);
-          if (rowvalid && j < cnt) q[(int64_t)j * P] = act_out_of_line(v, act);
+          if (rowvalid && j < cnt) {
+            float o = act_out_of_line(v, act);
+            if (rq) o = __fadd_rn(o, __ldg(rq + (int64_t)j * P));
+            q[(int64_t)j * P] = o;
+          }
         }
       }
     }
@@ -1212,7 +1221,8 @@ inline int encode_patch_map(CUtensorMap *tm, const float *base, int64_t W, int64
 // does not fit (caller falls back to the gathering producer).  `v` is the forward problem actually computed:
 // in = [batch][v.C][v.H][v.W], out = [batch][v.F][v.OH][v.OW].
 inline int conv_patch(tnn_context *ctx, const simt::ConvGeom &v, int batch, const float *in, const float *weights,
-                      bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate) {
+                      bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate,
+                      const float *residual = nullptr) {
   if (v.sy != 1 || v.sx != 1) return kNotTaken;
   const int kk = v.kh * v.kw;
   // a 1x1 / no-padding convolution has no 2-D structure: view every image as one row of H*W pixels
@@ -1268,21 +1278,22 @@ inline int conv_patch(tnn_context *ctx, const simt::ConvGeom &v, int batch, cons
   TmaPatchLoader la{TW, TH, WT, HT, WT * HT, (int)numAtoms, batch, flat ? 0 : v.ph, flat ? 0 : v.pw, v.kw, v.dy, v.dx, CB};
   TmaWeightsLoader lb{};
   ConvEpilogue epi{out, scale, bias, v.OH * v.OW, v.outImg, act, M, N, accumulate,
-                   TW, TH, WT, WT * HT, (int)OHe, (int)OWe, batch, 5};
+                   TW, TH, WT, WT * HT, (int)OHe, (int)OWe, batch, 5, residual};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo, &tmA) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo, &tmA);
 }
 
 // umma_halo.cuh
 int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const float *in, const float *weights,
-              bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate);
+              bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate,
+              const float *residual = nullptr);
 
 // conv forward: D[pixel][filter]; A = im2col gather (MN-major, producer warps), B = weights via TMA (K-major)
 inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
-                        const float *scale, const float *bias, int act, float *out) {
+                        const float *scale, const float *bias, int act, float *out, const float *residual = nullptr) {
   if (ctx->tma_activations) {
-    int rc = conv_patch(ctx, g, batch, in, weights, false, scale, bias, act, out, false);
+    int rc = conv_patch(ctx, g, batch, in, weights, false, scale, bias, act, out, false, residual);
     if (rc != kNotTaken) return rc;
-    rc = conv_halo(ctx, g, batch, in, weights, false, scale, bias, act, out, false);
+    rc = conv_halo(ctx, g, batch, in, weights, false, scale, bias, act, out, false, residual);
     if (rc != kNotTaken) return rc;
   }
   const int64_t M = (int64_t)batch * g.OH * g.OW;
@@ -1311,7 +1322,7 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   if (rc) return rc;
   Im2colPixelLoader la{in, g, M, g.H * g.W, kk};
   TmaWeightsLoader lb{};
-  ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0};
+  ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, residual};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
 }
 
@@ -1357,7 +1368,7 @@ inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int bat
   if (rc) return rc;
   Im2colPixelLoader la{delta, v, M, v.H * v.W, kk};
   TmaWeightsLoader lb{};
-  ConvEpilogue epi{in_delta, nullptr, nullptr, v.OH * v.OW, v.outImg, TNN_ACT_LINEAR, M, N, true, 0, 0, 0, 0, 0, 0, 0, 0};
+  ConvEpilogue epi{in_delta, nullptr, nullptr, v.OH * v.OW, v.outImg, TNN_ACT_LINEAR, M, N, true, 0, 0, 0, 0, 0, 0, 0, 0, nullptr};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
 }
 

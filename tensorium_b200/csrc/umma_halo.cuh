@@ -290,7 +290,8 @@ __global__ void __launch_bounds__(256) k_prepare_weights_halo(const float *__res
 
 // v = the forward problem computed (dgrad passes the virtual one); kNotTaken when the geometry does not fit
 inline int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const float *in, const float *weights,
-                     bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate) {
+                     bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate,
+                     const float *residual) {
   if (v.sy != 1 || v.sx != 1) return kNotTaken;
   const int kk = v.kh * v.kw;
   if (kk < 2 || v.C < 16) return kNotTaken;
@@ -334,7 +335,7 @@ inline int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const
   if (rc) return rc;
   HaloGeom g{in, v.C, v.H, v.W, v.ph, v.pw, v.kh, v.kw, v.dy, v.dx, HR, HC, PX, PY, batch, CB, kk, v.H * v.W, v.inImg};
   ConvEpilogue epi{out, scale, bias, v.OH * v.OW, v.outImg, act, mTiles * BM, N, accumulate,
-                   kPatchW, kPatchH, PX, PX * PY, v.OH, v.OW, batch, 7};
+                   kPatchW, kPatchH, PX, PX * PY, v.OH, v.OW, batch, 7, residual};
   const int64_t numTiles = mTiles * nTiles;
   const int64_t sms = ctx->prop.multiProcessorCount;
   const int grid = (int)(numTiles < sms ? numTiles : sms);

@@ -102,6 +102,10 @@ class TConvolutionalLayer:
                 self.x = TSingleTensor(shape, groups=batch)
                 self.x_norm = TSingleTensor(shape, groups=batch)
         self._bn_fold = None
+        # inference-time fusion of the shortcut layer that follows (set by TNNet.fuseShortcuts): the epilogue adds
+        # `_residual` and writes into the shortcut layer's output instead of this layer's own
+        self._residual = None
+        self._fused_out = None
         self._desc = nn.TNNCuda.conv_desc(batch, c, h, w, filters, kernelSize, kernelSize, padding, padding, stride,
                                           stride, dilation, dilation)
 
@@ -144,7 +148,16 @@ class TConvolutionalLayer:
             for t in (self.scales, self.rolling_mean, self.rolling_variance):
                 if not t.wasGPU():
                     t.pushToDevice()
-        if not self.isBatchNormalized:
+        if self._residual is not None and not state.isTraining:
+            sc = None
+            bi = self.biases
+            if self.isBatchNormalized:
+                sc, bi = self._folded_bn()
+            self._fused_out.setCUDA()
+            cu.conv2dForwardResidual(self._desc, state.input.devData, 0, self.weights.devData,
+                                     sc.devData if sc is not None else None, bi.devData, self.ActivationType,
+                                     self._residual.devData, 0, self._fused_out.devData, 0)
+        elif not self.isBatchNormalized:
             cu.conv2dForward(self._desc, state.input.devData, 0, self.weights.devData, None, self.biases.devData,
                              self.ActivationType, self.output.devData, 0)
         elif training_bn:
@@ -162,18 +175,22 @@ class TConvolutionalLayer:
         else:
             # inference batch-norm folded into the conv epilogue: out = act(conv*s + b'),
             # s = scale/max(sqrt(var),eps), b' = bias - mean*s
-            if self._bn_fold is None:
-                eps = np.float32(0.000001)
-                for t in (self.scales, self.rolling_mean, self.rolling_variance, self.biases):
-                    if t.wasGPU():
-                        t.pullFromDevice()
-                s = (self.scales.Data / np.maximum(np.sqrt(self.rolling_variance.Data), eps)).astype(np.float32)
-                b = (self.biases.Data - self.rolling_mean.Data * s).astype(np.float32)
-                self._bn_fold = (TSingleTensor(s.shape, 1, s), TSingleTensor(b.shape, 1, b))
-                self._bn_fold[0].pushToDevice()
-                self._bn_fold[1].pushToDevice()
-            cu.conv2dForward(self._desc, state.input.devData, 0, self.weights.devData, self._bn_fold[0].devData,
-                             self._bn_fold[1].devData, self.ActivationType, self.output.devData, 0)
+            sc, bi = self._folded_bn()
+            cu.conv2dForward(self._desc, state.input.devData, 0, self.weights.devData, sc.devData, bi.devData,
+                             self.ActivationType, self.output.devData, 0)
+
+    def _folded_bn(self):
+        if self._bn_fold is None:
+            eps = np.float32(0.000001)
+            for t in (self.scales, self.rolling_mean, self.rolling_variance, self.biases):
+                if t.wasGPU():
+                    t.pullFromDevice()
+            s = (self.scales.Data / np.maximum(np.sqrt(self.rolling_variance.Data), eps)).astype(np.float32)
+            b = (self.biases.Data - self.rolling_mean.Data * s).astype(np.float32)
+            self._bn_fold = (TSingleTensor(s.shape, 1, s), TSingleTensor(b.shape, 1, b))
+            self._bn_fold[0].pushToDevice()
+            self._bn_fold[1].pushToDevice()
+        return self._bn_fold
 
     def _forward_reference_sequence(self, cu, state):
         # nConvolutionLayer.pas:1040-1122, call for call

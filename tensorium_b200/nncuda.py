@@ -311,6 +311,12 @@ class TNNCuda:
         self._ck(self._l.tnn_conv2d_forward(self._h, C.byref(desc), _addr(in_), inOffset, _addr(weights),
                                             _addr(scale), _addr(bias), int(activation), _addr(out), outOffset))
 
+    def conv2dForwardResidual(self, desc, in_, inOffset, weights, scale, bias, activation, residual, residualOffset, out,
+                              outOffset):
+        self._ck(self._l.tnn_conv2d_forward_residual(self._h, C.byref(desc), _addr(in_), inOffset, _addr(weights),
+                                                     _addr(scale), _addr(bias), int(activation), _addr(residual),
+                                                     residualOffset, _addr(out), outOffset))
+
     def conv2dBackwardFilter(self, desc, in_, inOffset, delta, deltaOffset, weight_updates):
         self._ck(self._l.tnn_conv2d_backward_filter(self._h, C.byref(desc), _addr(in_), inOffset, _addr(delta),
                                                     deltaOffset, _addr(weight_updates)))

@@ -26,6 +26,8 @@ class TShortcutLayer:
     def forwardGPU(self, state: TNNetState, net: "TNNet"):
         cu = cuda()
         self.output.setCUDA()
+        if getattr(self, "_fused_into_conv", False) and not state.isTraining:
+            return  # the preceding convolution's epilogue already wrote input + layers[from].output here
         other = net.layers[self.inputLayers[0]].output
         # copy + addvv of the reference collapse into one out-of-place add (same arithmetic: a single fp32 add)
         cu.addvv(self.output.Size(), state.input.devData, 0, 1, other.devData, 0, 1, self.output.devData, 0, 1)
@@ -253,6 +255,30 @@ class TNNet:
                 out += l.gradients()
         return out
 
+    def fuseShortcuts(self):
+        """Inference-time graph fusion: a fused convolution whose output feeds ONLY the linear shortcut layer that
+        follows adds the shortcut's other operand in its epilogue (tnn_conv2d_forward_residual) and writes the
+        shortcut's output directly; the add kernel and one round trip of the tensor through HBM disappear.  Same
+        arithmetic as the separate layers (one fp32 add after the activation).  Returns the number of fused pairs.
+
+        OFF by default: measured on B200 (YOLOv3-416, batch 64) the step gets slower (29.6 -> 47.6 ms) because the
+        four epilogue warps read the residual with dependent, un-prefetched loads; it needs a TMA-staged residual
+        tile before it pays."""
+        used = set()  # layer outputs referenced by index from elsewhere in the graph
+        for l in self.layers:
+            used.update(getattr(l, "inputLayers", []))
+        n = 0
+        for i in range(len(self.layers) - 1):
+            c, sc = self.layers[i], self.layers[i + 1]
+            if (isinstance(c, TConvolutionalLayer) and c.fused and isinstance(sc, TShortcutLayer)
+                    and sc.ActivationType == nn.acLINEAR and i not in used and sc.inputLayers[0] < i
+                    and sc.output.Size() == c.output.Size()):
+                c._residual = self.layers[sc.inputLayers[0]].output
+                c._fused_out = sc.output
+                sc._fused_into_conv = True
+                n += 1
+        return n
+
     def predict(self, x_dev_tensor: TSingleTensor | None = None):
         st = TNNetState(input=x_dev_tensor or self.input, isTraining=False)
         return self.forward(st)
@@ -348,7 +374,7 @@ def init_yolov3_params(spec, c_in=3, seed=1234, objectness_bias=-4.0):
     return params
 
 
-def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=1234):
+def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=1234, fuse_shortcuts=False):
     """Builds the 107-layer net on the current `cuda` backend.  fuse_bn=True mirrors MSCOCOYolo.pas:327-340
     (Neural.fuseBatchNorm before predict)."""
     spec = yolov3_spec()
@@ -382,4 +408,7 @@ def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=12
             l = TYoloLayer(batch, c, h, w, item[1], YOLOV3_ANCHORS, 80, fused=fused)
         layers.append(l)
         c, h, w = l.outC, l.outH, l.outW
-    return TNNet(layers, batch, 3, size, size)
+    net = TNNet(layers, batch, 3, size, size)
+    if fuse_shortcuts and fused:
+        net.fuseShortcuts()
+    return net

@@ -74,3 +74,23 @@ def test_yolov3_small_against_oracle(cuda_backend, oracle, fused):
             assert np.array_equal(dp[i] > 0, rp[i] > 0)  # same surviving classes
             assert box_iou(db[i], rb[i]) >= 0.99
     assert total > 0  # the comparison is not vacuous
+
+
+def test_shortcut_fusion_is_bit_identical(cuda_backend):
+    """tnn_conv2d_forward_residual: conv epilogue + the following shortcut's add == the two separate layers."""
+    from tensorium_b200.nnet import build_yolov3, init_yolov3_params, yolov3_spec
+    cu = cuda_backend
+    size, batch = 64, 2
+    params = init_yolov3_params(yolov3_spec(), seed=8)
+    x = np.random.default_rng(2).random((batch, 3, size, size), dtype=np.float32)
+    outs = []
+    for fuse in (False, True):
+        net = build_yolov3(batch, size, params=params, fuse_shortcuts=fuse)
+        if fuse:
+            assert sum(getattr(l, "_fused_into_conv", False) for l in net.layers) == 23
+        cu.writeBuffer(net.input.devData, x.nbytes, x)
+        net.predict()
+        outs.append([net.layers[i].output.pullFromDevice().copy() for i in (4, 36, 61, 74)] +
+                    [l.output.pullFromDevice().copy() for l in net.yolo_layers()])
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)

@@ -72,13 +72,25 @@ def main():
             tms = torch.tensor([ms], device="cuda")
             torch.distributed.all_reduce(tms, op=torch.distributed.ReduceOp.MAX)
             ms = float(tms.item())
+    # replicas must hold bit-identical weights after the summed updates
+    in_sync = True
+    if world > 1:
+        sums = []
+        for l in net.layers:
+            if getattr(l, "trainable", False):
+                sums.append(float(np.abs(l.weights.pullFromDevice()).sum(dtype=np.float64)))
+                l.weights.setCUDA()
+        mine = torch.tensor(sums, dtype=torch.float64, device="cuda")
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        torch.distributed.all_gather(allv, mine)
+        in_sync = all(bool(torch.equal(allv[0], v)) for v in allv)
     if rank == 0:
         print(json.dumps({
             "metric": "cifar10_train_images_per_s", "value": a.batch * world * a.steps / (ms / 1e3), "unit": "images/s",
             "n_gpus": world, "steps": a.steps, "ms_per_step": ms / a.steps, "per_gpu_batch": a.batch,
             "math": a.math, "fused": not a.unfused, "launches_per_step": (cu.launch_count() - l0) / a.steps,
             "loss_first": costs[0] if costs else None, "loss_last": costs[-1] if costs else None,
-            "data": "synthetic", "e2e": "host batch copied in every step"}))
+            "replicas_in_sync": in_sync, "data": "synthetic", "e2e": "host batch copied in every step"}))
     if world > 1:
         torch.distributed.destroy_process_group()
 
