@@ -519,7 +519,25 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
     float *q = r.q + n * P;
     const float *rq = residual ? residual + (q - out) : nullptr;
     const bool leaky = act == TNN_ACT_LEAKY || act == TNN_ACT_REVLEAKY;
-    if (leaky || act == TNN_ACT_LINEAR) {
+    const bool plain = rq == nullptr && !accumulate;  // warp-uniform: the common case gets a loop without loads
+    if ((leaky || act == TNN_ACT_LINEAR) && plain) {
+      const float neg = leaky ? 0.1f : 1.0f;
+      const bool full = rowvalid && cnt == 32;
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 s4 = *reinterpret_cast<const float4 *>(scratch + j4);
+        const float4 b4 = *reinterpret_cast<const float4 *>(scratch + 32 + j4);
+        const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j4 + u;
+          float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s[u]), b[u]);
+          v = v < 0 ? neg * v : v;
+          if (full || (rowvalid && j < cnt)) *q = v;
+          q += P;
+        }
+      }
+    } else if (leaky || act == TNN_ACT_LINEAR) {
       const float neg = leaky ? 0.1f : 1.0f;
 #pragma unroll
       for (int j4 = 0; j4 < 32; j4 += 4) {

@@ -19,14 +19,21 @@
 namespace umma {
 
 constexpr int kPatchW = 8, kPatchH = 16;
-constexpr int kHaloItems = 6;   // (pixel, 4-channel chunk) work items per producer thread and halo (<= 1536 items)
+constexpr int kHaloGroup = 6;   // halo pixels a producer thread keeps in flight (loads) before it stores them
+constexpr int kHaloMaxPasses = 12;
 constexpr int kHaloMaxStages = 3, kHaloMaxBStages = 4;
 
+// Stride s in {1,2}: input pixel (s*a + ra, s*b + rb) lives in parity plane (ra,rb) at (a,b); tap (kr,kc) with
+// kr*dy - ph = s*sa + ra reads plane (ra,rb) shifted by (sa,sb) — a stride-1 access inside the plane.  s = 1 has
+// one plane.  Every plane holds HR x HC pixels starting at (oh0 + saMin, ow0 + sbMin) in plane coordinates.
 struct HaloGeom {
   const float *in;
-  int C, H, W, ph, pw, kh, kw, dy, dx;
-  int HR, HC;      // halo lines / columns that are filled
-  int PX, PY;      // patches per image row / column
+  int C, H, W, ph, pw, kh, kw, dy, dx, s;
+  int HR, HC;        // lines / columns per parity plane
+  int saMin, sbMin;  // smallest line / column shift of any tap
+  int NP;            // pixels per halo = s*s*HR*HC
+  int CH;            // channels per staged halo: 32 or 16
+  int PX, PY;        // patches per image row / column
   int batch, CB, kk, HW;
   int64_t inImg;
 };
@@ -36,9 +43,11 @@ struct HaloCtl {
   uint64_t b_full[kHaloMaxBStages], b_empty[kHaloMaxBStages];
   uint64_t tmem_full[2], tmem_empty[2];
   uint32_t tmem_base;
+  int tapoff[64];  // byte offset of each tap's view inside one precision copy of the halo
   alignas(16) float epi_sb[kEpilogueWarps][64];
 };
 
+__host__ __device__ inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
 template <bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -47,10 +56,11 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
   extern __shared__ uint8_t smem_raw[];
   __shared__ HaloCtl ctl;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int plane = g.HR * g.HC * 16;  // 4 channels of every halo pixel
-  const int haloBytes = plane * 8;     // one precision copy (32 channels)
+  const int Q = g.CH >> 2;            // 16-byte channel chunks per pixel
+  const int plane = g.NP * 16;        // one chunk (4 channels) of every halo pixel
+  const int haloBytes = plane * Q;    // one precision copy
   const int haloStage = haloBytes * (SPLIT ? 2 : 1);
-  const int bBytes = BN * BK * 4;
+  const int bBytes = BN * g.CH * 4;
   const int bStage = bBytes * (SPLIT ? 2 : 1);
   uint8_t *bRing = smem;  // TMA tiles need the 1024-byte alignment; the halos follow
   uint8_t *haloRing = smem + (size_t)BS * bStage;
@@ -72,6 +82,13 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
     }
     fence_barrier_init();
   }
+  if ((int)threadIdx.x < g.kk) {
+    const int tap = threadIdx.x;
+    const int kr = tap / g.kw, kc = tap - kr * g.kw;
+    const int sa = floor_div(kr * g.dy - g.ph, g.s), sb = floor_div(kc * g.dx - g.pw, g.s);
+    const int ra = kr * g.dy - g.ph - g.s * sa, rb = kc * g.dx - g.pw - g.s * sb;
+    ctl.tapoff[tap] = (((ra * g.s + rb) * g.HR + (sa - g.saMin)) * g.HC + (sb - g.sbMin)) * 16;
+  }
   if (warp == kMmaWarp) tmem_alloc(&ctl.tmem_base, accCols * 2);
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmBhi);
@@ -84,29 +101,28 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
 
   if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
     // ===================== producers: stage the halo of (tile, channel block) once =====================
+    // thread -> (chunk q, pixel lane): TPC threads share a chunk and walk the halo pixels TPC at a time, so a warp
+    // reads runs of one channel (coalesced) and writes consecutive 16-byte slots (conflict free)
     const int tid = threadIdx.x - kFirstProducerWarp * 32;
-    const int HP = g.HR * g.HC, items = HP * 8;
-    // per-thread item table (the same for every halo): shared-memory offset, global offset from the halo origin,
-    // and (line, column) for the bounds test
-    int soff[kHaloItems], goff[kHaloItems], rc[kHaloItems], q4[kHaloItems];
+    const int TPC = kProducerThreads / Q;  // 32 (CH = 32) or 64 (CH = 16)
+    const int q = tid / TPC, p0 = tid - q * TPC;
+    const int passes = (g.NP + TPC - 1) / TPC;  // <= kHaloMaxPasses (host checks)
+    const int HP = g.HR * g.HC;
+    // per-thread pixel table (the same for every halo): plane | line | column packed, -1 = no pixel
+    int pix[kHaloMaxPasses];
 #pragma unroll
-    for (int it = 0; it < kHaloItems; ++it) {
-      const int id = it * kProducerThreads + tid;
-      if (id < items) {
-        const int q = id / HP, p = id - q * HP;
-        const int r = p / g.HC, c = p - r * g.HC;
-        soff[it] = q * plane + (p << 4);
-        goff[it] = q * 4 * g.HW + r * g.W + c;
-        rc[it] = (r << 16) | c;
-        q4[it] = q * 4;
+    for (int it = 0; it < kHaloMaxPasses; ++it) {
+      const int pid = p0 + it * TPC;
+      if (it < passes && pid < g.NP) {
+        const int pl = pid / HP, rem = pid - pl * HP;
+        const int r = rem / g.HC, c = rem - r * g.HC;
+        pix[it] = (pl << 16) | (r << 8) | c;
       } else {
-        soff[it] = -1;
-        goff[it] = 0;
-        rc[it] = 0;
-        q4[it] = 0;
+        pix[it] = -1;
       }
     }
     const int patchesPerImg = g.PX * g.PY;
+    const int sbase = q * plane + p0 * 16;
     int hs = 0;
     uint32_t hphase = 0;
     for (int t = blockIdx.x; t < numTiles; t += gridDim.x) {
@@ -114,37 +130,50 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
       const int n = mt / patchesPerImg;
       const int rr = mt - n * patchesPerImg;
       const int py = rr / g.PX, px = rr - py * g.PX;
-      const int ih0 = py * kPatchH - g.ph, iw0 = px * kPatchW - g.pw;
-      const float *origin = g.in + (int64_t)n * g.inImg + (int64_t)ih0 * g.W + iw0;
+      const int a0 = py * kPatchH + g.saMin, b0 = px * kPatchW + g.sbMin;  // plane coordinates of the halo origin
+      const float *img = g.in + (int64_t)n * g.inImg;
       for (int cb = 0; cb < g.CB; ++cb) {
-        float4 v[kHaloItems];
-        const float *base = origin + (int64_t)cb * 32 * g.HW;
-        const int cleft = g.C - cb * 32;  // channels of this block that exist
+        const int c0 = cb * g.CH + q * 4;
+        const float *base = img + (int64_t)c0 * g.HW;
+        const int nc = g.C - c0;  // channels of this chunk that exist (<= 0: none)
+        uint8_t *hi = haloRing + (size_t)hs * haloStage + sbase;
+        bool waited = false;
 #pragma unroll
-        for (int it = 0; it < kHaloItems; ++it) {
-          const int r = rc[it] >> 16, c = rc[it] & 0xffff;
-          const bool inb = soff[it] >= 0 && (unsigned)(ih0 + r) < (unsigned)g.H && (unsigned)(iw0 + c) < (unsigned)g.W;
-          const float *q = base + goff[it];
-          const int nc = inb ? cleft - q4[it] : 0;
-          v[it].x = nc > 0 ? __ldg(q) : 0.f;
-          v[it].y = nc > 1 ? __ldg(q + g.HW) : 0.f;
-          v[it].z = nc > 2 ? __ldg(q + 2 * g.HW) : 0.f;
-          v[it].w = nc > 3 ? __ldg(q + 3 * g.HW) : 0.f;
-        }
-        mbar_wait_warp(&ctl.halo_empty[hs], hphase ^ 1);
-        uint8_t *hi = haloRing + (size_t)hs * haloStage;
-        uint8_t *lo = hi + haloBytes;
+        for (int g0 = 0; g0 < kHaloMaxPasses; g0 += kHaloGroup) {
+          if (g0 < passes) {
+            float4 v[kHaloGroup];
 #pragma unroll
-        for (int it = 0; it < kHaloItems; ++it) {
-          if (soff[it] >= 0) {
-            if (SPLIT) {
-              const float4 h = make_float4(tf32_hi(v[it].x), tf32_hi(v[it].y), tf32_hi(v[it].z), tf32_hi(v[it].w));
-              *reinterpret_cast<float4 *>(hi + soff[it]) = h;
-              *reinterpret_cast<float4 *>(lo + soff[it]) =
-                  make_float4(v[it].x - h.x, v[it].y - h.y, v[it].z - h.z, v[it].w - h.w);
-            } else {
-              *reinterpret_cast<float4 *>(hi + soff[it]) =
-                  make_float4(tf32_rna(v[it].x), tf32_rna(v[it].y), tf32_rna(v[it].z), tf32_rna(v[it].w));
+            for (int u = 0; u < kHaloGroup; ++u) {
+              const int e = pix[g0 + u];
+              const int pl = e >> 16, r = (e >> 8) & 0xff, c = e & 0xff;
+              const int ra = (g.s == 2) ? (pl >> 1) : 0, rb = (g.s == 2) ? (pl & 1) : 0;
+              const int ih = g.s * (a0 + r) + ra, iw = g.s * (b0 + c) + rb;
+              const bool inb = e >= 0 && (unsigned)ih < (unsigned)g.H && (unsigned)iw < (unsigned)g.W;
+              const float *src = base + (int64_t)ih * g.W + iw;
+              const int m = inb ? nc : 0;
+              v[u].x = m > 0 ? __ldg(src) : 0.f;
+              v[u].y = m > 1 ? __ldg(src + g.HW) : 0.f;
+              v[u].z = m > 2 ? __ldg(src + 2 * g.HW) : 0.f;
+              v[u].w = m > 3 ? __ldg(src + 3 * g.HW) : 0.f;
+            }
+            if (!waited) {
+              mbar_wait_warp(&ctl.halo_empty[hs], hphase ^ 1);
+              waited = true;
+            }
+#pragma unroll
+            for (int u = 0; u < kHaloGroup; ++u) {
+              if (pix[g0 + u] >= 0) {
+                uint8_t *d = hi + (g0 + u) * TPC * 16;
+                if (SPLIT) {
+                  const float4 h = make_float4(tf32_hi(v[u].x), tf32_hi(v[u].y), tf32_hi(v[u].z), tf32_hi(v[u].w));
+                  *reinterpret_cast<float4 *>(d) = h;
+                  *reinterpret_cast<float4 *>(d + haloBytes) =
+                      make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w);
+                } else {
+                  *reinterpret_cast<float4 *>(d) =
+                      make_float4(tf32_rna(v[u].x), tf32_rna(v[u].y), tf32_rna(v[u].z), tf32_rna(v[u].w));
+                }
+              }
             }
           }
         }
@@ -158,6 +187,12 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
     // ===================== MMA issuer: kh*kw shifted views of each staged halo =====================
     const uint32_t idesc = make_idesc(BN, false, false);
     const uint32_t halo_base = smem_u32(haloRing), b_base = smem_u32(bRing);
+    const int ksteps = g.CH >> 3;  // UMMA_K = 8 channels = two 16-byte chunks
+    // A: un-swizzled K-major (layout_type 0), LBO = next 16-byte k chunk (one plane), SBO = next 8-row group (a line)
+    const uint64_t a_base = make_desc(halo_base, (uint32_t)plane, (uint32_t)g.HC * 16u, 0);
+    const uint32_t a_kstep = (uint32_t)(2 * plane) >> 4;
+    // B: weights, SWIZZLE_128B (128-byte rows) or SWIZZLE_64B (64-byte rows)
+    const uint64_t b_desc = make_desc(b_base, 16, g.CH == 32 ? 1024u : 512u, g.CH == 32 ? 2u : 4u);
     int hs = 0, bs = 0, it = 0;
     uint32_t hphase = 0, bphase = 0;
     for (int t = blockIdx.x; t < numTiles; t += gridDim.x, ++it) {
@@ -168,30 +203,32 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols;
       for (int cb = 0; cb < g.CB; ++cb) {
         mbar_wait_warp(&ctl.halo_full[hs], hphase);
-        const uint32_t ha = halo_base + (uint32_t)hs * haloStage;
-        int kr = 0, kc = 0;
         for (int tap = 0; tap < g.kk; ++tap) {
           mbar_wait_warp(&ctl.b_full[bs], bphase);
           tc_fence_after();
+          const uint32_t shift = (uint32_t)ctl.tapoff[tap] >> 4;
           if (elect_one_sync()) {
-            const uint32_t sb = b_base + (uint32_t)bs * bStage;
-            const uint32_t shift = (uint32_t)((kr * g.dy * g.HC + kc * g.dx) << 4);
-            const uint32_t sbo = (uint32_t)g.HC * 16u;
+            // descriptors differ from the per-stage bases only in the 14-bit start-address field (16-byte units):
+            // build the bases once and add offsets — the single issuing thread is the bottleneck for small N
+            uint32_t a_lo32 = (uint32_t)a_base + (uint32_t)hs * (uint32_t)(haloStage >> 4) + shift;
+            uint32_t b_lo32 = (uint32_t)b_desc + (uint32_t)bs * (uint32_t)(bStage >> 4);
 #pragma unroll
-            for (int ks = 0; ks < BK / 8; ++ks) {
-              // un-swizzled K-major: layout_type 0, LBO = next 16-byte k chunk, SBO = next 8-row group
-              const uint64_t ah = make_desc(ha + shift + ks * 2 * plane, plane, sbo, 0);
-              const uint64_t bh = make_desc(sb + ks * 32, 16, 1024, 2);
+            for (int ks = 0; ks < 4; ++ks) {
+              if (ks >= ksteps) break;
+              const uint64_t ah = (a_base & 0xFFFFFFFF00000000ull) | a_lo32;
+              const uint64_t bh = (b_desc & 0xFFFFFFFF00000000ull) | b_lo32;
               const uint32_t acc = (cb != 0 || tap != 0 || ks != 0) ? 1u : 0u;
               if (SPLIT) {
-                const uint64_t al = make_desc(ha + haloBytes + shift + ks * 2 * plane, plane, sbo, 0);
-                const uint64_t bl = make_desc(sb + bBytes + ks * 32, 16, 1024, 2);
+                const uint64_t al = (a_base & 0xFFFFFFFF00000000ull) | (a_lo32 + (uint32_t)(haloBytes >> 4));
+                const uint64_t bl = (b_desc & 0xFFFFFFFF00000000ull) | (b_lo32 + (uint32_t)(bBytes >> 4));
                 mma_tf32(tmem_d, al, bh, idesc, acc);
                 mma_tf32(tmem_d, ah, bl, idesc, 1u);
                 mma_tf32(tmem_d, ah, bh, idesc, 1u);
               } else {
                 mma_tf32(tmem_d, ah, bh, idesc, acc);
               }
+              a_lo32 += a_kstep;
+              b_lo32 += 2;  // 32 bytes = one UMMA_K step inside the swizzled row
             }
             mma_commit(&ctl.b_empty[bs]);
             if (tap == g.kk - 1) {
@@ -201,7 +238,6 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
           }
           __syncwarp();
           if (++bs == BS) { bs = 0; bphase ^= 1; }
-          if (++kc == g.kw) { kc = 0; ++kr; }
         }
         if (++hs == HS) { hs = 0; hphase ^= 1; }
       }
@@ -219,8 +255,8 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
           mbar_wait(&ctl.b_empty[bs], bphase ^ 1);
           const uint32_t sb = b_base + (uint32_t)bs * bStage;
           mbar_arrive_expect_tx(&ctl.b_full[bs], (uint32_t)bStage);
-          tma_load_2d(sb, &tmBhi, kb * BK, nt * BN, &ctl.b_full[bs]);
-          if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, kb * BK, nt * BN, &ctl.b_full[bs]);
+          tma_load_2d(sb, &tmBhi, kb * g.CH, nt * BN, &ctl.b_full[bs]);
+          if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, kb * g.CH, nt * BN, &ctl.b_full[bs]);
           if (++bs == BS) { bs = 0; bphase ^= 1; }
         }
       }
@@ -261,20 +297,20 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, accCols * 2);
 }
 
-// weights in halo order: out[row][((cb*kk + tap)*32 + ci)] with channel = cb*32 + ci
+// weights in halo order: out[row][((cb*kk + tap)*CH + ci)] with channel = cb*CH + ci
 //   forward: W[row][channel][tap];   dgrad: W[channel][row][kk-1-tap]
 __global__ void __launch_bounds__(256) k_prepare_weights_halo(const float *__restrict__ w, int rows, int chans, int kk,
-                                                              int CB, int dgrad, float *__restrict__ hi,
+                                                              int CB, int CH, int dgrad, float *__restrict__ hi,
                                                               float *__restrict__ lo, int split) {
-  const int Kpad = kk * CB * 32;
+  const int Kpad = kk * CB * CH;
   const int64_t total = (int64_t)rows * Kpad;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
     const int r = (int)(i / Kpad);
     const int k = (int)(i - (int64_t)r * Kpad);
-    const int ci = k & 31, gq = k >> 5;
+    const int ci = k % CH, gq = k / CH;
     const int cb = gq / kk, tap = gq - cb * kk;
-    const int ch = cb * 32 + ci;
+    const int ch = cb * CH + ci;
     float v = 0.f;
     if (ch < chans)
       v = dgrad ? __ldg(w + ((int64_t)ch * rows + r) * kk + (kk - 1 - tap)) : __ldg(w + ((int64_t)r * chans + ch) * kk + tap);
@@ -288,15 +324,54 @@ __global__ void __launch_bounds__(256) k_prepare_weights_halo(const float *__res
   }
 }
 
+// K-major fp32 matrix [rows][Kpad] -> tiles of CH k x boxRows rows: SWIZZLE_128B for 128-byte rows, 64B for 64-byte
+inline int encode_weights_map_ch(CUtensorMap *tm, const float *base, int64_t rows, int64_t Kpad, int boxRows, int CH) {
+  if (CH == 32) return encode_weights_map(tm, base, rows, Kpad, boxRows);
+  EncodeTiledFn enc = get_encode_tiled();
+  TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kpad * 4};
+  cuuint32_t box[2] = {(cuuint32_t)CH, (cuuint32_t)boxRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tnn_set_error("cuTensorMapEncodeTiled (64B) failed with CUresult %d", (int)r);
+    return 6;
+  }
+  return 0;
+}
+
 // v = the forward problem computed (dgrad passes the virtual one); kNotTaken when the geometry does not fit
 inline int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const float *in, const float *weights,
                      bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate,
                      const float *residual) {
-  if (v.sy != 1 || v.sx != 1) return kNotTaken;
+  if (v.sy != v.sx || (v.sy != 1 && v.sy != 2)) return kNotTaken;
+  const int s = v.sy;
   const int kk = v.kh * v.kw;
-  if (kk < 2 || v.C < 16) return kNotTaken;
-  const int HR = kPatchH + (v.kh - 1) * v.dy, HC = kPatchW + (v.kw - 1) * v.dx;
-  if (HR * HC * 8 > kHaloItems * kProducerThreads) return kNotTaken;
+  if (kk < 2 || kk > 64 || v.C < 16) return kNotTaken;
+  // shift ranges of the taps inside a parity plane
+  int saMin = 1 << 30, saMax = -(1 << 30), sbMin = 1 << 30, sbMax = -(1 << 30);
+  for (int kr = 0; kr < v.kh; ++kr) {
+    const int sa = floor_div(kr * v.dy - v.ph, s);
+    saMin = sa < saMin ? sa : saMin;
+    saMax = sa > saMax ? sa : saMax;
+  }
+  for (int kc = 0; kc < v.kw; ++kc) {
+    const int sb = floor_div(kc * v.dx - v.pw, s);
+    sbMin = sb < sbMin ? sb : sbMin;
+    sbMax = sb > sbMax ? sb : sbMax;
+  }
+  const int HR = kPatchH + saMax - saMin, HC = kPatchW + sbMax - sbMin;
+  const int NP = s * s * HR * HC;
+  if (HR > 255 || HC > 255) return kNotTaken;
+  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  // channels per staged halo: 32 unless two stages of it do not fit next to the weight ring
+  int CH = 32;
+  if ((size_t)NP * 32 * 4 * (split ? 2 : 1) * 2 > 150 * 1024) CH = 16;
+  const int TPC = kProducerThreads / (CH / 4);
+  if ((NP + TPC - 1) / TPC > kHaloMaxPasses) return kNotTaken;
   const int PX = (v.OW + kPatchW - 1) / kPatchW, PY = (v.OH + kPatchH - 1) / kPatchH;
   const double util = (double)v.OW * v.OH / ((double)PX * kPatchW * PY * kPatchH);
   // measured on B200 (3xTF32, batch 64): 2.0x over the gathering kernel at 32->64 @208, 1.75x at 64->128 @104, 2.0x on
@@ -304,13 +379,13 @@ inline int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const
   if (util < 0.9) return kNotTaken;
   const int64_t mTiles = (int64_t)batch * PX * PY;
   if (mTiles >= (1ll << 24) || v.inImg >= (1ll << 31)) return kNotTaken;
-  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   const int64_t N = v.F;
-  int bn = N >= 128 ? 128 : (int)(((N + 15) / 16) * 16);
-  const int CB = (v.C + 31) / 32;
-  const int64_t K = (int64_t)kk * CB * 32;
-  const int haloStage = HR * HC * 128 * (split ? 2 : 1);
-  const int bStage = bn * BK * 4 * (split ? 2 : 1);
+  const int bn = N >= 128 ? 128 : (int)(((N + 15) / 16) * 16);
+  const int CB = (v.C + CH - 1) / CH;
+  const int64_t K = (int64_t)kk * CB * CH;
+  const int haloStage = NP * CH * 4 * (split ? 2 : 1);
+  const int bStage = bn * CH * 4 * (split ? 2 : 1);
+  if ((bStage % 1024) != 0) return kNotTaken;  // TMA tiles of the weight ring stay 1024-byte aligned
   int HS = 2, BS = 4;
   const int budget = 220 * 1024;
   while (BS > 2 && HS * haloStage + BS * bStage > budget) --BS;
@@ -324,16 +399,17 @@ inline int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const
   {
     int64_t blocks = cdiv64(N * K, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_prepare_weights_halo<<<(int)blocks, 256, 0, ctx->stream>>>(weights, (int)N, v.C, kk, CB, dgradWeights ? 1 : 0, whi,
-                                                                wlo, split ? 1 : 0);
+    k_prepare_weights_halo<<<(int)blocks, 256, 0, ctx->stream>>>(weights, (int)N, v.C, kk, CB, CH, dgradWeights ? 1 : 0,
+                                                                whi, wlo, split ? 1 : 0);
     TNN_LAUNCHED(ctx);
   }
   alignas(64) CUtensorMap tmHi, tmLo;
-  rc = encode_weights_map(&tmHi, whi, N, K, bn);
+  rc = encode_weights_map_ch(&tmHi, whi, N, K, bn, CH);
   if (rc) return rc;
-  rc = encode_weights_map(&tmLo, split ? wlo : whi, N, K, bn);
+  rc = encode_weights_map_ch(&tmLo, split ? wlo : whi, N, K, bn, CH);
   if (rc) return rc;
-  HaloGeom g{in, v.C, v.H, v.W, v.ph, v.pw, v.kh, v.kw, v.dy, v.dx, HR, HC, PX, PY, batch, CB, kk, v.H * v.W, v.inImg};
+  HaloGeom g{in, v.C, v.H, v.W, v.ph, v.pw, v.kh, v.kw, v.dy, v.dx, s, HR, HC, saMin, sbMin, NP, CH, PX, PY, batch, CB, kk,
+             v.H * v.W, v.inImg};
   ConvEpilogue epi{out, scale, bias, v.OH * v.OW, v.outImg, act, mTiles * BM, N, accumulate,
                    kPatchW, kPatchH, PX, PX * PY, v.OH, v.OW, batch, 7, residual};
   const int64_t numTiles = mTiles * nTiles;
