@@ -520,9 +520,10 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
     const float *rq = residual ? residual + (q - out) : nullptr;
     const bool leaky = act == TNN_ACT_LEAKY || act == TNN_ACT_REVLEAKY;
     const bool plain = rq == nullptr && !accumulate;  // warp-uniform: the common case gets a loop without loads
-    if ((leaky || act == TNN_ACT_LINEAR) && plain) {
+    if ((leaky || act == TNN_ACT_LINEAR) && plain && rowvalid && cnt == 32) {
+      // the hot loop: full chunk, nothing to read — FMUL, FADD, FMUL, FMNMX, STG and the pointer bump per column
+      // (leaky(v) = max(v, 0.1 v); linear: max(v, v))
       const float neg = leaky ? 0.1f : 1.0f;
-      const bool full = rowvalid && cnt == 32;
 #pragma unroll
       for (int j4 = 0; j4 < 32; j4 += 4) {
         const float4 s4 = *reinterpret_cast<const float4 *>(scratch + j4);
@@ -530,10 +531,8 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
         const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int j = j4 + u;
-          float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s[u]), b[u]);
-          v = v < 0 ? neg * v : v;
-          if (full || (rowvalid && j < cnt)) *q = v;
+          const float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j4 + u]), s[u]), b[u]);
+          *q = fmaxf(v, __fmul_rn(neg, v));
           q += P;
         }
       }

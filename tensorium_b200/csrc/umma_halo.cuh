@@ -21,7 +21,7 @@ namespace umma {
 constexpr int kPatchW = 8, kPatchH = 16;
 constexpr int kHaloGroup = 6;   // halo pixels a producer thread keeps in flight (loads) before it stores them
 constexpr int kHaloMaxPasses = 12;
-constexpr int kHaloMaxStages = 3, kHaloMaxBStages = 4;
+constexpr int kHaloMaxStages = 2, kHaloMaxBStages = 3;
 
 // Stride s in {1,2}: input pixel (s*a + ra, s*b + rb) lives in parity plane (ra,rb) at (a,b); tap (kr,kc) with
 // kr*dy - ph = s*sa + ra reads plane (ra,rb) shifted by (sa,sb) — a stride-1 access inside the plane.  s = 1 has
@@ -193,24 +193,26 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
     const uint32_t a_kstep = (uint32_t)(2 * plane) >> 4;
     // B: weights, SWIZZLE_128B (128-byte rows) or SWIZZLE_64B (64-byte rows)
     const uint64_t b_desc = make_desc(b_base, 16, g.CH == 32 ? 1024u : 512u, g.CH == 32 ? 2u : 4u);
-    int hs = 0, bs = 0, it = 0;
-    uint32_t hphase = 0, bphase = 0;
-    for (int t = blockIdx.x; t < numTiles; t += gridDim.x, ++it) {
-      const int as = it & 1;
-      const uint32_t use = (uint32_t)(it >> 1);
-      mbar_wait_warp(&ctl.tmem_empty[as], (use & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols;
-      for (int cb = 0; cb < g.CB; ++cb) {
-        mbar_wait_warp(&ctl.halo_full[hs], hphase);
-        for (int tap = 0; tap < g.kk; ++tap) {
-          mbar_wait_warp(&ctl.b_full[bs], bphase);
-          tc_fence_after();
-          const uint32_t shift = (uint32_t)ctl.tapoff[tap] >> 4;
-          if (elect_one_sync()) {
-            // descriptors differ from the per-stage bases only in the 14-bit start-address field (16-byte units):
-            // build the bases once and add offsets — the single issuing thread is the bottleneck for small N
-            uint32_t a_lo32 = (uint32_t)a_base + (uint32_t)hs * (uint32_t)(haloStage >> 4) + shift;
+    // ONE elected thread runs the whole issue loop (waits included): no warp-collective operation per tap, and the
+    // compiler keeps the descriptors in uniform registers
+    if (elect_one_sync()) {
+      int hs = 0, bs = 0, it = 0;
+      uint32_t hphase = 0, bphase = 0;
+      const int kk = g.kk, CB = g.CB;
+      for (int t = blockIdx.x; t < numTiles; t += gridDim.x, ++it) {
+        const int as = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait(&ctl.tmem_empty[as], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols;
+        for (int cb = 0; cb < CB; ++cb) {
+          mbar_wait(&ctl.halo_full[hs], hphase);
+          const uint32_t a_stage = (uint32_t)a_base + (uint32_t)hs * (uint32_t)(haloStage >> 4);
+          for (int tap = 0; tap < kk; ++tap) {
+            mbar_wait(&ctl.b_full[bs], bphase);
+            tc_fence_after();
+            // descriptors differ from the per-stage bases only in the 14-bit start-address field (16-byte units)
+            uint32_t a_lo32 = a_stage + ((uint32_t)ctl.tapoff[tap] >> 4);
             uint32_t b_lo32 = (uint32_t)b_desc + (uint32_t)bs * (uint32_t)(bStage >> 4);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
@@ -231,17 +233,17 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
               b_lo32 += 2;  // 32 bytes = one UMMA_K step inside the swizzled row
             }
             mma_commit(&ctl.b_empty[bs]);
-            if (tap == g.kk - 1) {
+            if (tap == kk - 1) {
               mma_commit(&ctl.halo_empty[hs]);
-              if (cb == g.CB - 1) mma_commit(&ctl.tmem_full[as]);
+              if (cb == CB - 1) mma_commit(&ctl.tmem_full[as]);
             }
+            if (++bs == BS) { bs = 0; bphase ^= 1; }
           }
-          __syncwarp();
-          if (++bs == BS) { bs = 0; bphase ^= 1; }
+          if (++hs == HS) { hs = 0; hphase ^= 1; }
         }
-        if (++hs == HS) { hs = 0; hphase ^= 1; }
       }
     }
+    __syncwarp();
   } else if (warp == kTmaWarp) {
     // ===================== TMA producer of the weight blocks: one per (channel block, tap) =====================
     if (lane == 0) {
@@ -386,11 +388,11 @@ inline int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const
   const int haloStage = NP * CH * 4 * (split ? 2 : 1);
   const int bStage = bn * CH * 4 * (split ? 2 : 1);
   if ((bStage % 1024) != 0) return kNotTaken;  // TMA tiles of the weight ring stay 1024-byte aligned
-  int HS = 2, BS = 4;
-  const int budget = 220 * 1024;
-  while (BS > 2 && HS * haloStage + BS * bStage > budget) --BS;
-  if (HS * haloStage + BS * bStage > budget) return kNotTaken;
-  if ((HS + 1) * haloStage + BS * bStage <= budget) ++HS;
+  // Two halo stages and three weight stages.  More of either is SLOWER (measured: 0.67 -> 0.78 ms at 32->64 @208
+  // with 3+4 stages, 1.02 -> 1.48 ms on the stride-2 layer with 2+8): shared memory comes out of the same 256 KB as
+  // the L1 that serves the producers' 32-byte-sector halo reads.
+  const int HS = 2, BS = 3;
+  if (HS * haloStage + BS * bStage > 220 * 1024) return kNotTaken;
   const size_t smemBytes = (size_t)HS * haloStage + (size_t)BS * bStage + 1024;
   const int nTiles = (int)cdiv64(N, bn);
   int rc = tnn_reserve_work(ctx, (size_t)N * K * sizeof(float) * 2);
