@@ -276,6 +276,11 @@ TNN_API int32_t tnn_conv2d_forward_residual(tnn_context *ctx, const tnn_conv_des
                                             const float *weights, const float *scale, const float *bias,
                                             int32_t activation, const float *residual, int64_t residualOffset,
                                             float *out, int64_t outOffset);
+/* Which kernel the last tnn_conv2d_forward* call on this context dispatched to (measurement tools attribute layer
+ * times to kernels with it): 0 none yet, 1 direct fp32 (k_conv_direct), 2 tcgen05 gathering implicit GEMM (k_umma
+ * with Im2colPixelLoader), 3 tcgen05 with TMA-fed activations (k_umma with TmaPatchLoader), 4 tcgen05 halo-tile
+ * (k_umma_halo), 5 CUDA-core implicit GEMM (simt::k_gemm, TNN_MATH_FP32). */
+TNN_API int32_t tnn_last_conv_kernel(tnn_context *ctx);
 /* backwardGPU wgrad (nConvolutionLayer.pas:1203-1232): weight_updates += sum_b delta_b * im2col(in_b)^T */
 TNN_API int32_t tnn_conv2d_backward_filter(tnn_context *ctx, const tnn_conv_desc *d, const float *in,
                                            int64_t inOffset, const float *delta, int64_t deltaOffset,

@@ -14,6 +14,7 @@ struct tnn_context {
   cudaDeviceProp prop;
   int math_mode;
   int tma_activations;  // 1: stride-1 convolutions fetch activations by TMA when the geometry allows (default)
+  int last_conv_kernel; // which kernel the last tnn_conv2d_forward took (TNN_CONV_KERNEL_*), for measurement tools
   int64_t launches;
   // scratch for two-stage reductions (partials + arrival counters), grown on demand
   float *red_partials;

@@ -203,6 +203,7 @@ int32_t tnn_conv2d_forward_residual(tnn_context *ctx, const tnn_conv_desc *d, co
   // tiny contractions (C*kh*kw <= 64) with few channels (the first layer), or any tiny contraction in FP32 mode:
   // exact-fp32 direct convolution in registers
   if (direct::supported(g) && (g.C < 16 || ctx->math_mode == TNN_MATH_FP32)) {
+    ctx->last_conv_kernel = 1;
     rc = direct::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out);
   } else {
     rc = umma::kNotTaken;
@@ -210,6 +211,7 @@ int32_t tnn_conv2d_forward_residual(tnn_context *ctx, const tnn_conv_desc *d, co
       rc = umma::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out, residual);
       if (rc != umma::kNotTaken) return rc;  // the tensor-core epilogues add the residual themselves
     }
+    ctx->last_conv_kernel = 5;
     simt::MatLoader la{weights, K, 0, true};
     simt::Im2colCols lb{in, g};
     ConvFwdEpi epi{out, scale, bias, g.OH * g.OW, g.outImg, activation};
@@ -218,6 +220,8 @@ int32_t tnn_conv2d_forward_residual(tnn_context *ctx, const tnn_conv_desc *d, co
   if (rc || !residual) return rc;
   return tnn_addvv(ctx, d->batch * g.outImg, out, 0, 1, residual, 0, 1, out, 0, 1);
 }
+
+int32_t tnn_last_conv_kernel(tnn_context *ctx) { return ctx ? ctx->last_conv_kernel : 0; }
 
 int32_t tnn_conv2d_forward(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,
                            const float *weights, const float *scale, const float *bias, int32_t activation,

@@ -1308,11 +1308,14 @@ int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const float 
 inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
                         const float *scale, const float *bias, int act, float *out, const float *residual = nullptr) {
   if (ctx->tma_activations) {
+    ctx->last_conv_kernel = 3;
     int rc = conv_patch(ctx, g, batch, in, weights, false, scale, bias, act, out, false, residual);
     if (rc != kNotTaken) return rc;
+    ctx->last_conv_kernel = 4;
     rc = conv_halo(ctx, g, batch, in, weights, false, scale, bias, act, out, false, residual);
     if (rc != kNotTaken) return rc;
   }
+  ctx->last_conv_kernel = 2;
   const int64_t M = (int64_t)batch * g.OH * g.OW;
   const int64_t N = g.F;
   const int kk = g.kh * g.kw;

@@ -352,6 +352,7 @@ inline int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const
   if (v.sy != v.sx || (v.sy != 1 && v.sy != 2)) return kNotTaken;
   const int s = v.sy;
   const int kk = v.kh * v.kw;
+  // (a 3-channel first layer was tried here too: 1.6 ms against 1.0 ms for the direct fp32 kernel)
   if (kk < 2 || kk > 64 || v.C < 16) return kNotTaken;
   // shift ranges of the taps inside a parity plane
   int saMin = 1 << 30, saMax = -(1 << 30), sbMin = 1 << 30, sbMax = -(1 << 30);

@@ -311,6 +311,12 @@ class TNNCuda:
         self._ck(self._l.tnn_conv2d_forward(self._h, C.byref(desc), _addr(in_), inOffset, _addr(weights),
                                             _addr(scale), _addr(bias), int(activation), _addr(out), outOffset))
 
+    CONV_KERNELS = {0: "none", 1: "direct::k_conv_direct", 2: "umma::k_umma<Im2colPixelLoader> (gather)",
+                    3: "umma::k_umma<TmaPatchLoader> (TMA activations)", 4: "umma::k_umma_halo", 5: "simt::k_gemm"}
+
+    def lastConvKernel(self) -> str:
+        return self.CONV_KERNELS.get(int(self._l.tnn_last_conv_kernel(self._h)), "?")
+
     def conv2dForwardResidual(self, desc, in_, inOffset, weights, scale, bias, activation, residual, residualOffset, out,
                               outOffset):
         self._ck(self._l.tnn_conv2d_forward_residual(self._h, C.byref(desc), _addr(in_), inOffset, _addr(weights),
