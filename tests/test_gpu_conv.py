@@ -163,22 +163,82 @@ def test_conv_forward_tma_activations(cuda_backend, oracle, mode, tol, geom):
     assert e1 < tol and e2 < tol, (e1, e2)
 
 
-def test_conv_tma_activations_index_exact(cuda_backend):
-    """Index-encoded input against one-hot filters: every output must be EXACTLY the input element the im2col
-    mapping names (small integers are exact in 3xTF32), so a misplaced shared-memory atom, a wrong tap shift or a
-    missing zero fill shows up as a wrong integer rather than a tolerance miss."""
+HALO_GEOMS = [  # k >= 2 on maps that fill the 16x8 patches: the halo-tile kernel (stride 1, and 2 via parity planes)
+    (2, 32, 32, 32, 32, 3, 1, 1),    # deepCIFAR10 c2
+    (2, 64, 16, 16, 64, 3, 1, 1),    # deepCIFAR10 c4: one patch row per image
+    (1, 32, 48, 40, 64, 3, 1, 1),    # YOLO-like, 3 x 5 patches
+    (2, 64, 64, 64, 128, 3, 1, 2),   # stride 2: four parity planes, 16-channel halo stages (SWIZZLE_64B weights)
+    (2, 48, 64, 48, 40, 3, 1, 2),    # stride 2, C = 48 (three 16-channel stages), ragged filter tile
+    (1, 32, 64, 64, 24, 5, 2, 2),    # 5x5 stride 2: taps shift by -1, 0, +1 inside the planes
+    (1, 20, 32, 32, 16, 3, 1, 1),    # C = 20: the channel block is zero padded to 32
+    (1, 16, 34, 34, 32, 3, 0, 1),    # no padding: output 32 x 32
+    (1, 32, 32, 24, 160, 3, 1, 1),   # two filter tiles (128 + 32): the halo is staged once per filter tile
+]
+
+
+@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32)])
+@pytest.mark.parametrize("geom", HALO_GEOMS)
+def test_conv_forward_halo_kernel(cuda_backend, oracle, mode, tol, geom):
     cu = cuda_backend
-    B, C, H, W, k, p = 2, 32, 16, 24, 3, 1
-    x = (np.arange(B * C * H * W) % 4093).astype(np.float32).reshape(B, C, H, W)
+    B, C, H, W, F, k, p, s = geom
+    rng = np.random.default_rng(sum(geom) + 11)
+    x, w, b = conv_case(rng, B, C, H, W, F, k)
+    want = oracle.conv2d(x, w, p, s, s, 1, k, k)
+    oracle.forward_bias(want, b, B)
+    oracle.activate_array(want, oracle.ACT["LEAKY"])
+    dx, dw, db, dout = Dev(cu, x), Dev(cu, w), Dev(cu, b), Dev(cu, n=want.size)
+    cu.fill(want.size, dout.ptr, 0, 777.0, 1)
+    cu.set_math_mode(mode)
+    try:
+        cu.conv2dForward(cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s), dx.ptr, 0, dw.ptr, None, db.ptr,
+                         oracle.ACT["LEAKY"], dout.ptr, 0)
+        assert "halo" in cu.lastConvKernel()  # the geometry really exercises the halo kernel
+    finally:
+        cu.set_math_mode(X3)
+    got = dout.read(want.shape)
+    e1, e2 = rel_max(got, want), rel_elem(got, want, floor=1.0)
+    assert e1 < tol and e2 < tol, (e1, e2)
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_conv_halo_index_exact(cuda_backend, stride):
+    """Index-encoded input against one-hot filters on the halo kernel: every output is EXACTLY the input element the
+    im2col mapping names (shifted descriptor views, parity planes, zero-filled borders)."""
+    cu = cuda_backend
+    B, C, H, W, k, p = 2, 32, 32, 16, 3, 1
+    c_, h_, w_ = np.meshgrid(np.arange(C), np.arange(H), np.arange(W), indexing="ij")
+    x = np.broadcast_to((c_ * 4096 + h_ * 64 + w_ + 1).astype(np.float32), (B, C, H, W)).copy()
+    x[1] += 131072.0
     taps = [(c, kr, kc) for c in (0, 5, 31) for kr in range(k) for kc in range(k)]
     F = len(taps)
     w = np.zeros((F, C, k, k), np.float32)
     for f, (c, kr, kc) in enumerate(taps):
         w[f, c, kr, kc] = 1
     xp = np.pad(x, ((0, 0), (0, 0), (p, p), (p, p)))
-    want = np.stack([xp[:, c, kr:kr + H, kc:kc + W] for (c, kr, kc) in taps], axis=1)
+    OH, OW = (H + 2 * p - k) // stride + 1, (W + 2 * p - k) // stride + 1
+    want = np.stack([xp[:, c, kr:kr + stride * (OH - 1) + 1:stride, kc:kc + stride * (OW - 1) + 1:stride]
+                     for (c, kr, kc) in taps], axis=1)
     dx, dw, dout = Dev(cu, x), Dev(cu, w), Dev(cu, n=want.size)
-    cu.conv2dForward(cu.conv_desc(B, C, H, W, F, k, k, p, p, 1, 1), dx.ptr, 0, dw.ptr, None, None, 4, dout.ptr, 0)
+    cu.conv2dForward(cu.conv_desc(B, C, H, W, F, k, k, p, p, stride, stride), dx.ptr, 0, dw.ptr, None, None, 4,
+                     dout.ptr, 0)
+    assert "halo" in cu.lastConvKernel()
+    assert np.array_equal(dout.read(want.shape), want)
+
+
+def test_conv_tma_activations_index_exact(cuda_backend):
+    """The same for the TMA-fed 1x1 path: out[f] must be EXACTLY channel c_f of the input (atoms in the right place,
+    ragged last atom zero filled)."""
+    cu = cuda_backend
+    B, C, H, W = 2, 64, 10, 12   # 120 pixels per image: 3 full atoms + one of 24
+    x = (np.arange(B * C * H * W) % 4093).astype(np.float32).reshape(B, C, H, W)
+    chans = [0, 5, 31, 32, 63]
+    w = np.zeros((len(chans), C, 1, 1), np.float32)
+    for f, c in enumerate(chans):
+        w[f, c] = 1
+    want = x[:, chans]
+    dx, dw, dout = Dev(cu, x), Dev(cu, w), Dev(cu, n=want.size)
+    cu.conv2dForward(cu.conv_desc(B, C, H, W, len(chans), 1, 1, 0, 0, 1, 1), dx.ptr, 0, dw.ptr, None, None, 4, dout.ptr, 0)
+    assert "TmaPatchLoader" in cu.lastConvKernel()
     assert np.array_equal(dout.read(want.shape), want)
 
 
