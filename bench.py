@@ -186,6 +186,9 @@ def run_ours(args, rank, world, local_rank):
     cu.set_stream(stream.cuda_stream)
     cu.set_math_mode(MATH[args.math])
     net = build_yolov3(BATCH, SIZE, seed=1234)
+    # shortcut fusion into the conv epilogue: "" (off, default), "gather" or "all".  Measured: the batched-load variant
+    # of the residual epilogue costs the un-fused kernels 1.2 ms of code-size / register pressure and wins back 0.5 ms.
+    FUSE = os.environ.get("TNN_FUSE_SHORTCUTS", "")
     x_host = torch.from_numpy(synthetic_images(BATCH, rank_seed(rank))).pin_memory()
     nbytes_in = x_host.numel() * 4
     cu.writeBuffer(net.input.devData, nbytes_in, x_host.numpy())
@@ -254,6 +257,9 @@ def run_ours(args, rank, world, local_rank):
         cu.finish()
         cu_copy.finish()
 
+    step_resident()  # first pass: every conv layer learns which kernel it dispatches to
+    if FUSE:
+        nf = net.fuseShortcuts(None if FUSE == "all" else (FUSE,))
     for _ in range(max(args.warmup, 3)):
         step_resident()
     sampler = ClockSampler(local_rank) if rank == 0 else None

@@ -143,6 +143,10 @@ class TConvolutionalLayer:
         return self._forward_reference_sequence(cu, state)
 
     def _forward_fused(self, cu, state):
+        self._forward_fused_body(cu, state)
+        self._last_kernel = cu.lastConvKernel()  # which kernel the backend dispatched to (see fuseShortcuts)
+
+    def _forward_fused_body(self, cu, state):
         training_bn = self.isBatchNormalized and state.isTraining and not state.adversarial
         if self.isBatchNormalized:
             for t in (self.scales, self.rolling_mean, self.rolling_variance):

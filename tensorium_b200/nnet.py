@@ -255,15 +255,18 @@ class TNNet:
                 out += l.gradients()
         return out
 
-    def fuseShortcuts(self):
+    def fuseShortcuts(self, only_kernels=None):
         """Inference-time graph fusion: a fused convolution whose output feeds ONLY the linear shortcut layer that
         follows adds the shortcut's other operand in its epilogue (tnn_conv2d_forward_residual) and writes the
         shortcut's output directly; the add kernel and one round trip of the tensor through HBM disappear.  Same
         arithmetic as the separate layers (one fp32 add after the activation).  Returns the number of fused pairs.
 
-        OFF by default: measured on B200 (YOLOv3-416, batch 64) the step gets slower (29.6 -> 47.6 ms) because the
-        four epilogue warps read the residual with dependent, un-prefetched loads; it needs a TMA-staged residual
-        tile before it pays."""
+        `only_kernels`: substrings of TNNCuda.lastConvKernel() — fuse only convolutions that ran on one of those
+        kernels in a PREVIOUS forward.
+
+        OFF by default.  Measured on B200 (YOLOv3-416, batch 64): with the residual read column by column the step
+        goes 29.6 -> 47.6 ms; with the loads batched 16 columns at a time the fused step is 29.3 ms but the extra
+        epilogue code costs every un-fused launch too (28.5 -> 29.7 ms).  It needs a TMA-staged residual tile."""
         used = set()  # layer outputs referenced by index from elsewhere in the graph
         for l in self.layers:
             used.update(getattr(l, "inputLayers", []))
@@ -272,7 +275,8 @@ class TNNet:
             c, sc = self.layers[i], self.layers[i + 1]
             if (isinstance(c, TConvolutionalLayer) and c.fused and isinstance(sc, TShortcutLayer)
                     and sc.ActivationType == nn.acLINEAR and i not in used and sc.inputLayers[0] < i
-                    and sc.output.Size() == c.output.Size()):
+                    and sc.output.Size() == c.output.Size()
+                    and (only_kernels is None or any(k in getattr(c, "_last_kernel", "") for k in only_kernels))):
                 c._residual = self.layers[sc.inputLayers[0]].output
                 c._fused_out = sc.output
                 sc._fused_into_conv = True
