@@ -186,8 +186,9 @@ def run_ours(args, rank, world, local_rank):
     cu.set_stream(stream.cuda_stream)
     cu.set_math_mode(MATH[args.math])
     net = build_yolov3(BATCH, SIZE, seed=1234)
-    # shortcut fusion into the conv epilogue: "" (off, default), "gather" or "all".  Measured: the batched-load variant
-    # of the residual epilogue costs the un-fused kernels 1.2 ms of code-size / register pressure and wins back 0.5 ms.
+    # shortcut fusion into the conv epilogue: "" (off, default), "gather" or "all".  Measured (B200, batch 64): 27.7 ms
+    # un-fused, 28.0 ms with the MMA-bound gathering layers fused, 28.9 ms with all 23 fused — the residual read in
+    # the four epilogue warps costs what the separate add kernels cost, so it stays off.
     FUSE = os.environ.get("TNN_FUSE_SHORTCUTS", "")
     x_host = torch.from_numpy(synthetic_images(BATCH, rank_seed(rank))).pin_memory()
     nbytes_in = x_host.numel() * 4

@@ -476,7 +476,10 @@ struct TmaPatchLoader {
 __device__ __noinline__ float act_out_of_line(float v, int a) { return tnn_act(v, a); }
 
 // Row context per thread (its TMEM lane = row m), then one call per column.
-struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
+// EXTRA = false: the lean instantiation for plain forward convolutions (no residual, no accumulation) — the kernel
+// is sensitive to epilogue code size, so the rarely used paths live in their own instantiation
+template <bool EXTRA>
+struct ConvEpilogueT {  // out[b][f][p] = act(acc*scale[f] + bias[f])
   float *out;
   const float *scale, *bias;
   int P;
@@ -519,7 +522,7 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
     float *q = r.q + n * P;
     const float *rq = residual ? residual + (q - out) : nullptr;
     const bool leaky = act == TNN_ACT_LEAKY || act == TNN_ACT_REVLEAKY;
-    const bool plain = rq == nullptr && !accumulate;  // warp-uniform: the common case gets a loop without loads
+    const bool plain = !EXTRA || (rq == nullptr && !accumulate);  // the common case gets a loop without loads
     if ((leaky || act == TNN_ACT_LINEAR) && plain && rowvalid && cnt == 32) {
       // the hot loop: full chunk, nothing to read — FMUL, FADD, FMUL, FMNMX, STG and the pointer bump per column
       // (leaky(v) = max(v, 0.1 v); linear: max(v, v))
@@ -536,21 +539,35 @@ struct ConvEpilogue {  // out[b][f][p] = act(acc*scale[f] + bias[f])
           q += P;
         }
       }
-    } else if (leaky || act == TNN_ACT_LINEAR) {
+    } else if (EXTRA && (leaky || act == TNN_ACT_LINEAR)) {
+      // residual add (the shortcut that follows) and/or accumulation into the output (dgrad): fetch the operands of
+      // 16 columns FIRST so the loads are in flight together — two memory round trips per chunk instead of 32
       const float neg = leaky ? 0.1f : 1.0f;
+      const bool both = rq != nullptr && accumulate;
 #pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        const float4 s4 = *reinterpret_cast<const float4 *>(scratch + j4);
-        const float4 b4 = *reinterpret_cast<const float4 *>(scratch + 32 + j4);
-        const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+      for (int h = 0; h < 32; h += 16) {
+        float ex[16];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int j = j4 + u;
-          float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s[u]), b[u]);
-          v = v < 0 ? neg * v : v;
-          if (rowvalid && j < cnt) {
-            if (rq) v = __fadd_rn(v, __ldg(rq + (int64_t)j * P));
-            q[(int64_t)j * P] = accumulate ? q[(int64_t)j * P] + v : v;
+        for (int j = 0; j < 16; ++j) {
+          const bool on = rowvalid && (h + j) < cnt;
+          const float *src = rq ? rq + (int64_t)(h + j) * P : q + (int64_t)(h + j) * P;
+          ex[j] = (on && (rq || accumulate)) ? *src : 0.f;   // the residual if there is one, else the old output
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 16; j4 += 4) {
+          const float4 s4 = *reinterpret_cast<const float4 *>(scratch + h + j4);
+          const float4 b4 = *reinterpret_cast<const float4 *>(scratch + 32 + h + j4);
+          const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = h + j4 + u;
+            float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), s[u]), b[u]);
+            v = fmaxf(v, __fmul_rn(neg, v));
+            v = __fadd_rn(v, ex[j4 + u]);                       // + residual, or + old output
+            if (rowvalid && j < cnt) {
+              float *dst = q + (int64_t)j * P;
+              *dst = both ? __fadd_rn(*dst, v) : v;             // residual AND accumulate: re-read the old value
+            }
           }
         }
       }
@@ -1294,8 +1311,13 @@ inline int conv_patch(tnn_context *ctx, const simt::ConvGeom &v, int batch, cons
   if (rc) return rc;
   TmaPatchLoader la{TW, TH, WT, HT, WT * HT, (int)numAtoms, batch, flat ? 0 : v.ph, flat ? 0 : v.pw, v.kw, v.dy, v.dx, CB};
   TmaWeightsLoader lb{};
-  ConvEpilogue epi{out, scale, bias, v.OH * v.OW, v.outImg, act, M, N, accumulate,
-                   TW, TH, WT, WT * HT, (int)OHe, (int)OWe, batch, 5, residual};
+  if (accumulate || residual) {
+    ConvEpilogueT<true> epi{out, scale, bias, v.OH * v.OW, v.outImg, act, M, N, accumulate,
+                            TW, TH, WT, WT * HT, (int)OHe, (int)OWe, batch, 5, residual};
+    return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo, &tmA) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo, &tmA);
+  }
+  ConvEpilogueT<false> epi{out, scale, bias, v.OH * v.OW, v.outImg, act, M, N, false,
+                           TW, TH, WT, WT * HT, (int)OHe, (int)OWe, batch, 5, nullptr};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo, &tmA) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo, &tmA);
 }
 
@@ -1342,7 +1364,11 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   if (rc) return rc;
   Im2colPixelLoader la{in, g, M, g.H * g.W, kk};
   TmaWeightsLoader lb{};
-  ConvEpilogue epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, residual};
+  if (residual) {
+    ConvEpilogueT<true> epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, residual};
+    return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
+  }
+  ConvEpilogueT<false> epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, nullptr};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
 }
 
@@ -1388,7 +1414,7 @@ inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int bat
   if (rc) return rc;
   Im2colPixelLoader la{delta, v, M, v.H * v.W, kk};
   TmaWeightsLoader lb{};
-  ConvEpilogue epi{in_delta, nullptr, nullptr, v.OH * v.OW, v.outImg, TNN_ACT_LINEAR, M, N, true, 0, 0, 0, 0, 0, 0, 0, 0, nullptr};
+  ConvEpilogueT<true> epi{in_delta, nullptr, nullptr, v.OH * v.OW, v.outImg, TNN_ACT_LINEAR, M, N, true, 0, 0, 0, 0, 0, 0, 0, 0, nullptr};
   return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
 }
 

@@ -49,9 +49,9 @@ struct HaloCtl {
 
 __host__ __device__ inline int floor_div(int a, int b) { return (a >= 0) ? a / b : -((-a + b - 1) / b); }
 
-template <bool SPLIT>
+template <bool SPLIT, bool EXTRA>
 __global__ void __launch_bounds__(kThreads, 1)
-k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS, int BS, uint32_t accCols,
+k_umma_halo(HaloGeom g, ConvEpilogueT<EXTRA> epi, int mTiles, int nTiles, int BN, int HS, int BS, uint32_t accCols,
             const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ HaloCtl ctl;
@@ -274,7 +274,7 @@ k_umma_halo(HaloGeom g, ConvEpilogue epi, int mTiles, int nTiles, int BN, int HS
       const int64_t m = (int64_t)mt * BM + quad * 32 + lane;
       const int64_t n0 = (int64_t)nt * BN;
       bool mvalid;
-      ConvEpilogue::Row rcx = epi.row(m, mvalid);
+      typename ConvEpilogueT<EXTRA>::Row rcx = epi.row(m, mvalid);
       mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
@@ -413,14 +413,22 @@ inline int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const
   if (rc) return rc;
   HaloGeom g{in, v.C, v.H, v.W, v.ph, v.pw, v.kh, v.kw, v.dy, v.dx, s, HR, HC, saMin, sbMin, NP, CH, PX, PY, batch, CB, kk,
              v.H * v.W, v.inImg};
-  ConvEpilogue epi{out, scale, bias, v.OH * v.OW, v.outImg, act, mTiles * BM, N, accumulate,
-                   kPatchW, kPatchH, PX, PX * PY, v.OH, v.OW, batch, 7, residual};
   const int64_t numTiles = mTiles * nTiles;
   const int64_t sms = ctx->prop.multiProcessorCount;
   const int grid = (int)(numTiles < sms ? numTiles : sms);
-  auto kern = split ? k_umma_halo<true> : k_umma_halo<false>;
-  TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-  kern<<<grid, kThreads, smemBytes, ctx->stream>>>(g, epi, (int)mTiles, nTiles, bn, HS, BS, pow2_cols(bn), tmHi, tmLo);
+  if (accumulate || residual) {
+    ConvEpilogueT<true> epi{out, scale, bias, v.OH * v.OW, v.outImg, act, mTiles * BM, N, accumulate,
+                            kPatchW, kPatchH, PX, PX * PY, v.OH, v.OW, batch, 7, residual};
+    auto kern = split ? k_umma_halo<true, true> : k_umma_halo<false, true>;
+    TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    kern<<<grid, kThreads, smemBytes, ctx->stream>>>(g, epi, (int)mTiles, nTiles, bn, HS, BS, pow2_cols(bn), tmHi, tmLo);
+  } else {
+    ConvEpilogueT<false> epi{out, scale, bias, v.OH * v.OW, v.outImg, act, mTiles * BM, N, false,
+                             kPatchW, kPatchH, PX, PX * PY, v.OH, v.OW, batch, 7, nullptr};
+    auto kern = split ? k_umma_halo<true, false> : k_umma_halo<false, false>;
+    TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+    kern<<<grid, kThreads, smemBytes, ctx->stream>>>(g, epi, (int)mTiles, nTiles, bn, HS, BS, pow2_cols(bn), tmHi, tmLo);
+  }
   TNN_LAUNCHED(ctx);
   return 0;
 }

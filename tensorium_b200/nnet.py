@@ -264,9 +264,10 @@ class TNNet:
         `only_kernels`: substrings of TNNCuda.lastConvKernel() — fuse only convolutions that ran on one of those
         kernels in a PREVIOUS forward.
 
-        OFF by default.  Measured on B200 (YOLOv3-416, batch 64): with the residual read column by column the step
-        goes 29.6 -> 47.6 ms; with the loads batched 16 columns at a time the fused step is 29.3 ms but the extra
-        epilogue code costs every un-fused launch too (28.5 -> 29.7 ms).  It needs a TMA-staged residual tile."""
+        OFF by default.  Measured on B200 (YOLOv3-416, batch 64): 27.7 ms un-fused, 28.0 ms with the gathering-kernel
+        layers fused, 28.9 ms with all fused (residual loads batched 16 columns at a time; column by column it was
+        47.6 ms).  The read costs the four epilogue warps what the separate add kernels cost; it would take a
+        TMA-staged residual tile to win."""
         used = set()  # layer outputs referenced by index from elsewhere in the graph
         for l in self.layers:
             used.update(getattr(l, "inputLayers", []))
