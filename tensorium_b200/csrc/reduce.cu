@@ -124,6 +124,26 @@ inline int64_t block_size(int64_t total, int64_t channels, int64_t groups) {
 
 extern "C" {
 
+// block size 1 (connected layers: src is [batch][channels]): a column sum — 32 channels x 8 batch slices per CTA, reads
+// coalesced along the channels, slices folded in a fixed order (deterministic)
+__global__ void __launch_bounds__(256) k_column_sum(const float *__restrict__ src, int64_t channels, int64_t batch,
+                                                    float *__restrict__ dst) {
+  __shared__ float part[8][33];
+  const int cx = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int64_t c = (int64_t)blockIdx.x * 32 + cx;
+  float a = 0.f;
+  if (c < channels)
+    for (int64_t b = sl; b < batch; b += 8) a += src[b * channels + c];
+  part[sl][cx] = a;
+  __syncthreads();
+  if (sl == 0 && c < channels) {
+    float t = part[0][cx];
+#pragma unroll
+    for (int i = 1; i < 8; ++i) t += part[i][cx];
+    dst[c] = dst[c] + t;
+  }
+}
+
 // backwardBias nncuda.pas:602-622; CPU twin addSums ntensors.pas:7729-7781: dst[f] += sum_{b,block} src
 int32_t tnn_backward_bias(tnn_context *ctx, int64_t dstSize, float *dst, int64_t srcSize, const float *src,
                           int64_t srcOffset, int64_t incb, int64_t batch) {
@@ -132,6 +152,11 @@ int32_t tnn_backward_bias(tnn_context *ctx, int64_t dstSize, float *dst, int64_t
   const int64_t bs = block_size(srcSize, dstSize, batch);
   TNN_REQUIRE(bs > 0, "tensor sizes do not align");
   const float *s = src + srcOffset;
+  if (bs == 1 && dstSize >= 32) {
+    k_column_sum<<<(unsigned)((dstSize + 31) / 32), 256, 0, ctx->stream>>>(s, dstSize, batch, dst);
+    TNN_LAUNCHED(ctx);
+    return 0;
+  }
   return launch_reduce<1>(
       ctx, dstSize, batch, bs, [s] __device__(int64_t i, int, float(&a)[1]) { a[0] += s[i]; },
       [dst] __device__(int c, const float(&t)[1]) { dst[c] = dst[c] + t[0]; });

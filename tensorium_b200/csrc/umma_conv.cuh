@@ -1151,8 +1151,12 @@ template <typename LA, typename LB>
 int gemm_launch(tnn_context *ctx, LA la, LB lb, int64_t M, int64_t N, int64_t Ktot, float alpha, float beta, float *C,
                 int64_t ldc, bool allowSplitK) {
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
-  Plan p = make_plan(ctx, M, N, Ktot, split, LB::kMnMajor, allowSplitK && beta == 1.0f);
+  // split-K needs C += partial sums: natural for beta = 1; for beta = 0 a contiguous C is zeroed first (few-tile GEMMs
+  // like the connected layers' batch x outputs products would otherwise run on a handful of SMs)
+  const bool zeroFirst = beta == 0.0f && ldc == N;
+  Plan p = make_plan(ctx, M, N, Ktot, split, LB::kMnMajor, allowSplitK && (beta == 1.0f || zeroFirst));
   if (p.sched.kSplits > 1) {
+    if (beta == 0.0f) TNN_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), ctx->stream));
     GemmAtomicEpilogue epi{C, ldc, alpha, beta, M, N};
     return split ? launch<true>(ctx, p, la, lb, epi) : launch<false>(ctx, p, la, lb, epi);
   }
