@@ -7,6 +7,7 @@
 #include "umma_conv.cuh"
 #include "conv_direct.cuh"
 #include "umma_halo.cuh"
+#include "umma_wgrad.cuh"
 
 namespace {
 
@@ -240,6 +241,10 @@ int32_t tnn_conv2d_backward_filter(tnn_context *ctx, const tnn_conv_desc *d, con
   const int64_t N = (int64_t)g.C * g.kh * g.kw;
   const int64_t Kt = d->batch * (int64_t)g.OH * g.OW;
   if (ctx->math_mode != TNN_MATH_FP32) {
+    if (ctx->tma_activations) {  // (the same A/B switch as the forward kernels: 0 keeps the round-1 gathering GEMM)
+      rc = umma::conv_wgrad_tiles(ctx, g, (int)d->batch, in, delta, weight_updates);
+      if (rc != umma::kNotTaken) return rc;
+    }
     rc = umma::conv_backward_filter(ctx, g, (int)d->batch, in, delta, weight_updates);
     if (rc != umma::kNotTaken) return rc;
   }

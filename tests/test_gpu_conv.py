@@ -247,6 +247,10 @@ BWD_GEOMS = GEOMS[:6] + [
     (4, 64, 16, 16, 64, 3, 1, 1),    # deepCIFAR10 c4 shape
     (2, 128, 8, 8, 128, 3, 1, 1),    # deepCIFAR10 c6 shape (P = 64)
     (4, 16, 12, 12, 40, 1, 0, 1),    # 1x1, P = 144 (not a multiple of 32: CUDA-core wgrad)
+    (2, 48, 16, 16, 160, 3, 1, 1),   # tile wgrad: two channel blocks (32 + 16), two filter tiles (128 + 32)
+    (1, 16, 12, 16, 24, 3, 1, 1),    # tile wgrad: 2 x 16 pixel tiles, half-empty channel block
+    (2, 32, 8, 8, 16, 1, 0, 1),      # tile wgrad of a 1x1 convolution (one tap, 4 x 8 tiles)
+    (1, 24, 16, 32, 40, 2, 0, 1),    # 2x2 kernel, no padding: output 15 x 31 (not tileable: split-K GEMM wgrad)
 ]
 
 
