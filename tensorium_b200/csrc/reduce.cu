@@ -152,7 +152,7 @@ int32_t tnn_backward_bias(tnn_context *ctx, int64_t dstSize, float *dst, int64_t
   const int64_t bs = block_size(srcSize, dstSize, batch);
   TNN_REQUIRE(bs > 0, "tensor sizes do not align");
   const float *s = src + srcOffset;
-  if (bs == 1 && dstSize >= 32) {
+  if (bs == 1) {
     k_column_sum<<<(unsigned)((dstSize + 31) / 32), 256, 0, ctx->stream>>>(s, dstSize, batch, dst);
     TNN_LAUNCHED(ctx);
     return 0;
@@ -292,15 +292,8 @@ int32_t tnn_yolo_activate(tnn_context *ctx, int64_t batch, int64_t n, int64_t cl
                                 });
 }
 
-// rolling = (1-m)*rolling + m*stat  (nbaselayer.pas:590-608: scale then axpy, separately rounded)
-__global__ void k_rolling(int64_t n, float *rm, const float *mean, float *rv, const float *var, float m) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  rm[i] = __fadd_rn(__fmul_rn(m, mean[i]), __fmul_rn(1 - m, rm[i]));
-  rv[i] = __fadd_rn(__fmul_rn(m, var[i]), __fmul_rn(1 - m, rv[i]));
-}
-
-// training batchNormGPU (nbaselayer.pas:583-643) + ActivateArray: 2 reduction reads + 1 read / 3 writes
+// training batchNormGPU (nbaselayer.pas:583-643) + ActivateArray: 1 reduction read + 1 read / 3 writes; the rolling
+// averages follow nbaselayer.pas:590-608 (scale then axpy, separately rounded)
 int32_t tnn_batchnorm_forward_training(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize,
                                        float *out, float *x, float *x_norm, float *mean, float *variance,
                                        float *rolling_mean, float *rolling_variance, float bn_momentum,
@@ -308,11 +301,30 @@ int32_t tnn_batchnorm_forward_training(tnn_context *ctx, int64_t batch, int64_t 
   TNN_CHECK_CTX(ctx);
   TNN_REQUIRE(activation == TNN_ACT_LINEAR || tnn_act_is_elementwise(activation), "activation not elementwise");
   const int64_t total = batch * channels * blockSize;
-  int rc = tnn_means_and_vars(ctx, total, channels, batch, out, 0, mean, variance);
+  // Statistics in ONE read: sums of d = x - s and d*d, with s = the channel's first element as the shift (so the
+  // subtraction in  var = (sum d^2 - (sum d)^2/N)/(N-1)  cancels little), finished in double; the rolling averages
+  // are updated by the same finaliser.  (The reference reads the tensor twice: MeansAndVars ntensors.pas:9102-9177.)
+  const float *src = out;
+  const double S = (double)(batch * blockSize);
+  const float m = bn_momentum;
+  int rc = launch_reduce<2>(
+      ctx, channels, batch, blockSize,
+      [src, blockSize] __device__(int64_t i, int c, float(&acc)[2]) {
+        const float d = src[i] - __ldg(src + (int64_t)c * blockSize);
+        acc[0] += d;
+        acc[1] = fmaf(d, d, acc[1]);
+      },
+      [src, blockSize, mean, variance, rolling_mean, rolling_variance, S, m] __device__(int c, const float(&t)[2]) {
+        const double sd = (double)t[0], sq = (double)t[1];
+        const float mu = (float)((double)src[(int64_t)c * blockSize] + sd / S);
+        double var = (sq - sd * sd / S) / (S - 1.0);
+        const float v = (float)(var > 0.0 ? var : 0.0);
+        mean[c] = mu;
+        variance[c] = v;
+        rolling_mean[c] = __fadd_rn(__fmul_rn(m, mu), __fmul_rn(1 - m, rolling_mean[c]));
+        rolling_variance[c] = __fadd_rn(__fmul_rn(m, v), __fmul_rn(1 - m, rolling_variance[c]));
+      });
   if (rc) return rc;
-  k_rolling<<<(int)cdiv64(channels, 256), 256, 0, ctx->stream>>>(channels, rolling_mean, mean, rolling_variance,
-                                                                variance, bn_momentum);
-  TNN_LAUNCHED(ctx);
   const int a = activation;
   const bool block1 = blockSize == 1;
   return planemap::launch<0, 2>(

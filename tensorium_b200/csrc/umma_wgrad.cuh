@@ -218,7 +218,7 @@ inline int conv_wgrad_tiles(tnn_context *ctx, const simt::ConvGeom &g, int batch
                             float *weight_updates) {
   if (g.sy != 1 || g.sx != 1) return kNotTaken;
   const int kk = g.kh * g.kw;
-  if (kk * kWgBRows > 512 || g.C < 8) return kNotTaken;                       // one 32-column accumulator per tap
+  if (kk * kWgBRows > 512) return kNotTaken;                                  // one 32-column accumulator per tap
   if ((g.OW % 4) != 0 || (((uintptr_t)delta) & 15) != 0) return kNotTaken;    // 16-byte delta chunks
   int TW = 0;
   for (int tw = 32; tw >= 8; tw >>= 1)
