@@ -107,6 +107,21 @@ TNN_API int32_t tnn_event_create(tnn_context *ctx, tnn_event **ev);
 TNN_API int32_t tnn_event_record(tnn_context *ctx, tnn_event *ev);       /* after all work queued on ctx so far */
 TNN_API int32_t tnn_stream_wait_event(tnn_context *ctx, tnn_event *ev);  /* later work on ctx waits for ev    */
 TNN_API int32_t tnn_event_destroy(tnn_event *ev);
+TNN_API int32_t tnn_event_synchronize(tnn_event *ev);                    /* the HOST waits for ev            */
+/* CUDA-graph capture of everything queued on the context's stream between begin and end (launch-bound inner loops:
+ * a CIFAR training step is ~110 small kernels).  No allocation may happen while capturing: run the step once eagerly
+ * first so the scratch buffers have their final size.  tnn_graph_launch replays the captured launches. */
+typedef struct tnn_graph tnn_graph;
+TNN_API int32_t tnn_graph_begin_capture(tnn_context *ctx);
+TNN_API int32_t tnn_graph_end_capture(tnn_context *ctx, tnn_graph **graph);
+TNN_API int32_t tnn_graph_launch(tnn_context *ctx, tnn_graph *graph);
+TNN_API int32_t tnn_graph_destroy(tnn_graph *graph);
+/* a 64-bit device counter for values that must change between replays of a graph (dropout seeds): *ctr += inc */
+TNN_API int32_t tnn_counter_add(tnn_context *ctx, uint64_t *ctr, uint64_t inc);
+/* page-locked host memory for tnn_write_buffer_async / tnn_read_buffer_async (a pageable source makes the "async"
+ * copy synchronous); freed with tnn_host_free */
+TNN_API int32_t tnn_host_alloc(tnn_context *ctx, int64_t bytes, void **host);
+TNN_API int32_t tnn_host_free(tnn_context *ctx, void *host);
 
 /* ------------------------------------------------------------------ activations (nncuda.pas:524-580) */
 /* ActivateArray(N, x, offset, activation): in place; no-op for acLINEAR.  CPU twin: activate_array nactivation.pas:508-621 */
@@ -209,6 +224,9 @@ TNN_API int32_t tnn_upsample(tnn_context *ctx, int64_t aBatch, int64_t aChannels
 /* forwardDropout / backwardDropout nncuda.pas:1512-1538; `seed` replaces the wrapper's random($10000000) */
 TNN_API int32_t tnn_forward_dropout(tnn_context *ctx, int64_t N, const float *src, float probability, float scale,
                                     float *rnd, float *dst, uint64_t seed);
+/* the same with the seed read on the device: seed = *seed_dev + seed_offset (graph replays) */
+TNN_API int32_t tnn_forward_dropout_dev(tnn_context *ctx, int64_t N, const float *src, float probability, float scale,
+                                        float *rnd, float *dst, const uint64_t *seed_dev, uint64_t seed_offset);
 TNN_API int32_t tnn_backward_dropout(tnn_context *ctx, int64_t N, const float *src, float probability, float scale,
                                      const float *rnd, float *dst);
 

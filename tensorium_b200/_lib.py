@@ -48,6 +48,15 @@ SIGNATURES = {
     "tnn_event_record": (i32, [ctxp, vp]),
     "tnn_stream_wait_event": (i32, [ctxp, vp]),
     "tnn_event_destroy": (i32, [vp]),
+    "tnn_event_synchronize": (i32, [vp]),
+    "tnn_graph_begin_capture": (i32, [ctxp]),
+    "tnn_graph_end_capture": (i32, [ctxp, C.POINTER(vp)]),
+    "tnn_graph_launch": (i32, [ctxp, vp]),
+    "tnn_graph_destroy": (i32, [vp]),
+    "tnn_counter_add": (i32, [ctxp, vp, C.c_uint64]),
+    "tnn_forward_dropout_dev": (i32, [ctxp, i64, fptr, f32, f32, fptr, fptr, vp, C.c_uint64]),
+    "tnn_host_alloc": (i32, [ctxp, i64, C.POINTER(vp)]),
+    "tnn_host_free": (i32, [ctxp, vp]),
     "tnn_activate_array": (i32, [ctxp, i64, fptr, i64, i32]),
     "tnn_activate_array_swish": (i32, [ctxp, i64, fptr, i64, fptr, fptr]),
     "tnn_derive_array": (i32, [ctxp, i64, fptr, i64, i32, fptr]),

@@ -209,6 +209,81 @@ int32_t tnn_event_destroy(tnn_event *ev) {
   return 0;
 }
 
+struct tnn_graph {
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  int64_t launches;  // kernel launches captured (tnn_launch_count advances by this much per replay)
+};
+
+int32_t tnn_graph_begin_capture(tnn_context *ctx) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(!ctx->capturing, "already capturing");
+  TNN_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+  ctx->capturing = 1;
+  ctx->capture_launches0 = ctx->launches;
+  return 0;
+}
+
+int32_t tnn_graph_end_capture(tnn_context *ctx, tnn_graph **graph) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(ctx->capturing && graph != nullptr, "not capturing");
+  ctx->capturing = 0;
+  tnn_graph *g = new tnn_graph();
+  g->launches = ctx->launches - ctx->capture_launches0;
+  ctx->launches = ctx->capture_launches0;  // nothing ran yet
+  cudaError_t e = cudaStreamEndCapture(ctx->stream, &g->graph);
+  if (e == cudaSuccess) e = cudaGraphInstantiate(&g->exec, g->graph, 0);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    delete g;
+    tnn_set_error("graph capture failed: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  *graph = g;
+  return 0;
+}
+
+int32_t tnn_graph_launch(tnn_context *ctx, tnn_graph *graph) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(graph != nullptr, "null graph");
+  TNN_CUDA(cudaGraphLaunch(graph->exec, ctx->stream));
+  ctx->launches += graph->launches;
+  return 0;
+}
+
+int32_t tnn_graph_destroy(tnn_graph *graph) {
+  if (graph) {
+    cudaGraphExecDestroy(graph->exec);
+    cudaGraphDestroy(graph->graph);
+    delete graph;
+  }
+  return 0;
+}
+
+int32_t tnn_event_synchronize(tnn_event *ev) {
+  if (!ev) {
+    tnn_set_error("tnn_event_synchronize: null event");
+    return 1;
+  }
+  TNN_CUDA(cudaEventSynchronize(ev->ev));
+  return 0;
+}
+
+int32_t tnn_host_alloc(tnn_context *ctx, int64_t bytes, void **host) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(host != nullptr && bytes > 0, "bad arguments");
+  *host = nullptr;
+  TNN_CUDA(cudaSetDevice(ctx->device));
+  TNN_CUDA(cudaHostAlloc(host, (size_t)bytes, cudaHostAllocDefault));
+  return 0;
+}
+
+int32_t tnn_host_free(tnn_context *ctx, void *host) {
+  TNN_CHECK_CTX(ctx);
+  if (host) TNN_CUDA(cudaFreeHost(host));
+  return 0;
+}
+
 int32_t tnn_finish(tnn_context *ctx) {
   TNN_CHECK_CTX(ctx);
   TNN_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -218,6 +293,8 @@ int32_t tnn_finish(tnn_context *ctx) {
 }  // extern "C"
 
 int tnn_reserve_reduction(tnn_context *ctx, size_t partial_floats, size_t counters) {
+  TNN_REQUIRE(!ctx->capturing || (ctx->red_partials_bytes >= partial_floats * sizeof(float) && ctx->red_counters_n >= counters),
+              "scratch buffer would grow during graph capture: run the step once eagerly first");
   if (ctx->red_partials_bytes < partial_floats * sizeof(float)) {
     // the old buffer may still be in use by kernels queued on the stream
     TNN_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -241,6 +318,7 @@ int tnn_reserve_reduction(tnn_context *ctx, size_t partial_floats, size_t counte
 
 int tnn_reserve_work(tnn_context *ctx, size_t bytes) {
   if (ctx->work_bytes < bytes) {
+    TNN_REQUIRE(!ctx->capturing, "scratch buffer would grow during graph capture: run the step once eagerly first");
     TNN_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->work) TNN_CUDA(cudaFree(ctx->work));
     ctx->work = nullptr;

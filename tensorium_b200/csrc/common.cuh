@@ -16,6 +16,8 @@ struct tnn_context {
   int tma_activations;  // 1: stride-1 convolutions fetch activations by TMA when the geometry allows (default)
   int last_conv_kernel; // which kernel the last tnn_conv2d_forward took (TNN_CONV_KERNEL_*), for measurement tools
   int64_t launches;
+  int capturing;              // between tnn_graph_begin_capture and tnn_graph_end_capture
+  int64_t capture_launches0;
   // scratch for two-stage reductions (partials + arrival counters), grown on demand
   float *red_partials;
   size_t red_partials_bytes;

@@ -367,6 +367,23 @@ __global__ void k_dropout_fwd(int64_t n, uint64_t seed, float probability, float
     dst[i] = r < probability ? 0.f : src[i] * scale;
   }
 }
+__global__ void k_dropout_fwd_dev(int64_t n, const unsigned long long *seed_dev, unsigned long long off, float probability,
+                                  float scale, const float *src, float *rnd, float *dst) {
+  const unsigned long long seed = *seed_dev + off;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads) {
+    unsigned long long x = seed + (unsigned long long)i;
+    x ^= x >> 12;
+    x ^= x << 25;
+    x ^= x >> 27;
+    x *= 0x2545F4914F6CDD1DULL;
+    float r = (float)(x % 0x10000000ull);
+    r /= (float)0x10000000ull;
+    rnd[i] = r;
+    dst[i] = r < probability ? 0.f : src[i] * scale;
+  }
+}
+__global__ void k_counter_add(unsigned long long *ctr, unsigned long long inc) { *ctr += inc; }
 __global__ void k_dropout_bwd(int64_t n, float probability, float scale, const float *src, const float *rnd,
                               float *dst) {
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -378,6 +395,23 @@ int32_t tnn_forward_dropout(tnn_context *ctx, int64_t N, const float *src, float
   TNN_CHECK_CTX(ctx);
   if (N <= 0) return 0;
   k_dropout_fwd<<<grid_for(N, kThreads), kThreads, 0, ctx->stream>>>(N, seed, probability, scale, src, rnd, dst);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+int32_t tnn_forward_dropout_dev(tnn_context *ctx, int64_t N, const float *src, float probability, float scale,
+                                float *rnd, float *dst, const uint64_t *seed_dev, uint64_t seed_offset) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(seed_dev != nullptr, "null seed pointer");
+  if (N <= 0) return 0;
+  k_dropout_fwd_dev<<<grid_for(N, kThreads), kThreads, 0, ctx->stream>>>(
+      N, (const unsigned long long *)seed_dev, (unsigned long long)seed_offset, probability, scale, src, rnd, dst);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+int32_t tnn_counter_add(tnn_context *ctx, uint64_t *ctr, uint64_t inc) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(ctr != nullptr, "null counter");
+  k_counter_add<<<1, 1, 0, ctx->stream>>>((unsigned long long *)ctr, (unsigned long long)inc);
   TNN_LAUNCHED(ctx);
   return 0;
 }

@@ -55,7 +55,15 @@ __global__ void __launch_bounds__(kRT) k_channel_reduce(int64_t channels, int64_
   for (int k = 0; k < NACC; ++k) a[k] = 0.f;
   for (int64_t b = b0; b < b1; ++b) {
     const int64_t base = (b * channels + c) * blockSize;
-    for (int64_t r = r0 + threadIdx.x; r < r1; r += kRT) acc(base + r, c, a);
+    int64_t r = r0 + threadIdx.x;
+    // four independent elements per trip: the loads of one trip are in flight together
+    for (; r + 3 * kRT < r1; r += 4 * kRT) {
+      acc(base + r, c, a);
+      acc(base + r + kRT, c, a);
+      acc(base + r + 2 * kRT, c, a);
+      acc(base + r + 3 * kRT, c, a);
+    }
+    for (; r < r1; r += kRT) acc(base + r, c, a);
   }
   __shared__ float sm[NACC][kRT / 32];
   __shared__ bool is_last;

@@ -140,6 +140,48 @@ class TNNCuda:
     def waitEvent(self, ev: int):
         self._ck(self._l.tnn_stream_wait_event(self._h, C.c_void_p(ev)))
 
+    # ---- CUDA graphs (launch-bound inner loops)
+    def beginCapture(self):
+        self._ck(self._l.tnn_graph_begin_capture(self._h))
+
+    def endCapture(self) -> int:
+        g = C.c_void_p()
+        self._ck(self._l.tnn_graph_end_capture(self._h, C.byref(g)))
+        return g.value
+
+    def launchGraph(self, graph: int):
+        self._ck(self._l.tnn_graph_launch(self._h, graph))
+
+    def destroyGraph(self, graph: int):
+        self._l.tnn_graph_destroy(graph)
+
+    def counterAdd(self, ctr, inc: int):
+        self._ck(self._l.tnn_counter_add(self._h, _addr(ctr), inc & 0xFFFFFFFFFFFFFFFF))
+
+    def forwardDropoutDev(self, N, src, probability, scale, rnd, dst, seed_dev, seed_offset):
+        self._ck(self._l.tnn_forward_dropout_dev(self._h, N, _addr(src), probability, scale, _addr(rnd), _addr(dst),
+                                                 _addr(seed_dev), seed_offset & 0xFFFFFFFFFFFFFFFF))
+
+    def syncEvent(self, ev: int):
+        self._ck(self._l.tnn_event_synchronize(ev))
+
+    def allocHost(self, shape, dtype=np.float32) -> np.ndarray:
+        """Page-locked host array (for writeBufferAsync / readBufferAsync); release with freeHost."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        self._ck(self._l.tnn_host_alloc(self._h, n, C.byref(p)))
+        buf = (C.c_char * n).from_address(p.value)
+        a = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        a.flags.writeable = True
+        self._pinned = getattr(self, "_pinned", {})
+        self._pinned[a.ctypes.data] = p.value
+        return a
+
+    def freeHost(self, a: np.ndarray):
+        p = getattr(self, "_pinned", {}).pop(a.ctypes.data, None)
+        if p:
+            self._ck(self._l.tnn_host_free(self._h, p))
+
     def destroyEvent(self, ev: int):
         self._l.tnn_event_destroy(C.c_void_p(ev))
 

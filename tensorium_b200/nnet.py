@@ -215,6 +215,9 @@ class TNNet:
         """nnet.pas:378-403: every layer but the last; a data-parallel run first sums the update buffers."""
         if self.bucket is not None:
             self.bucket.all_reduce()
+        self._update_layers()
+
+    def _update_layers(self):
         arg = TUpdateArgs(batch=self.batch * self.subdivisions * self.replicas, learningRate=self.learningRate,
                           momentum=self.momentum, decay=self.decay, replicas=self.replicas)
         for l in self.layers[:-1]:
@@ -230,18 +233,90 @@ class TNNet:
 
     def trainBatch(self, x: np.ndarray | None = None, truth: np.ndarray | None = None):
         """One iteration of trainEpoch's loop body (nnet.pas:497-520): load, Propagate, update when due."""
+        cu = cuda()
         if self.truth is None:
             out = self.layers[-1].output
-            self.truth = TSingleTensor(out.FShape, groups=self.batch)
-        if x is not None:
-            self.input.Data[...] = x.reshape(self.input.FShape)
-            self.input.setCPU()
-        if truth is not None:
-            self.truth.Data[...] = truth.reshape(self.truth.FShape)
-            self.truth.setCPU()
+            self.truth = TSingleTensor(out.FShape, groups=self.batch, host=False)
+        if x is not None and truth is not None:
+            # The reference copies the batch synchronously (input.setCPU -> pushToDevice).  Here the batch goes through
+            # two page-locked staging buffers and asynchronous copies, so the host keeps enqueuing the next step
+            # while the GPU runs this one; an event per buffer keeps the host from overwriting a buffer whose copy
+            # has not run yet.
+            if getattr(self, "_stage", None) is None:
+                self._stage = [(cu.allocHost(self.input.FShape), cu.allocHost(self.truth.FShape), cu.createEvent())
+                               for _ in range(2)]
+                for _, _, ev in self._stage:
+                    cu.recordEvent(ev)
+                self._stage_i = 0
+            sx, st, ev = self._stage[self._stage_i & 1]
+            self._stage_i += 1
+            cu.syncEvent(ev)
+            sx[...] = x.reshape(self.input.FShape)
+            st[...] = truth.reshape(self.truth.FShape)
+            cu.writeBufferAsync(self.input.devData, sx.nbytes, sx.ctypes.data)
+            cu.writeBufferAsync(self.truth.devData, st.nbytes, st.ctypes.data)
+            cu.recordEvent(ev)
+            self.input.setCUDA()
+            self.truth.setCUDA()
+        else:
+            if x is not None:
+                self.input.Data[...] = x.reshape(self.input.FShape)
+                self.input.setCPU()
+            if truth is not None:
+                self.truth.Data[...] = truth.reshape(self.truth.FShape)
+                self.truth.setCPU()
+        if getattr(self, "_graphs", None) is not None:
+            return self._replay()
         self.Propagate()
         if self.seen % (self.batch * self.subdivisions) == 0:
             self.update()
+
+    # ---- CUDA-graph replay of the training step (the step is ~110 small launches: launch-bound from any host)
+    GRAPH_SEED_STEP = 0x9E3779B97F4A7C15  # the dropout seed counter advances by this much per step (masks decorrelate)
+
+    def enableGraph(self, seed: int = 0x1234567):
+        """Capture forward+backward (and update) of ONE training step into CUDA graphs and replay them from then on.
+        Call after at least one eager trainBatch (scratch buffers must have their final size, every parameter must be
+        on the device).  Dropout seeds move to a device counter: layer i, step t uses seed + t*GRAPH_SEED_STEP +
+        (i+1)*2^40.  With a gradient bucket attached the all-reduce stays eager between the two graphs."""
+        assert self.subdivisions == 1, "graph mode updates every step"
+        cu = cuda()
+        self._seed_ctr = TSingleTensor((1,), groups=1, host=True, dtype=np.int64)
+        self._seed_ctr.Data[0] = np.int64(np.uint64(seed & 0xFFFFFFFFFFFFFFFF).astype(np.int64))
+        self._seed_ctr.pushToDevice()
+        self._seed_host = seed & 0xFFFFFFFFFFFFFFFF
+        for i, l in enumerate(self.layers):
+            if hasattr(l, "seed_dev"):
+                l.seed_dev = (self._seed_ctr.devData, ((i + 1) << 40) & 0xFFFFFFFFFFFFFFFF)
+        cu.finish()
+        cu.beginCapture()
+        self.Propagate()
+        cu.counterAdd(self._seed_ctr.devData, self.GRAPH_SEED_STEP)
+        if self.bucket is None:
+            self.update()
+            self._graphs = (cu.endCapture(), None)
+        else:
+            g1 = cu.endCapture()
+            cu.beginCapture()
+            self._update_layers()
+            self._graphs = (g1, cu.endCapture())
+        self.seen -= self.batch  # the capture pass did not run anything
+
+    def dropout_seed(self, layer_index: int, step: int) -> int:
+        """The seed dropout layer `layer_index` used at graph step `step` (0-based) — for parity checks."""
+        return (self._seed_host + step * self.GRAPH_SEED_STEP + ((layer_index + 1) << 40)) & 0xFFFFFFFFFFFFFFFF
+
+    def _replay(self):
+        cu = cuda()
+        g1, g2 = self._graphs
+        cu.launchGraph(g1)
+        self.seen += self.batch
+        for l in self.layers:  # the loss tensor is new after every replay
+            if hasattr(l, "_cost_stale"):
+                l._cost_stale = True
+        if g2 is not None:
+            self.bucket.all_reduce()
+            cu.launchGraph(g2)
 
     def cost(self) -> float:
         """nnet.pas:551-563: mean of the layers' cost[0]."""

@@ -73,12 +73,19 @@ class TDropoutLayer:
         self.train = True
         self._rng = rng or np.random.default_rng(0)
         self.seed = None  # tests pin it; otherwise drawn per call like the wrapper's random($10000000)
+        # graph replays cannot take a new host-side seed per step: (device counter, offset) -> seed = *counter + offset
+        self.seed_dev = None
 
     def forwardGPU(self, state: TNNetState, net=None):
         if not state.input.wasGPU():
             state.input.pushToDevice()
         self.output = state.input
         if not state.isTraining:
+            return
+        if self.seed_dev is not None:
+            ctr, off = self.seed_dev
+            cuda().forwardDropoutDev(self.output.Size(), self.output.devData, self.probability, self.scale,
+                                     self.rand.devData, self.output.devData, ctr, off)
             return
         seed = self.seed if self.seed is not None else int(self._rng.integers(0, 0x10000000))
         self.last_seed = seed

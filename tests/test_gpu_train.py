@@ -195,3 +195,34 @@ def test_maxpool_softmax_dropout_layers(cuda_backend, oracle):
     assert dl.output is st.input
     assert np.array_equal(st.input.pullFromDevice(), want)
     assert 0.15 < (want == 0).mean() < 0.45
+
+
+def test_graph_replay_matches_eager_training(cuda_backend):
+    """The captured CUDA graph of a training step (device-side dropout seeds) follows the eager step kernel for kernel:
+    same weights after four steps up to the order of the fp32 atomics in the split reductions."""
+    from tensorium_b200 import models
+    from tensorium_b200.train_layers import TDropoutLayer
+    B = 16
+    nets = [models.deepCIFAR10(B, seed=21, learningRate=0.01) for _ in range(2)]
+    eager, graph = nets
+    batches = [_batch(B, 300 + i) for i in range(6)]
+    for net in nets:  # two identical eager steps first (graph capture needs warm scratch buffers)
+        for i in range(2):
+            for li, l in enumerate(net.layers):
+                if isinstance(l, TDropoutLayer):
+                    l.seed = 1000 * i + li
+            net.trainBatch(*batches[i])
+    graph.enableGraph(seed=0xABCDEF)
+    for step in range(4):
+        x, t = batches[2 + step]
+        for li, l in enumerate(eager.layers):
+            if isinstance(l, TDropoutLayer):
+                l.seed = graph.dropout_seed(li, step)
+        eager.trainBatch(x, t)
+        graph.trainBatch(x, t)
+        assert abs(graph.cost() - eager.cost()) <= 1e-4 * abs(eager.cost()), (step, graph.cost(), eager.cost())
+    for le, lg in zip(_trainables(eager), _trainables(graph)):
+        assert rel_max(lg.weights.pullFromDevice(), le.weights.pullFromDevice()) <= 1e-4
+    for le, lg in zip(eager.layers, graph.layers):
+        if isinstance(le, TDropoutLayer):
+            assert np.array_equal(lg.rand.pullFromDevice(), le.rand.pullFromDevice())  # same masks

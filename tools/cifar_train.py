@@ -26,6 +26,8 @@ def main():
     ap.add_argument("--math", default="3xtf32", choices=["fp32", "3xtf32", "tf32"])
     ap.add_argument("--unfused", action="store_true", help="issue the reference's own cuda.<op> sequence")
     ap.add_argument("--loss-every", type=int, default=10)
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from the host instead of replaying "
+                                                              "the captured CUDA graph of the step")
     a = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -57,6 +59,10 @@ def main():
 
         for i in range(a.warmup):
             step(i)
+        if not a.no_graph and not a.unfused:
+            net.enableGraph()
+            for i in range(2):
+                step(i)
         l0 = cu.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if world > 1:
@@ -88,7 +94,7 @@ def main():
         print(json.dumps({
             "metric": "cifar10_train_images_per_s", "value": a.batch * world * a.steps / (ms / 1e3), "unit": "images/s",
             "n_gpus": world, "steps": a.steps, "ms_per_step": ms / a.steps, "per_gpu_batch": a.batch,
-            "math": a.math, "fused": not a.unfused, "launches_per_step": (cu.launch_count() - l0) / a.steps,
+            "math": a.math, "fused": not a.unfused, "cuda_graph": (not a.no_graph and not a.unfused), "launches_per_step": (cu.launch_count() - l0) / a.steps,
             "loss_first": costs[0] if costs else None, "loss_last": costs[-1] if costs else None,
             "replicas_in_sync": in_sync, "data": "synthetic", "e2e": "host batch copied in every step"}))
     if world > 1:
