@@ -25,6 +25,7 @@ constexpr int kWgARows = 128, kWgBRows = 32;    // delta rows per CTA (M), input
 constexpr int kWgLboA = kWgARows * 16 + 16;     // 2064
 constexpr int kWgLboB = kWgBRows * 16 + 16;     // 528
 constexpr int kWgStages = 2;
+constexpr int kWgMaxA = 4, kWgMaxB = 9;         // work items (16-byte chunks) per producer thread and tile
 
 struct WgradGeom {
   const float *in, *delta;
@@ -88,55 +89,98 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma_wgrad(WgradGeom g) {
     const int bItems = g.kw * g.HL * g.CPL * kWgBRows;   // (kc, line, chunk j, c)
     int stage = 0;
     uint32_t phase = 0;
+    // per-thread item tables (the same for every tile): shared-memory offset and source offset from the tile origin
+    int aSm[kWgMaxA], aSrc[kWgMaxA];
+#pragma unroll
+    for (int u = 0; u < kWgMaxA; ++u) {
+      const int it = tid + u * kProducerThreads;
+      if (it < aItems) {
+        const int f = it / (kWgKT / 4), q = it - f * (kWgKT / 4);
+        const int dh = q / g.CPL, j = q - dh * g.CPL;
+        aSm[u] = q * kWgLboA + f * 16;
+        aSrc[u] = f * g.P + dh * g.OW + 4 * j;
+      } else {
+        aSm[u] = -1;
+        aSrc[u] = 0;
+      }
+    }
+    int bSm[kWgMaxB], bSrc[kWgMaxB], bLC[kWgMaxB];  // bLC: line | column offset (+ 64 so it is non-negative) packed
+#pragma unroll
+    for (int u = 0; u < kWgMaxB; ++u) {
+      const int it = tid + u * kProducerThreads;
+      if (it < bItems) {
+        const int j = it % g.CPL;
+        int rest = it / g.CPL;
+        const int c = rest % kWgBRows;
+        rest /= kWgBRows;
+        const int l = rest % g.HL, kc = rest / g.HL;
+        const int dw = kc * g.dx - g.pw + 4 * j;
+        bSm[u] = (c0 + c < g.C) ? kc * bCopy + (l * g.CPL + j) * kWgLboB + c * 16 : -2 - (kc * bCopy + (l * g.CPL + j) * kWgLboB + c * 16);
+        bSrc[u] = c * g.HW + (l - g.ph) * g.W + dw;
+        bLC[u] = (l << 16) | (dw + 64);
+      } else {
+        bSm[u] = -1;
+        bSrc[u] = 0;
+        bLC[u] = 0;
+      }
+    }
     for (int i = 0; i < myTiles; ++i) {
       const int t = slice + i * g.G;
       const int b = t / tilesPerImg;
       const int r = t - b * tilesPerImg;
       const int ty = r / g.tilesX, tx = r - ty * g.tilesX;
       const int oh0 = ty * g.TH, ow0 = tx * g.TW;
-      const float *dimg = g.delta + (int64_t)b * g.outImg + (int64_t)f0 * g.P;
-      const float *iimg = g.in + (int64_t)b * g.inImg + (int64_t)c0 * g.HW;
-      mbar_wait_warp(&ctl.empty[stage], phase ^ 1);
-      uint8_t *sa = smem + (size_t)stage * stageBytes;
-      uint8_t *sb = sa + aBytes * (SPLIT ? 2 : 1);
-      // ---- A: lanes walk the chunks of a delta row (coalesced 16-byte loads)
-      for (int it = tid; it < aItems; it += kProducerThreads) {
-        const int f = it / (kWgKT / 4), q = it - f * (kWgKT / 4);
-        const int dh = q / g.CPL, j = q - dh * g.CPL;
-        const float4 v = __ldg(reinterpret_cast<const float4 *>(dimg + (int64_t)f * g.P + (oh0 + dh) * g.OW + ow0 + 4 * j));
-        uint8_t *d = sa + q * kWgLboA + f * 16;
-        if (SPLIT) {
-          const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-          *reinterpret_cast<float4 *>(d) = h;
-          *reinterpret_cast<float4 *>(d + aBytes) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        } else {
-          *reinterpret_cast<float4 *>(d) = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
-        }
-      }
-      // ---- B: item = (kc, line, c, j) with j fastest: a warp reads runs of one channel line
-      for (int it = tid; it < bItems; it += kProducerThreads) {
-        const int j = it % g.CPL;
-        int rest = it / g.CPL;
-        const int c = rest % kWgBRows;
-        rest /= kWgBRows;
-        const int l = rest % g.HL, kc = rest / g.HL;
-        const int ih = oh0 - g.ph + l;
-        const int iw = ow0 - g.pw + kc * g.dx + 4 * j;
+      const float *dsrc = g.delta + (int64_t)b * g.outImg + (int64_t)f0 * g.P + oh0 * g.OW + ow0;
+      const float *isrc = g.in + (int64_t)b * g.inImg + (int64_t)c0 * g.HW + (int64_t)oh0 * g.W + ow0;
+      // ---- all loads of the tile first (in flight together, and before the wait: they overlap the MMAs still
+      //      reading this stage), then the stores
+      float4 va[kWgMaxA], vb[kWgMaxB];
+#pragma unroll
+      for (int u = 0; u < kWgMaxA; ++u)
+        va[u] = aSm[u] >= 0 ? __ldg(reinterpret_cast<const float4 *>(dsrc + aSrc[u])) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < kWgMaxB; ++u) {
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + c < g.C && (unsigned)ih < (unsigned)g.H) {
-          const float *src = iimg + (int64_t)c * g.HW + (int64_t)ih * g.W + iw;
+        const int ih = oh0 - g.ph + (bLC[u] >> 16);
+        const int iw = ow0 + (bLC[u] & 0xffff) - 64;
+        if (bSm[u] >= 0 && (unsigned)ih < (unsigned)g.H) {
+          const float *src = isrc + bSrc[u];
           if ((unsigned)(iw + 0) < (unsigned)g.W) v.x = __ldg(src + 0);
           if ((unsigned)(iw + 1) < (unsigned)g.W) v.y = __ldg(src + 1);
           if ((unsigned)(iw + 2) < (unsigned)g.W) v.z = __ldg(src + 2);
           if ((unsigned)(iw + 3) < (unsigned)g.W) v.w = __ldg(src + 3);
         }
-        uint8_t *d = sb + kc * bCopy + (l * g.CPL + j) * kWgLboB + c * 16;
-        if (SPLIT) {
-          const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
-          *reinterpret_cast<float4 *>(d) = h;
-          *reinterpret_cast<float4 *>(d + bBytes) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        } else {
-          *reinterpret_cast<float4 *>(d) = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+        vb[u] = v;
+      }
+      mbar_wait_warp(&ctl.empty[stage], phase ^ 1);
+      uint8_t *sa = smem + (size_t)stage * stageBytes;
+      uint8_t *sb = sa + aBytes * (SPLIT ? 2 : 1);
+#pragma unroll
+      for (int u = 0; u < kWgMaxA; ++u) {
+        if (aSm[u] >= 0) {
+          uint8_t *d = sa + aSm[u];
+          const float4 v = va[u];
+          if (SPLIT) {
+            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            *reinterpret_cast<float4 *>(d) = h;
+            *reinterpret_cast<float4 *>(d + aBytes) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          } else {
+            *reinterpret_cast<float4 *>(d) = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kWgMaxB; ++u) {
+        if (bSm[u] != -1) {
+          uint8_t *d = sb + (bSm[u] >= 0 ? bSm[u] : -2 - bSm[u]);  // channels past C: the zero loaded above is stored
+          const float4 v = vb[u];
+          if (SPLIT) {
+            const float4 h = make_float4(tf32_hi(v.x), tf32_hi(v.y), tf32_hi(v.z), tf32_hi(v.w));
+            *reinterpret_cast<float4 *>(d) = h;
+            *reinterpret_cast<float4 *>(d + bBytes) = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+          } else {
+            *reinterpret_cast<float4 *>(d) = make_float4(tf32_rna(v.x), tf32_rna(v.y), tf32_rna(v.z), tf32_rna(v.w));
+          }
         }
       }
       fence_proxy_async();
@@ -226,6 +270,7 @@ inline int conv_wgrad_tiles(tnn_context *ctx, const simt::ConvGeom &g, int batch
   if (!TW) return kNotTaken;
   const int TH = kWgKT / TW, CPL = TW / 4;
   const int HL = TH + (g.kh - 1) * g.dy;
+  if (g.kw * HL * CPL * kWgBRows > kWgMaxB * kProducerThreads || HL > 255 || g.pw > 60) return kNotTaken;
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   const int aBytes = (kWgKT / 4) * kWgLboA, bBytes = g.kw * HL * CPL * kWgLboB;
   const size_t stageBytes = (size_t)(aBytes + bBytes) * (split ? 2 : 1);
