@@ -294,6 +294,11 @@ TNN_API int32_t tnn_conv2d_forward_residual(tnn_context *ctx, const tnn_conv_des
                                             const float *weights, const float *scale, const float *bias,
                                             int32_t activation, const float *residual, int64_t residualOffset,
                                             float *out, int64_t outOffset);
+/* Declare a weight tensor immutable (is_static = 1) or mutable again (0).  While static, the convolution entry points
+ * keep their re-ordered / TF32-split copy of it across calls instead of re-deriving it per call (inference: the
+ * 75 prepare launches of a YOLOv3 step disappear).  The caller must not modify the buffer while it is static;
+ * declaring it again (either value) drops the cached copies — do that after changing the contents. */
+TNN_API int32_t tnn_set_weights_static(tnn_context *ctx, const float *weights, int32_t is_static);
 /* Which kernel the last tnn_conv2d_forward* call on this context dispatched to (measurement tools attribute layer
  * times to kernels with it): 0 none yet, 1 direct fp32 (k_conv_direct), 2 tcgen05 gathering implicit GEMM (k_umma
  * with Im2colPixelLoader), 3 tcgen05 with TMA-fed activations (k_umma with TmaPatchLoader), 4 tcgen05 halo-tile

@@ -101,6 +101,7 @@ SIGNATURES = {
     "tnn_add_dots": (i32, [ctxp, i64, i64, i64, fptr, fptr, i64, fptr]),
     "tnn_conv2d_forward": (i32, [ctxp, C.POINTER(ConvDesc), fptr, i64, fptr, fptr, fptr, i32, fptr, i64]),
     "tnn_last_conv_kernel": (i32, [ctxp]),
+    "tnn_set_weights_static": (i32, [ctxp, fptr, i32]),
     "tnn_conv2d_forward_residual": (i32, [ctxp, C.POINTER(ConvDesc), fptr, i64, fptr, fptr, fptr, i32, fptr, i64, fptr,
                                           i64]),
     "tnn_conv2d_backward_filter": (i32, [ctxp, C.POINTER(ConvDesc), fptr, i64, fptr, i64, fptr]),

@@ -2,12 +2,16 @@
 // Replaces TNNCuda<T>.Create/Destroy/createDeviceBuffer/readBuffer/writeBuffer/finish
 // (reference: source/nncuda.pas:443-522,1575-1584).
 #include <stdarg.h>
+#include <map>
+#include <set>
+#include <tuple>
 #include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
+void tnn_wcache_destroy(tnn_context *ctx);
 
 void tnn_set_error(const char *fmt, ...) {
   va_list ap;
@@ -76,6 +80,8 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     // kernel-selection switch for A/B measurements: TNN_TMA_ACT=0 keeps the gathering producer everywhere
     const char *e = getenv("TNN_TMA_ACT");
     ctx->tma_activations = (e && e[0] == '0') ? 0 : 1;
+    const char *p2 = getenv("TNN_PAIR");
+    ctx->pair_mma = (p2 && p2[0] == '1') ? 1 : 0;
   }
   *out = ctx;
   return 0;
@@ -88,6 +94,7 @@ int32_t tnn_destroy(tnn_context *ctx) {
   if (ctx->red_partials) cudaFree(ctx->red_partials);
   if (ctx->red_counters) cudaFree(ctx->red_counters);
   if (ctx->work) cudaFree(ctx->work);
+  tnn_wcache_destroy(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -137,9 +144,14 @@ int32_t tnn_create_device_buffer(tnn_context *ctx, int64_t bytes, float **mem) {
   return 0;
 }
 
+void tnn_wcache_forget(tnn_context *ctx, const float *mem);
+
 int32_t tnn_free_device_buffer(tnn_context *ctx, float *mem) {
   TNN_CHECK_CTX(ctx);
-  if (mem) TNN_CUDA(cudaFree(mem));
+  if (mem) {
+    tnn_wcache_forget(ctx, mem);  // a later allocation may reuse the address
+    TNN_CUDA(cudaFree(mem));
+  }
   return 0;
 }
 
@@ -313,6 +325,75 @@ int tnn_reserve_reduction(tnn_context *ctx, size_t partial_floats, size_t counte
     TNN_CUDA(cudaMemsetAsync(ctx->red_counters, 0, n * sizeof(unsigned int), ctx->stream));
     ctx->red_counters_n = n;
   }
+  return 0;
+}
+
+struct tnn_wcache {
+  std::set<const float *> statics;
+  std::map<std::tuple<const float *, int, int, size_t>, float *> copies;  // (weights, kind, math mode, count) -> buffer
+};
+
+static void wcache_drop(tnn_context *ctx, const float *weights) {
+  if (!ctx->wcache) return;
+  for (auto it = ctx->wcache->copies.begin(); it != ctx->wcache->copies.end();) {
+    if (std::get<0>(it->first) == weights) {
+      cudaFree(it->second);
+      it = ctx->wcache->copies.erase(it);
+    } else {
+      ++it;
+    }
+  }
+}
+
+extern "C" int32_t tnn_set_weights_static(tnn_context *ctx, const float *weights, int32_t is_static) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(weights != nullptr, "null weights");
+  if (!ctx->wcache) ctx->wcache = new tnn_wcache();
+  TNN_CUDA(cudaStreamSynchronize(ctx->stream));  // kernels still reading an old prepared copy
+  wcache_drop(ctx, weights);                     // (re)declaring invalidates what was prepared from the old contents
+  if (is_static) ctx->wcache->statics.insert(weights);
+  else ctx->wcache->statics.erase(weights);
+  return 0;
+}
+
+void tnn_wcache_forget(tnn_context *ctx, const float *mem) {
+  if (!ctx->wcache || !ctx->wcache->statics.count(mem)) return;
+  cudaStreamSynchronize(ctx->stream);
+  wcache_drop(ctx, mem);
+  ctx->wcache->statics.erase(mem);
+}
+
+void tnn_wcache_destroy(tnn_context *ctx) {
+  if (!ctx->wcache) return;
+  for (auto &kv : ctx->wcache->copies) cudaFree(kv.second);
+  delete ctx->wcache;
+  ctx->wcache = nullptr;
+}
+
+int tnn_weight_buffer(tnn_context *ctx, const float *weights, int kind, size_t count, float **hi, float **lo, bool *fresh) {
+  if (ctx->wcache && ctx->wcache->statics.count(weights)) {
+    const auto key = std::make_tuple(weights, kind, ctx->math_mode, count);
+    auto it = ctx->wcache->copies.find(key);
+    if (it != ctx->wcache->copies.end()) {
+      *hi = it->second;
+      *lo = it->second + count;
+      *fresh = false;
+      return 0;
+    }
+    TNN_REQUIRE(!ctx->capturing, "a static weight copy would be allocated during graph capture: run the step once first");
+    float *buf = nullptr;
+    TNN_CUDA(cudaMalloc((void **)&buf, 2 * count * sizeof(float)));
+    ctx->wcache->copies[key] = buf;
+    *hi = buf;
+    *lo = buf + count;
+    *fresh = true;
+    return 0;
+  }
+  int rc = tnn_reserve_work(ctx, 2 * count * sizeof(float));
+  if (rc) return rc;
+  *hi = ctx->work;
+  *lo = ctx->work + count;
+  *fresh = true;
   return 0;
 }
 

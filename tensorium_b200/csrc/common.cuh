@@ -14,6 +14,7 @@ struct tnn_context {
   cudaDeviceProp prop;
   int math_mode;
   int tma_activations;  // 1: stride-1 convolutions fetch activations by TMA when the geometry allows (default)
+  int pair_mma;         // 1: wide layers of the gathering path run on CTA pairs (tcgen05.mma.cta_group::2)
   int last_conv_kernel; // which kernel the last tnn_conv2d_forward took (TNN_CONV_KERNEL_*), for measurement tools
   int64_t launches;
   int capturing;              // between tnn_graph_begin_capture and tnn_graph_end_capture
@@ -26,7 +27,14 @@ struct tnn_context {
   // scratch for the contraction kernels (pre-split / transposed weight copies, split-K partials)
   float *work;
   size_t work_bytes;
+  // prepared copies of weight tensors the caller declared immutable (tnn_set_weights_static)
+  struct tnn_wcache *wcache;
 };
+
+// Buffer for the prepared (re-ordered, TF32-split) copy of `weights`: hi plane then lo plane, `count` floats each.
+// *fresh tells the caller to run its prepare kernel; it is false when `weights` is static and a copy in this layout
+// (`kind`, math mode, count) is already cached.
+int tnn_weight_buffer(tnn_context *ctx, const float *weights, int kind, size_t count, float **hi, float **lo, bool *fresh);
 
 void tnn_set_error(const char *fmt, ...);
 

@@ -8,6 +8,7 @@
 #include "conv_direct.cuh"
 #include "umma_halo.cuh"
 #include "umma_wgrad.cuh"
+#include "umma_conv2.cuh"
 
 namespace {
 

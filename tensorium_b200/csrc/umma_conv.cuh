@@ -1295,11 +1295,11 @@ inline int conv_patch(tnn_context *ctx, const simt::ConvGeom &v, int batch, cons
   const int64_t K = (int64_t)kk * CB * 32;
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
-  const size_t plane = (size_t)N * K * sizeof(float);
-  int rc = tnn_reserve_work(ctx, plane * 2);
+  float *whi, *wlo;
+  bool fresh;
+  int rc = tnn_weight_buffer(ctx, weights, dgradWeights ? 2 : 1, (size_t)N * K, &whi, &wlo, &fresh);
   if (rc) return rc;
-  float *whi = ctx->work, *wlo = ctx->work + (size_t)N * K;
-  {
+  if (fresh) {
     int64_t blocks = cdiv64(N * K, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_prepare_weights_patch<<<(int)blocks, 256, 0, ctx->stream>>>(weights, (int)N, v.C, kk, CB, dgradWeights ? 1 : 0, whi,
@@ -1330,6 +1330,10 @@ int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const float 
               bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate,
               const float *residual = nullptr);
 
+// umma_conv2.cuh
+int conv_forward_pair(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
+                      const float *scale, const float *bias, int act, float *out);
+
 // conv forward: D[pixel][filter]; A = im2col gather (MN-major, producer warps), B = weights via TMA (K-major)
 inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
                         const float *scale, const float *bias, int act, float *out, const float *residual = nullptr) {
@@ -1341,6 +1345,11 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
     rc = conv_halo(ctx, g, batch, in, weights, false, scale, bias, act, out, false, residual);
     if (rc != kNotTaken) return rc;
   }
+  if (ctx->pair_mma && residual == nullptr) {
+    ctx->last_conv_kernel = 6;
+    int rc = conv_forward_pair(ctx, g, batch, in, weights, scale, bias, act, out);
+    if (rc != kNotTaken) return rc;
+  }
   ctx->last_conv_kernel = 2;
   const int64_t M = (int64_t)batch * g.OH * g.OW;
   const int64_t N = g.F;
@@ -1350,12 +1359,11 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
   const int64_t Kpad = (int64_t)p.sched.kBlocks * BK;
-  const size_t plane = (size_t)N * Kpad * sizeof(float);
-  int rc = tnn_reserve_work(ctx, plane * 2);
+  float *whi, *wlo;
+  bool fresh;
+  int rc = tnn_weight_buffer(ctx, weights, 3, (size_t)N * Kpad, &whi, &wlo, &fresh);
   if (rc) return rc;
-  float *whi = ctx->work;
-  float *wlo = ctx->work + (size_t)N * Kpad;
-  {
+  if (fresh) {
     int64_t blocks = cdiv64(N * Kpad, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_prepare_weights<<<(int)blocks, 256, 0, ctx->stream>>>(weights, N, g.C, kk, Kpad, whi, wlo, split ? 1 : 0);
@@ -1402,10 +1410,11 @@ inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int bat
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
   const int64_t Kpad = (int64_t)p.sched.kBlocks * BK;
-  int rc = tnn_reserve_work(ctx, (size_t)N * Kpad * sizeof(float) * 2);
+  float *whi, *wlo;
+  bool fresh;
+  int rc = tnn_weight_buffer(ctx, weights, 4, (size_t)N * Kpad, &whi, &wlo, &fresh);
   if (rc) return rc;
-  float *whi = ctx->work, *wlo = ctx->work + (size_t)N * Kpad;
-  {
+  if (fresh) {
     int64_t blocks = cdiv64(N * Kpad, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_prepare_weights_dgrad<<<(int)blocks, 256, 0, ctx->stream>>>(weights, g.F, g.C, kk, Kpad, whi, wlo, split ? 1 : 0);

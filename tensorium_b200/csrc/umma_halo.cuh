@@ -396,10 +396,11 @@ inline int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const
   if (HS * haloStage + BS * bStage > 220 * 1024) return kNotTaken;
   const size_t smemBytes = (size_t)HS * haloStage + (size_t)BS * bStage + 1024;
   const int nTiles = (int)cdiv64(N, bn);
-  int rc = tnn_reserve_work(ctx, (size_t)N * K * sizeof(float) * 2);
+  float *whi, *wlo;
+  bool fresh;
+  int rc = tnn_weight_buffer(ctx, weights, (dgradWeights ? 6 : 5) + (CH == 16 ? 2 : 0), (size_t)N * K, &whi, &wlo, &fresh);
   if (rc) return rc;
-  float *whi = ctx->work, *wlo = ctx->work + (size_t)N * K;
-  {
+  if (fresh) {
     int64_t blocks = cdiv64(N * K, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
     k_prepare_weights_halo<<<(int)blocks, 256, 0, ctx->stream>>>(weights, (int)N, v.C, kk, CB, CH, dgradWeights ? 1 : 0,

@@ -135,6 +135,10 @@ class TConvolutionalLayer:
             state.input.pushToDevice()
         if not self.weights.wasGPU():
             self.weights.pushToDevice()
+            # inference: the weights do not change between calls, the backend keeps its prepared copy
+            # (declaring again after a push invalidates the copy made from the old contents)
+            if self.fused and not self.train:
+                cu.setWeightsStatic(self.weights.devData, True)
         if not self.biases.wasGPU():
             self.biases.pushToDevice()
         self.output.setCUDA()

@@ -354,7 +354,12 @@ class TNNCuda:
                                             _addr(scale), _addr(bias), int(activation), _addr(out), outOffset))
 
     CONV_KERNELS = {0: "none", 1: "direct::k_conv_direct", 2: "umma::k_umma<Im2colPixelLoader> (gather)",
-                    3: "umma::k_umma<TmaPatchLoader> (TMA activations)", 4: "umma::k_umma_halo", 5: "simt::k_gemm"}
+                    3: "umma::k_umma<TmaPatchLoader> (TMA activations)", 4: "umma::k_umma_halo", 5: "simt::k_gemm",
+                    6: "umma::k_umma_pair (gather, CTA pairs)"}
+
+    def setWeightsStatic(self, weights, is_static: bool = True):
+        """The backend may keep its re-ordered / TF32-split copy of `weights` across calls (inference)."""
+        self._ck(self._l.tnn_set_weights_static(self._h, _addr(weights), int(bool(is_static))))
 
     def lastConvKernel(self) -> str:
         return self.CONV_KERNELS.get(int(self._l.tnn_last_conv_kernel(self._h)), "?")

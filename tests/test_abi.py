@@ -26,7 +26,7 @@ def test_header_declares_the_tnncuda_surface():
               "add_dots", "forward_scale", "forward_scale_add", "forward_dropout", "backward_dropout", "cost_l2",
               "clamp", "inverse_sqrt"]:
         assert "tnn_" + m in syms, m
-    for m in ["conv2d_forward", "conv2d_forward_residual", "last_conv_kernel", "event_synchronize", "host_alloc", "host_free", "conv2d_backward_filter", "conv2d_backward_data", "sgd_update",
+    for m in ["conv2d_forward", "conv2d_forward_residual", "last_conv_kernel", "set_weights_static", "event_synchronize", "host_alloc", "host_free", "conv2d_backward_filter", "conv2d_backward_data", "sgd_update",
               "batchnorm_forward_training", "batchnorm_forward_inference", "batchnorm_backward"]:
         assert "tnn_" + m in syms, m
 

@@ -351,3 +351,31 @@ def test_conv_roundtrip_linearity_large(cuda_backend):
         cu.conv2dForward(desc, dx.ptr, 0, dw.ptr, None, None, 4, do.ptr, 0)
         outs.append(do.read())
     assert rel_max(outs[2], 0.5 * outs[0].astype(np.float64) + outs[1]) < 1e-5
+
+
+def test_static_weights_cache(cuda_backend, oracle):
+    """tnn_set_weights_static: same results as the per-call preparation, and re-declaring after a change picks up the
+    new contents (on each of the three tensor-core kernels)."""
+    cu = cuda_backend
+    rng = np.random.default_rng(77)
+    for geom in [(2, 32, 32, 32, 64, 3, 1, 1), (2, 64, 26, 26, 48, 3, 1, 1), (2, 64, 16, 16, 32, 1, 0, 1)]:
+        B, C, H, W, F, k, p, s = geom
+        x, w, b = conv_case(rng, B, C, H, W, F, k)
+        desc = cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s)
+        dx, dw, db, dout = Dev(cu, x), Dev(cu, w), Dev(cu, b), Dev(cu, n=B * F * H * W)
+
+        def run():
+            cu.conv2dForward(desc, dx.ptr, 0, dw.ptr, None, db.ptr, oracle.ACT["LEAKY"], dout.ptr, 0)
+            return dout.read((B, F, H, W))
+        base = run()
+        cu.setWeightsStatic(dw.ptr, True)
+        assert np.array_equal(run(), base) and np.array_equal(run(), base)  # first call prepares, second reuses
+        w2 = (w * 0.5).astype(np.float32)
+        dw.write(w2)
+        cu.setWeightsStatic(dw.ptr, True)  # contents changed: declare again
+        want = oracle.conv2d(x, w2, p, s, s, 1, k, k)
+        oracle.forward_bias(want, b, B)
+        oracle.activate_array(want, oracle.ACT["LEAKY"])
+        assert rel_max(run(), want) < TOL_3XTF32
+        cu.setWeightsStatic(dw.ptr, False)
+        assert rel_max(run(), want) < TOL_3XTF32
