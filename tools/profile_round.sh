@@ -25,8 +25,13 @@ ncu --set full --clock-control none --import-source on -k regex:k_umma -c 1 -s 2
     python tools/conv_one.py 3xtf32 64,256,52,128,1,1 > $O/ncu_tma.log 2>&1
 # (4) CIFAR-10 training
 python tools/cifar_train.py --batch 128 --steps 50 > $O/cifar_b128.json 2>$O/cifar.err
+python tools/cifar_train.py --batch 128 --steps 50 --no-graph > $O/cifar_b128_nograph.json 2>>$O/cifar.err
 python tools/cifar_train.py --batch 512 --steps 30 > $O/cifar_b512.json 2>>$O/cifar.err
 python tools/cifar_train.py --batch 128 --steps 30 --unfused > $O/cifar_b128_unfused.json 2>>$O/cifar.err
+python bench.py --steps 5 --warmup 3 --no-cpu --math tf32 > $O/bench_tf32.json 2>/dev/null
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file $O/cifar_launches.csv \
-    python tools/cifar_train.py --batch 128 --steps 4 --warmup 3 > $O/ncu_cifar.log 2>&1
+    python tools/cifar_train.py --batch 128 --steps 4 --warmup 3 --no-graph > $O/ncu_cifar.log 2>&1
+python tools/conv_one.py 3xtf32 128,32,32,32,3,1 > /dev/null 2>&1 && \
+TNN_BWD=1 ncu --set full --clock-control none --import-source on -k regex:k_umma_wgrad -c 1 -s 1 -o $O/r01_wgrad_c32f32 \
+    python tools/conv_one.py 3xtf32 128,32,32,32,3,1 > $O/ncu_wgrad.log 2>&1
 ls -la $O
