@@ -431,6 +431,37 @@ struct TmaWeightsLoader {
   __device__ __forceinline__ void store(const Regs &, uint8_t *, uint8_t *, int, int) const {}
 };
 
+// TF32 mode: the producers, not the tensor pipe, are the bound of the wide layers, and the general load form costs
+// ~8 instructions per element.  Full channel groups of taps inside the image take an unpredicated path with one
+// pointer bump per load: 0.438 -> 0.400 ms at 256->512 @26^2.  (In 3xTF32 the same code LOSES 6 %, and its mere
+// presence costs 2 % — hence a separate loader type that only the TF32 instantiation uses.)
+struct Im2colPixelLoaderFast : Im2colPixelLoader {
+  __device__ __forceinline__ void load(TileCtx &cx, Regs &r, int64_t, int, const int *lut) const {
+    const int c0 = cx.cg * 16;
+    const bool on = (cx.tapmask >> cx.tap) & 1ull;
+    const float *q = cx.base + (int64_t)c0 * HW + lut[cx.tap];
+    const int nc = on ? g.C - c0 : 0;
+    if (nc >= 16) {
+      const int64_t hw = HW;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        r.v[j] = __ldg(q);
+        q += hw;
+      }
+    } else {
+      const uint32_t hw = (uint32_t)HW;
+      uint32_t off = 0;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        r.v[j] = (j < nc) ? __ldg(q + off) : 0.f;
+        off += hw;
+      }
+    }
+    cx.tap += 2;
+    if (cx.tap >= kk) { cx.tap -= kk; ++cx.cg; if (cx.tap >= kk) { cx.tap -= kk; ++cx.cg; } }
+  }
+};
+
 // Activations fetched by TMA (stride-1 convolutions whose rows are 16-byte aligned and whose kernel columns
 // shift by multiples of 4 pixels — in practice the 1x1 convolutions; see conv_patch for the measured reason).  The 128 rows of a tile are
 // four independent "atoms" of 32 output pixels, each a TH x TW patch (TH*TW = 32) of one image; for kernel tap
@@ -1375,13 +1406,14 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   rc = encode_weights_map(&tmLo, split ? wlo : whi, N, Kpad, p.BN);
   if (rc) return rc;
   Im2colPixelLoader la{in, g, M, g.H * g.W, kk};
+  Im2colPixelLoaderFast laf{{in, g, M, g.H * g.W, kk}};
   TmaWeightsLoader lb{};
   if (residual) {
     ConvEpilogueT<true> epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, residual};
-    return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
+    return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, laf, lb, epi, &tmHi, &tmLo);
   }
   ConvEpilogueT<false> epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, nullptr};
-  return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
+  return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, laf, lb, epi, &tmHi, &tmLo);
 }
 
 // dgrad (nConvolutionLayer.pas:1250-1275: TN gemm + col2im) for stride 1 / dilation 1:
@@ -1426,9 +1458,10 @@ inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int bat
   rc = encode_weights_map(&tmLo, split ? wlo : whi, N, Kpad, p.BN);
   if (rc) return rc;
   Im2colPixelLoader la{delta, v, M, v.H * v.W, kk};
+  Im2colPixelLoaderFast laf{{delta, v, M, v.H * v.W, kk}};
   TmaWeightsLoader lb{};
   ConvEpilogueT<true> epi{in_delta, nullptr, nullptr, v.OH * v.OW, v.outImg, TNN_ACT_LINEAR, M, N, true, 0, 0, 0, 0, 0, 0, 0, 0, nullptr};
-  return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, la, lb, epi, &tmHi, &tmLo);
+  return split ? launch<true>(ctx, p, la, lb, epi, &tmHi, &tmLo) : launch<false>(ctx, p, laf, lb, epi, &tmHi, &tmLo);
 }
 
 // wgrad (nConvolutionLayer.pas:1203-1232: im2col + NT gemm, beta = 1, batch accumulated):
