@@ -1,0 +1,37 @@
+"""BASELINE config 1: standalone SGEMM sweep through tnn_gemm (M = N = K in 256..8192; NN / NT / TN) with a sampled
+fp64 check.  usage: sgemm_sweep.py [math]"""
+import os, sys, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+from tensorium_b200 import tensor
+from util import Dev
+MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+math = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
+cu = tensor.initCUDART(0)
+cu.set_math_mode(MATH[math])
+rng = np.random.default_rng(0)
+print(f"math={math}")
+for n in (256, 512, 1024, 2048, 4096, 8192):
+    A = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    B = rng.uniform(-1, 1, (n, n)).astype(np.float32)
+    dA, dB, dC = Dev(cu, A), Dev(cu, B), Dev(cu, n=n * n)
+    row = []
+    for name, ta, tb in (("NN", 0, 0), ("NT", 0, 1), ("TN", 1, 0)):
+        for _ in range(2):
+            cu.gemm(ta, tb, n, n, n, 1.0, dA.ptr, 0, n, dB.ptr, 0, n, 0.0, dC.ptr, 0, n)
+        cu.finish()
+        reps = 3 if n >= 4096 else 10
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            cu.gemm(ta, tb, n, n, n, 1.0, dA.ptr, 0, n, dB.ptr, 0, n, 0.0, dC.ptr, 0, n)
+        cu.finish()
+        dt = (time.perf_counter() - t0) / reps
+        C = dC.read((n, n))
+        idx = rng.integers(0, n, (64, 2))
+        opA = A.T if ta else A
+        opB = B.T if tb else B
+        ref = np.array([np.dot(opA[i].astype(np.float64), opB[:, j].astype(np.float64)) for i, j in idx])
+        err = np.abs(C[idx[:, 0], idx[:, 1]] - ref).max() / np.abs(ref).max()
+        row.append(f"{name} {dt*1e3:8.3f} ms {2.0*n**3/dt/1e12:7.1f} TF/s err {err:.1e}")
+    print(f"n={n:5d}  " + "  |  ".join(row), flush=True)
