@@ -80,6 +80,8 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     // kernel-selection switch for A/B measurements: TNN_TMA_ACT=0 keeps the gathering producer everywhere
     const char *e = getenv("TNN_TMA_ACT");
     ctx->tma_activations = (e && e[0] == '0') ? 0 : 1;
+    const char *g = getenv("TNN_TMA_GEMM");
+    ctx->tma_gemm = (g && g[0] == '0') ? 0 : 1;
     const char *p2 = getenv("TNN_PAIR");
     ctx->pair_mma = (p2 && p2[0] == '1') ? 1 : 0;
   }

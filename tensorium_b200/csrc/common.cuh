@@ -14,6 +14,7 @@ struct tnn_context {
   cudaDeviceProp prop;
   int math_mode;
   int tma_activations;  // 1: stride-1 convolutions fetch activations by TMA when the geometry allows (default)
+  int tma_gemm;         // 1: aligned SGEMM operands are fetched by TMA (default; TNN_TMA_GEMM=0 turns it off)
   int pair_mma;         // 1: wide layers of the gathering path run on CTA pairs (tcgen05.mma.cta_group::2)
   int last_conv_kernel; // which kernel the last tnn_conv2d_forward took (TNN_CONV_KERNEL_*), for measurement tools
   int64_t launches;

@@ -9,6 +9,7 @@
 #include "umma_halo.cuh"
 #include "umma_wgrad.cuh"
 #include "umma_conv2.cuh"
+#include "umma_gemm.cuh"
 
 namespace {
 
@@ -160,7 +161,11 @@ int32_t tnn_gemm_strided_batched(tnn_context *ctx, int32_t transA, int32_t trans
     return 0;
   }
   if (ctx->math_mode != TNN_MATH_FP32 && umma::gemm_supported(ctx, M, N, K)) {
-    int rc = umma::gemm(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
+    int rc = ctx->tma_gemm ? umma::gemm_tma(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,
+                                            strideC, (int)batchCount)
+                           : umma::kNotTaken;
+    if (rc != umma::kNotTaken) return rc;
+    rc = umma::gemm(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc, strideC,
                         (int)batchCount, false);
     if (rc != umma::kNotTaken) return rc;
   }

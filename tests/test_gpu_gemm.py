@@ -49,7 +49,8 @@ def test_gemm_fp32_nn_bit_exact_with_fma_oracle(cuda_backend, oracle):
 
 @pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32)])
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0), (1, 1)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (256, 256, 512), (130, 70, 200), (1000, 300, 77), (512, 1024, 2048)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (256, 256, 512), (130, 70, 200), (1000, 300, 77), (512, 1024, 2048),
+                                   (132, 72, 200), (1000, 300, 76), (260, 520, 36)])  # ragged but 16-byte aligned: TMA-fed kernel
 def test_gemm_tensor_core_modes(cuda_backend, oracle, mode, tol, ta, tb, M, N, K):
     got, want, C0 = run_gemm(cuda_backend, oracle, mode, ta, tb, M, N, K, 1.0, 0.0, seed=K)
     e1, e2 = rel_max(got, want), rel_elem(got, want, floor=1.0)
