@@ -197,9 +197,25 @@ def test_maxpool_softmax_dropout_layers(cuda_backend, oracle):
     assert 0.15 < (want == 0).mean() < 0.45
 
 
+def _copy_training_state(src, dst):
+    """Parameters, momentum buffers and rolling statistics of `src` -> `dst` (device buffers stay where they are)."""
+    for ls, ld in zip(src.layers, dst.layers):
+        for name in ("weights", "biases", "scales", "weight_updates", "bias_updates", "scale_updates", "rolling_mean",
+                     "rolling_variance"):
+            ts, td = getattr(ls, name, None), getattr(ld, name, None)
+            if ts is None or td is None or not ts.devData:
+                continue
+            td.Data[...] = ts.pullFromDevice()
+            ts.setCUDA()
+            td.pushToDevice()
+
+
 def test_graph_replay_matches_eager_training(cuda_backend):
     """The captured CUDA graph of a training step (device-side dropout seeds) follows the eager step kernel for kernel:
-    same weights after four steps up to the order of the fp32 atomics in the split reductions."""
+    from the same parameters, same cost and same parameters after the step, up to the order of the fp32 atomics in the
+    split reductions.  The two replicas are re-synchronised after every step: tools/determinism_probe.py shows that
+    an ulp of such noise can flip the winner of a near-tie max-pool window one step later, which moves weights by
+    ~1e-3 and is a property of fp32 atomics, not of the graph path."""
     from tensorium_b200 import models
     from tensorium_b200.train_layers import TDropoutLayer
     B = 16
@@ -214,15 +230,20 @@ def test_graph_replay_matches_eager_training(cuda_backend):
             net.trainBatch(*batches[i])
     graph.enableGraph(seed=0xABCDEF)
     for step in range(4):
+        _copy_training_state(eager, graph)
         x, t = batches[2 + step]
         for li, l in enumerate(eager.layers):
             if isinstance(l, TDropoutLayer):
                 l.seed = graph.dropout_seed(li, step)
         eager.trainBatch(x, t)
         graph.trainBatch(x, t)
-        assert abs(graph.cost() - eager.cost()) <= 1e-4 * abs(eager.cost()), (step, graph.cost(), eager.cost())
-    for le, lg in zip(_trainables(eager), _trainables(graph)):
-        assert rel_max(lg.weights.pullFromDevice(), le.weights.pullFromDevice()) <= 1e-4
-    for le, lg in zip(eager.layers, graph.layers):
-        if isinstance(le, TDropoutLayer):
-            assert np.array_equal(lg.rand.pullFromDevice(), le.rand.pullFromDevice())  # same masks
+        assert abs(graph.cost() - eager.cost()) <= 1e-5 * abs(eager.cost()), (step, graph.cost(), eager.cost())
+        for le, lg in zip(_trainables(eager), _trainables(graph)):
+            assert rel_max(lg.weights.pullFromDevice(), le.weights.pullFromDevice()) <= 1e-5, step
+            le.weights.setCUDA()
+            lg.weights.setCUDA()
+        for le, lg in zip(eager.layers, graph.layers):
+            if isinstance(le, TDropoutLayer):
+                assert np.array_equal(lg.rand.pullFromDevice(), le.rand.pullFromDevice())  # same masks
+                le.rand.setCUDA()
+                lg.rand.setCUDA()
