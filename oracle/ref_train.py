@@ -202,3 +202,25 @@ def build_deepcifar10(batch, params, size=32, c_in=3, classes=10, dropout=0.2, *
     L.append(RefConnected(batch, 1024, classes, A["LINEAR"], p["w"], p["b"]))
     L.append(RefSoftmax(batch, classes))
     return RefNet(L, batch, **hyper)
+
+
+def lenet_mnist_params(seed=5):
+    """Random-init parameters of leNetMNIST (nmodels.pas:50-64)."""
+    rng = np.random.default_rng(seed)
+    P = []
+    for c, f in ((1, 6), (6, 16), (16, 120)):
+        s = np.sqrt(2.0 / (25 * c))
+        P.append(dict(w=rng.uniform(-s, s, (f, c * 25)).astype(f32), b=rng.uniform(-0.1, 0.1, f).astype(f32)))
+    for n_in, n_out in ((120, 84), (84, 10)):
+        s = np.sqrt(2.0 / n_in)
+        P.append(dict(w=rng.uniform(-s, s, (n_out, n_in)).astype(f32), b=rng.uniform(-0.1, 0.1, n_out).astype(f32)))
+    return P
+
+
+def build_lenet_mnist(batch, params, **hyper):
+    A = orc.ACT
+    cv = lambda p, c, h, pad: RefConvTrain(batch, c, h, h, p["b"].size, 5, 1, pad, A["RELU"], False, p["w"], p["b"])
+    L = [cv(params[0], 1, 28, 2), RefMaxPool(batch, 6, 28, 28, 2), cv(params[1], 6, 14, 0), RefMaxPool(batch, 16, 10, 10, 2),
+         cv(params[2], 16, 5, 0), RefConnected(batch, 120, 84, A["RELU"], params[3]["w"], params[3]["b"]),
+         RefConnected(batch, 84, 10, A["LINEAR"], params[4]["w"], params[4]["b"]), RefSoftmax(batch, 10)]
+    return RefNet(L, batch, **hyper)

@@ -3,6 +3,10 @@
 deepCIFAR10 follows source/nmodels.pas:82-111 layer for layer (the net examples/CIFAR10Conv trains):
 2x[conv3x3 relu BN] - maxpool2 at 32, 64 and 128 filters, dropout .2, connected 2048->1024 relu,
 dropout .2, connected 1024->10 linear, softmax.
+
+leNetMNIST follows source/nmodels.pas:50-64 (the convolutional alternative of examples/MNISTConnected,
+MNISTConnected.pas:52): conv5x5 pad 2 (1->6) - maxpool2 - conv5x5 (6->16) - maxpool2 - conv5x5 (16->120) -
+connected 120->84 relu - connected 84->10 linear - softmax; ReLU, no batch normalisation, so the biases learn.
 """
 from __future__ import annotations
 
@@ -33,14 +37,31 @@ def deepCIFAR10(batch=1, size=32, channels=3, classes=10, fused=True, seed=0, pa
     L.append(TDropoutLayer(batch, dropout, 1024, rng=rng))
     L.append(TConnectedLayer(batch, 1, 1024, classes, nn.acLINEAR, rng=rng))
     L.append(TSoftmaxLayer(batch, classes))
-    if params is not None:
-        trainable = [l for l in L if getattr(l, "trainable", False)]
-        assert len(trainable) == len(params)
-        for l, p in zip(trainable, params):
-            l.weights.Data[...] = p["w"].reshape(l.weights.FShape)
-            l.biases.Data[...] = p["b"]
-            if "scales" in p:
-                l.scales.Data[...] = p["scales"]
-                l.rolling_mean.Data[...] = p["rm"]
-                l.rolling_variance.Data[...] = p["rv"]
+    _load_params(L, params)
     return TNNet(L, batch, channels, size, size, **hyper)
+
+
+def _load_params(L, params):
+    if params is None:
+        return
+    trainable = [l for l in L if getattr(l, "trainable", False)]
+    assert len(trainable) == len(params)
+    for l, p in zip(trainable, params):
+        l.weights.Data[...] = p["w"].reshape(l.weights.FShape)
+        l.biases.Data[...] = p["b"]
+        if "scales" in p:
+            l.scales.Data[...] = p["scales"]
+            l.rolling_mean.Data[...] = p["rm"]
+            l.rolling_variance.Data[...] = p["rv"]
+
+
+def leNetMNIST(batch=1, fused=True, seed=0, params=None, **hyper):
+    """Returns a TNNet in training mode; `params`: optional list of 5 dicts (3 conv, 2 connected: w, b)."""
+    rng = np.random.default_rng(seed)
+    conv = lambda h, c, f, pad: TConvolutionalLayer(batch, h, h, c, f, 5, 1, pad, nn.acRELU, False, train=True,
+                                                    fused=fused, rng=rng, host_output=False)
+    L = [conv(28, 1, 6, 2), TMaxPoolLayer(batch, 28, 28, 6, 2), conv(14, 6, 16, 0), TMaxPoolLayer(batch, 10, 10, 16, 2),
+         conv(5, 16, 120, 0), TConnectedLayer(batch, 1, 120, 84, nn.acRELU, rng=rng),
+         TConnectedLayer(batch, 1, 84, 10, nn.acLINEAR, rng=rng), TSoftmaxLayer(batch, 10)]
+    _load_params(L, params)
+    return TNNet(L, batch, 1, 28, 28, **hyper)

@@ -50,8 +50,19 @@ def _force_forward_state(gnet, rnet):
                 t.pushToDevice()
 
 
-@pytest.mark.parametrize("fused,mode,tol", [(True, X3, 1e-4), (False, X3, 1e-4), (True, FP32, 2e-5), (True, TF32, 5e-3)])
-def test_deepcifar10_training_steps(cuda_backend, oracle, fused, mode, tol):
+def _mnist_batch(B, seed):
+    rng = np.random.default_rng(seed)
+    x = rng.uniform(0, 1, (B, 1, 28, 28)).astype(np.float32)
+    t = np.zeros((B, 10), np.float32)
+    t[np.arange(B), rng.integers(0, 10, B)] = 1
+    return x, t
+
+
+@pytest.mark.parametrize("model,fused,mode,tol", [("cifar", True, X3, 1e-4), ("cifar", False, X3, 1e-4),
+                                                  ("cifar", True, FP32, 2e-5), ("cifar", True, TF32, 5e-3),
+                                                  ("mnist", True, X3, 1e-4), ("mnist", False, X3, 1e-4)])
+def test_training_steps_match_the_oracle(cuda_backend, oracle, model, fused, mode, tol):
+    """deepCIFAR10 (SURVEY config 3) and leNetMNIST (config 1, B=32) against the oracle's step, tensor by tensor."""
     from oracle import ref_train as rt
     from tensorium_b200 import models
     from tensorium_b200.layers import TNNetState
@@ -59,14 +70,21 @@ def test_deepcifar10_training_steps(cuda_backend, oracle, fused, mode, tol):
     cu = cuda_backend
     cu.set_math_mode(mode)
     try:
-        B, steps = 8, 3
+        steps = 3
         hyper = dict(momentum=0.9, decay=0.0001)
-        P = rt.deepcifar10_params(seed=11)
-        rnet = rt.build_deepcifar10(B, P, learning_rate=0.01, **hyper)
-        gnet = models.deepCIFAR10(B, fused=fused, params=P, learningRate=0.01, **hyper)
+        if model == "cifar":
+            B, make_batch = 8, _batch
+            P = rt.deepcifar10_params(seed=11)
+            rnet = rt.build_deepcifar10(B, P, learning_rate=0.01, **hyper)
+            gnet = models.deepCIFAR10(B, fused=fused, params=P, learningRate=0.01, **hyper)
+        else:
+            B, make_batch = 32, _mnist_batch
+            P = rt.lenet_mnist_params(seed=5)
+            rnet = rt.build_lenet_mnist(B, P, learning_rate=0.01, **hyper)
+            gnet = models.leNetMNIST(B, fused=fused, params=P, learningRate=0.01, **hyper)
         gnet.truth = TSingleTensor((B, 10), groups=B)
         for it in range(steps):
-            x, t = _batch(B, 100 + it)
+            x, t = make_batch(B, 100 + it)
             _pin_seeds(gnet, rnet, it)
             rcost = rnet.propagate(x.copy(), t)
             gnet.input.Data[...] = x
@@ -108,7 +126,7 @@ def test_deepcifar10_training_steps(cuda_backend, oracle, fused, mode, tol):
         # the reference's first-iteration quirk is mirrored: a layer above a dropout sees an unassigned
         # state.delta on the very first backward (ndropoutlayer.pas:172 wires it afterwards), so the conv
         # stack only starts learning at iteration 2; by now every conv layer has non-zero updates
-        for g in _trainables(gnet)[:6]:
+        for g in _trainables(gnet)[:6 if model == "cifar" else 5]:
             assert np.abs(g.weight_updates.pullFromDevice()).max() > 0
     finally:
         cu.set_math_mode(X3)

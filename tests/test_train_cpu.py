@@ -73,6 +73,24 @@ def test_oracle_training_step_learns(oracle):
     assert costs[-1] < 0.2 * costs[0], costs
 
 
+def test_oracle_lenet_mnist_learns(oracle):
+    """SURVEY config 1 (leNetMNIST, nmodels.pas:50-64): shapes chain 28 -> 14 -> 10 -> 5 -> 1 and one batch is fitted."""
+    from oracle import ref_train as rt
+    B = 8
+    net = rt.build_lenet_mnist(B, rt.lenet_mnist_params(seed=1), learning_rate=0.05)
+    assert [l.output.shape[1:] for l in net.layers[:5]] == [(6, 28, 28), (6, 14, 14), (16, 10, 10), (16, 5, 5), (120, 1, 1)]
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 1, (B, 1, 28, 28)).astype(np.float32)
+    t = np.zeros((B, 10), np.float32)
+    t[np.arange(B), rng.integers(0, 10, B)] = 1
+    costs = []
+    for it in range(30):
+        costs.append(net.propagate(x.copy(), t) / B)
+        net.update()
+    assert costs[-1] < 0.5 * costs[0], costs
+    assert np.abs(net.layers[0].bias_updates).max() > 0  # no batch norm: the convolution biases learn
+
+
 def _small_net(rt, orc, batch, P, replicas=1):
     A = orc.ACT
     L = [rt.RefConvTrain(batch, 3, 8, 8, 8, 3, 1, 1, A["RELU"], False, P[0]["w"], P[0]["b"]),

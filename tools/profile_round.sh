@@ -34,4 +34,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-fi
 python tools/conv_one.py 3xtf32 128,32,32,32,3,1 > /dev/null 2>&1 && \
 TNN_BWD=1 ncu --set full --clock-control none --import-source on -k regex:k_umma_wgrad -c 1 -s 1 -o $O/r01_wgrad_c32f32 \
     python tools/conv_one.py 3xtf32 128,32,32,32,3,1 > $O/ncu_wgrad.log 2>&1
+# (5) SGEMM sweep (BASELINE config "sgemm") and one full capture of the TMA-fed GEMM kernel
+python tools/sgemm_sweep.py 3xtf32 > $O/sgemm_3xtf32.txt 2>&1
+python tools/sgemm_sweep.py tf32 > $O/sgemm_tf32.txt 2>&1
+TNN_TMA_GEMM=0 python tools/sgemm_sweep.py 3xtf32 > $O/sgemm_3xtf32_regstaged.txt 2>&1
+python tools/sgemm_sweep.py 3xtf32 4096 > /dev/null 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_umma_gemm -c 1 -s 2 -o $O/r01_sgemm_nn4096 \
+    python tools/sgemm_sweep.py 3xtf32 4096 > $O/ncu_sgemm.log 2>&1
 ls -la $O

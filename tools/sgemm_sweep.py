@@ -1,5 +1,6 @@
 """BASELINE config 1: standalone SGEMM sweep through tnn_gemm (M = N = K in 256..8192; NN / NT / TN) with a sampled
-fp64 check.  usage: sgemm_sweep.py [math]"""
+fp64 check; host-timed around a stream synchronise, so the n <= 512 rows are launch latency.
+usage: sgemm_sweep.py [math [n]]"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,7 +13,8 @@ cu = tensor.initCUDART(0)
 cu.set_math_mode(MATH[math])
 rng = np.random.default_rng(0)
 print(f"math={math}")
-for n in (256, 512, 1024, 2048, 4096, 8192):
+SIZES = (int(sys.argv[2]),) if len(sys.argv) > 2 else (256, 512, 1024, 2048, 4096, 8192)
+for n in SIZES:
     A = rng.uniform(-1, 1, (n, n)).astype(np.float32)
     B = rng.uniform(-1, 1, (n, n)).astype(np.float32)
     dA, dB, dC = Dev(cu, A), Dev(cu, B), Dev(cu, n=n * n)

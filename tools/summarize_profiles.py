@@ -135,7 +135,10 @@ if __name__ == "__main__":
     for rep, title in (("r01_gather_c256f512", "gathering tcgen05 conv, 256->512 3x3 @26x26, batch 64 (conv_one.py 64,256,26,512,3,1)"),
                        ("r01_halo_c64f128", "halo-tile tcgen05 conv, 64->128 3x3 @104x104, batch 64 (conv_one.py 64,64,104,128,3,1)"),
                        ("r01_tma1x1_c256f128", "TMA-activation tcgen05 conv, 256->128 1x1 @52x52, batch 64 (conv_one.py 64,256,52,128,1,1)"),
-                       ("r01_wgrad_c32f32", "tile wgrad, 32->32 3x3 @32x32, batch 128 (TNN_BWD=1 conv_one.py 128,32,32,32,3,1)")):
+                       ("r01_wgrad_c32f32", "tile wgrad, 32->32 3x3 @32x32, batch 128 (TNN_BWD=1 conv_one.py 128,32,32,32,3,1)"),
+                       ("r01_sgemm_nn4096", "TMA-fed SGEMM, NN 4096^3 (sgemm_sweep.py 3xtf32 4096)")):
+        if not os.path.exists(os.path.join(SRC, rep + ".ncu-rep")):
+            continue
         full_capture(os.path.join(SRC, rep + ".ncu-rep"), os.path.join(DST, f"{TAG}_ncu_{rep[4:]}.txt"), title)
     for a, b in (("bench_line.json", f"{TAG}_bench_line.json"), ("conv_layers.json", f"{TAG}_conv_layers_3xtf32.json"),
                  ("launches.csv", f"{TAG}_launches.csv")):
@@ -143,5 +146,12 @@ if __name__ == "__main__":
     with open(os.path.join(DST, f"{TAG}_cifar_train.jsonl"), "w") as f:
         for n_ in ("cifar_b128.json", "cifar_b128_nograph.json", "cifar_b512.json", "cifar_b128_unfused.json"):
             f.write(open(os.path.join(SRC, n_)).read().strip() + "\n")
+    if os.path.exists(os.path.join(SRC, "sgemm_3xtf32.txt")):
+        with open(os.path.join(DST, f"{TAG}_sgemm_sweep.txt"), "w") as f:
+            f.write("# tools/sgemm_sweep.py on B200: C = A*B through tnn_gemm, M = N = K = n, fp64-checked on 64 sampled entries\n")
+            for n_, title in (("sgemm_3xtf32.txt", "TMA-fed operands (default)"), ("sgemm_tf32.txt", "TMA-fed operands, TF32 mode"),
+                              ("sgemm_3xtf32_regstaged.txt", "TNN_TMA_GEMM=0: register-staged loaders (the path unaligned operands take)")):
+                if os.path.exists(os.path.join(SRC, n_)):
+                    f.write(f"## {title}\n" + open(os.path.join(SRC, n_)).read())
     if os.path.exists(os.path.join(SRC, "bench_tf32.json")):
         open(os.path.join(DST, f"{TAG}_bench_line_tf32.json"), "w").write(open(os.path.join(SRC, "bench_tf32.json")).read())
