@@ -94,3 +94,60 @@ def test_shortcut_fusion_is_bit_identical(cuda_backend):
                     [l.output.pullFromDevice().copy() for l in net.yolo_layers()])
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+def test_cfg_and_weights_file_build_the_same_net(cuda_backend, tmp_path):
+    """yolov3.cfg text + a .weights file (tensorium_b200/darknet.py; nparser.pas:1140-1182, 1275-1330) give the net that
+    build_yolov3 assembles from the same parameters: every head output bit-identical."""
+    from tensorium_b200 import darknet as dn
+    from tensorium_b200.nnet import build_yolov3, init_yolov3_params, yolov3_spec
+    cu = cuda_backend
+    size, batch = 96, 2
+    spec = yolov3_spec()
+    params = init_yolov3_params(spec, seed=8, objectness_bias=-1.5)
+    path = tmp_path / "yolov3.weights"
+    path.write_bytes(dn.write_weights(params, spec, 3, size, size, seen=640))
+    x = np.random.default_rng(9).random((batch, 3, size, size), dtype=np.float32)
+    a = build_yolov3(batch, size, params=params)
+    b = dn.load_cfg(dn.yolov3_cfg(size=size, batch=batch), weights=str(path), fuse_bn=True)
+    assert b.seen == 640 and len(b.layers) == 107
+    for net in (a, b):
+        cu.writeBuffer(net.input.devData, x.nbytes, x)
+        net.predict()
+    heads = [i for i, it in enumerate(spec) if it[0] == "yolo"]
+    for i in heads:
+        assert np.array_equal(a.layers[i].output.pullFromDevice(), b.layers[i].output.pullFromDevice())
+    # and the parameters read back from the built net reproduce the file (fused batch norm excluded: build unfused)
+    c = dn.load_cfg(dn.yolov3_cfg(size=size, batch=batch), weights=str(path), fuse_bn=False)
+    _, spec_c = dn.cfg_to_spec(dn.parse_cfg(dn.yolov3_cfg(size=size, batch=batch)))
+    assert dn.write_weights(dn.net_params(c, spec_c), spec_c, 3, size, size, seen=640) == path.read_bytes()
+
+
+def test_cfg_built_training_net_steps(cuda_backend):
+    """A [convolutional]/[maxpool]/[dropout]/[connected]/[softmax] cfg builds a trainable net whose loss goes down and
+    whose saved weights reload to the same predictions."""
+    from tensorium_b200 import darknet as dn
+    cfg = ("[net]\nbatch=16\nwidth=16\nheight=16\nchannels=3\nlearning_rate=0.02\nmomentum=0.9\ndecay=0.0001\n"
+           "[convolutional]\nbatch_normalize=1\nfilters=16\nsize=3\nstride=1\npad=1\nactivation=relu\n"
+           "[maxpool]\nsize=2\nstride=2\npadding=0\n"
+           "[convolutional]\nbatch_normalize=1\nfilters=32\nsize=3\nstride=1\npad=1\nactivation=relu\n"
+           "[maxpool]\nsize=2\nstride=2\npadding=0\n[dropout]\nprobability=0.1\n"
+           "[connected]\noutput=10\nactivation=linear\n[softmax]\n")
+    net = dn.load_cfg(cfg, train=True)
+    assert (net.learningRate, net.batch) == (0.02, 16)
+    rng = np.random.default_rng(0)
+    x = rng.uniform(0, 1, (16, 3, 16, 16)).astype(np.float32)
+    t = np.zeros((16, 10), np.float32)
+    t[np.arange(16), rng.integers(0, 10, 16)] = 1
+    costs = []
+    for _ in range(25):
+        net.trainBatch(x, t)
+        costs.append(net.cost())
+    assert costs[-1] < 0.3 * costs[0], costs
+    _, spec = dn.cfg_to_spec(dn.parse_cfg(cfg))
+    blob = dn.write_weights(dn.net_params(net, spec), spec, 3, 16, 16, seen=25 * 16)
+    again, hdr = dn.read_weights(blob, spec, 3, 16, 16)
+    assert hdr["seen"] == 400
+    for p, l in zip(again, net.layers):
+        if p is not None:
+            assert np.array_equal(p["w"].reshape(-1), l.weights.pullFromDevice().reshape(-1))
