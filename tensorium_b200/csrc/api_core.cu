@@ -81,7 +81,7 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     const char *e = getenv("TNN_TMA_ACT");
     ctx->tma_activations = (e && e[0] == '0') ? 0 : 1;
     const char *g = getenv("TNN_TMA_GEMM");
-    ctx->tma_gemm = (g && g[0] == '0') ? 0 : 1;
+    ctx->tma_gemm = (g && g[0] >= '0' && g[0] <= '3') ? g[0] - '0' : 1;  // 2 / 3: force 32 / 16 k per stage
     const char *p2 = getenv("TNN_PAIR");
     ctx->pair_mma = (p2 && p2[0] == '1') ? 1 : 0;
   }

@@ -59,15 +59,17 @@ struct GemmVecEpilogue {  // C[m][n] = alpha*acc + beta*C, float4 stores on full
 };
 
 // AMN / BMN: the operand is contiguous along m / n (transA / !transB); otherwise along k.
-template <bool SPLIT, bool AMN, bool BMN, typename EPI>
+// KB = k extent of one pipeline stage: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B; twice the
+// stages in the same shared memory, which is what hides the landing + low-half latency in 3xTF32 mode).
+template <bool SPLIT, bool AMN, bool BMN, int KB, typename EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 k_umma_gemm(EPI epi, TileSched sched, int BN, int stages, uint32_t accCols, const __grid_constant__ CUtensorMap tmA,
             const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ SharedCtl ctl;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int aBytes = BM * BK * 4;
-  const int bBytes = BN * BK * 4;
+  constexpr int aBytes = BM * KB * 4;
+  const int bBytes = BN * KB * 4;
   const int stageBytes = (aBytes + bBytes) * (SPLIT ? 2 : 1);
   const int bOff = (SPLIT ? 2 : 1) * aBytes;  // stage layout: A | A_lo | B | B_lo   (TF32: A | B)
   const int warp = threadIdx.x >> 5;
@@ -162,10 +164,11 @@ k_umma_gemm(EPI epi, TileSched sched, int BN, int stages, uint32_t accCols, cons
           // k-contiguous: SWIZZLE_128B rows, 8-row groups 1024 B apart, one UMMA_K = 8 step = +32 B.
           // m/n-contiguous: 4 KB atoms (32 k x 32 m/n) side by side; inside an atom 8-k groups are 512 B... the
           // descriptor walks LBO = 4096 between atoms, SBO = 512 between k groups, one UMMA_K step = +1024 B.
-          constexpr uint32_t a_lbo = AMN ? 4096 : 16, a_sbo = AMN ? 512 : 1024, a_lt = AMN ? 1u : 2u;
-          constexpr uint32_t b_lbo = BMN ? 4096 : 16, b_sbo = BMN ? 512 : 1024, b_lt = BMN ? 1u : 2u;
+          constexpr uint32_t kAtom = KB * 128, kSboK = KB == 32 ? 1024 : 512, kLtK = KB == 32 ? 2u : 4u;
+          constexpr uint32_t a_lbo = AMN ? kAtom : 16, a_sbo = AMN ? 512 : kSboK, a_lt = AMN ? 1u : kLtK;
+          constexpr uint32_t b_lbo = BMN ? kAtom : 16, b_sbo = BMN ? 512 : kSboK, b_lt = BMN ? 1u : kLtK;
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {
+          for (int ks = 0; ks < KB / 8; ++ks) {
             const uint32_t aoff = AMN ? ks * 1024 : ks * 32;
             const uint32_t boff = BMN ? ks * 1024 : ks * 32;
             const uint64_t ah = make_desc(sa + aoff, a_lbo, a_sbo, a_lt);
@@ -205,14 +208,14 @@ k_umma_gemm(EPI epi, TileSched sched, int BN, int stages, uint32_t accCols, cons
           mbar_arrive_expect_tx(&ctl.araw[stage], (uint32_t)(aBytes + bBytes));
           if (AMN) {
 #pragma unroll
-            for (int a = 0; a < BM / 32; ++a) tma_load_2d(sa + a * 4096, &tmA, m0 + a * 32, kb * BK, &ctl.araw[stage]);
+            for (int a = 0; a < BM / 32; ++a) tma_load_2d(sa + a * (KB * 128), &tmA, m0 + a * 32, kb * KB, &ctl.araw[stage]);
           } else {
-            tma_load_2d(sa, &tmA, kb * BK, m0, &ctl.araw[stage]);
+            tma_load_2d(sa, &tmA, kb * KB, m0, &ctl.araw[stage]);
           }
           if (BMN) {
-            for (int a = 0; a < (BN >> 5); ++a) tma_load_2d(sb + a * 4096, &tmB, n0 + a * 32, kb * BK, &ctl.araw[stage]);
+            for (int a = 0; a < (BN >> 5); ++a) tma_load_2d(sb + a * (KB * 128), &tmB, n0 + a * 32, kb * KB, &ctl.araw[stage]);
           } else {
-            tma_load_2d(sb, &tmB, kb * BK, n0, &ctl.araw[stage]);
+            tma_load_2d(sb, &tmB, kb * KB, n0, &ctl.araw[stage]);
           }
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
@@ -259,16 +262,17 @@ k_umma_gemm(EPI epi, TileSched sched, int BN, int stages, uint32_t accCols, cons
 // rows x K operand, k-contiguous (ld floats between rows): boxes of 32 k x boxRows rows, SWIZZLE_128B.
 // m/n-contiguous (ld floats between k): boxes of 32 m/n x 32 k, SWIZZLE_128B_ATOM_32B.
 inline int encode_gemm_operand(CUtensorMap *tm, const float *base, bool mnContig, int64_t rows, int64_t K, int64_t ld,
-                               int boxRows) {
+                               int boxRows, int kb) {
   EncodeTiledFn enc = get_encode_tiled();
   TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)(mnContig ? rows : K), (cuuint64_t)(mnContig ? K : rows)};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  cuuint32_t box[2] = {32, (cuuint32_t)(mnContig ? 32 : boxRows)};
+  cuuint32_t box[2] = {(cuuint32_t)(mnContig ? 32 : kb), (cuuint32_t)(mnContig ? kb : boxRows)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mnContig ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   mnContig ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                            : (kb == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     tnn_set_error("cuTensorMapEncodeTiled (gemm operand) failed with CUresult %d", (int)r);
@@ -277,35 +281,63 @@ inline int encode_gemm_operand(CUtensorMap *tm, const float *base, bool mnContig
   return 0;
 }
 
-template <bool SPLIT, bool AMN, bool BMN, typename EPI>
+template <bool SPLIT, bool AMN, bool BMN, int KB, typename EPI>
 int launch_gemm_tma(tnn_context *ctx, const Plan &p, EPI epi, const CUtensorMap &tmA, const CUtensorMap &tmB) {
-  auto kern = k_umma_gemm<SPLIT, AMN, BMN, EPI>;
+  auto kern = k_umma_gemm<SPLIT, AMN, BMN, KB, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
   kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(epi, p.sched, p.BN, p.stages, p.accCols, tmA, tmB);
   TNN_LAUNCHED(ctx);
   return 0;
 }
 
-template <bool AMN, bool BMN>
+// make_plan with a stage of KB k (the tile scheduler counts k-blocks of KB)
+inline Plan make_gemm_plan(tnn_context *ctx, int64_t M, int64_t N, int64_t K, bool split, bool bMnMajor, bool allowSplitK,
+                           int kb) {
+  Plan p = make_plan(ctx, M, N, K, split, bMnMajor, false);
+  const size_t stageBytes = (size_t)(BM + p.BN) * kb * 4 * (split ? 2 : 1);
+  int st = (int)((200 * 1024) / stageBytes);
+  p.stages = st > kMaxStages ? kMaxStages : st < 2 ? 2 : st;
+  p.smemBytes = stageBytes * p.stages + 1024;
+  TileSched &s = p.sched;
+  s.kBlocks = (int)cdiv64(K, kb);
+  if (s.kBlocks < 1) s.kBlocks = 1;
+  const int64_t sms = ctx->prop.multiProcessorCount;
+  const int64_t tiles = (int64_t)s.mTiles * s.nTiles;
+  int64_t ks = 1;
+  const int perSplitMin = 8 * (BK / kb);  // same k extent per split as the register-staged plan
+  if (allowSplitK && tiles < sms && s.kBlocks >= 2 * perSplitMin) {
+    ks = sms / tiles;
+    const int64_t maxs = s.kBlocks / perSplitMin;
+    if (ks > maxs) ks = maxs;
+    if (ks < 1) ks = 1;
+  }
+  s.kBlocksPerSplit = (int)cdiv64(s.kBlocks, ks);
+  s.kSplits = (int)cdiv64(s.kBlocks, s.kBlocksPerSplit);
+  s.numTiles = s.mTiles * s.nTiles * s.kSplits;
+  p.grid = (int)(s.numTiles < sms ? s.numTiles : sms);
+  return p;
+}
+
+template <bool AMN, bool BMN, int KB>
 int gemm_tma_one(tnn_context *ctx, int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t lda,
                  const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   const bool zeroFirst = beta == 0.0f && ldc == N;
-  Plan p = make_plan(ctx, M, N, K, split, BMN, beta == 1.0f || zeroFirst);
+  Plan p = make_gemm_plan(ctx, M, N, K, split, BMN, beta == 1.0f || zeroFirst, KB);
   alignas(64) CUtensorMap tmA, tmB;
-  int rc = encode_gemm_operand(&tmA, A, AMN, M, K, lda, BM);
+  int rc = encode_gemm_operand(&tmA, A, AMN, M, K, lda, BM, KB);
   if (rc) return rc;
-  rc = encode_gemm_operand(&tmB, B, BMN, N, K, ldb, p.BN);
+  rc = encode_gemm_operand(&tmB, B, BMN, N, K, ldb, p.BN, KB);
   if (rc) return rc;
   if (p.sched.kSplits > 1) {
     if (beta == 0.0f) TNN_CUDA(cudaMemsetAsync(C, 0, (size_t)M * N * sizeof(float), ctx->stream));
     GemmAtomicEpilogue epi{C, ldc, alpha, beta, M, N};
-    return split ? launch_gemm_tma<true, AMN, BMN>(ctx, p, epi, tmA, tmB)
-                 : launch_gemm_tma<false, AMN, BMN>(ctx, p, epi, tmA, tmB);
+    return split ? launch_gemm_tma<true, AMN, BMN, KB>(ctx, p, epi, tmA, tmB)
+                 : launch_gemm_tma<false, AMN, BMN, KB>(ctx, p, epi, tmA, tmB);
   }
   GemmVecEpilogue epi{C, ldc, alpha, beta, M, N, ((((uintptr_t)C) & 15) == 0 && (ldc % 4) == 0) ? 1 : 0};
-  return split ? launch_gemm_tma<true, AMN, BMN>(ctx, p, epi, tmA, tmB)
-               : launch_gemm_tma<false, AMN, BMN>(ctx, p, epi, tmA, tmB);
+  return split ? launch_gemm_tma<true, AMN, BMN, KB>(ctx, p, epi, tmA, tmB)
+               : launch_gemm_tma<false, AMN, BMN, KB>(ctx, p, epi, tmA, tmB);
 }
 
 // kNotTaken unless every operand meets the TMA rules (16-byte aligned base and row pitch, 32-bit coordinates).
@@ -317,14 +349,20 @@ inline int gemm_tma(tnn_context *ctx, bool tA, bool tB, int64_t M, int64_t N, in
   };
   if (!ok(A, lda, sA) || !ok(B, ldb, sB) || K < BK || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31))
     return kNotTaken;
+  // 3xTF32 stages are twice as large: half-depth stages keep four of them in flight (ctx->tma_gemm == 2 forces 32)
+  const bool kb16 = ctx->tma_gemm == 3 || (ctx->tma_gemm == 1 && ctx->math_mode == TNN_MATH_3XTF32);
   for (int z = 0; z < batch; ++z) {
     const float *Az = A + z * sA, *Bz = B + z * sB;
     float *Cz = C + z * sC;
     int rc;
-    if (!tA && tB) rc = gemm_tma_one<false, false>(ctx, M, N, K, alpha, Az, lda, Bz, ldb, beta, Cz, ldc);
-    else if (!tA && !tB) rc = gemm_tma_one<false, true>(ctx, M, N, K, alpha, Az, lda, Bz, ldb, beta, Cz, ldc);
-    else if (tA && !tB) rc = gemm_tma_one<true, true>(ctx, M, N, K, alpha, Az, lda, Bz, ldb, beta, Cz, ldc);
-    else rc = gemm_tma_one<true, false>(ctx, M, N, K, alpha, Az, lda, Bz, ldb, beta, Cz, ldc);
+#define TNN_GEMM_CASE(AMN, BMN)                                                                             \
+  (kb16 ? gemm_tma_one<AMN, BMN, 16>(ctx, M, N, K, alpha, Az, lda, Bz, ldb, beta, Cz, ldc)                   \
+        : gemm_tma_one<AMN, BMN, 32>(ctx, M, N, K, alpha, Az, lda, Bz, ldb, beta, Cz, ldc))
+    if (!tA && tB) rc = TNN_GEMM_CASE(false, false);
+    else if (!tA && !tB) rc = TNN_GEMM_CASE(false, true);
+    else if (tA && !tB) rc = TNN_GEMM_CASE(true, true);
+    else rc = TNN_GEMM_CASE(true, false);
+#undef TNN_GEMM_CASE
     if (rc) return rc;
   }
   return 0;
