@@ -82,6 +82,10 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     ctx->tma_activations = (e && e[0] == '0') ? 0 : 1;
     const char *g = getenv("TNN_TMA_GEMM");
     ctx->tma_gemm = (g && g[0] >= '0' && g[0] <= '3') ? g[0] - '0' : 1;  // 2 / 3: force 32 / 16 k per stage
+    const char *k16 = getenv("TNN_GATHER_KB16");
+    ctx->gather_kb16 = (k16 && k16[0] == '1') ? 1 : 0;  // measured slower (173 vs 195 TFLOP/s): off unless asked for
+    const char *pk = getenv("TNN_PATCH_KB16");
+    ctx->patch_kb16 = (pk && pk[0] == '1') ? 1 : 0;  // measured: no difference (97.3 vs 96.6 TFLOP/s), so the 32-k path stays
     const char *p2 = getenv("TNN_PAIR");
     ctx->pair_mma = (p2 && p2[0] == '1') ? 1 : 0;
   }

@@ -28,6 +28,7 @@
 //            descriptor: SWIZZLE_128B_BASE32B, LBO = 512 (next 32-element atom along M/N),
 //            SBO = (R/32)*512 (next 4-row k group), advance two SBO per UMMA_K=8 step
 #pragma once
+#include <type_traits>
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched through cudaGetDriverEntryPoint)
 #include <stdlib.h>
 #include <string.h>
@@ -416,6 +417,51 @@ struct Im2colPixelLoader {
   }
 };
 
+// k extent of one pipeline stage: 32 unless the A loader says otherwise
+template <typename L, typename = void>
+struct StageK { static constexpr int v = BK; };
+template <typename L>
+struct StageK<L, std::void_t<decltype(L::kKB)>> { static constexpr int v = L::kKB; };
+
+// Same gather with 16-k stages: one (channel group, tap) per stage, each thread stages 8 of its 16 channels.  The
+// A tile is k-outermost (2 KB per 4 k x 128 pixels), so a 16-k stage is simply the first half of the 32-k layout;
+// half-size stages put four of them in flight where 3xTF32 at BN = 256 only has room for two 32-k stages.
+struct Im2colPixelLoader16 : Im2colPixelLoader {
+  static constexpr int kKB = 16;
+  static constexpr int kPrefetch = 2 * TNN_PIXEL_PREFETCH;
+  struct Regs { float v[8]; };
+  __device__ __noinline__ TileCtx tile_ctx(int r, int64_t mn0, int tid, int kb0) const {
+    TileCtx c = Im2colPixelLoader::tile_ctx(r, mn0, tid, 0);
+    c.cg = kb0 / kk;
+    c.tap = kb0 - c.cg * kk;
+    return c;
+  }
+  __device__ __forceinline__ void load(TileCtx &cx, Regs &r, int64_t, int tid, const int *lut) const {
+    const int c0 = cx.cg * 16 + (tid >> 7) * 8;
+    const bool on = (cx.tapmask >> cx.tap) & 1ull;
+    const float *q = cx.base + (int64_t)c0 * HW + lut[cx.tap];
+    const int nc = on ? g.C - c0 : 0;
+    const uint32_t hw = (uint32_t)HW;
+    uint32_t off = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      r.v[j] = (j < nc) ? __ldg(q + off) : 0.f;
+      off += hw;
+    }
+    if (++cx.tap == kk) { cx.tap = 0; ++cx.cg; }
+  }
+  template <bool SPLIT>
+  __device__ __forceinline__ void store(const Regs &r, uint8_t *hi, uint8_t *lo, int, int tid) const {
+    const int row = tid & 127, khalf = tid >> 7;
+    const uint32_t rowpart = (uint32_t)((row >> 5) << 9) + (uint32_t)((row & 7) << 2) + (uint32_t)khalf * 2u * 2048u;
+    uint32_t soff[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) soff[q] = rowpart + (uint32_t)(q << 7) + (uint32_t)(((((row & 31) >> 3) ^ q)) << 5);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sts_elem<SPLIT>(hi, lo, soff[j & 3] + (uint32_t)((j >> 2) * 2048), r.v[j]);
+  }
+};
+
 // weights pre-split into a zero-padded K-major copy [F][Kpad] (hi and lo planes) and fetched by TMA
 struct TmaWeightsLoader {
   static constexpr bool kTmaA = false;
@@ -499,6 +545,11 @@ struct TmaPatchLoader {
     ow0 = (r - hy * WT) * TW;
     if (atom >= numAtoms) n = batch;
   }
+};
+
+// 16-channel stages (CB counts 16-channel blocks): atoms of 16 k x 32 pixels, 2 KB apart
+struct TmaPatchLoader16 : TmaPatchLoader {
+  static constexpr int kKB = 16;
 };
 
 // ------------------------------------------------------------------ epilogues
@@ -704,8 +755,10 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
   __shared__ SharedCtl ctl;
   // 1024B-aligned operand ring
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const int aBytes = BM * BK * 4;
-  const int bBytes = BN * BK * 4;
+  constexpr int KB = StageK<LA>::v;
+  static_assert(KB == BK || (LB::kTma && LA::kMnMajor), "16-k stages: MN-major A (gathered or TMA patches) + TMA weights only");
+  const int aBytes = BM * KB * 4;
+  const int bBytes = BN * KB * 4;
   const int stageBytes = (aBytes + bBytes) * (SPLIT ? 2 : 1);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -856,14 +909,15 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
           const uint32_t sb = sa + (SPLIT ? 2 : 1) * aBytes;
           const uint32_t sb_lo = sb + bBytes;
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ++ks) {
+          for (int ks = 0; ks < KB / 8; ++ks) {
             // MN-major: LBO 512, SBO (R/32)*512, one UMMA_K=8 step = two 4-row k groups.  K-major: SBO 1024, +32B.
             const uint32_t aoff = LA::kTmaA ? ks * 1024 : LA::kMnMajor ? ks * 2 * (BM / 32) * 512 : ks * 32;
             const uint32_t boff = LB::kMnMajor ? ks * 2 * (BN / 32) * 512 : ks * 32;
-            const uint32_t a_lbo = LA::kTmaA ? 4096 : LA::kMnMajor ? 512 : 16;
+            const uint32_t a_lbo = LA::kTmaA ? KB * 128 : LA::kMnMajor ? 512 : 16;
             const uint32_t a_sbo = LA::kTmaA ? 512 : LA::kMnMajor ? (BM / 32) * 512 : 1024;
-            const uint32_t b_lbo = LB::kMnMajor ? 512 : 16, b_sbo = LB::kMnMajor ? (BN / 32) * 512 : 1024;
-            const uint32_t a_lt = LA::kMnMajor ? 1u : 2u, b_lt = LB::kMnMajor ? 1u : 2u;
+            // K-major B rows are 128 B (SWIZZLE_128B) or, with 16-k stages, 64 B (SWIZZLE_64B: 8-row groups of 512 B)
+            const uint32_t b_lbo = LB::kMnMajor ? 512 : 16, b_sbo = LB::kMnMajor ? (BN / 32) * 512 : (KB == BK ? 1024 : 512);
+            const uint32_t a_lt = LA::kMnMajor ? 1u : 2u, b_lt = LB::kMnMajor ? 1u : (KB == BK ? 2u : 4u);
             const uint64_t ah = make_desc(sa + aoff, a_lbo, a_sbo, a_lt);
             const uint64_t bh = make_desc(sb + boff, b_lbo, b_sbo, b_lt);
             const uint32_t acc = (kb != kb0 || ks != 0) ? 1u : 0u;
@@ -914,7 +968,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
             mbar_arrive_expect_tx(&ctl.araw[stage], (uint32_t)aBytes);
 #pragma unroll
             for (int a = 0; a < 4; ++a)
-              tma_load_4d(sa + a * 4096, &tmA, aw[a] + kc * la.dx, ah[a] + kr * la.dy, cb * 32, an[a], &ctl.araw[stage]);
+              tma_load_4d(sa + a * (KB * 128), &tmA, aw[a] + kc * la.dx, ah[a] + kr * la.dy, cb * KB, an[a], &ctl.araw[stage]);
             if (++cb == la.CB) {
               cb = 0;
               if (++kc == la.kw) { kc = 0; ++kr; }
@@ -922,8 +976,8 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
           }
           const uint32_t sb = smem_base + (uint32_t)stage * stageBytes + (SPLIT ? 2 : 1) * aBytes;
           mbar_arrive_expect_tx(&ctl.full[stage], (uint32_t)bBytes * (SPLIT ? 2 : 1));
-          tma_load_2d(sb, &tmBhi, (int)(kb * BK), (int)(nt * BN), &ctl.full[stage]);
-          if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, (int)(kb * BK), (int)(nt * BN), &ctl.full[stage]);
+          tma_load_2d(sb, &tmBhi, (int)(kb * KB), (int)(nt * BN), &ctl.full[stage]);
+          if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, (int)(kb * KB), (int)(nt * BN), &ctl.full[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -1267,14 +1321,32 @@ inline int encode_weights_map(CUtensorMap *tm, const float *base, int64_t rows, 
   return 0;
 }
 
+// same matrix as tiles of 16 k x boxRows rows (64-byte rows: SWIZZLE_64B)
+inline int encode_weights_map16(CUtensorMap *tm, const float *base, int64_t rows, int64_t Kpad, int boxRows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kpad * 4};
+  cuuint32_t box[2] = {16, (cuuint32_t)boxRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tnn_set_error("cuTensorMapEncodeTiled (16-k weights) failed with CUresult %d", (int)r);
+    return 6;
+  }
+  return 0;
+}
+
 // NCHW activations {W, H, C, N}; box = one atom of one k-block: {TW, TH, 32, 1} = 4 KB
 inline int encode_patch_map(CUtensorMap *tm, const float *base, int64_t W, int64_t H, int64_t C, int64_t N, int TW,
-                            int TH) {
+                            int TH, int kb = BK) {
   EncodeTiledFn enc = get_encode_tiled();
   TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)C, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * C * 4};
-  cuuint32_t box[4] = {(cuuint32_t)TW, (cuuint32_t)TH, 32, 1};
+  cuuint32_t box[4] = {(cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)kb, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1338,6 +1410,32 @@ inline int conv_patch(tnn_context *ctx, const simt::ConvGeom &v, int batch, cons
     TNN_LAUNCHED(ctx);
   }
   alignas(64) CUtensorMap tmHi, tmLo, tmA;
+  if (split && ctx->patch_kb16) {
+    // 16-channel stages: the same weight copy read as 16-k boxes, twice the stages in flight (what lifted the TMA-fed
+    // SGEMM from 166 to 221 TFLOP/s).  No gain here (97.3 vs 96.6 TFLOP/s over the 28 YOLOv3 1x1 layers): the small-C
+    // layers sit on the HBM roofline, the wide ones are not stage-depth bound -> opt-in (TNN_PATCH_KB16=1)
+    const size_t stageBytes = (size_t)(BM + p.BN) * 16 * 4 * 2;
+    int st = (int)((200 * 1024) / stageBytes);
+    p.stages = st > kMaxStages ? kMaxStages : st;
+    p.smemBytes = stageBytes * p.stages + 1024;
+    p.sched.kBlocks = p.sched.kBlocksPerSplit = (int)(K / 16);
+    rc = encode_weights_map16(&tmHi, whi, N, K, p.BN);
+    if (rc) return rc;
+    rc = encode_weights_map16(&tmLo, wlo, N, K, p.BN);
+    if (rc) return rc;
+    rc = encode_patch_map(&tmA, in, We, He, v.C, batch, TW, TH, 16);
+    if (rc) return rc;
+    TmaPatchLoader16 la16{{TW, TH, WT, HT, WT * HT, (int)numAtoms, batch, flat ? 0 : v.ph, flat ? 0 : v.pw, v.kw, v.dy, v.dx,
+                           2 * CB}};
+    if (accumulate || residual) {
+      ConvEpilogueT<true> epi{out, scale, bias, v.OH * v.OW, v.outImg, act, M, N, accumulate,
+                              TW, TH, WT, WT * HT, (int)OHe, (int)OWe, batch, 5, residual};
+      return launch<true>(ctx, p, la16, TmaWeightsLoader{}, epi, &tmHi, &tmLo, &tmA);
+    }
+    ConvEpilogueT<false> epi{out, scale, bias, v.OH * v.OW, v.outImg, act, M, N, false,
+                             TW, TH, WT, WT * HT, (int)OHe, (int)OWe, batch, 5, nullptr};
+    return launch<true>(ctx, p, la16, TmaWeightsLoader{}, epi, &tmHi, &tmLo, &tmA);
+  }
   rc = encode_weights_map(&tmHi, whi, N, K, p.BN);
   if (rc) return rc;
   rc = encode_weights_map(&tmLo, split ? wlo : whi, N, K, p.BN);
@@ -1389,10 +1487,20 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   if (kk > 64 || g.inImg >= (1ll << 31)) return kNotTaken;  // tap mask is 64 bits, offsets 32 bits
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
-  const int64_t Kpad = (int64_t)p.sched.kBlocks * BK;
+  // 16-k stages keep twice as many in flight in the same shared memory.  That is what lifts the TMA-fed SGEMM by 30 %,
+  // but here the producers pay every stage's wait/fence/arrive twice: 173 vs 195 TFLOP/s on the YOLOv3 layers -> opt-in
+  const bool kb16 = split && residual == nullptr && ctx->gather_kb16;
+  if (kb16) {
+    const size_t stageBytes = (size_t)(BM + p.BN) * 16 * 4 * 2;
+    int st = (int)((200 * 1024) / stageBytes);
+    p.stages = st > kMaxStages ? kMaxStages : st;
+    p.smemBytes = stageBytes * p.stages + 1024;
+    p.sched.kBlocks = p.sched.kBlocksPerSplit = (int)(K / 16);
+  }
+  const int64_t Kpad = kb16 ? K : (int64_t)p.sched.kBlocks * BK;
   float *whi, *wlo;
   bool fresh;
-  int rc = tnn_weight_buffer(ctx, weights, 3, (size_t)N * Kpad, &whi, &wlo, &fresh);
+  int rc = tnn_weight_buffer(ctx, weights, kb16 ? 9 : 3, (size_t)N * Kpad, &whi, &wlo, &fresh);
   if (rc) return rc;
   if (fresh) {
     int64_t blocks = cdiv64(N * Kpad, 256);
@@ -1401,10 +1509,15 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
     TNN_LAUNCHED(ctx);
   }
   alignas(64) CUtensorMap tmHi, tmLo;
-  rc = encode_weights_map(&tmHi, whi, N, Kpad, p.BN);
+  rc = kb16 ? encode_weights_map16(&tmHi, whi, N, Kpad, p.BN) : encode_weights_map(&tmHi, whi, N, Kpad, p.BN);
   if (rc) return rc;
-  rc = encode_weights_map(&tmLo, split ? wlo : whi, N, Kpad, p.BN);
+  rc = kb16 ? encode_weights_map16(&tmLo, wlo, N, Kpad, p.BN) : encode_weights_map(&tmLo, split ? wlo : whi, N, Kpad, p.BN);
   if (rc) return rc;
+  if (kb16) {
+    Im2colPixelLoader16 la16{{in, g, M, g.H * g.W, kk}};
+    ConvEpilogueT<false> epi{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, nullptr};
+    return launch<true>(ctx, p, la16, TmaWeightsLoader{}, epi, &tmHi, &tmLo);
+  }
   Im2colPixelLoader la{in, g, M, g.H * g.W, kk};
   Im2colPixelLoaderFast laf{{in, g, M, g.H * g.W, kk}};
   TmaWeightsLoader lb{};
