@@ -732,7 +732,12 @@ struct SharedCtl {
 
 struct TileSched {  // tiles are numbered m fastest, then n, then k-split (32-bit: divisions stay cheap and small)
   int mTiles, nTiles, kSplits, kBlocks, kBlocksPerSplit, numTiles;
+  // Tiles [wideTiles, numTiles) are half-width: when the last wave would fill less than half of the SMs, each of its
+  // tiles is split in two along n (TMA-fed B only), so that wave costs half a tile instead of a whole one.
+  int wideTiles;
+  __device__ __forceinline__ int half(int t) const { return t >= wideTiles ? 1 + ((t - wideTiles) & 1) : 0; }
   __device__ __noinline__ void decode(int t, int &mt, int &nt, int &kb0, int &kb1) const {
+    if (t >= wideTiles) t = wideTiles + ((t - wideTiles) >> 1);
     const unsigned r = (unsigned)t / (unsigned)mTiles;
     mt = t - (int)r * mTiles;
     const unsigned ks = r / (unsigned)nTiles;
@@ -887,7 +892,6 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one elected thread) =====================
-    const uint32_t idesc = make_idesc(BN, LA::kMnMajor, LB::kMnMajor);
     const uint32_t smem_base = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;
@@ -895,6 +899,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
     for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x, ++it) {
       int mt, nt, kb0, kb1;
       sched.decode(t, mt, nt, kb0, kb1);
+      const uint32_t idesc = make_idesc(sched.half(t) ? BN >> 1 : BN, LA::kMnMajor, LB::kMnMajor);
       const int as = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
       mbar_wait_warp(&ctl.tmem_empty[as], (use & 1) ^ 1);  // epilogue has drained this accumulator buffer
@@ -947,6 +952,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
       for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x) {
         int mt, nt, kb0, kb1;
         sched.decode(t, mt, nt, kb0, kb1);
+        const int n0 = nt * BN + (sched.half(t) == 2 ? BN >> 1 : 0);
         int an[4], ah[4], aw[4];  // TmaPatchLoader: image and input origin (tap 0) of the tile's four atoms
         int tap = 0, cb = 0, kr = 0, kc = 0;
         if constexpr (LA::kTmaA) {
@@ -976,8 +982,9 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
           }
           const uint32_t sb = smem_base + (uint32_t)stage * stageBytes + (SPLIT ? 2 : 1) * aBytes;
           mbar_arrive_expect_tx(&ctl.full[stage], (uint32_t)bBytes * (SPLIT ? 2 : 1));
-          tma_load_2d(sb, &tmBhi, (int)(kb * KB), (int)(nt * BN), &ctl.full[stage]);
-          if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, (int)(kb * KB), (int)(nt * BN), &ctl.full[stage]);
+          // a half-width tile loads the full box from its own first row: the MMA reads the first BN/2 rows of it
+          tma_load_2d(sb, &tmBhi, (int)(kb * KB), n0, &ctl.full[stage]);
+          if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, (int)(kb * KB), n0, &ctl.full[stage]);
           if (++stage == stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -992,13 +999,15 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
       const int as = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
       const int64_t m = (int64_t)mt * BM + quad * 32 + lane;
-      const int64_t n0 = (int64_t)nt * BN;
+      const int hf = sched.half(t);
+      const int bn = hf ? BN >> 1 : BN;  // width of this tile
+      const int64_t n0 = (int64_t)nt * BN + (hf == 2 ? BN >> 1 : 0);
       bool mvalid;
       typename EPI::Row rc = epi.row(m, mvalid);
       mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
-      const int nChunks = (BN + 31) >> 5;  // 32-column chunks; chunk i starts at column 32*i (< accCols)
+      const int nChunks = (bn + 31) >> 5;  // 32-column chunks; chunk i starts at column 32*i (< accCols)
       for (int ci = 0; ci < nChunks; ++ci) {
         const int c0 = ci * 32;
         uint32_t r[32];
@@ -1009,7 +1018,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
           if (lane == 0) mbar_arrive(&ctl.tmem_empty[as]);
         }
         {
-          int64_t cnt = min((int64_t)(BN - c0), epi.cols - (n0 + c0));  // warp-uniform
+          int64_t cnt = min((int64_t)(bn - c0), epi.cols - (n0 + c0));  // warp-uniform
           if (cnt > 32) cnt = 32;
           if (cnt > 0) epi.store_chunk(rc, n0 + c0, r, (int)cnt, mvalid, ctl.epi_sb[quad]);
         }
@@ -1210,8 +1219,21 @@ inline Plan make_plan(tnn_context *ctx, int64_t M, int64_t N, int64_t K, bool sp
   s.kBlocksPerSplit = (int)cdiv64(s.kBlocks, ks);
   s.kSplits = (int)cdiv64(s.kBlocks, s.kBlocksPerSplit);
   s.numTiles = s.mTiles * s.nTiles * s.kSplits;
+  s.wideTiles = s.numTiles;
   p.grid = (int)(s.numTiles < sms ? s.numTiles : sms);
   return p;
+}
+
+// Split the tiles of a last wave that fills at most half of the SMs in two along n (callers with TMA-fed B only).
+inline void split_tail_wave(tnn_context *ctx, Plan &p) {
+  TileSched &s = p.sched;
+  const int sms = ctx->prop.multiProcessorCount;
+  if (!ctx->tail_split || s.kSplits != 1 || (p.BN % 32) != 0) return;
+  const int rem = s.numTiles % sms;
+  if (rem == 0 || 2 * rem > sms) return;
+  s.wideTiles = s.numTiles - rem;
+  s.numTiles = s.wideTiles + 2 * rem;
+  p.grid = s.numTiles < sms ? s.numTiles : sms;
 }
 
 template <bool SPLIT, typename LA, typename LB, typename EPI>
@@ -1398,6 +1420,7 @@ inline int conv_patch(tnn_context *ctx, const simt::ConvGeom &v, int batch, cons
   const int64_t K = (int64_t)kk * CB * 32;
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
+  split_tail_wave(ctx, p);
   float *whi, *wlo;
   bool fresh;
   int rc = tnn_weight_buffer(ctx, weights, dgradWeights ? 2 : 1, (size_t)N * K, &whi, &wlo, &fresh);
@@ -1487,6 +1510,7 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   if (kk > 64 || g.inImg >= (1ll << 31)) return kNotTaken;  // tap mask is 64 bits, offsets 32 bits
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
+  // no split_tail_wave here: a half-width tile costs this kernel a whole A gather (measured: 17.50 vs 17.35 ms/step)
   // 16-k stages keep twice as many in flight in the same shared memory.  That is what lifts the TMA-fed SGEMM by 30 %,
   // but here the producers pay every stage's wait/fence/arrive twice: 173 vs 195 TFLOP/s on the YOLOv3 layers -> opt-in
   const bool kb16 = split && residual == nullptr && ctx->gather_kb16;
@@ -1554,6 +1578,7 @@ inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int bat
   const int64_t K = (int64_t)((v.C + 15) / 16) * kk * 16;
   const bool split = ctx->math_mode == TNN_MATH_3XTF32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
+  // no split_tail_wave here: a half-width tile costs this kernel a whole A gather (measured: 17.50 vs 17.35 ms/step)
   const int64_t Kpad = (int64_t)p.sched.kBlocks * BK;
   float *whi, *wlo;
   bool fresh;

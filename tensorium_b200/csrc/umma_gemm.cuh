@@ -142,7 +142,6 @@ k_umma_gemm(EPI epi, TileSched sched, int BN, int stages, uint32_t accCols, cons
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer (one elected thread) =====================
-    const uint32_t idesc = make_idesc(BN, AMN, BMN);
     const uint32_t smem_base = smem_u32(smem);
     int stage = 0;
     uint32_t phase = 0;
@@ -150,6 +149,7 @@ k_umma_gemm(EPI epi, TileSched sched, int BN, int stages, uint32_t accCols, cons
     for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x, ++it) {
       int mt, nt, kb0, kb1;
       sched.decode(t, mt, nt, kb0, kb1);
+      const uint32_t idesc = make_idesc(sched.half(t) ? BN >> 1 : BN, AMN, BMN);
       const int as = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
       mbar_wait_warp(&ctl.tmem_empty[as], (use & 1) ^ 1);
@@ -200,7 +200,7 @@ k_umma_gemm(EPI epi, TileSched sched, int BN, int stages, uint32_t accCols, cons
       for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x) {
         int mt, nt, kb0, kb1;
         sched.decode(t, mt, nt, kb0, kb1);
-        const int m0 = mt * BM, n0 = nt * BN;
+        const int m0 = mt * BM, n0 = nt * BN + (sched.half(t) == 2 ? BN >> 1 : 0);  // half tile: full box from its first row
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&ctl.empty[stage], phase ^ 1);
           const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
@@ -231,13 +231,15 @@ k_umma_gemm(EPI epi, TileSched sched, int BN, int stages, uint32_t accCols, cons
       const int as = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
       const int64_t m = (int64_t)mt * BM + quad * 32 + lane;
-      const int64_t n0 = (int64_t)nt * BN;
+      const int hf = sched.half(t);
+      const int bn = hf ? BN >> 1 : BN;
+      const int64_t n0 = (int64_t)nt * BN + (hf == 2 ? BN >> 1 : 0);
       bool mvalid;
       typename EPI::Row rc = epi.row(m, mvalid);
       mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
-      const int nChunks = (BN + 31) >> 5;
+      const int nChunks = (bn + 31) >> 5;
       for (int ci = 0; ci < nChunks; ++ci) {
         const int c0 = ci * 32;
         uint32_t r[32];
@@ -247,7 +249,7 @@ k_umma_gemm(EPI epi, TileSched sched, int BN, int stages, uint32_t accCols, cons
           __syncwarp();
           if (lane == 0) mbar_arrive(&ctl.tmem_empty[as]);
         }
-        int64_t cnt = min((int64_t)(BN - c0), epi.cols - (n0 + c0));
+        int64_t cnt = min((int64_t)(bn - c0), epi.cols - (n0 + c0));
         if (cnt > 32) cnt = 32;
         if (cnt > 0) epi.store_chunk(rc, n0 + c0, r, (int)cnt, mvalid, nullptr);
       }
@@ -314,6 +316,8 @@ inline Plan make_gemm_plan(tnn_context *ctx, int64_t M, int64_t N, int64_t K, bo
   s.kBlocksPerSplit = (int)cdiv64(s.kBlocks, ks);
   s.kSplits = (int)cdiv64(s.kBlocks, s.kBlocksPerSplit);
   s.numTiles = s.mTiles * s.nTiles * s.kSplits;
+  s.wideTiles = s.numTiles;
+  split_tail_wave(ctx, p);
   p.grid = (int)(s.numTiles < sms ? s.numTiles : sms);
   return p;
 }
