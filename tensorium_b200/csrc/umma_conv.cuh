@@ -36,6 +36,9 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 
+#ifndef TNN_TAIL_TILES
+#define TNN_TAIL_TILES 1  // 0 compiles the half-width tail tiles out (A/B builds)
+#endif
 #ifndef TNN_PIXEL_PREFETCH
 #define TNN_PIXEL_PREFETCH 3  // k-blocks of im2col loads kept in flight per producer thread
 #endif
@@ -735,9 +738,9 @@ struct TileSched {  // tiles are numbered m fastest, then n, then k-split (32-bi
   // Tiles [wideTiles, numTiles) are half-width: when the last wave would fill less than half of the SMs, each of its
   // tiles is split in two along n (TMA-fed B only), so that wave costs half a tile instead of a whole one.
   int wideTiles;
-  __device__ __forceinline__ int half(int t) const { return t >= wideTiles ? 1 + ((t - wideTiles) & 1) : 0; }
+  __device__ __forceinline__ int half(int t) const { return (TNN_TAIL_TILES && t >= wideTiles) ? 1 + ((t - wideTiles) & 1) : 0; }
   __device__ __noinline__ void decode(int t, int &mt, int &nt, int &kb0, int &kb1) const {
-    if (t >= wideTiles) t = wideTiles + ((t - wideTiles) >> 1);
+    if (TNN_TAIL_TILES && t >= wideTiles) t = wideTiles + ((t - wideTiles) >> 1);
     const unsigned r = (unsigned)t / (unsigned)mTiles;
     mt = t - (int)r * mTiles;
     const unsigned ks = r / (unsigned)nTiles;
@@ -1228,7 +1231,7 @@ inline Plan make_plan(tnn_context *ctx, int64_t M, int64_t N, int64_t K, bool sp
 inline void split_tail_wave(tnn_context *ctx, Plan &p) {
   TileSched &s = p.sched;
   const int sms = ctx->prop.multiProcessorCount;
-  if (!ctx->tail_split || s.kSplits != 1 || (p.BN % 32) != 0) return;
+  if (!TNN_TAIL_TILES || !ctx->tail_split || s.kSplits != 1 || (p.BN % 32) != 0) return;
   const int rem = s.numTiles % sms;
   if (rem == 0 || 2 * rem > sms) return;
   s.wideTiles = s.numTiles - rem;

@@ -50,5 +50,8 @@ TNN_TMA_GEMM=0 python tools/sgemm_sweep.py 3xtf32 > $O/sgemm_3xtf32_regstaged.tx
 python tools/sgemm_sweep.py 3xtf32 4096 > /dev/null 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:k_umma_gemm -c 1 -s 2 -o $O/r01_sgemm_nn4096 \
     python tools/sgemm_sweep.py 3xtf32 4096 > $O/ncu_sgemm.log 2>&1
+python tools/conv_one.py 3xtf32 64,3,416,32,3,1 > $O/one_direct.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:k_conv_direct -c 1 -s 1 -o $O/r01_direct_c3f32 \
+    python tools/conv_one.py 3xtf32 64,3,416,32,3,1 > $O/ncu_direct.log 2>&1
 fi
 ls -la $O

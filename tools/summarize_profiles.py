@@ -101,6 +101,7 @@ KEYS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak
         "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
         "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+        "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size"]
 
 
@@ -136,7 +137,8 @@ if __name__ == "__main__":
                        ("r01_halo_c64f128", "halo-tile tcgen05 conv, 64->128 3x3 @104x104, batch 64 (conv_one.py 64,64,104,128,3,1)"),
                        ("r01_tma1x1_c256f128", "TMA-activation tcgen05 conv, 256->128 1x1 @52x52, batch 64 (conv_one.py 64,256,52,128,1,1)"),
                        ("r01_wgrad_c32f32", "tile wgrad, 32->32 3x3 @32x32, batch 128 (TNN_BWD=1 conv_one.py 128,32,32,32,3,1)"),
-                       ("r01_sgemm_nn4096", "TMA-fed SGEMM, NN 4096^3 (sgemm_sweep.py 3xtf32 4096)")):
+                       ("r01_sgemm_nn4096", "TMA-fed SGEMM, NN 4096^3 (sgemm_sweep.py 3xtf32 4096)"),
+                       ("r01_direct_c3f32", "direct fp32 first layer, 3->32 3x3 @416x416, batch 64 (conv_one.py 64,3,416,32,3,1)")):
         if not os.path.exists(os.path.join(SRC, rep + ".ncu-rep")):
             continue
         full_capture(os.path.join(SRC, rep + ".ncu-rep"), os.path.join(DST, f"{TAG}_ncu_{rep[4:]}.txt"), title)
