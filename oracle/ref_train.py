@@ -224,3 +224,62 @@ def build_lenet_mnist(batch, params, **hyper):
          cv(params[2], 16, 5, 0), RefConnected(batch, 120, 84, A["RELU"], params[3]["w"], params[3]["b"]),
          RefConnected(batch, 84, 10, A["LINEAR"], params[4]["w"], params[4]["b"]), RefSoftmax(batch, 10)]
     return RefNet(L, batch, **hyper)
+
+
+class RefLSTM:
+    """TLSTMLayer.forward (source/nlstmlayer.pas:518-611): eight linear connected layers (wf wi wg wo on the hidden
+    state, uf ui ug uo on the step's input; constructor :42-82, `batch := aBatch div aSteps`), gates
+    f,i,o = logistic, g = tanh, c = c*f + i*g, h = tanh(c)*o; step t reads input rows [t*batch, (t+1)*batch)."""
+    GATES = ("f", "i", "g", "o")
+
+    def __init__(self, batch_total, inputs, outputs, steps, params):
+        assert batch_total % steps == 0
+        self.batch, self.inputs, self.outputs, self.steps = batch_total // steps, inputs, outputs, steps
+        self.w = {g: np.ascontiguousarray(params["w" + g]["w"], f32).reshape(outputs, outputs) for g in self.GATES}
+        self.u = {g: np.ascontiguousarray(params["u" + g]["w"], f32).reshape(outputs, inputs) for g in self.GATES}
+        self.bw = {g: np.ascontiguousarray(params["w" + g]["b"], f32) for g in self.GATES}
+        self.bu = {g: np.ascontiguousarray(params["u" + g]["b"], f32) for g in self.GATES}
+        self.output = np.zeros((batch_total, outputs), f32)
+        self.cell = np.zeros((batch_total, outputs), f32)
+        self.c = np.zeros((self.batch, outputs), f32)
+        self.h = np.zeros((self.batch, outputs), f32)
+
+    def _connected(self, x, w, b, n_in):
+        out = np.zeros((self.batch, self.outputs), f32)
+        orc.sgemm(False, True, self.batch, self.outputs, n_in, 1.0, x, n_in, w, n_in, 0.0, out, self.outputs)
+        orc.forward_bias(out, b, self.batch)
+        return out
+
+    def forward(self, x, training=False):
+        A = orc.ACT
+        x = np.ascontiguousarray(x, f32).reshape(self.steps * self.batch, self.inputs)
+        B = self.batch
+        for t in range(self.steps):
+            xt = np.ascontiguousarray(x[t * B:(t + 1) * B])
+            gate = {}
+            for g in self.GATES:
+                wo = self._connected(self.h, self.w[g], self.bw[g], self.outputs)
+                uo = self._connected(xt, self.u[g], self.bu[g], self.inputs)
+                gate[g] = (wo + uo).astype(f32)  # addvv
+                orc.activate_array(gate[g], A["TANH"] if g == "g" else A["LOGISTIC"])
+            temp = (gate["i"] * gate["g"]).astype(f32)           # mulvv
+            self.c = (self.c * gate["f"]).astype(f32)            # _c.Multiply(_f)
+            self.c = (self.c + temp).astype(f32)                 # _c.add(temp)
+            self.h = self.c.copy()
+            orc.activate_array(self.h, A["TANH"])
+            self.h = (self.h * gate["o"]).astype(f32)
+            self.cell[t * B:(t + 1) * B] = self.c
+            self.output[t * B:(t + 1) * B] = self.h
+        return self.output
+
+
+def lstm_params(inputs, outputs, seed=0):
+    """TConnectedLayer's init for the eight sub-layers (nconnectedlayer.pas:80-81: U(-r, r), r = sqrt(2/inputs));
+    biases drawn non-zero so that the parity test exercises them."""
+    rng = np.random.default_rng(seed)
+    P = {}
+    for g in RefLSTM.GATES:
+        for kind, n_in in (("w", outputs), ("u", inputs)):
+            r = np.sqrt(2.0 / n_in)
+            P[kind + g] = dict(w=rng.uniform(-r, r, (outputs, n_in)).astype(f32), b=rng.uniform(-0.1, 0.1, outputs).astype(f32))
+    return P

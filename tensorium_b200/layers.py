@@ -29,6 +29,7 @@ class TNNetState:  # source/ntypes.pas:46-63 (fields used on this path)
     isTraining: bool = False
     adversarial: bool = False
     step: int = 0
+    inputStep: int = 0
     index: int = 0
     truth: TSingleTensor | None = None
 

@@ -105,8 +105,8 @@ class TConnectedLayer:
     trainable = True
 
     def __init__(self, batch, steps, inputs, outputs, activation=nn.acLINEAR, train=True, rng=None):
-        assert steps == 1, "recurrent stepping is outside the hot path"
-        self.batch, self.inputs, self.outputs = batch, inputs, outputs
+        self.batch, self.inputs, self.outputs, self.steps = batch, inputs, outputs, steps
+        assert steps == 1 or not train, "backward through time is not built (forward stepping only, rnn_layers.py)"
         self.ActivationType = activation
         self.train = train
         self.learningRateScale = 1.0
@@ -114,7 +114,7 @@ class TConnectedLayer:
         r = np.sqrt(2.0 / inputs)  # nconnectedlayer.pas:80-81
         self.weights = TSingleTensor((outputs, inputs), groups=1, data=rng.uniform(-r, r, (outputs, inputs)))
         self.biases = TSingleTensor((outputs,), groups=1)
-        self.output = TSingleTensor((batch, outputs), groups=batch, host=False)
+        self.output = TSingleTensor((batch * steps, outputs), groups=batch * steps, host=False)
         if train:
             self.delta = TSingleTensor((batch, outputs), groups=batch, host=False)
             self.weight_updates = TSingleTensor((outputs, inputs), groups=1)
@@ -131,11 +131,12 @@ class TConnectedLayer:
         self._push(state.input, self.weights, self.biases)
         self.output.setCUDA()
         outputStep = self.batch * self.outputs
-        cu.gemm(False, True, self.batch, self.outputs, self.inputs, 1.0, state.input.devData, 0, self.inputs,
-                self.weights.devData, 0, self.inputs, 0.0, self.output.devData, 0, self.outputs)
-        cu.forwardBias(outputStep, self.output.devData, 0, self.biases.Size(), self.biases.devData, 1,
-                       self.output.Groups)
-        cu.ActivateArray(outputStep, self.output.devData, 0, self.ActivationType)
+        offset = getattr(state, "step", 0) * outputStep if self.steps > 1 else 0  # nconnectedlayer.pas:620-622
+        in_off = getattr(state, "inputStep", 0) * self.batch * self.inputs if self.steps > 1 else 0
+        cu.gemm(False, True, self.batch, self.outputs, self.inputs, 1.0, state.input.devData, in_off, self.inputs,
+                self.weights.devData, 0, self.inputs, 0.0, self.output.devData, offset, self.outputs)
+        cu.forwardBias(outputStep, self.output.devData, offset, self.biases.Size(), self.biases.devData, 1, self.batch)
+        cu.ActivateArray(outputStep, self.output.devData, offset, self.ActivationType)
 
     # nconnectedlayer.pas:745-871
     def backwardGPU(self, state: TNNetState):

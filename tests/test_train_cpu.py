@@ -173,3 +173,23 @@ def test_bucket_layout():
     assert all((b.ptr(i) - b.ptr(0)) % 256 == 0 for i in range(4))
     b.view(2)[0] = 7
     assert b.flat[128] == 7 and b.all_reduce() is None  # world 1: no-op
+
+
+def test_oracle_lstm_matches_float64_formula(oracle):
+    """RefLSTM (nlstmlayer.pas:518-611) against the textbook recurrence in float64."""
+    from oracle import ref_train as rt
+    steps, B, n_in, n_out = 5, 3, 7, 6
+    P = rt.lstm_params(n_in, n_out, seed=4)
+    x = np.random.default_rng(1).uniform(-1, 1, (steps * B, n_in)).astype(np.float32)
+    got = rt.RefLSTM(steps * B, n_in, n_out, steps, P).forward(x).copy()
+    sig = lambda v: 1 / (1 + np.exp(-v))
+    h = np.zeros((B, n_out)); c = np.zeros((B, n_out))
+    want = np.zeros((steps * B, n_out))
+    for t in range(steps):
+        xt = x[t * B:(t + 1) * B].astype(np.float64)
+        z = {g: h @ P["w" + g]["w"].T.astype(np.float64) + P["w" + g]["b"] + xt @ P["u" + g]["w"].T.astype(np.float64)
+             + P["u" + g]["b"] for g in "figo"}
+        c = c * sig(z["f"]) + sig(z["i"]) * np.tanh(z["g"])
+        h = np.tanh(c) * sig(z["o"])
+        want[t * B:(t + 1) * B] = h
+    assert np.abs(got - want).max() <= 2e-6
