@@ -227,6 +227,14 @@ TNN_API int32_t tnn_forward_dropout(tnn_context *ctx, int64_t N, const float *sr
 /* the same with the seed read on the device: seed = *seed_dev + seed_offset (graph replays) */
 TNN_API int32_t tnn_forward_dropout_dev(tnn_context *ctx, int64_t N, const float *src, float probability, float scale,
                                         float *rnd, float *dst, const uint64_t *seed_dev, uint64_t seed_offset);
+
+/* One launch for the element-wise part of an LSTM step (replaces the 15 operator calls of TLSTMLayer.forwardGPU,
+ * source/nlstmlayer.pas:934-973).  wz = h(t-1) W^T, [batch][4*hidden] in gate order f|i|g|o without bias; bw[4*hidden]
+ * the hidden-side biases; uz + uzOffset = x(t) U^T + bu in the same layout.  Updates c and h [batch][hidden] in place
+ * and stores them at cell_out + outOffset / h_out + outOffset (offsets in elements). */
+TNN_API int32_t tnn_lstm_gates(tnn_context *ctx, int64_t batch, int64_t hidden, const float *wz, const float *bw,
+                               const float *uz, int64_t uzOffset, float *c, float *h, float *cell_out, float *h_out,
+                               int64_t outOffset);
 TNN_API int32_t tnn_backward_dropout(tnn_context *ctx, int64_t N, const float *src, float probability, float scale,
                                      const float *rnd, float *dst);
 

@@ -164,10 +164,38 @@ int32_t tnn_derive_array(tnn_context *ctx, int64_t N, const float *x, int64_t of
 
 // nncuda.pas:582-600; CPU twin ntensors.pas:7709-7727 (incb is accepted and, like the reference kernel
 // cuda_sgemm.cu:277-284, not used)
+// plane size 1 (connected layers: dst[row][c] += bias[c]): the plane-map kernel would give every element its own
+// plane; one pass over rows of C instead (float4 when C and the base allow)
+__global__ void k_bias_rows(int64_t n, int C, float *__restrict__ dst, const float *__restrict__ bias) {
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += nthreads)
+    dst[i] = dst[i] + __ldg(bias + (int)(i % C));
+}
+__global__ void k_bias_rows4(int64_t n4, int C4, float4 *__restrict__ dst, const float4 *__restrict__ bias) {
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += nthreads) {
+    float4 v = dst[i];
+    const float4 b = __ldg(bias + (int)(i % C4));
+    v.x = v.x + b.x; v.y = v.y + b.y; v.z = v.z + b.z; v.w = v.w + b.w;
+    dst[i] = v;
+  }
+}
+
 int32_t tnn_forward_bias(tnn_context *ctx, int64_t dstSize, float *dst, int64_t offset, int64_t srcSize,
                          const float *src, int64_t incb, int64_t batch) {
   TNN_CHECK_CTX(ctx);
   (void)incb;
+  if (srcSize > 0 && batch > 0 && dstSize == srcSize * batch && srcSize < (1ll << 31) && dst && src) {
+    float *d = dst + offset;
+    if ((srcSize & 3) == 0 && ((((uintptr_t)d) | ((uintptr_t)src)) & 15) == 0) {
+      k_bias_rows4<<<grid_for(dstSize / 4, kThreads), kThreads, 0, ctx->stream>>>(dstSize / 4, (int)(srcSize / 4), (float4 *)d,
+                                                                                  (const float4 *)src);
+    } else {
+      k_bias_rows<<<grid_for(dstSize, kThreads), kThreads, 0, ctx->stream>>>(dstSize, (int)srcSize, d, src);
+    }
+    TNN_LAUNCHED(ctx);
+    return 0;
+  }
   return planemap::launch<0, 0>(ctx, dst + offset, nullptr, nullptr, nullptr, nullptr, dstSize, srcSize, batch,
                                [src] __device__(float &v, float, float, float &, float &, int c) { v = v + __ldg(src + c); });
 }
@@ -420,6 +448,48 @@ int32_t tnn_backward_dropout(tnn_context *ctx, int64_t N, const float *src, floa
   TNN_CHECK_CTX(ctx);
   if (N <= 0) return 0;
   k_dropout_bwd<<<grid_for(N, kThreads), kThreads, 0, ctx->stream>>>(N, probability, scale, src, rnd, dst);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
+// ---- LSTM gate update (nlstmlayer.pas:934-973: 4 addvv + 4 activate + mulvv + fmavv + copy + activate + mulvv +
+// 2 copies -> 1 launch).  wz = h(t-1) W^T for the four gates [batch][4*hidden] (f | i | g | o, no bias yet),
+// uz = x(t) U^T + bu, same layout.  Same order of operations per element as the operator sequence:
+// z = (wz + bw) + uz; c = c*f + i*g; h = tanh(c)*o.
+__global__ void k_lstm_gates(int64_t n, int hidden, const float *__restrict__ wz, const float *__restrict__ bw,
+                             const float *__restrict__ uz, float *__restrict__ c, float *__restrict__ h,
+                             float *__restrict__ cell_out, float *__restrict__ h_out) {
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += nthreads) {
+    const int64_t b = e / hidden;
+    const int j = (int)(e - b * hidden);
+    const int64_t row = b * 4 * hidden;
+    float z[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int64_t k = row + (int64_t)g * hidden + j;
+      z[g] = __fadd_rn(__fadd_rn(wz[k], __ldg(bw + g * hidden + j)), uz[k]);
+    }
+    const float f = tnn_act(z[0], TNN_ACT_LOGISTIC), i = tnn_act(z[1], TNN_ACT_LOGISTIC);
+    const float g = tnn_act(z[2], TNN_ACT_TANH), o = tnn_act(z[3], TNN_ACT_LOGISTIC);
+    const float cn = __fadd_rn(__fmul_rn(c[e], f), __fmul_rn(i, g));  // as tnn_fmavv: separately rounded product and sum
+    const float hn = __fmul_rn(o, tnn_act(cn, TNN_ACT_TANH));
+    c[e] = cn;
+    h[e] = hn;
+    cell_out[e] = cn;
+    h_out[e] = hn;
+  }
+}
+int32_t tnn_lstm_gates(tnn_context *ctx, int64_t batch, int64_t hidden, const float *wz, const float *bw,
+                       const float *uz, int64_t uzOffset, float *c, float *h, float *cell_out, float *h_out,
+                       int64_t outOffset) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(wz && bw && uz && c && h && cell_out && h_out, "null pointer");
+  const int64_t n = batch * hidden;
+  if (n <= 0) return 0;
+  TNN_REQUIRE(hidden < (1ll << 29), "hidden size too large");
+  k_lstm_gates<<<grid_for(n, kThreads), kThreads, 0, ctx->stream>>>(n, (int)hidden, wz, bw, uz + uzOffset, c, h,
+                                                                    cell_out + outOffset, h_out + outOffset);
   TNN_LAUNCHED(ctx);
   return 0;
 }

@@ -259,6 +259,10 @@ class TNNCuda:
     def copy(self, N, src, srcOffset, inca, dst, dstOffset, incb):
         self._ck(self._l.tnn_copy(self._h, N, _addr(src), srcOffset, inca, _addr(dst), dstOffset, incb))
 
+    def lstmGates(self, batch, hidden, wz, bw, uz, uzOffset, c, h, cell_out, h_out, outOffset):
+        self._ck(self._l.tnn_lstm_gates(self._h, batch, hidden, _addr(wz), _addr(bw), _addr(uz), uzOffset, _addr(c),
+                                        _addr(h), _addr(cell_out), _addr(h_out), outOffset))
+
     def fmavss(self, N, src, offset, scalar, bias, dst):
         self._ck(self._l.tnn_fmavss(self._h, N, _addr(src), offset, scalar, bias, _addr(dst)))
 

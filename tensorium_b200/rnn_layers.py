@@ -4,10 +4,13 @@
                operators exist on `cuda.*`)
 
 Forward only in this round.  `fused=False` issues the reference's own operator sequence (8 connected-layer forwards +
-4 addvv + 4 activations + mulvv + fmavv + copy + activation + mulvv + 2 copies per step).  `fused=True` (default) is the
-B200-first ordering of the same arithmetic: the four input projections do not depend on the recurrence, so they are
-computed for ALL steps up front as four [steps*batch, inputs] x [inputs, outputs] GEMMs — large enough for the TMA-fed
-tensor-core SGEMM — and only the four hidden-state GEMMs stay inside the step loop.
+4 addvv + 4 activations + mulvv + fmavv + copy + activation + mulvv + 2 copies per step: 28 launches).  `fused=True`
+(default) is the B200-first ordering of the same arithmetic, 2 launches per step:
+  * the input projections do not depend on the recurrence: ONE [steps*batch, inputs] x [inputs, 4*outputs] GEMM up
+    front over the four gates' stacked weights (large enough for the TMA-fed tensor-core SGEMM) + one bias pass;
+  * per step one [batch, outputs] x [outputs, 4*outputs] GEMM on the hidden state and one `lstmGates` launch for
+    everything element-wise (`tnn_lstm_gates`).
+The eight TConnectedLayer objects stay the owners of the parameters; `pack()` refreshes the stacked copies.
 """
 from __future__ import annotations
 
@@ -45,7 +48,23 @@ class TLSTMLayer:
         self.output, self.Cell = dev(B * steps), dev(B * steps)
         self._f, self._i, self._g, self._o, self._c, self._h, self.temp = (dev(B) for _ in range(7))
         self.outC, self.outH, self.outW = outputs, 1, 1
+        if fused:
+            self.w_all = TSingleTensor((4 * outputs, outputs), groups=1)
+            self.u_all = TSingleTensor((4 * outputs, inputs), groups=1)
+            self.bw_all = TSingleTensor((4 * outputs,), groups=1)
+            self.bu_all = TSingleTensor((4 * outputs,), groups=1)
+            self.wz = TSingleTensor((B, 4 * outputs), groups=B, host=False)
+            self.uz = TSingleTensor((B * steps, 4 * outputs), groups=B * steps, host=False)
+            self.pack()
         self.reset()
+
+    def pack(self):
+        """Stack the four gates' parameters (f | i | g | o) for the fused path; call again after changing them."""
+        host = lambda t: t.pullFromDevice() if t.wasGPU() else t.Data
+        for dst, src in ((self.w_all, [self.w[g].weights for g in GATES]), (self.u_all, [self.u[g].weights for g in GATES]),
+                         (self.bw_all, [self.w[g].biases for g in GATES]), (self.bu_all, [self.u[g].biases for g in GATES])):
+            dst.Data[...] = np.concatenate([host(t).reshape(dst.Data.shape[0] // 4, -1) for t in src]).reshape(dst.Data.shape)
+            dst.pushToDevice()
 
     def reset(self):
         """Zero the carried cell and hidden state (fresh tensors are zero in the reference)."""
@@ -63,24 +82,27 @@ class TLSTMLayer:
         s = TNNetState(isTraining=state.isTraining, workspace=state.workspace, index=state.index)
         gate = dict(f=self._f, i=self._i, g=self._g, o=self._o)
         if self.fused:
-            # all steps of the input projections at once: output rows [t*B, (t+1)*B) are step t's, as in the loop
-            for g in GATES:
-                l = self.u[g]
-                l._push(l.weights, l.biases)
-                l.output.setCUDA()
-                cu.gemm(False, True, B * self.steps, self.outputs, self.inputs, 1.0, state.input.devData, 0,
-                        self.inputs, l.weights.devData, 0, self.inputs, 0.0, l.output.devData, 0, self.outputs)
-                cu.forwardBias(n * self.steps, l.output.devData, 0, l.biases.Size(), l.biases.devData, 1,
-                               B * self.steps)
+            H4 = 4 * self.outputs
+            # all steps of the input projections at once: rows [t*B, (t+1)*B) of uz are step t's
+            cu.gemm(False, True, B * self.steps, H4, self.inputs, 1.0, state.input.devData, 0, self.inputs,
+                    self.u_all.devData, 0, self.inputs, 0.0, self.uz.devData, 0, H4)
+            cu.forwardBias(B * self.steps * H4, self.uz.devData, 0, H4, self.bu_all.devData, 1, B * self.steps)
+            for i in range(self.steps):
+                cu.gemm(False, True, B, H4, self.outputs, 1.0, self._h.devData, 0, self.outputs, self.w_all.devData, 0,
+                        self.outputs, 0.0, self.wz.devData, 0, H4)
+                cu.lstmGates(B, self.outputs, self.wz.devData, self.bw_all.devData, self.uz.devData, i * B * H4,
+                             self._c.devData, self._h.devData, self.Cell.devData, self.output.devData, i * n)
+            for t in (self.output, self.Cell, self._c, self._h):
+                t.setCUDA()
+            return
         for i in range(self.steps):
             offset = i * n
             s.step, s.inputStep, s.input = i, 0, self._h
             for g in GATES:
                 self.w[g].forwardGPU(s)
-            if not self.fused:
-                s.inputStep, s.input = i, state.input
-                for g in GATES:
-                    self.u[g].forwardGPU(s)
+            s.inputStep, s.input = i, state.input
+            for g in GATES:
+                self.u[g].forwardGPU(s)
             for g in GATES:
                 cu.addvv(n, self.w[g].output.devData, offset, 1, self.u[g].output.devData, offset, 1,
                          gate[g].devData, 0, 1)

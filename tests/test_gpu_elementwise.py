@@ -36,7 +36,8 @@ def test_activations_against_fixture(cuda_backend, oracle):
             assert rel_elem(g, f[f"grad_{name}"]) < 2e-6, name
 
 
-@pytest.mark.parametrize("B,C,HW", [(2, 3, 169), (3, 5, 1024), (1, 7, 13), (4, 32, 4096), (2, 4, 1), (1, 1, 5000)])
+@pytest.mark.parametrize("B,C,HW", [(2, 3, 169), (3, 5, 1024), (1, 7, 13), (4, 32, 4096), (2, 4, 1), (1, 1, 5000),
+                                    (64, 40, 1), (3, 10, 1), (300, 1024, 1)])  # HW = 1: the connected layers' row-broadcast path
 def test_bias_scale_normalize(cuda_backend, oracle, B, C, HW):
     cu = cuda_backend
     rng = np.random.default_rng(B * 100 + C)
