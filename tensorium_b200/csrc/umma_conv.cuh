@@ -714,9 +714,21 @@ struct GemmAtomicEpilogue {  // split-k: C += alpha*acc
   __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt,
                                               bool rowvalid, float *) const {
     if (!rowvalid) return;
+    float *q = r.q + n;
+    if (cnt == 32 && (reinterpret_cast<uintptr_t>(q) & 15) == 0) {
+      // 16-byte vector reductions: a quarter of the instructions and of the L2 reduction operations (each lane owns
+      // a different row, so every scalar red is its own sector operation)
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + j), "f"(alpha * __uint_as_float(acc[j])),
+                     "f"(alpha * __uint_as_float(acc[j + 1])), "f"(alpha * __uint_as_float(acc[j + 2])),
+                     "f"(alpha * __uint_as_float(acc[j + 3]))
+                     : "memory");
+      return;
+    }
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      if (j < cnt) atomicAdd(r.q + n + j, alpha * __uint_as_float(acc[j]));
+      if (j < cnt) atomicAdd(q + j, alpha * __uint_as_float(acc[j]));
   }
 };
 
