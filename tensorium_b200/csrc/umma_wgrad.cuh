@@ -241,13 +241,39 @@ __global__ void __launch_bounds__(kThreads, 1) k_umma_wgrad(WgradGeom g) {
       const int f = warp * 32 + lane;  // TMEM lane = delta row
       const bool fvalid = f < Fv;
       float *row = g.wu + (int64_t)(f0 + (fvalid ? f : 0)) * g.ldw;
-      for (int tap = 0; tap < g.kk; ++tap) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)tap * kWgBRows, r);
-        if (fvalid) {
+      const uint32_t tbase = tmem_base + ((uint32_t)(warp * 32) << 16);
+      if (g.kk == 9 && (g.C & 3) == 0 && (reinterpret_cast<uintptr_t>(row) & 15) == 0 && (g.ldw & 3) == 0) {
+        // 3x3: the 4 channels x 9 taps a thread holds for one channel group are 36 CONSECUTIVE floats of its weight
+        // row (index c*9 + tap): nine 16-byte vector reductions instead of 36 scalar ones, each of which would be
+        // its own L2 operation (every lane owns a different row)
+        for (int cg = 0; cg < kWgBRows / 4; ++cg) {  // warp-uniform trip count
+          uint32_t r[9][4];
 #pragma unroll
-          for (int c = 0; c < kWgBRows; ++c)
-            if (c0 + c < g.C) atomicAdd(row + (int64_t)(c0 + c) * g.kk + tap, __uint_as_float(r[c]));
+          for (int tap = 0; tap < 9; ++tap) tmem_ld4_nowait(tbase + (uint32_t)(tap * kWgBRows + cg * 4), r[tap]);
+          tmem_ld_wait();
+          const int c = c0 + cg * 4;
+          if (fvalid && c < g.C) {
+            float *q = row + (int64_t)c * 9;
+#pragma unroll
+            for (int v = 0; v < 9; ++v) {
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(q + 4 * v),
+                           "f"(__uint_as_float(r[(4 * v) % 9][(4 * v) / 9])),
+                           "f"(__uint_as_float(r[(4 * v + 1) % 9][(4 * v + 1) / 9])),
+                           "f"(__uint_as_float(r[(4 * v + 2) % 9][(4 * v + 2) / 9])),
+                           "f"(__uint_as_float(r[(4 * v + 3) % 9][(4 * v + 3) / 9]))
+                           : "memory");
+            }
+          }
+        }
+      } else {
+        for (int tap = 0; tap < g.kk; ++tap) {
+          uint32_t r[32];
+          tmem_ld32(tbase + (uint32_t)tap * kWgBRows, r);
+          if (fvalid) {
+#pragma unroll
+            for (int c = 0; c < kWgBRows; ++c)
+              if (c0 + c < g.C) atomicAdd(row + (int64_t)(c0 + c) * g.kk + tap, __uint_as_float(r[c]));
+          }
         }
       }
     }
