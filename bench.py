@@ -176,16 +176,13 @@ def run_ours(args, rank, world, local_rank):
 
     torch.cuda.set_device(local_rank)
     if world > 1:
-        # keep stdout to the single JSON line (NCCL prints its version banner there at VERSION/INFO level)
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     cu = tensor.initCUDART(local_rank)  # raises if libtensorium_b200.so / a B200 is missing: no fallback
     cu.set_stream(stream.cuda_stream)
     cu.set_math_mode(MATH[args.math])
-    net = build_yolov3(BATCH, SIZE, seed=1234)
+    net = build_yolov3(BATCH, SIZE, seed=1234, channels_last=args.layout == "nhwc")
     # shortcut fusion into the conv epilogue: "" (off, default), "gather" or "all".  Measured (B200, batch 64): 27.7 ms
     # un-fused, 28.0 ms with the MMA-bound gathering layers fused, 28.9 ms with all 23 fused — the residual read in
     # the four epilogue warps costs what the separate add kernels cost, so it stays off.
@@ -299,7 +296,16 @@ def run_ours(args, rank, world, local_rank):
     conv_ms = sum(p["ms"] for p in per_layer)
     conv_flops = float(net.conv_flops())
     peaks, which = load_peaks()
+    # TF32 dense peak: measured on this pool's B200s with tools/measure_peaks.py (cuBLAS TF32 8192^3, sustained — the
+    # kernels are timed inside a long step); MEASURED_PEAKS.json carries bf16 only
+    tf32_src = f"TF32 dense = bf16_tflops_sustained/2 of {which} MEASURED_PEAKS.json"
     tf32_peak = float(peaks.get("tf32_tflops_sustained", peaks["bf16_tflops_sustained"] / 2.0))
+    ppath = os.path.join(ROOT, "profiles", "r02_peaks.json")
+    if "tf32_tflops_sustained" not in peaks and os.path.exists(ppath):
+        pj = json.load(open(ppath))
+        tf32_peak = float(pj["tf32_tflops_sustained"])
+        tf32_src = ("profiles/r02_peaks.json: cuBLAS TF32 8192^3 sustained over 4 s on a B200 of this pool "
+                    f"(burst {pj['tf32_tflops']:.0f}; tools/measure_peaks.py)")
     # the convolutions dispatch to several kernels; the roofline object describes the one with the largest share of
     # the step, `by_kernel` lists them all (algorithmic FLOPs of their launches / their summed CUDA-event time)
     by_kernel = {}
@@ -343,7 +349,7 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": f"YOLOv3-{SIZE} inference, 107 layers (75 conv), BN folded, random-init weights",
                        "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": SIZE,
-                       "math": args.math, "parallelism": f"batch-sharded x{world}, no collective",
+                       "math": args.math, "layout": args.layout, "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "activations streamed per step = 14.6 GB per GPU, far larger than the 126 MB L2 (no flush needed)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes_in,
                     "d2h_bytes_per_step": nbytes_out, "ms_per_step": ms_e2e / args.steps},
@@ -354,7 +360,7 @@ def run_ours(args, rank, world, local_rank):
                          "compulsory_bytes": dom["compulsory_bytes"] / dom["launches"],
                          "kernel": f"{dom_name}: tcgen05 kind::tf32 implicit-GEMM conv, {dom['launches']} launches/step",
                          "avg_launch_ms": dom["ms"] / dom["launches"],
-                         "peak_source": f"TF32 dense = bf16_tflops_sustained/2 of {which} MEASURED_PEAKS.json",
+                         "peak_source": tf32_src,
                          "kernel_ms_per_step": dom["ms"], "share_of_step": dom["share_of_step"],
                          "mma_issue_factor": 3 if args.math == "3xtf32" else 1,
                          "issued_frac": achieved * (3 if args.math == "3xtf32" else 1) / tf32_peak,
@@ -379,6 +385,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--math", default="3xtf32", choices=list(MATH))
+    ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"],
+                    help="internal activation layout of the graph: channels-innermost (TMA im2col kernels) or planar")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-images", type=int, default=2)
     ap.add_argument("--layers-out", default="", help="write the per-conv-layer timing table (JSON) here")

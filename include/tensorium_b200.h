@@ -310,7 +310,8 @@ TNN_API int32_t tnn_set_weights_static(tnn_context *ctx, const float *weights, i
 /* Which kernel the last tnn_conv2d_forward* call on this context dispatched to (measurement tools attribute layer
  * times to kernels with it): 0 none yet, 1 direct fp32 (k_conv_direct), 2 tcgen05 gathering implicit GEMM (k_umma
  * with Im2colPixelLoader), 3 tcgen05 with TMA-fed activations (k_umma with TmaPatchLoader), 4 tcgen05 halo-tile
- * (k_umma_halo), 5 CUDA-core implicit GEMM (simt::k_gemm, TNN_MATH_FP32). */
+ * (k_umma_halo), 5 CUDA-core implicit GEMM (simt::k_gemm, TNN_MATH_FP32), 7 tcgen05 with TMA im2col-mode
+ * activations on channels-innermost tensors (nhwc::k_conv_nhwc), 8 direct fp32 writing channels-innermost rows. */
 TNN_API int32_t tnn_last_conv_kernel(tnn_context *ctx);
 /* backwardGPU wgrad (nConvolutionLayer.pas:1203-1232): weight_updates += sum_b delta_b * im2col(in_b)^T */
 TNN_API int32_t tnn_conv2d_backward_filter(tnn_context *ctx, const tnn_conv_desc *d, const float *in,
@@ -352,6 +353,40 @@ TNN_API int32_t tnn_yolo_activate(tnn_context *ctx, int64_t batch, int64_t n, in
 /* out[b][cOff..cOff+c] = in  — per-image channel concat used by route layers */
 TNN_API int32_t tnn_concat_channels(tnn_context *ctx, int64_t batch, int64_t c, int64_t blockSize, const float *in,
                                     int64_t outChannels, int64_t cOffset, float *out);
+
+/* ------------------------------------------------------------------ channels-innermost (NHWC) inference graph
+ * New with this backend.  The reference keeps every activation planar (NCHW) because its GEMM consumes a
+ * materialised im2col matrix; on B200 the convolution reads its operands through the TMA unit, whose im2col mode
+ * wants the channel index innermost.  A graph may therefore keep its INTERNAL activations as rows of channels,
+ *   act[(b*H + h)*W + w][pitch],  channels 0..C-1 of a pixel contiguous, `pitch` >= C floats between pixels
+ * (pitch > C lets a layer write straight into its slice of a route/concat buffer), and convert at the graph edges:
+ * the first layer reads the planar image, the head layers write planar outputs for the yolo layer / host decode.
+ * Same arithmetic as tnn_conv2d_forward (same products, fp32 accumulation, scale/bias/activation epilogue). */
+typedef enum { TNN_LAYOUT_NCHW = 0, TNN_LAYOUT_NHWC = 1 } tnn_layout;
+/* forwardGPU steps 2-5 (nConvolutionLayer.pas:1040-1122) on channels-innermost activations:
+ *   out = act( conv(in, weights) * scale[f] + bias[f] ),  weights [filters][c*kh*kw] as always.
+ * inLayout NHWC: inPitch a multiple of 4 floats, 16-byte aligned base (channels past c read as zero) — tcgen05 implicit GEMM, activations and
+ *   weights by TMA (im2col mode), output by TMA store (outLayout NHWC) or as planes (outLayout NCHW, outPitch ignored).
+ * inLayout NCHW: only for small contractions (c*kh*kw <= 64, the image layer) with outLayout NHWC. */
+TNN_API int32_t tnn_conv2d_forward_nhwc(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,
+                                        int64_t inPitch, int32_t inLayout, const float *weights, const float *scale,
+                                        const float *bias, int32_t activation, float *out, int64_t outOffset,
+                                        int64_t outPitch, int32_t outLayout);
+/* [batch][channels][blockSize] -> [batch][blockSize][outPitch] and back */
+TNN_API int32_t tnn_nchw_to_nhwc(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize, const float *in,
+                                 float *out, int64_t outPitch);
+TNN_API int32_t tnn_nhwc_to_nchw(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize, const float *in,
+                                 int64_t inPitch, float *out);
+/* rows of `channels` floats with independent pitches: out = in (route / concat slices, nconcatlayer.pas:214-220) and
+ * out = a + b (shortcut, naddlayer.pas:891-910) */
+TNN_API int32_t tnn_rows_copy(tnn_context *ctx, int64_t rows, int64_t channels, const float *in, int64_t inPitch,
+                              float *out, int64_t outPitch);
+TNN_API int32_t tnn_rows_add(tnn_context *ctx, int64_t rows, int64_t channels, const float *a, int64_t aPitch,
+                             const float *b, int64_t bPitch, float *out, int64_t outPitch);
+/* upSample forward (nupsamplelayer.pas:190-206) on channels-innermost rows: out[b][h*s+i][w*s+j][:] = scale*in[b][h][w][:] */
+TNN_API int32_t tnn_upsample_nhwc(tnn_context *ctx, int64_t batch, int64_t channels, int64_t inHeight, int64_t inWidth,
+                                  int64_t stride, float scale, const float *in, int64_t inPitch, float *out,
+                                  int64_t outPitch);
 
 #ifdef __cplusplus
 }

@@ -115,6 +115,13 @@ SIGNATURES = {
     "tnn_sgd_update": (i32, [ctxp, i64, fptr, fptr, f32, f32, f32]),
     "tnn_yolo_activate": (i32, [ctxp, i64, i64, i64, i64, fptr, f32]),
     "tnn_concat_channels": (i32, [ctxp, i64, i64, i64, fptr, i64, i64, fptr]),
+    "tnn_conv2d_forward_nhwc": (i32, [ctxp, C.POINTER(ConvDesc), fptr, i64, i64, i32, fptr, fptr, fptr, i32, fptr, i64,
+                                      i64, i32]),
+    "tnn_nchw_to_nhwc": (i32, [ctxp, i64, i64, i64, fptr, fptr, i64]),
+    "tnn_nhwc_to_nchw": (i32, [ctxp, i64, i64, i64, fptr, i64, fptr]),
+    "tnn_rows_copy": (i32, [ctxp, i64, i64, fptr, i64, fptr, i64]),
+    "tnn_rows_add": (i32, [ctxp, i64, i64, fptr, i64, fptr, i64, fptr, i64]),
+    "tnn_upsample_nhwc": (i32, [ctxp, i64, i64, i64, i64, i64, f32, fptr, i64, fptr, i64]),
 }
 
 _lib = None

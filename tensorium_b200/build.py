@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtensorium_b200.so")
-SOURCES = ["api_core.cu", "elementwise.cu", "reduce.cu", "misc.cu", "contract.cu"]
+SOURCES = ["api_core.cu", "elementwise.cu", "reduce.cu", "misc.cu", "contract.cu", "conv_nhwc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--extended-lambda", "-std=c++17",

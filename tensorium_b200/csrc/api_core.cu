@@ -88,6 +88,8 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     ctx->patch_kb16 = (pk && pk[0] == '1') ? 1 : 0;  // measured: no difference (97.3 vs 96.6 TFLOP/s), so the 32-k path stays
     const char *ts = getenv("TNN_TAIL_SPLIT");
     ctx->tail_split = (ts && ts[0] == '0') ? 0 : 1;
+    const char *nk = getenv("TNN_NHWC_KB");
+    ctx->nhwc_kb = (nk && atoi(nk) == 32) ? 32 : (nk && atoi(nk) == 16) ? 16 : 0;
     const char *p2 = getenv("TNN_PAIR");
     ctx->pair_mma = (p2 && p2[0] == '1') ? 1 : 0;
   }

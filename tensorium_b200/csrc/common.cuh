@@ -18,6 +18,7 @@ struct tnn_context {
   int gather_kb16;      // 1: the gathering 3xTF32 convolution runs 16-k pipeline stages (TNN_GATHER_KB16=1; slower, kept for A/B runs)
   int patch_kb16;       // 1: TMA-activation convolutions run 16-channel pipeline stages in 3xTF32 mode (TNN_PATCH_KB16=1; no measurable gain, opt-in)
   int tail_split;       // 1: a last wave that fills <= half of the SMs runs as half-width tiles (default; TNN_TAIL_SPLIT=0)
+  int nhwc_kb;          // channels per pipeline stage of the NHWC convolution in 3xTF32 mode: 0 = default (16), 16 or 32 (TNN_NHWC_KB)
   int pair_mma;         // 1: wide layers of the gathering path run on CTA pairs (tcgen05.mma.cta_group::2)
   int last_conv_kernel; // which kernel the last tnn_conv2d_forward took (TNN_CONV_KERNEL_*), for measurement tools
   int64_t launches;

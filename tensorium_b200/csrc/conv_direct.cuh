@@ -16,12 +16,13 @@ constexpr int FT = 32;    // filters per CTA pass
 constexpr int KMAX = 64;  // largest contraction handled here
 constexpr int THREADS = 128;
 
-__device__ __noinline__ float act_slow(float v, int a) { return tnn_act(v, a); }
+static __device__ __noinline__ float act_slow(float v, int a) { return tnn_act(v, a); }
 
 template <bool K3S1>
 __global__ void __launch_bounds__(THREADS, 3)
 k_conv_direct(simt::ConvGeom g, int batch, const float *__restrict__ in, const float *__restrict__ w,
-              const float *__restrict__ scale, const float *__restrict__ bias, int act, float *__restrict__ out) {
+              const float *__restrict__ scale, const float *__restrict__ bias, int act, float *__restrict__ out,
+              int64_t outPitch) {  // outPitch != 0: channels-innermost output rows of `outPitch` floats (NHWC)
   __shared__ __align__(16) float ws[KMAX][FT];  // ws[k][f] = w[f0+f][k]
   const int K = g.C * g.kh * g.kw;
   const int f0 = blockIdx.y * FT;
@@ -109,6 +110,44 @@ k_conv_direct(simt::ConvGeom g, int batch, const float *__restrict__ in, const f
     }
   }
 
+  if (outPitch) {
+    // channels-innermost rows: the thread's PIX pixels are consecutive rows, each 32 filters = 128 contiguous bytes
+    const bool leaky = act == TNN_ACT_LEAKY || act == TNN_ACT_REVLEAKY;
+    const bool simple = leaky || act == TNN_ACT_LINEAR;
+    float *opix = out + (((int64_t)b * g.OH + oh) * g.OW + ow0) * outPitch + f0;
+    const bool vec4 = (f0 + FT <= g.F) && ((outPitch & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+#pragma unroll
+    for (int f = 0; f < FT; f += 4) {
+      float s[4], bi[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[u] = (scale && f0 + f + u < g.F) ? __ldg(scale + f0 + f + u) : 1.0f;
+        bi[u] = (bias && f0 + f + u < g.F) ? __ldg(bias + f0 + f + u) : 0.0f;
+      }
+#pragma unroll
+      for (int p = 0; p < PIX; ++p) {
+        float v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          float y = acc[p][f + u];
+          if (scale) y = __fmul_rn(y, s[u]);
+          if (bias) y = __fadd_rn(y, bi[u]);
+          v[u] = simple ? (leaky ? (y < 0 ? 0.1f * y : y) : y) : act_slow(y, act);
+        }
+        if (ow0 + p < g.OW) {
+          float *o = opix + (int64_t)p * outPitch + f;
+          if (vec4) {
+            *reinterpret_cast<float4 *>(o) = make_float4(v[0], v[1], v[2], v[3]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              if (f0 + f + u < g.F) o[u] = v[u];
+          }
+        }
+      }
+    }
+    return;
+  }
   const int P = g.OH * g.OW;
   float *orow = out + (int64_t)b * g.outImg + (int64_t)oh * g.OW + ow0;
   const bool vec = (ow0 + PIX <= g.OW) && ((reinterpret_cast<uintptr_t>(orow) & 15) == 0) && ((P & 3) == 0);
@@ -142,15 +181,15 @@ k_conv_direct(simt::ConvGeom g, int batch, const float *__restrict__ in, const f
 inline bool supported(const simt::ConvGeom &g) { return (int64_t)g.C * g.kh * g.kw <= KMAX; }
 
 inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
-                        const float *scale, const float *bias, int act, float *out) {
+                        const float *scale, const float *bias, int act, float *out, int64_t outPitch = 0) {
   const int owq = (g.OW + PIX - 1) / PIX;
   const int64_t total = (int64_t)batch * g.OH * owq;
   dim3 grid((unsigned)cdiv64(total, THREADS), (unsigned)cdiv64(g.F, FT));
   TNN_REQUIRE(grid.y <= 65535, "too many filter tiles");
   if (g.kh == 3 && g.kw == 3 && g.sy == 1 && g.sx == 1 && g.dy == 1 && g.dx == 1)
-    k_conv_direct<true><<<grid, THREADS, 0, ctx->stream>>>(g, batch, in, weights, scale, bias, act, out);
+    k_conv_direct<true><<<grid, THREADS, 0, ctx->stream>>>(g, batch, in, weights, scale, bias, act, out, outPitch);
   else
-    k_conv_direct<false><<<grid, THREADS, 0, ctx->stream>>>(g, batch, in, weights, scale, bias, act, out);
+    k_conv_direct<false><<<grid, THREADS, 0, ctx->stream>>>(g, batch, in, weights, scale, bias, act, out, outPitch);
   TNN_LAUNCHED(ctx);
   return 0;
 }

@@ -1,0 +1,656 @@
+// conv_nhwc.cu — implicit-GEMM convolution on channels-innermost (NHWC) activations, every operand moved by TMA.
+//
+// Replaces, for a graph that keeps its activations channels-innermost between layers, the per-image im2col +
+// gemmStridedBatched + forwardBias | batch-norm + ActivateArray sequence of TConvolutionalLayer.forwardGPU
+// (reference: source/nConvolutionLayer.pas:1040-1122).  No column buffer exists and no thread gathers:
+//
+//   D[pixel m][filter n] (TMEM, fp32) = sum over (tap, channel) A(m, tap, c) * W(n, tap, c)
+//
+//   A  activations [B][H][W][pitch] fp32: ONE cp.async.bulk.tensor.4d ... im2col load per k-block delivers the
+//      128 consecutive output pixels of a tile (linearised over image, row, column — rows and images are crossed
+//      by the TMA unit's own traversal) x KB channels of one kernel tap, padding and the batch tail zero-filled,
+//      as a K-major SWIZZLE_128B (KB = 32) / SWIZZLE_64B (KB = 16) tile: exactly what tcgen05.mma reads.
+//   W  weights: the pre-split [F][tap][Cpad] copy (hi and lo TF32 planes, k_prepare_weights_patch) by tiled TMA.
+//   D  epilogue: tcgen05.ld -> *scale[f] + bias[f] -> activation -> swizzled staging tile in shared memory ->
+//      cp.async.bulk.tensor.2d store (UTMASTG) of 32 pixels x 32 filters; rows past the last pixel and filters
+//      past F are clipped by the TMA unit.  Head layers write NCHW instead (the yolo layer and the host decode
+//      read planes), with the coalesced per-plane epilogue of umma_conv.cuh.
+//
+// Warp roles (448 threads, one persistent CTA per SM): 0-3 epilogue, 4-11 derive the 3xTF32 low half of the A
+// tile in shared memory (lo = x - trunc_tf32(x); the raw tile IS the high half because kind::tf32 reads the top
+// 19 bits), 12 MMA issue, 13 TMA.  In TF32 mode nobody touches the tiles: TMA -> mbarrier -> MMA.
+#include "umma_conv.cuh"
+#include "conv_direct.cuh"
+
+namespace nhwc {
+using namespace umma;
+
+typedef CUresult (*EncodeIm2colFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                   const cuuint64_t *, const int *, const int *, cuuint32_t, cuuint32_t,
+                                   const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeIm2colFn get_encode_im2col() {
+  static EncodeIm2colFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeIm2colFn)p;
+  }
+  return fn;
+}
+
+// im2col-mode load: coordinates {c, w, h, n} of the tile's first pixel at tap (0,0), tap offsets {offw, offh}
+__device__ __forceinline__ void tma_load_im2col(uint32_t dst_smem, const CUtensorMap *tmap, int c, int w, int h, int n,
+                                                uint32_t offw, uint32_t offh, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], "
+      "[%6], {%7, %8};" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c), "r"(w), "r"(h), "r"(n), "r"(smem_u32(bar)), "h"((uint16_t)offw),
+      "h"((uint16_t)offh)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tmap, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+struct Geo {
+  int OW, OHW;             // output row length, output pixels per image
+  int sx, sy, pw, ph, dx, dy, kw;
+  int cBlocks;             // k-blocks per kernel tap (Cpad / KB)
+  int M;                   // batch * OH * OW
+};
+
+// epilogue that writes channels-innermost rows through the TMA store (scale/bias/activation like ConvEpilogueT)
+struct NhwcEpilogue {
+  static constexpr bool kTmaStore = true;
+  const float *scale, *bias;
+  int act;
+  int64_t rows, cols;  // M, F
+};
+// NCHW planes (head layers): the epilogue of the NCHW kernels
+struct NchwEpilogue : ConvEpilogueT<false> {
+  static constexpr bool kTmaStore = false;
+};
+
+struct Ctl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t araw[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+  alignas(16) float epi_sb[kEpilogueWarps][64];
+};
+
+constexpr int kStageTile = 32 * 32 * 4;  // one epilogue staging tile: 32 pixels x 32 filters
+constexpr int kStageBufs = 2;            // per epilogue warp
+
+template <bool SPLIT, int KB, typename EPI>
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCols,
+            const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+            const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ Ctl ctl;
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int aBytes = BM * KB * 4;
+  const int bBytes = BN * KB * 4;
+  const int stageBytes = (aBytes + bBytes) * (SPLIT ? 2 : 1);
+  const int bOff = (SPLIT ? 2 : 1) * aBytes;  // stage layout: A | A_lo | B_hi | B_lo   (TF32: A | B)
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&ctl.full[s], kProducerWarps);
+      mbar_init(&ctl.empty[s], 1);
+      mbar_init(&ctl.araw[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl.tmem_full[s], 1);
+      mbar_init(&ctl.tmem_empty[s], kEpilogueWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc(&ctl.tmem_base, accCols * 2);
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBhi);
+    if (SPLIT) tma_prefetch_desc(&tmBlo);
+    if (EPI::kTmaStore) tma_prefetch_desc(&tmOut);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl.tmem_base;
+
+  if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
+    // ===================== 3xTF32 only: low half of the landed A tile =====================
+    if (SPLIT) {
+      const int tid = threadIdx.x - kFirstProducerWarp * 32;
+      int64_t remaining = 0;
+      for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x) {
+        int mt, nt, k0, k1;
+        sched.decode(t, mt, nt, k0, k1);
+        remaining += k1 - k0;
+      }
+      int stage = 0;
+      uint32_t phase = 0;
+      for (; remaining > 0; --remaining) {
+        mbar_wait_warp(&ctl.araw[stage], phase);
+        uint8_t *sa = smem + (size_t)stage * stageBytes;
+#pragma unroll
+        for (int i = 0; i < aBytes / (16 * kProducerThreads); ++i) {
+          const int off = (i * kProducerThreads + tid) * 16;
+          const float4 v = *reinterpret_cast<const float4 *>(sa + off);
+          *reinterpret_cast<float4 *>(sa + aBytes + off) =
+              make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ctl.full[stage]);
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer (one elected thread) =====================
+    const uint32_t smem_base = smem_u32(smem);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x, ++it) {
+      int mt, nt, kb0, kb1;
+      sched.decode(t, mt, nt, kb0, kb1);
+      const uint32_t idesc = make_idesc(sched.half(t) ? BN >> 1 : BN, false, false);
+      const int as = (int)(it & 1);
+      const uint32_t use = (uint32_t)(it >> 1);
+      mbar_wait_warp(&ctl.tmem_empty[as], (use & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        mbar_wait_warp(SPLIT ? &ctl.full[stage] : &ctl.araw[stage], phase);
+        tc_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
+          const uint32_t sb = sa + bOff;
+          // K-major rows of KB floats: 8-row groups are 8*KB*4 bytes apart, one UMMA_K = 8 step = +32 bytes
+          constexpr uint32_t kSbo = KB == 32 ? 1024 : 512, kLt = KB == 32 ? 2u : 4u;
+#pragma unroll
+          for (int ks = 0; ks < KB / 8; ++ks) {
+            const uint64_t ah = make_desc(sa + ks * 32, 16, kSbo, kLt);
+            const uint64_t bh = make_desc(sb + ks * 32, 16, kSbo, kLt);
+            const uint32_t acc = (kb != kb0 || ks != 0) ? 1u : 0u;
+            if (SPLIT) {
+              const uint64_t al = make_desc(sa + aBytes + ks * 32, 16, kSbo, kLt);
+              const uint64_t bl = make_desc(sb + bBytes + ks * 32, 16, kSbo, kLt);
+              mma_tf32(tmem_d, al, bh, idesc, acc);  // small terms first
+              mma_tf32(tmem_d, ah, bl, idesc, 1u);
+              mma_tf32(tmem_d, ah, bh, idesc, 1u);
+            } else {
+              mma_tf32(tmem_d, ah, bh, idesc, acc);
+            }
+          }
+          mma_commit(&ctl.empty[stage]);
+          if (kb == kb1 - 1) mma_commit(&ctl.tmem_full[as]);
+        }
+        __syncwarp();
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kTmaWarp) {
+    // ===================== TMA producer of both operand tiles (one thread) =====================
+    if (lane == 0) {
+      const uint32_t smem_base = smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x) {
+        int mt, nt, kb0, kb1;
+        sched.decode(t, mt, nt, kb0, kb1);
+        const int n0 = nt * BN + (sched.half(t) == 2 ? BN >> 1 : 0);
+        // first pixel of the tile -> (image, row, column); the TMA unit walks on from there
+        const int m0 = mt * BM;
+        const int img = m0 / g.OHW;
+        const int rem = m0 - img * g.OHW;
+        const int oh0 = rem / g.OW;
+        const int ow0 = rem - oh0 * g.OW;
+        const int cw = ow0 * g.sx - g.pw, ch = oh0 * g.sy - g.ph;
+        int tap = kb0 / g.cBlocks;
+        int cb = kb0 - tap * g.cBlocks;
+        int kr = tap / g.kw;
+        int kc = tap - kr * g.kw;
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&ctl.empty[stage], phase ^ 1);
+          const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
+          const uint32_t sb = sa + bOff;
+          mbar_arrive_expect_tx(&ctl.araw[stage], (uint32_t)(aBytes + bBytes * (SPLIT ? 2 : 1)));
+          tma_load_im2col(sa, &tmA, cb * KB, cw, ch, img, (uint32_t)(kc * g.dx), (uint32_t)(kr * g.dy), &ctl.araw[stage]);
+          tma_load_2d(sb, &tmBhi, kb * KB, n0, &ctl.araw[stage]);
+          if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, kb * KB, n0, &ctl.araw[stage]);
+          if (++cb == g.cBlocks) {
+            cb = 0;
+            if (++kc == g.kw) { kc = 0; ++kr; }
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps 0-3 =====================
+    const int quad = warp;
+    int it = 0;
+    uint8_t *stg = smem + (size_t)stages * stageBytes + (size_t)quad * (kStageBufs * kStageTile);
+    int sbuf = 0;
+    float *scratch = ctl.epi_sb[quad];
+    for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x, ++it) {
+      int mt, nt, kb0, kb1;
+      sched.decode(t, mt, nt, kb0, kb1);
+      const int as = (int)(it & 1);
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int hf = sched.half(t);
+      const int bn = hf ? BN >> 1 : BN;
+      const int64_t n0 = (int64_t)nt * BN + (hf == 2 ? BN >> 1 : 0);
+      const int row0 = mt * BM + quad * 32;  // first pixel row of this warp
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
+      const int nChunks = (bn + 31) >> 5;
+      if constexpr (EPI::kTmaStore) {
+        mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
+        tc_fence_after();
+        const bool leaky = epi.act == TNN_ACT_LEAKY || epi.act == TNN_ACT_REVLEAKY;
+        const bool simple = leaky || epi.act == TNN_ACT_LINEAR;
+        const float neg = leaky ? 0.1f : 1.0f;
+        for (int ci = 0; ci < nChunks; ++ci) {
+          const int c0 = ci * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_d + (uint32_t)c0, r);
+          if (ci == nChunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl.tmem_empty[as]);
+          }
+          int64_t cnt = min((int64_t)(bn - c0), epi.cols - (n0 + c0));  // warp-uniform
+          if (cnt > 32) cnt = 32;
+          if (cnt <= 0 || row0 >= epi.rows) continue;
+          const int64_t n = n0 + c0;
+          __syncwarp();
+          scratch[lane] = (epi.scale && lane < cnt) ? __ldg(epi.scale + n + lane) : 1.0f;
+          scratch[32 + lane] = (epi.bias && lane < cnt) ? __ldg(epi.bias + n + lane) : 0.0f;
+          if (lane == 0) bulk_wait_read<kStageBufs - 1>();  // the staging tile written two chunks ago has been read
+          __syncwarp();
+          uint8_t *tile = stg + sbuf * kStageTile;
+          uint8_t *rowp = tile + lane * 128;
+#pragma unroll
+          for (int j4 = 0; j4 < 32; j4 += 4) {
+            const float4 s4 = *reinterpret_cast<const float4 *>(scratch + j4);
+            const float4 b4 = *reinterpret_cast<const float4 *>(scratch + 32 + j4);
+            const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+            float o[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float v = __fadd_rn(__fmul_rn(__uint_as_float(r[j4 + u]), s[u]), b[u]);
+              o[u] = simple ? fmaxf(v, __fmul_rn(neg, v)) : act_out_of_line(v, epi.act);
+            }
+            // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) — conflict-free and what the TMA store expects
+            *reinterpret_cast<float4 *>(rowp + ((((j4 >> 2) ^ (lane & 7))) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmOut, smem_u32(tile), (int)n, row0);
+            bulk_commit();
+          }
+          sbuf ^= 1;
+        }
+      } else {
+        const int64_t m = (int64_t)row0 + lane;
+        bool mvalid;
+        typename EPI::Row rc = epi.row(m, mvalid);
+        mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
+        tc_fence_after();
+        for (int ci = 0; ci < nChunks; ++ci) {
+          const int c0 = ci * 32;
+          uint32_t r[32];
+          tmem_ld32(tmem_d + (uint32_t)c0, r);
+          if (ci == nChunks - 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ctl.tmem_empty[as]);
+          }
+          int64_t cnt = min((int64_t)(bn - c0), epi.cols - (n0 + c0));
+          if (cnt > 32) cnt = 32;
+          if (cnt > 0) epi.store_chunk(rc, n0 + c0, r, (int)cnt, mvalid, scratch);
+        }
+      }
+    }
+    if (EPI::kTmaStore && lane == 0) bulk_wait_all();  // the staging tiles must outlive their stores
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, accCols * 2);
+}
+
+// activations [B][H][W][pitch] as the im2col-mode tensor {C, W, H, N}: box = 128 pixels x kb channels of one tap
+static int encode_im2col_map(CUtensorMap *tm, const float *base, const simt::ConvGeom &g, int batch, int64_t pitch, int kb) {
+  EncodeIm2colFn enc = get_encode_im2col();
+  TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeIm2col is not available from the driver");
+  cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * g.W * 4, (cuuint64_t)pitch * g.W * g.H * 4};
+  // bounding box of the tap-(0,0) position of an output pixel (the convention of the im2col mode: lower corner
+  // = -padding, upper corner = padding - (k-1)*dilation, measured from the far edge)
+  int lower[2] = {-g.pw, -g.ph};
+  int upper[2] = {g.pw - (g.kw - 1) * g.dx, g.ph - (g.kh - 1) * g.dy};
+  cuuint32_t estr[4] = {1, (cuuint32_t)g.sx, (cuuint32_t)g.sy, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, lower, upper, (cuuint32_t)kb, BM,
+                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, kb == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tnn_set_error("cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
+    return 6;
+  }
+  return 0;
+}
+
+// output rows [M][pitch] (channels innermost): 32 x 32 store boxes, SWIZZLE_128B staging
+static int encode_out_map(CUtensorMap *tm, float *base, int64_t M, int64_t F, int64_t pitch) {
+  EncodeTiledFn enc = get_encode_tiled();
+  TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)F, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tnn_set_error("cuTensorMapEncodeTiled (NHWC output) failed with CUresult %d", (int)r);
+    return 6;
+  }
+  return 0;
+}
+
+template <bool SPLIT, int KB, typename EPI>
+static int launch_nhwc(tnn_context *ctx, const Plan &p, const Geo &geo, EPI epi, const CUtensorMap &tmA,
+                       const CUtensorMap &tmHi, const CUtensorMap &tmLo, const CUtensorMap &tmOut) {
+  auto kern = k_conv_nhwc<SPLIT, KB, EPI>;
+  TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
+  kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(epi, p.sched, geo, p.BN, p.stages, p.accCols, tmA, tmHi, tmLo, tmOut);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
+static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, int64_t inPitch,
+                        const float *weights, const float *scale, const float *bias, int act, float *out,
+                        int64_t outPitch, bool outNchw) {
+  const int kk = g.kh * g.kw;
+  TNN_REQUIRE((inPitch % 4) == 0 && inPitch >= g.C && (((uintptr_t)in) & 15) == 0,
+              "NHWC input needs a pixel pitch that is a multiple of 4 floats and a 16-byte aligned base");
+  TNN_REQUIRE(g.sx <= 8 && g.sy <= 8 && g.pw <= 128 && g.ph <= 128 && (g.kw - 1) * g.dx - g.pw <= 128 &&
+                  (g.kh - 1) * g.dy - g.ph <= 128, "geometry outside the TMA im2col limits");
+  const int64_t M = (int64_t)batch * g.OH * g.OW;
+  const int64_t N = g.F;
+  TNN_REQUIRE(M < (1ll << 31) - BM, "too many output pixels");
+  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  const int CB = (g.C + 31) / 32;       // 32-channel blocks per tap (the weight copy's k order)
+  const int64_t K = (int64_t)kk * CB * 32;
+  // 3xTF32 stages carry four tiles: half-depth (16-channel) stages keep four of them in flight
+  const int KB = split ? (ctx->nhwc_kb ? ctx->nhwc_kb : 16) : 32;
+  Plan p = make_plan(ctx, M, N, K, split, false, false);
+  // half-width tail tiles: the TMA store writes whole 32-filter boxes, so a half tile must be a multiple of 32 wide
+  if (outNchw || (p.BN % 64) == 0) split_tail_wave(ctx, p);
+  const size_t stageBytes = (size_t)(BM + p.BN) * KB * 4 * (split ? 2 : 1);
+  const size_t epiBytes = outNchw ? 0 : (size_t)kEpilogueWarps * kStageBufs * kStageTile;
+  int st = (int)((225 * 1024 - epiBytes) / stageBytes);
+  p.stages = st > kMaxStages ? kMaxStages : st;
+  TNN_REQUIRE(p.stages >= 2, "tile does not fit shared memory");
+  p.smemBytes = stageBytes * p.stages + epiBytes + 1024;
+  p.sched.kBlocks = p.sched.kBlocksPerSplit = (int)(K / KB);
+  float *whi, *wlo;
+  bool fresh;
+  int rc = tnn_weight_buffer(ctx, weights, 1, (size_t)N * K, &whi, &wlo, &fresh);
+  if (rc) return rc;
+  if (fresh) {
+    int64_t blocks = cdiv64(N * K, 256);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_prepare_weights_patch<<<(int)blocks, 256, 0, ctx->stream>>>(weights, (int)N, g.C, kk, CB, 0, whi, wlo, split ? 1 : 0);
+    TNN_LAUNCHED(ctx);
+  }
+  alignas(64) CUtensorMap tmA, tmHi, tmLo, tmOut;
+  rc = encode_im2col_map(&tmA, in, g, batch, inPitch, KB);
+  if (rc) return rc;
+  rc = KB == 16 ? encode_weights_map16(&tmHi, whi, N, K, p.BN) : encode_weights_map(&tmHi, whi, N, K, p.BN);
+  if (rc) return rc;
+  rc = KB == 16 ? encode_weights_map16(&tmLo, split ? wlo : whi, N, K, p.BN)
+                : encode_weights_map(&tmLo, split ? wlo : whi, N, K, p.BN);
+  if (rc) return rc;
+  Geo geo{g.OW, g.OH * g.OW, g.sx, g.sy, g.pw, g.ph, g.dx, g.dy, g.kw, CB * 32 / KB, (int)M};
+  if (outNchw) {
+    memset(&tmOut, 0, sizeof(tmOut));
+    NchwEpilogue epi{{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, nullptr}};
+    if (!split) return launch_nhwc<false, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+    return KB == 16 ? launch_nhwc<true, 16>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut)
+                    : launch_nhwc<true, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+  }
+  TNN_REQUIRE((outPitch % 4) == 0 && outPitch >= N && (((uintptr_t)out) & 15) == 0,
+              "NHWC output needs a pixel pitch that is a multiple of 4 floats and a 16-byte aligned base");
+  rc = encode_out_map(&tmOut, out, M, N, outPitch);
+  if (rc) return rc;
+  NhwcEpilogue epi{scale, bias, act, M, N};
+  if (!split) return launch_nhwc<false, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+  return KB == 16 ? launch_nhwc<true, 16>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut)
+                  : launch_nhwc<true, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+}
+
+// ------------------------------------------------------------------ layout companions (HBM-bound)
+// [B][C][HW] <-> [B][HW][pitch]: 32 x 32 tiles through shared memory, both sides coalesced
+__global__ void __launch_bounds__(256) k_nchw_to_nhwc(const float *__restrict__ in, float *__restrict__ out, int C, int HW,
+                                                      int64_t pitch) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float *src = in + (int64_t)b * C * HW;
+  float *dst = out + (int64_t)b * HW * pitch;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, p = p0 + tx;
+    t[j][tx] = (c < C && p < HW) ? __ldg(src + (int64_t)c * HW + p) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int p = p0 + j, c = c0 + tx;
+    if (p < HW && c < C) dst[(int64_t)p * pitch + c] = t[tx][j];
+  }
+}
+__global__ void __launch_bounds__(256) k_nhwc_to_nchw(const float *__restrict__ in, float *__restrict__ out, int C, int HW,
+                                                      int64_t pitch) {
+  __shared__ float t[32][33];
+  const int b = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float *src = in + (int64_t)b * HW * pitch;
+  float *dst = out + (int64_t)b * C * HW;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int p = p0 + j, c = c0 + tx;
+    t[j][tx] = (p < HW && c < C) ? __ldg(src + (int64_t)p * pitch + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j, p = p0 + tx;
+    if (c < C && p < HW) dst[(int64_t)c * HW + p] = t[tx][j];
+  }
+}
+
+// rows of C floats with independent pitches: out = a (+ b).  float4 when everything is 16-byte aligned.
+template <bool ADD>
+__global__ void __launch_bounds__(256) k_rows(int64_t rows, int C4, const float4 *__restrict__ a, int64_t lda4,
+                                              const float4 *__restrict__ b, int64_t ldb4, float4 *__restrict__ out,
+                                              int64_t ldo4) {
+  const int64_t total = rows * C4;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const int64_t r = i / C4;
+    const int c = (int)(i - r * C4);
+    float4 v = __ldg(a + r * lda4 + c);
+    if (ADD) {
+      const float4 w = __ldg(b + r * ldb4 + c);
+      v = make_float4(__fadd_rn(v.x, w.x), __fadd_rn(v.y, w.y), __fadd_rn(v.z, w.z), __fadd_rn(v.w, w.w));
+    }
+    out[r * ldo4 + c] = v;
+  }
+}
+
+// nearest-neighbour upsample of channels-innermost rows (TUpsampleLayer.forwardGPU, nupsamplelayer.pas:190-206):
+// out[b][h*s+i][w*s+j][c] = scale * in[b][h][w][c]
+__global__ void __launch_bounds__(256) k_upsample_nhwc(int64_t total, int C4, int W, int H, int s, float scale,
+                                                       const float4 *__restrict__ in, int64_t ldi4,
+                                                       float4 *__restrict__ out, int64_t ldo4) {
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  const int OW = W * s, OH = H * s;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const int64_t px = i / C4;
+    const int c = (int)(i - px * C4);
+    const int ow = (int)(px % OW);
+    const int64_t t = px / OW;
+    const int oh = (int)(t % OH);
+    const int64_t b = t / OH;
+    float4 v = __ldg(in + ((b * H + oh / s) * W + ow / s) * ldi4 + c);
+    if (scale != 1.0f) v = make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+    out[px * ldo4 + c] = v;
+  }
+}
+
+static int grid_for(int64_t total) {
+  int64_t blocks = cdiv64(total, 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  return (int)(blocks < 1 ? 1 : blocks);
+}
+
+}  // namespace nhwc
+
+// ------------------------------------------------------------------ C ABI
+namespace {
+int fill_geom_nhwc(const tnn_conv_desc *d, simt::ConvGeom &g) {
+  TNN_REQUIRE(d != nullptr, "null conv descriptor");
+  TNN_REQUIRE(d->batch > 0 && d->c > 0 && d->h > 0 && d->w > 0 && d->filters > 0 && d->kh > 0 && d->kw > 0,
+              "non-positive conv dimension");
+  TNN_REQUIRE(d->stride_y > 0 && d->stride_x > 0 && d->dilation_y > 0 && d->dilation_x > 0 && d->pad_h >= 0 &&
+                  d->pad_w >= 0, "bad stride/dilation/padding");
+  const int64_t OH = (d->h + 2 * d->pad_h - (d->dilation_y * (d->kh - 1) + 1)) / d->stride_y + 1;
+  const int64_t OW = (d->w + 2 * d->pad_w - (d->dilation_x * (d->kw - 1) + 1)) / d->stride_x + 1;
+  TNN_REQUIRE(OH > 0 && OW > 0, "empty convolution output");
+  TNN_REQUIRE(d->batch * OH * OW < (1ll << 31) && d->batch * d->h * d->w < (1ll << 31) &&
+                  d->c * d->kh * d->kw < (1ll << 31), "convolution too large for 32-bit pixel indices");
+  g.C = (int)d->c; g.H = (int)d->h; g.W = (int)d->w; g.F = (int)d->filters;
+  g.kh = (int)d->kh; g.kw = (int)d->kw; g.ph = (int)d->pad_h; g.pw = (int)d->pad_w;
+  g.sy = (int)d->stride_y; g.sx = (int)d->stride_x; g.dy = (int)d->dilation_y; g.dx = (int)d->dilation_x;
+  g.OH = (int)OH; g.OW = (int)OW;
+  g.inImg = d->c * d->h * d->w;
+  g.outImg = d->filters * OH * OW;
+  return 0;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t tnn_conv2d_forward_nhwc(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,
+                                int64_t inPitch, int32_t inLayout, const float *weights, const float *scale,
+                                const float *bias, int32_t activation, float *out, int64_t outOffset, int64_t outPitch,
+                                int32_t outLayout) {
+  TNN_CHECK_CTX(ctx);
+  simt::ConvGeom g;
+  int rc = fill_geom_nhwc(d, g);
+  if (rc) return rc;
+  TNN_REQUIRE(activation == TNN_ACT_LINEAR || tnn_act_is_elementwise(activation), "activation not elementwise");
+  TNN_REQUIRE((inLayout == TNN_LAYOUT_NCHW || inLayout == TNN_LAYOUT_NHWC) &&
+                  (outLayout == TNN_LAYOUT_NCHW || outLayout == TNN_LAYOUT_NHWC), "unknown layout");
+  TNN_REQUIRE(ctx->math_mode != TNN_MATH_FP32, "the channels-innermost path runs on the tensor cores (3xTF32 / TF32 mode)");
+  in += inOffset;
+  out += outOffset;
+  if (inLayout == TNN_LAYOUT_NCHW) {
+    // planar input (the image fed to the first layer): direct fp32 convolution writing channels-innermost rows
+    TNN_REQUIRE(outLayout == TNN_LAYOUT_NHWC && direct::supported(g),
+                "NCHW input is only taken by the small-contraction direct kernel (C*kh*kw <= 64) writing NHWC");
+    ctx->last_conv_kernel = 8;
+    return direct::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out, outPitch);
+  }
+  ctx->last_conv_kernel = 7;
+  return nhwc::conv_forward(ctx, g, (int)d->batch, in, inPitch, weights, scale, bias, activation, out, outPitch,
+                            outLayout == TNN_LAYOUT_NCHW);
+}
+
+int32_t tnn_nchw_to_nhwc(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize, const float *in,
+                         float *out, int64_t outPitch) {
+  TNN_CHECK_CTX(ctx);
+  if (batch <= 0 || channels <= 0 || blockSize <= 0) return 0;
+  TNN_REQUIRE(outPitch >= channels && batch <= 65535 && cdiv64(channels, 32) <= 65535, "bad shape");
+  dim3 grid((unsigned)cdiv64(blockSize, 32), (unsigned)cdiv64(channels, 32), (unsigned)batch);
+  nhwc::k_nchw_to_nhwc<<<grid, 256, 0, ctx->stream>>>(in, out, (int)channels, (int)blockSize, outPitch);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
+int32_t tnn_nhwc_to_nchw(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize, const float *in,
+                         int64_t inPitch, float *out) {
+  TNN_CHECK_CTX(ctx);
+  if (batch <= 0 || channels <= 0 || blockSize <= 0) return 0;
+  TNN_REQUIRE(inPitch >= channels && batch <= 65535 && cdiv64(channels, 32) <= 65535, "bad shape");
+  dim3 grid((unsigned)cdiv64(blockSize, 32), (unsigned)cdiv64(channels, 32), (unsigned)batch);
+  nhwc::k_nhwc_to_nchw<<<grid, 256, 0, ctx->stream>>>(in, out, (int)channels, (int)blockSize, inPitch);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
+int32_t tnn_rows_copy(tnn_context *ctx, int64_t rows, int64_t channels, const float *in, int64_t inPitch, float *out,
+                      int64_t outPitch) {
+  TNN_CHECK_CTX(ctx);
+  if (rows <= 0 || channels <= 0) return 0;
+  TNN_REQUIRE(((channels | inPitch | outPitch) % 4) == 0 && ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0,
+              "rows must be 16-byte aligned multiples of 4 floats");
+  nhwc::k_rows<false><<<nhwc::grid_for(rows * channels / 4), 256, 0, ctx->stream>>>(
+      rows, (int)(channels / 4), reinterpret_cast<const float4 *>(in), inPitch / 4, nullptr, 0,
+      reinterpret_cast<float4 *>(out), outPitch / 4);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
+int32_t tnn_rows_add(tnn_context *ctx, int64_t rows, int64_t channels, const float *a, int64_t aPitch, const float *b,
+                     int64_t bPitch, float *out, int64_t outPitch) {
+  TNN_CHECK_CTX(ctx);
+  if (rows <= 0 || channels <= 0) return 0;
+  TNN_REQUIRE(((channels | aPitch | bPitch | outPitch) % 4) == 0 &&
+                  ((((uintptr_t)a) | ((uintptr_t)b) | ((uintptr_t)out)) & 15) == 0,
+              "rows must be 16-byte aligned multiples of 4 floats");
+  nhwc::k_rows<true><<<nhwc::grid_for(rows * channels / 4), 256, 0, ctx->stream>>>(
+      rows, (int)(channels / 4), reinterpret_cast<const float4 *>(a), aPitch / 4, reinterpret_cast<const float4 *>(b),
+      bPitch / 4, reinterpret_cast<float4 *>(out), outPitch / 4);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
+int32_t tnn_upsample_nhwc(tnn_context *ctx, int64_t batch, int64_t channels, int64_t inHeight, int64_t inWidth,
+                          int64_t stride, float scale, const float *in, int64_t inPitch, float *out, int64_t outPitch) {
+  TNN_CHECK_CTX(ctx);
+  if (batch <= 0 || channels <= 0) return 0;
+  TNN_REQUIRE(stride >= 1 && ((channels | inPitch | outPitch) % 4) == 0 &&
+                  ((((uintptr_t)in) | ((uintptr_t)out)) & 15) == 0, "rows must be 16-byte aligned multiples of 4 floats");
+  const int64_t total = batch * inHeight * stride * inWidth * stride * (channels / 4);
+  nhwc::k_upsample_nhwc<<<nhwc::grid_for(total), 256, 0, ctx->stream>>>(
+      total, (int)(channels / 4), (int)inWidth, (int)inHeight, (int)stride, scale, reinterpret_cast<const float4 *>(in),
+      inPitch / 4, reinterpret_cast<float4 *>(out), outPitch / 4);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
+}  // extern "C"

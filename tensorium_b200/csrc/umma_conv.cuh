@@ -566,7 +566,7 @@ struct TmaPatchLoader16 : TmaPatchLoader {
 // ------------------------------------------------------------------ epilogues
 // activations other than linear / leaky: one out-of-line copy (the switch is large; inlining it into the unrolled
 // epilogue blew the kernel up to 300 KB of SASS)
-__device__ __noinline__ float act_out_of_line(float v, int a) { return tnn_act(v, a); }
+static __device__ __noinline__ float act_out_of_line(float v, int a) { return tnn_act(v, a); }
 
 // Row context per thread (its TMEM lane = row m), then one call per column.
 // EXTRA = false: the lean instantiation for plain forward convolutions (no residual, no accumulation) — the kernel
@@ -1057,7 +1057,7 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
 // ------------------------------------------------------------------ weight preparation (TMA path)
 // hi/lo (3xTF32) or rna-rounded (TF32) zero-padded copy of W[F][C*kk] -> [F][Kpad] in the loader's k order:
 // k = (cg*kk + tap)*16 + ci  <-  W[f][(cg*16+ci)*kk + tap]
-__global__ void __launch_bounds__(256) k_prepare_weights(const float *__restrict__ w, int64_t F, int C, int kk,
+static __global__ void __launch_bounds__(256) k_prepare_weights(const float *__restrict__ w, int64_t F, int C, int kk,
                                                          int64_t Kpad, float *__restrict__ hi, float *__restrict__ lo,
                                                          int split) {
   const int64_t total = F * Kpad;
@@ -1081,7 +1081,7 @@ __global__ void __launch_bounds__(256) k_prepare_weights(const float *__restrict
 
 // dgrad as a forward convolution of delta: rows = input channel c, contraction over (filter group, flipped tap, f16)
 // out[c][(fg*kk + tapv)*16 + fi] = W[fg*16+fi][c][kk-1-tapv]      (W is [F][C*kk])
-__global__ void __launch_bounds__(256) k_prepare_weights_dgrad(const float *__restrict__ w, int F, int C, int kk,
+static __global__ void __launch_bounds__(256) k_prepare_weights_dgrad(const float *__restrict__ w, int F, int C, int kk,
                                                                int64_t Kpad, float *__restrict__ hi,
                                                                float *__restrict__ lo, int split) {
   const int64_t total = (int64_t)C * Kpad;
@@ -1106,7 +1106,7 @@ __global__ void __launch_bounds__(256) k_prepare_weights_dgrad(const float *__re
 // TmaPatchLoader k order, forward and dgrad in one kernel:  k = (tap*CB + cb)*32 + ci,  channel = cb*32 + ci
 //   forward: out[f][k] = W[f][channel][tap]                         (rows = F, channels = C)
 //   dgrad:   out[c][k] = W[channel][c][kk-1-tap]                    (rows = C, channels = F; flipped taps)
-__global__ void __launch_bounds__(256) k_prepare_weights_patch(const float *__restrict__ w, int rows, int chans, int kk,
+static __global__ void __launch_bounds__(256) k_prepare_weights_patch(const float *__restrict__ w, int rows, int chans, int kk,
                                                                int CB, int dgrad, float *__restrict__ hi,
                                                                float *__restrict__ lo, int split) {
   const int Kpad = kk * CB * 32;

@@ -107,6 +107,10 @@ class TConvolutionalLayer:
         # `_residual` and writes into the shortcut layer's output instead of this layer's own
         self._residual = None
         self._fused_out = None
+        # channels-innermost inference graph (TNNet.setChannelsLast): layouts / pixel pitches of the two activations
+        self.in_layout = self.out_layout = nn.TNNCuda.LAYOUT_NCHW
+        self.out_pitch = 0   # 0 = dense (filters floats per pixel)
+        self._in_nhwc = None  # private channels-innermost copy of a planar input the direct kernel cannot take
         self._desc = nn.TNNCuda.conv_desc(batch, c, h, w, filters, kernelSize, kernelSize, padding, padding, stride,
                                           stride, dilation, dilation)
 
@@ -157,6 +161,23 @@ class TConvolutionalLayer:
             for t in (self.scales, self.rolling_mean, self.rolling_variance):
                 if not t.wasGPU():
                     t.pushToDevice()
+        NHWC = nn.TNNCuda.LAYOUT_NHWC
+        if self.in_layout == NHWC or self.out_layout == NHWC:
+            assert not state.isTraining, "the channels-innermost path is an inference graph"
+            sc, bi = self._folded_bn() if self.isBatchNormalized else (None, self.biases)
+            src, in_layout, in_pitch = state.input, self.in_layout, getattr(state.input, "pitch", 0) or self.c
+            if in_layout != NHWC and self.c * self.kernelSize * self.kernelSize > 64:
+                # planar input with a contraction the direct kernel does not take: convert once per call
+                if self._in_nhwc is None:
+                    pitch = (self.c + 3) // 4 * 4
+                    self._in_nhwc = TSingleTensor((self.batch, self.h, self.w, pitch), groups=self.batch, host=False)
+                    self._in_nhwc.pitch = pitch
+                cu.nchwToNhwc(self.batch, self.c, self.h * self.w, src.devData, self._in_nhwc.devData, self._in_nhwc.pitch)
+                src, in_layout, in_pitch = self._in_nhwc, NHWC, self._in_nhwc.pitch
+            cu.conv2dForwardNhwc(self._desc, src.devData, 0, in_pitch, in_layout, self.weights.devData,
+                                 sc.devData if sc is not None else None, bi.devData, self.ActivationType,
+                                 self.output.devData, 0, self.out_pitch or self.filters, self.out_layout)
+            return
         if self._residual is not None and not state.isTraining:
             sc = None
             bi = self.biases
@@ -194,6 +215,7 @@ class TConvolutionalLayer:
             for t in (self.scales, self.rolling_mean, self.rolling_variance, self.biases):
                 if t.wasGPU():
                     t.pullFromDevice()
+                    t.setCUDA()  # the device copy is still the current one: a later forward must not re-push the host copy
             s = (self.scales.Data / np.maximum(np.sqrt(self.rolling_variance.Data), eps)).astype(np.float32)
             b = (self.biases.Data - self.rolling_mean.Data * s).astype(np.float32)
             self._bn_fold = (TSingleTensor(s.shape, 1, s), TSingleTensor(b.shape, 1, b))

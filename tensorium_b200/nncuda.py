@@ -359,7 +359,8 @@ class TNNCuda:
 
     CONV_KERNELS = {0: "none", 1: "direct::k_conv_direct", 2: "umma::k_umma<Im2colPixelLoader> (gather)",
                     3: "umma::k_umma<TmaPatchLoader> (TMA activations)", 4: "umma::k_umma_halo", 5: "simt::k_gemm",
-                    6: "umma::k_umma_pair (gather, CTA pairs)"}
+                    6: "umma::k_umma_pair (gather, CTA pairs)",
+                    7: "nhwc::k_conv_nhwc (TMA im2col activations, TMA store)", 8: "direct::k_conv_direct (NHWC out)"}
 
     def setWeightsStatic(self, weights, is_static: bool = True):
         """The backend may keep its re-ordered / TF32-split copy of `weights` across calls (inference)."""
@@ -411,3 +412,29 @@ class TNNCuda:
     def concatChannels(self, batch, c, blockSize, in_, outChannels, cOffset, out):
         self._ck(self._l.tnn_concat_channels(self._h, batch, c, blockSize, _addr(in_), outChannels, cOffset,
                                              _addr(out)))
+
+    # ---- channels-innermost (NHWC) inference graph (include/tensorium_b200.h, last section)
+    LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+
+    def conv2dForwardNhwc(self, desc, in_, inOffset, inPitch, inLayout, weights, scale, bias, activation, out,
+                          outOffset, outPitch, outLayout):
+        self._ck(self._l.tnn_conv2d_forward_nhwc(self._h, C.byref(desc), _addr(in_), inOffset, inPitch, int(inLayout),
+                                                 _addr(weights), _addr(scale), _addr(bias), int(activation),
+                                                 _addr(out), outOffset, outPitch, int(outLayout)))
+
+    def nchwToNhwc(self, batch, channels, blockSize, in_, out, outPitch):
+        self._ck(self._l.tnn_nchw_to_nhwc(self._h, batch, channels, blockSize, _addr(in_), _addr(out), outPitch))
+
+    def nhwcToNchw(self, batch, channels, blockSize, in_, inPitch, out):
+        self._ck(self._l.tnn_nhwc_to_nchw(self._h, batch, channels, blockSize, _addr(in_), inPitch, _addr(out)))
+
+    def rowsCopy(self, rows, channels, in_, inPitch, out, outPitch):
+        self._ck(self._l.tnn_rows_copy(self._h, rows, channels, _addr(in_), inPitch, _addr(out), outPitch))
+
+    def rowsAdd(self, rows, channels, a, aPitch, b, bPitch, out, outPitch):
+        self._ck(self._l.tnn_rows_add(self._h, rows, channels, _addr(a), aPitch, _addr(b), bPitch, _addr(out),
+                                      outPitch))
+
+    def upSampleNhwc(self, batch, channels, inHeight, inWidth, stride, scale, in_, inPitch, out, outPitch):
+        self._ck(self._l.tnn_upsample_nhwc(self._h, batch, channels, inHeight, inWidth, stride, scale, _addr(in_),
+                                           inPitch, _addr(out), outPitch))

@@ -29,6 +29,7 @@ class TShortcutLayer:
         if getattr(self, "_fused_into_conv", False) and not state.isTraining:
             return  # the preceding convolution's epilogue already wrote input + layers[from].output here
         other = net.layers[self.inputLayers[0]].output
+        # (channels-innermost graph: both operands are dense rows of c floats — the same flat add)
         # copy + addvv of the reference collapse into one out-of-place add (same arithmetic: a single fp32 add)
         cu.addvv(self.output.Size(), state.input.devData, 0, 1, other.devData, 0, 1, self.output.devData, 0, 1)
         cu.ActivateArray(self.output.Size(), self.output.devData, 0, self.ActivationType)
@@ -54,7 +55,11 @@ class TConcatLayer:
         off = 0
         for li, c in zip(self.inputLayers, self._cs):
             src = net.layers[li].output
-            if self.batch == 1 or len(self.inputLayers) == 1:
+            if getattr(self, "layout", "NCHW") == "NHWC":
+                # channels-innermost: every source is a column slice of the output rows
+                cu.rowsCopy(self.batch * self.h * self.w, c, src.devData, getattr(src, "pitch", 0) or c,
+                            self.output.devData + 4 * off, self.outC)
+            elif self.batch == 1 or len(self.inputLayers) == 1:
                 cu.copy(src.Size(), src.devData, 0, 1, self.output.devData, off * self.h * self.w, 1)
             else:
                 cu.concatChannels(self.batch, c, self.h * self.w, src.devData, self.outC, off, self.output.devData)
@@ -72,6 +77,10 @@ class TUpsampleLayer:
 
     def forwardGPU(self, state: TNNetState, net: "TNNet"):
         self.output.setCUDA()
+        if getattr(self, "layout", "NCHW") == "NHWC":
+            cuda().upSampleNhwc(self.batch, self.c, self.h, self.w, self.stride, self.scale, state.input.devData,
+                                getattr(state.input, "pitch", 0) or self.c, self.output.devData, self.c)
+            return
         cuda().upSample(self.batch, self.c, self.h, self.w, state.input.devData, self.stride, 1, self.scale,
                         self.output.devData)
 
@@ -114,9 +123,11 @@ class TYoloLayer:
                     cu.fmavss(2 * wh, self.output.devData, bbox_index, self.scaleXY, 0.5 * (1 - self.scaleXY),
                               self.output.devData)
 
-    def getDetections(self, pred: np.ndarray, netw, neth, thresh, abatch=0):
-        """pred: host copy of this layer's output [batch, c, h, w].  Returns (boxes[n,4] xywh relative, objectness[n],
-        prob[n,classes]) following nyololayer.pas:399-441 with relative=True, letter=False."""
+    def getDetections(self, pred: np.ndarray, netw, neth, thresh, abatch=0, img_w=None, img_h=None, relative=True,
+                      letter=False):
+        """pred: host copy of this layer's output [batch, c, h, w].  Returns (boxes[n,4] xywh, objectness[n],
+        prob[n,classes]) following nyololayer.pas:399-441 (+ correctBoxes :443-498; the MSCOCO sample calls
+        Detections(img.w, img.h, thresh, relative=true, letter=false), MSCOCOYolo.pas:364)."""
         wh = self.w * self.h
         p = pred[abatch].reshape(self.n, self.classes + 5, wh)
         boxes, objs, probs = [], [], []
@@ -137,7 +148,32 @@ class TYoloLayer:
                     probs.append(pr)
         if not boxes:
             return np.zeros((0, 4), np.float32), np.zeros(0, np.float32), np.zeros((0, self.classes), np.float32)
-        return np.asarray(boxes, np.float32), np.asarray(objs, np.float32), np.stack(probs)
+        boxes = correctBoxes(np.asarray(boxes, np.float32), img_w or netw, img_h or neth, netw, neth, relative, letter)
+        return boxes, np.asarray(objs, np.float32), np.stack(probs)
+
+
+def correctBoxes(boxes, w, h, netw, neth, relative=True, letter=False):
+    """TYoloLayer.correctBoxes nyololayer.pas:443-498: undo the letter-box embedding of a (w x h) image in the
+    (netw x neth) network input; relative=False scales to image pixels."""
+    if letter:
+        if (netw / w) < (neth / h):
+            new_w, new_h = netw, (h * netw) // w
+        else:
+            new_h, new_w = neth, (w * neth) // h
+    else:
+        new_w, new_h = netw, neth
+    deltaw, deltah = np.float32(netw - new_w), np.float32(neth - new_h)
+    ratiow, ratioh = np.float32(new_w / netw), np.float32(new_h / neth)
+    b = boxes.astype(np.float64)
+    b[:, 0] = (b[:, 0] - deltaw / 2.0 / netw) / ratiow
+    b[:, 1] = (b[:, 1] - deltah / 2.0 / neth) / ratioh
+    b[:, 2] *= 1 / np.float64(ratiow)
+    b[:, 3] *= 1 / np.float64(ratioh)
+    b = b.astype(np.float32)
+    if not relative:
+        b[:, 0] *= np.float32(w); b[:, 2] *= np.float32(w)
+        b[:, 1] *= np.float32(h); b[:, 3] *= np.float32(h)
+    return b
 
 
 def box_iou(a, b):
@@ -359,6 +395,41 @@ class TNNet:
                 n += 1
         return n
 
+    def setChannelsLast(self, on: bool = True):
+        """Inference graph with channels-innermost (NHWC) INTERNAL activations (include/tensorium_b200.h, last section):
+        the first convolution reads the planar image, every convolution that feeds a yolo layer writes planes, and all
+        tensors in between are rows of channels — what the TMA im2col-mode convolution kernel reads and writes.
+        Shortcut adds are layout-blind, routes copy column slices, upsample repeats rows.  Same arithmetic per layer as
+        the planar graph."""
+        NCHW, NHWC = nn.TNNCuda.LAYOUT_NCHW, nn.TNNCuda.LAYOUT_NHWC
+        n = len(self.layers)
+        feeds_yolo = [i + 1 < n and isinstance(self.layers[i + 1], TYoloLayer) for i in range(n)]
+        for i, l in enumerate(self.layers):
+            if isinstance(l, TConvolutionalLayer):
+                assert l.fused, "channels-last needs the fused entry points"
+                l.in_layout = NHWC if (on and i > 0) else NCHW
+                l.out_layout = NHWC if (on and not feeds_yolo[i]) else NCHW
+                l.output.layout = "NHWC" if l.out_layout == NHWC else "NCHW"
+            elif isinstance(l, (TShortcutLayer, TConcatLayer, TUpsampleLayer)):
+                l.layout = "NHWC" if on else "NCHW"
+                l.output.layout = l.layout
+            elif isinstance(l, TYoloLayer):
+                pass
+            else:
+                assert not on, f"layer {i} ({l.layerType}) has no channels-innermost path"
+        self.channels_last = bool(on)
+        return self
+
+    def output_nchw(self, i: int) -> np.ndarray:
+        """Host copy of layer i's output in the reference's planar order, whatever the internal layout."""
+        l = self.layers[i]
+        data = l.output.pullFromDevice()
+        l.output.setCUDA()
+        if getattr(l.output, "layout", "NCHW") == "NHWC":
+            b, c, h, w = l.output.FShape
+            return np.ascontiguousarray(data.reshape(b, h, w, c).transpose(0, 3, 1, 2))
+        return data.copy()
+
     def predict(self, x_dev_tensor: TSingleTensor | None = None):
         st = TNNetState(input=x_dev_tensor or self.input, isTraining=False)
         return self.forward(st)
@@ -371,12 +442,13 @@ class TNNet:
         return sum(2 * l.batch * l.filters * l.outH * l.outW * l.c * l.kernelSize ** 2 for l in self.layers
                    if isinstance(l, TConvolutionalLayer))
 
-    def Detections(self, thresh=0.45, nms=0.45, abatch=0, host_outputs=None):
-        """nnet.pas:584-677 + MSCOCOYolo.pas:252-253: gather yolo detections of one image, then NMS."""
+    def Detections(self, thresh=0.45, nms=0.45, abatch=0, host_outputs=None, img_w=None, img_h=None, relative=True,
+                   letter=False):
+        """nnet.pas:584-677 + MSCOCOYolo.pas:252-253,364: gather yolo detections of one image, then NMS."""
         bs, os_, ps = [], [], []
         for li, l in enumerate(self.yolo_layers()):
             pred = host_outputs[li] if host_outputs is not None else l.output.pullFromDevice()
-            b, o, p = l.getDetections(pred, self.w, self.h, thresh, abatch)
+            b, o, p = l.getDetections(pred, self.w, self.h, thresh, abatch, img_w, img_h, relative, letter)
             bs.append(b), os_.append(o), ps.append(p)
         boxes, objs, probs = np.concatenate(bs), np.concatenate(os_), np.concatenate(ps)
         return doNMSSort(boxes, objs, probs, nms)
@@ -454,7 +526,8 @@ def init_yolov3_params(spec, c_in=3, seed=1234, objectness_bias=-4.0):
     return params
 
 
-def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=1234, fuse_shortcuts=False):
+def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=1234, fuse_shortcuts=False,
+                 channels_last=False):
     """Builds the 107-layer net on the current `cuda` backend.  fuse_bn=True mirrors MSCOCOYolo.pas:327-340
     (Neural.fuseBatchNorm before predict)."""
     spec = yolov3_spec()
@@ -489,6 +562,8 @@ def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=12
         layers.append(l)
         c, h, w = l.outC, l.outH, l.outW
     net = TNNet(layers, batch, 3, size, size)
-    if fuse_shortcuts and fused:
+    if channels_last:
+        net.setChannelsLast()
+    elif fuse_shortcuts and fused:
         net.fuseShortcuts()
     return net

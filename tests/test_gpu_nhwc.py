@@ -1,0 +1,158 @@
+"""Parity of the channels-innermost (NHWC) convolution path — TMA im2col-mode activations, TMA weights, TMA store —
+against the oracle (the reference's CPU im2col + sgemm, source/ntensors.pas:8252-8349), through the C ABI.
+The oracle works on NCHW tensors; the tests convert at the edges (host side, numpy transposes) so the kernel is
+checked on exactly the reference's inputs and outputs."""
+import numpy as np
+import pytest
+
+from util import TOL_3XTF32, TOL_TF32, Dev, rel_elem, rel_max
+
+pytestmark = pytest.mark.gpu
+FP32, X3, TF32 = 0, 1, 2
+NCHW, NHWC = 0, 1
+
+
+def to_nhwc(x, pitch=None):
+    B, C, H, W = x.shape
+    pitch = pitch or C
+    out = np.full((B, H, W, pitch), 555.0, np.float32)  # the pad lanes must never be read as data
+    out[..., :C] = x.transpose(0, 2, 3, 1)
+    return out
+
+
+def from_nhwc(y, C):
+    return np.ascontiguousarray(y[..., :C].transpose(0, 3, 1, 2))
+
+
+def conv_case(rng, B, C, H, W, F, k):
+    x = rng.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    s = np.sqrt(2.0 / (k * k * C))
+    w = rng.uniform(-s, s, (F, C * k * k)).astype(np.float32)
+    b = rng.uniform(-0.5, 0.5, F).astype(np.float32)
+    return x, w, b
+
+
+# (B, C, H, W, F, k, pad, stride, inPitch, outPitch)   pitch 0 = dense
+GEOMS = [
+    (2, 32, 16, 16, 32, 3, 1, 1, 0, 0),      # one 32-channel block per tap, 512 pixels = 4 tiles
+    (2, 64, 13, 13, 128, 3, 1, 1, 0, 0),     # 13-wide rows: tiles cross rows and images, ragged last tile
+    (3, 32, 26, 26, 64, 3, 1, 2, 0, 0),      # stride 2 (traversal stride of the TMA walk)
+    (1, 128, 52, 52, 64, 1, 0, 1, 0, 0),     # 1x1 bottleneck
+    (2, 48, 12, 10, 40, 3, 1, 1, 0, 0),      # C = 48: second 32-block half empty (TMA zero fill), F = 40 (BN 48)
+    (2, 36, 9, 9, 24, 3, 1, 1, 40, 28),      # C = 36 inside pitch-40 rows, output into pitch-28 rows
+    (1, 16, 20, 24, 272, 3, 1, 1, 0, 0),     # two filter tiles (256 + 16)
+    (2, 64, 8, 8, 96, 5, 2, 1, 0, 0),        # 5x5
+    (1, 32, 17, 15, 32, 3, 0, 1, 0, 0),      # no padding
+    (2, 32, 14, 14, 64, 3, 2, 1, 0, 0),      # padding 2 with a 3x3 kernel (output larger than input)
+    (1, 32, 31, 29, 48, 3, 1, 2, 0, 64),     # stride 2 on odd sizes, output slice of a 64-wide concat buffer
+    (4, 256, 13, 13, 512, 3, 1, 1, 0, 0),    # the YOLO 13x13 shape (K = 2304), 6 tiles x 2 filter tiles
+]
+
+
+@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32)])
+@pytest.mark.parametrize("geom", GEOMS)
+def test_conv_forward_nhwc(cuda_backend, oracle, mode, tol, geom):
+    cu = cuda_backend
+    B, C, H, W, F, k, p, s, ip, op = geom
+    ip, op = ip or C, op or F
+    rng = np.random.default_rng(sum(geom) + 3)
+    x, w, b = conv_case(rng, B, C, H, W, F, k)
+    sc = rng.uniform(0.5, 1.5, F).astype(np.float32)
+    want = oracle.conv2d(x, w, p, s, s, 1, k, k)
+    oracle.forward_scale(want, sc, B)
+    oracle.forward_bias(want, b, B)
+    oracle.activate_array(want, oracle.ACT["LEAKY"])
+    OH, OW = want.shape[2], want.shape[3]
+    dx, dw, db, ds = Dev(cu, to_nhwc(x, ip)), Dev(cu, w), Dev(cu, b), Dev(cu, sc)
+    dout = Dev(cu, n=B * OH * OW * op)
+    cu.fill(dout.n, dout.ptr, 0, 777.0, 1)
+    desc = cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s)
+    cu.set_math_mode(mode)
+    try:
+        cu.conv2dForwardNhwc(desc, dx.ptr, 0, ip, NHWC, dw.ptr, ds.ptr, db.ptr, oracle.ACT["LEAKY"], dout.ptr, 0, op, NHWC)
+        assert "k_conv_nhwc" in cu.lastConvKernel()
+    finally:
+        cu.set_math_mode(X3)
+    raw = dout.read((B, OH, OW, op))
+    got = from_nhwc(raw, F)
+    e1, e2 = rel_max(got, want), rel_elem(got, want, floor=1.0)
+    assert e1 < tol and e2 < tol, (e1, e2)
+    if op > F:
+        assert np.all(raw[..., F:] == 777.0)  # the neighbouring slice of the concat buffer is untouched
+
+
+@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32)])
+def test_conv_forward_nhwc_planar_output(cuda_backend, oracle, mode, tol):
+    """Head layers: channels-innermost input, NCHW output planes (255 filters, linear, bias only)."""
+    cu = cuda_backend
+    B, C, H, W, F, k, p, s = 3, 64, 13, 13, 255, 1, 0, 1
+    rng = np.random.default_rng(77)
+    x, w, b = conv_case(rng, B, C, H, W, F, k)
+    want = oracle.conv2d(x, w, p, s, s, 1, k, k)
+    oracle.forward_bias(want, b, B)
+    dx, dw, db, dout = Dev(cu, to_nhwc(x)), Dev(cu, w), Dev(cu, b), Dev(cu, n=want.size)
+    cu.set_math_mode(mode)
+    try:
+        cu.conv2dForwardNhwc(cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s), dx.ptr, 0, C, NHWC, dw.ptr, None, db.ptr,
+                             oracle.ACT["LINEAR"], dout.ptr, 0, 0, NCHW)
+    finally:
+        cu.set_math_mode(X3)
+    got = dout.read(want.shape)
+    assert rel_max(got, want) < tol and rel_elem(got, want, floor=1.0) < tol
+
+
+def test_first_layer_planar_input_to_nhwc(cuda_backend, oracle):
+    """The image layer: NCHW 3-channel input, direct fp32 kernel, channels-innermost output — exact fp32 FMA sums."""
+    cu = cuda_backend
+    B, C, H, W, F, k, p, s = 2, 3, 20, 24, 32, 3, 1, 1
+    rng = np.random.default_rng(5)
+    x, w, b = conv_case(rng, B, C, H, W, F, k)
+    oracle.set_mode(oracle.MODE_FMA)
+    try:
+        want = oracle.conv2d(x, w, p, s, s, 1, k, k)
+    finally:
+        oracle.set_mode(oracle.MODE_PAS)
+    oracle.forward_bias(want, b, B)
+    dx, dw, db = Dev(cu, x), Dev(cu, w), Dev(cu, b)
+    dout = Dev(cu, n=B * H * W * F)
+    desc = cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s)
+    cu.conv2dForwardNhwc(desc, dx.ptr, 0, 0, NCHW, dw.ptr, None, db.ptr, oracle.ACT["LINEAR"], dout.ptr, 0, F, NHWC)
+    assert "NHWC" in cu.lastConvKernel()
+    assert np.array_equal(from_nhwc(dout.read((B, H, W, F)), F), want)
+    # leaky: the kernel multiplies by 0.1f in fp32, the Pascal expression by the double 0.1 (one rounding apart)
+    cu.conv2dForwardNhwc(desc, dx.ptr, 0, 0, NCHW, dw.ptr, None, db.ptr, oracle.ACT["LEAKY"], dout.ptr, 0, F, NHWC)
+    oracle.activate_array(want, oracle.ACT["LEAKY"])
+    assert rel_elem(from_nhwc(dout.read((B, H, W, F)), F), want) < 2e-7
+
+
+def test_layout_companions(cuda_backend):
+    """nchw<->nhwc, pitched row copy / add (route, shortcut) and the channels-innermost upsample: bit-exact."""
+    cu = cuda_backend
+    rng = np.random.default_rng(11)
+    B, C, H, W = 3, 44, 7, 9
+    x = rng.uniform(-1, 1, (B, C, H, W)).astype(np.float32)
+    dx = Dev(cu, x)
+    pitch = 48
+    dn = Dev(cu, n=B * H * W * pitch)
+    cu.fill(dn.n, dn.ptr, 0, 9.0, 1)
+    cu.nchwToNhwc(B, C, H * W, dx.ptr, dn.ptr, pitch)
+    got = dn.read((B, H, W, pitch))
+    assert np.array_equal(got[..., :C], x.transpose(0, 2, 3, 1)) and np.all(got[..., C:] == 9.0)
+    db = Dev(cu, n=x.size)
+    cu.nhwcToNchw(B, C, H * W, dn.ptr, pitch, db.ptr)
+    assert np.array_equal(db.read(x.shape), x)
+    # route: two sources into slices of one concat buffer; shortcut: a + b
+    y = rng.uniform(-1, 1, (B, H, W, 20)).astype(np.float32)
+    dy = Dev(cu, y)
+    dc = Dev(cu, n=B * H * W * 64)
+    cu.rowsCopy(B * H * W, C, dn.ptr, pitch, dc.ptr, 64)
+    cu.rowsCopy(B * H * W, 20, dy.ptr, 20, dc.ptr + 44 * 4, 64)
+    cat = dc.read((B, H, W, 64))
+    assert np.array_equal(cat[..., :44], got[..., :44]) and np.array_equal(cat[..., 44:], y)
+    ds = Dev(cu, n=B * H * W * 20)
+    cu.rowsAdd(B * H * W, 20, dy.ptr, 20, dc.ptr + 44 * 4, 64, ds.ptr, 20)
+    assert np.array_equal(ds.read(y.shape), y + y)
+    # upsample x2
+    du = Dev(cu, n=B * 2 * H * 2 * W * 20)
+    cu.upSampleNhwc(B, 20, H, W, 2, 1.0, dy.ptr, 20, du.ptr, 20)
+    assert np.array_equal(du.read((B, 2 * H, 2 * W, 20)), y.repeat(2, axis=1).repeat(2, axis=2))
