@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 BATCH = 64
 SIZE = 416
 METRIC = "YOLOv3-416 inference images/sec"
-MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16x3": 3}
 
 
 def load_peaks():

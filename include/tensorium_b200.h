@@ -59,7 +59,10 @@ typedef enum {
 typedef enum {
   TNN_MATH_FP32 = 0,   /* CUDA-core FMA, fp32 exact products (reference: cublasSgemm SIMT / sgemm1_nn) */
   TNN_MATH_3XTF32 = 1, /* tcgen05 kind::tf32, big/small split, 3 MMAs: fp32-level accuracy (default)   */
-  TNN_MATH_TF32 = 2    /* tcgen05 kind::tf32, single MMA (optional fast mode, 5e-3 tolerance)           */
+  TNN_MATH_TF32 = 2,   /* tcgen05 kind::tf32, single MMA (optional fast mode, 5e-3 tolerance)           */
+  TNN_MATH_BF16X3 = 3  /* tcgen05 kind::f16 on bf16 big/small halves, 3 MMAs at twice the TF32 rate: the same 1e-4
+                          gate as 3xTF32 (16+ mantissa bits per operand, fp32 accumulation).  Taken by the
+                          channels-innermost convolution; every other contraction runs 3xTF32 in this mode.     */
 } tnn_math_mode;
 
 /* ------------------------------------------------------------------ lifetime / device */

@@ -90,8 +90,6 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     ctx->tail_split = (ts && ts[0] == '0') ? 0 : 1;
     const char *nk = getenv("TNN_NHWC_KB");
     ctx->nhwc_kb = (nk && atoi(nk) == 32) ? 32 : (nk && atoi(nk) == 16) ? 16 : 0;
-    const char *p2 = getenv("TNN_PAIR");
-    ctx->pair_mma = (p2 && p2[0] == '1') ? 1 : 0;
   }
   *out = ctx;
   return 0;
@@ -135,7 +133,7 @@ void *tnn_get_stream(tnn_context *ctx) { return ctx ? (void *)ctx->stream : null
 
 int32_t tnn_set_math_mode(tnn_context *ctx, int32_t mode) {
   TNN_CHECK_CTX(ctx);
-  TNN_REQUIRE(mode >= TNN_MATH_FP32 && mode <= TNN_MATH_TF32, "unknown math mode");
+  TNN_REQUIRE(mode >= TNN_MATH_FP32 && mode <= TNN_MATH_BF16X3, "unknown math mode");
   ctx->math_mode = mode;
   return 0;
 }

@@ -19,7 +19,6 @@ struct tnn_context {
   int patch_kb16;       // 1: TMA-activation convolutions run 16-channel pipeline stages in 3xTF32 mode (TNN_PATCH_KB16=1; no measurable gain, opt-in)
   int tail_split;       // 1: a last wave that fills <= half of the SMs runs as half-width tiles (default; TNN_TAIL_SPLIT=0)
   int nhwc_kb;          // channels per pipeline stage of the NHWC convolution in 3xTF32 mode: 0 = default (16), 16 or 32 (TNN_NHWC_KB)
-  int pair_mma;         // 1: wide layers of the gathering path run on CTA pairs (tcgen05.mma.cta_group::2)
   int last_conv_kernel; // which kernel the last tnn_conv2d_forward took (TNN_CONV_KERNEL_*), for measurement tools
   int64_t launches;
   int capturing;              // between tnn_graph_begin_capture and tnn_graph_end_capture
@@ -42,6 +41,11 @@ struct tnn_context {
 int tnn_weight_buffer(tnn_context *ctx, const float *weights, int kind, size_t count, float **hi, float **lo, bool *fresh);
 
 void tnn_set_error(const char *fmt, ...);
+
+// fp32-class accuracy modes split every operand in two (3xTF32: TF32 hi/lo, 3 MMAs; BF16x3: bf16 hi/lo, 3 MMAs)
+static inline bool tnn_math_is_split(const tnn_context *ctx) {
+  return ctx->math_mode == TNN_MATH_3XTF32 || ctx->math_mode == TNN_MATH_BF16X3;
+}
 
 #define TNN_CHECK_CTX(ctx)                         \
   do {                                             \

@@ -8,7 +8,6 @@
 #include "conv_direct.cuh"
 #include "umma_halo.cuh"
 #include "umma_wgrad.cuh"
-#include "umma_conv2.cuh"
 #include "umma_gemm.cuh"
 
 namespace {

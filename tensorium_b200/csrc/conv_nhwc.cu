@@ -19,6 +19,14 @@
 // Warp roles (448 threads, one persistent CTA per SM): 0-3 epilogue, 4-11 derive the 3xTF32 low half of the A
 // tile in shared memory (lo = x - trunc_tf32(x); the raw tile IS the high half because kind::tf32 reads the top
 // 19 bits), 12 MMA issue, 13 TMA.  In TF32 mode nobody touches the tiles: TMA -> mbarrier -> MMA.
+//
+// BF16x3 mode (TNN_MATH_BF16X3): the same pipeline with every fp32 operand split into two bf16 numbers,
+// hi = bf16_rn(x), lo = bf16_rn(x - hi) (x = hi + lo to 2^-18 relative), and D += A_lo*B_hi + A_hi*B_lo + A_hi*B_hi
+// issued as tcgen05.mma kind::f16 — bf16 products are exact in fp32 and the accumulation is the same fp32 TMEM
+// accumulator, so the result stays inside the 1e-4 gate of 3xTF32 while the tensor pipe does half the work
+// (3 bf16 MMAs = 1.5 TF32-MMA equivalents per k instead of 3): the 3xTF32 kernels run at the board's power cap, so
+// fewer tensor FLOPs per output is what makes them faster.  The producer warps convert the landed fp32 A tile into
+// the two bf16 K-major tiles (64-byte rows, SWIZZLE_64B); the weights are pre-split bf16 planes fetched by TMA.
 #include "umma_conv.cuh"
 #include "conv_direct.cuh"
 
@@ -64,6 +72,42 @@ __device__ __forceinline__ void bulk_wait_read() {
 }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// D[tmem] (+)= A * B with bf16 operands (kind::f16), fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor: D = F32, A = B = BF16, K-major both, M = 128, N = n
+__host__ __device__ inline uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+// two floats -> packed bf16x2 (round to nearest even), low half = first argument
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+  return r;
+}
+// split 8 consecutive floats into 8 bf16 high parts and 8 bf16 low parts (each one 16-byte chunk)
+__device__ __forceinline__ void split_bf16x8(const float4 &a, const float4 &b, uint4 &hi, uint4 &lo) {
+  const float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    h[i] = pack_bf16x2(x[2 * i], x[2 * i + 1]);
+    const float h0 = __uint_as_float(h[i] << 16), h1 = __uint_as_float(h[i] & 0xFFFF0000u);
+    l[i] = pack_bf16x2(x[2 * i] - h0, x[2 * i + 1] - h1);
+  }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+enum { MODE_TF32 = 0, MODE_3X = 1, MODE_BF16X3 = 2 };
+
 struct Geo {
   int OW, OHW;             // output row length, output pixels per image
   int sx, sy, pw, ph, dx, dy, kw;
@@ -96,7 +140,7 @@ struct Ctl {
 constexpr int kStageTile = 32 * 32 * 4;  // one epilogue staging tile: 32 pixels x 32 filters
 constexpr int kStageBufs = 2;            // per epilogue warp
 
-template <bool SPLIT, int KB, typename EPI>
+template <int MODE, int KB, typename EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCols,
             const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
@@ -104,10 +148,14 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
   extern __shared__ uint8_t smem_raw[];
   __shared__ Ctl ctl;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr int aBytes = BM * KB * 4;
-  const int bBytes = BN * KB * 4;
-  const int stageBytes = (aBytes + bBytes) * (SPLIT ? 2 : 1);
-  const int bOff = (SPLIT ? 2 : 1) * aBytes;  // stage layout: A | A_lo | B_hi | B_lo   (TF32: A | B)
+  constexpr bool SPLIT = MODE != MODE_TF32;   // producers touch the landed A tile; two B planes
+  constexpr bool BF = MODE == MODE_BF16X3;
+  static_assert(!BF || KB == 32, "bf16 stages are 32 channels deep (64-byte bf16 rows)");
+  constexpr int aBytes = BM * KB * 4;                 // the landed fp32 A tile
+  const int bBytes = BN * KB * (BF ? 2 : 4);          // one weight plane of the stage
+  // stage layout: 3xTF32  A(=hi) | A_lo | B_hi | B_lo;   TF32  A | B;   BF16x3  A raw | A_hi | A_lo | B_hi | B_lo (bf16 tiles)
+  const int bOff = BF ? 2 * aBytes : (SPLIT ? 2 : 1) * aBytes;
+  const int stageBytes = bOff + bBytes * (SPLIT ? 2 : 1);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -150,12 +198,31 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
       for (; remaining > 0; --remaining) {
         mbar_wait_warp(&ctl.araw[stage], phase);
         uint8_t *sa = smem + (size_t)stage * stageBytes;
+        if constexpr (BF) {
+          // raw tile: row r = 128 bytes, 16-byte chunk c at c ^ (r & 7) (SWIZZLE_128B).  bf16 tiles: row r = 64 bytes,
+          // 16-byte chunk j (8 k) at j ^ ((r >> 1) & 3) (SWIZZLE_64B).  One unit = 8 consecutive k of one row.
+          uint8_t *shi = sa + aBytes, *slo = shi + aBytes / 2;
 #pragma unroll
-        for (int i = 0; i < aBytes / (16 * kProducerThreads); ++i) {
-          const int off = (i * kProducerThreads + tid) * 16;
-          const float4 v = *reinterpret_cast<const float4 *>(sa + off);
-          *reinterpret_cast<float4 *>(sa + aBytes + off) =
-              make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+          for (int i = 0; i < (BM * 4) / kProducerThreads; ++i) {
+            const int u = i * kProducerThreads + tid;
+            const int r = u >> 2, j = u & 3;
+            const uint8_t *rowp = sa + r * 128;
+            const float4 a = *reinterpret_cast<const float4 *>(rowp + (((2 * j) ^ (r & 7)) << 4));
+            const float4 b = *reinterpret_cast<const float4 *>(rowp + (((2 * j + 1) ^ (r & 7)) << 4));
+            uint4 hi, lo;
+            split_bf16x8(a, b, hi, lo);
+            const int o = r * 64 + ((j ^ ((r >> 1) & 3)) << 4);
+            *reinterpret_cast<uint4 *>(shi + o) = hi;
+            *reinterpret_cast<uint4 *>(slo + o) = lo;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < aBytes / (16 * kProducerThreads); ++i) {
+            const int off = (i * kProducerThreads + tid) * 16;
+            const float4 v = *reinterpret_cast<const float4 *>(sa + off);
+            *reinterpret_cast<float4 *>(sa + aBytes + off) =
+                make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+          }
         }
         fence_proxy_async();
         __syncwarp();
@@ -172,7 +239,8 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
     for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x, ++it) {
       int mt, nt, kb0, kb1;
       sched.decode(t, mt, nt, kb0, kb1);
-      const uint32_t idesc = make_idesc(sched.half(t) ? BN >> 1 : BN, false, false);
+      const uint32_t idesc = BF ? make_idesc_bf16(sched.half(t) ? BN >> 1 : BN)
+                                : make_idesc(sched.half(t) ? BN >> 1 : BN, false, false);
       const int as = (int)(it & 1);
       const uint32_t use = (uint32_t)(it >> 1);
       mbar_wait_warp(&ctl.tmem_empty[as], (use & 1) ^ 1);
@@ -186,6 +254,19 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
           const uint32_t sb = sa + bOff;
           // K-major rows of KB floats: 8-row groups are 8*KB*4 bytes apart, one UMMA_K = 8 step = +32 bytes
           constexpr uint32_t kSbo = KB == 32 ? 1024 : 512, kLt = KB == 32 ? 2u : 4u;
+          if constexpr (BF) {
+            // bf16 tiles: 64-byte rows (32 k), SWIZZLE_64B, 8-row groups 512 bytes apart; UMMA_K = 16 -> +32 bytes
+            const uint32_t shi = sa + aBytes, slo = shi + aBytes / 2;
+#pragma unroll
+            for (int ks = 0; ks < KB / 16; ++ks) {
+              const uint64_t ah = make_desc(shi + ks * 32, 16, 512, 4u), al = make_desc(slo + ks * 32, 16, 512, 4u);
+              const uint64_t bh = make_desc(sb + ks * 32, 16, 512, 4u), bl = make_desc(sb + bBytes + ks * 32, 16, 512, 4u);
+              const uint32_t acc = (kb != kb0 || ks != 0) ? 1u : 0u;
+              mma_bf16(tmem_d, al, bh, idesc, acc);  // small terms first
+              mma_bf16(tmem_d, ah, bl, idesc, 1u);
+              mma_bf16(tmem_d, ah, bh, idesc, 1u);
+            }
+          } else
 #pragma unroll
           for (int ks = 0; ks < KB / 8; ++ks) {
             const uint64_t ah = make_desc(sa + ks * 32, 16, kSbo, kLt);
@@ -340,6 +421,46 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, accCols * 2);
 }
 
+// bf16 big/small planes of the weights in the kernel's k order:  k = (tap*CB + cb)*32 + ci,  channel = cb*32 + ci
+//   hi[f][k] = bf16_rn(W[f][channel][tap]),  lo[f][k] = bf16_rn(W - hi)        (zero for channel >= C)
+static __global__ void __launch_bounds__(256) k_prepare_weights_bf16(const float *__restrict__ w, int rows, int chans, int kk,
+                                                                     int CB, uint16_t *__restrict__ hi,
+                                                                     uint16_t *__restrict__ lo) {
+  const int Kpad = kk * CB * 32;
+  const int64_t total = (int64_t)rows * Kpad;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const int r = (int)(i / Kpad);
+    const int k = (int)(i - (int64_t)r * Kpad);
+    const int ci = k & 31, g = k >> 5;
+    const int tap = g / CB, cb = g - tap * CB;
+    const int ch = cb * 32 + ci;
+    const float v = ch < chans ? __ldg(w + ((int64_t)r * chans + ch) * kk + tap) : 0.f;
+    const uint32_t h = pack_bf16x2(v, 0.f) & 0xFFFFu;
+    const float hf = __uint_as_float(h << 16);
+    hi[i] = (uint16_t)h;
+    lo[i] = (uint16_t)(pack_bf16x2(v - hf, 0.f) & 0xFFFFu);
+  }
+}
+
+// bf16 matrix [rows][Kpad] (k contiguous) -> tiles of 32 k x boxRows rows, 64-byte rows: SWIZZLE_64B
+static int encode_weights_map_bf16(CUtensorMap *tm, const uint16_t *base, int64_t rows, int64_t Kpad, int boxRows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
+  cuuint32_t box[2] = {32, (cuuint32_t)boxRows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tnn_set_error("cuTensorMapEncodeTiled (bf16 weights) failed with CUresult %d", (int)r);
+    return 6;
+  }
+  return 0;
+}
+
 // activations [B][H][W][pitch] as the im2col-mode tensor {C, W, H, N}: box = 128 pixels x kb channels of one tap
 static int encode_im2col_map(CUtensorMap *tm, const float *base, const simt::ConvGeom &g, int batch, int64_t pitch, int kb) {
   EncodeIm2colFn enc = get_encode_im2col();
@@ -379,10 +500,10 @@ static int encode_out_map(CUtensorMap *tm, float *base, int64_t M, int64_t F, in
   return 0;
 }
 
-template <bool SPLIT, int KB, typename EPI>
+template <int MODE, int KB, typename EPI>
 static int launch_nhwc(tnn_context *ctx, const Plan &p, const Geo &geo, EPI epi, const CUtensorMap &tmA,
                        const CUtensorMap &tmHi, const CUtensorMap &tmLo, const CUtensorMap &tmOut) {
-  auto kern = k_conv_nhwc<SPLIT, KB, EPI>;
+  auto kern = k_conv_nhwc<MODE, KB, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
   kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(epi, p.sched, geo, p.BN, p.stages, p.accCols, tmA, tmHi, tmLo, tmOut);
   TNN_LAUNCHED(ctx);
@@ -400,15 +521,17 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   const int64_t M = (int64_t)batch * g.OH * g.OW;
   const int64_t N = g.F;
   TNN_REQUIRE(M < (1ll << 31) - BM, "too many output pixels");
-  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  const bool bf = ctx->math_mode == TNN_MATH_BF16X3;
+  const bool split = tnn_math_is_split(ctx);
   const int CB = (g.C + 31) / 32;       // 32-channel blocks per tap (the weight copy's k order)
   const int64_t K = (int64_t)kk * CB * 32;
-  // 3xTF32 stages carry four tiles: half-depth (16-channel) stages keep four of them in flight
-  const int KB = split ? (ctx->nhwc_kb ? ctx->nhwc_kb : 16) : 32;
+  // 3xTF32 stages carry four fp32 tiles: half-depth (16-channel) stages keep four of them in flight
+  const int KB = bf ? 32 : split ? (ctx->nhwc_kb ? ctx->nhwc_kb : 16) : 32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
   // half-width tail tiles: the TMA store writes whole 32-filter boxes, so a half tile must be a multiple of 32 wide
   if (outNchw || (p.BN % 64) == 0) split_tail_wave(ctx, p);
-  const size_t stageBytes = (size_t)(BM + p.BN) * KB * 4 * (split ? 2 : 1);
+  const size_t stageBytes = bf ? (size_t)BM * KB * 8 + (size_t)p.BN * KB * 4
+                               : (size_t)(BM + p.BN) * KB * 4 * (split ? 2 : 1);
   const size_t epiBytes = outNchw ? 0 : (size_t)kEpilogueWarps * kStageBufs * kStageTile;
   int st = (int)((225 * 1024 - epiBytes) / stageBytes);
   p.stages = st > kMaxStages ? kMaxStages : st;
@@ -417,38 +540,50 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   p.sched.kBlocks = p.sched.kBlocksPerSplit = (int)(K / KB);
   float *whi, *wlo;
   bool fresh;
-  int rc = tnn_weight_buffer(ctx, weights, 1, (size_t)N * K, &whi, &wlo, &fresh);
+  // bf16 planes take half the floats of the fp32 ones (N*K is a multiple of 32)
+  int rc = tnn_weight_buffer(ctx, weights, 1, bf ? (size_t)N * K / 2 : (size_t)N * K, &whi, &wlo, &fresh);
   if (rc) return rc;
   if (fresh) {
     int64_t blocks = cdiv64(N * K, 256);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_prepare_weights_patch<<<(int)blocks, 256, 0, ctx->stream>>>(weights, (int)N, g.C, kk, CB, 0, whi, wlo, split ? 1 : 0);
+    if (bf)
+      k_prepare_weights_bf16<<<(int)blocks, 256, 0, ctx->stream>>>(weights, (int)N, g.C, kk, CB, (uint16_t *)whi, (uint16_t *)wlo);
+    else
+      k_prepare_weights_patch<<<(int)blocks, 256, 0, ctx->stream>>>(weights, (int)N, g.C, kk, CB, 0, whi, wlo, split ? 1 : 0);
     TNN_LAUNCHED(ctx);
   }
   alignas(64) CUtensorMap tmA, tmHi, tmLo, tmOut;
   rc = encode_im2col_map(&tmA, in, g, batch, inPitch, KB);
   if (rc) return rc;
-  rc = KB == 16 ? encode_weights_map16(&tmHi, whi, N, K, p.BN) : encode_weights_map(&tmHi, whi, N, K, p.BN);
-  if (rc) return rc;
-  rc = KB == 16 ? encode_weights_map16(&tmLo, split ? wlo : whi, N, K, p.BN)
-                : encode_weights_map(&tmLo, split ? wlo : whi, N, K, p.BN);
+  if (bf) {
+    rc = encode_weights_map_bf16(&tmHi, (const uint16_t *)whi, N, K, p.BN);
+    if (rc) return rc;
+    rc = encode_weights_map_bf16(&tmLo, (const uint16_t *)wlo, N, K, p.BN);
+  } else {
+    rc = KB == 16 ? encode_weights_map16(&tmHi, whi, N, K, p.BN) : encode_weights_map(&tmHi, whi, N, K, p.BN);
+    if (rc) return rc;
+    rc = KB == 16 ? encode_weights_map16(&tmLo, split ? wlo : whi, N, K, p.BN)
+                  : encode_weights_map(&tmLo, split ? wlo : whi, N, K, p.BN);
+  }
   if (rc) return rc;
   Geo geo{g.OW, g.OH * g.OW, g.sx, g.sy, g.pw, g.ph, g.dx, g.dy, g.kw, CB * 32 / KB, (int)M};
+  auto go = [&](auto epi) -> int {
+    if (bf) return launch_nhwc<MODE_BF16X3, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+    if (!split) return launch_nhwc<MODE_TF32, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+    return KB == 16 ? launch_nhwc<MODE_3X, 16>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut)
+                    : launch_nhwc<MODE_3X, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+  };
   if (outNchw) {
     memset(&tmOut, 0, sizeof(tmOut));
     NchwEpilogue epi{{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, nullptr}};
-    if (!split) return launch_nhwc<false, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
-    return KB == 16 ? launch_nhwc<true, 16>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut)
-                    : launch_nhwc<true, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+    return go(epi);
   }
   TNN_REQUIRE((outPitch % 4) == 0 && outPitch >= N && (((uintptr_t)out) & 15) == 0,
               "NHWC output needs a pixel pitch that is a multiple of 4 floats and a 16-byte aligned base");
   rc = encode_out_map(&tmOut, out, M, N, outPitch);
   if (rc) return rc;
   NhwcEpilogue epi{scale, bias, act, M, N};
-  if (!split) return launch_nhwc<false, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
-  return KB == 16 ? launch_nhwc<true, 16>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut)
-                  : launch_nhwc<true, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+  return go(epi);
 }
 
 // ------------------------------------------------------------------ layout companions (HBM-bound)

@@ -1280,7 +1280,7 @@ inline bool gemm_supported(tnn_context *, int64_t M, int64_t N, int64_t K) {
 template <typename LA, typename LB>
 int gemm_launch(tnn_context *ctx, LA la, LB lb, int64_t M, int64_t N, int64_t Ktot, float alpha, float beta, float *C,
                 int64_t ldc, bool allowSplitK) {
-  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  const bool split = tnn_math_is_split(ctx);
   // split-K needs C += partial sums: natural for beta = 1; for beta = 0 a contiguous C is zeroed first (few-tile GEMMs
   // like the connected layers' batch x outputs products would otherwise run on a handful of SMs)
   const bool zeroFirst = beta == 0.0f && ldc == N;
@@ -1441,7 +1441,7 @@ inline int conv_patch(tnn_context *ctx, const simt::ConvGeom &v, int batch, cons
   const int64_t M = cdiv64(numAtoms, 4) * BM;  // rows incl. patch padding
   const int64_t N = v.F;
   const int64_t K = (int64_t)kk * CB * 32;
-  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  const bool split = tnn_math_is_split(ctx);
   Plan p = make_plan(ctx, M, N, K, split, false, false);
   split_tail_wave(ctx, p);
   float *whi, *wlo;
@@ -1505,10 +1505,6 @@ int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const float 
               bool dgradWeights, const float *scale, const float *bias, int act, float *out, bool accumulate,
               const float *residual = nullptr);
 
-// umma_conv2.cuh
-int conv_forward_pair(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
-                      const float *scale, const float *bias, int act, float *out);
-
 // conv forward: D[pixel][filter]; A = im2col gather (MN-major, producer warps), B = weights via TMA (K-major)
 inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
                         const float *scale, const float *bias, int act, float *out, const float *residual = nullptr) {
@@ -1520,18 +1516,13 @@ inline int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
     rc = conv_halo(ctx, g, batch, in, weights, false, scale, bias, act, out, false, residual);
     if (rc != kNotTaken) return rc;
   }
-  if (ctx->pair_mma && residual == nullptr) {
-    ctx->last_conv_kernel = 6;
-    int rc = conv_forward_pair(ctx, g, batch, in, weights, scale, bias, act, out);
-    if (rc != kNotTaken) return rc;
-  }
   ctx->last_conv_kernel = 2;
   const int64_t M = (int64_t)batch * g.OH * g.OW;
   const int64_t N = g.F;
   const int kk = g.kh * g.kw;
   const int64_t K = (int64_t)((g.C + 15) / 16) * kk * 16;  // contraction length in the (cg, tap, ci) order
   if (kk > 64 || g.inImg >= (1ll << 31)) return kNotTaken;  // tap mask is 64 bits, offsets 32 bits
-  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  const bool split = tnn_math_is_split(ctx);
   Plan p = make_plan(ctx, M, N, K, split, false, false);
   // no split_tail_wave here: a half-width tile costs this kernel a whole A gather (measured: 17.50 vs 17.35 ms/step)
   // 16-k stages keep twice as many in flight in the same shared memory.  That is what lifts the TMA-fed SGEMM by 30 %,
@@ -1599,7 +1590,7 @@ inline int conv_backward_data(tnn_context *ctx, const simt::ConvGeom &g, int bat
   const int64_t M = (int64_t)batch * v.OH * v.OW;
   const int64_t N = v.F;
   const int64_t K = (int64_t)((v.C + 15) / 16) * kk * 16;
-  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  const bool split = tnn_math_is_split(ctx);
   Plan p = make_plan(ctx, M, N, K, split, false, false);
   // no split_tail_wave here: a half-width tile costs this kernel a whole A gather (measured: 17.50 vs 17.35 ms/step)
   const int64_t Kpad = (int64_t)p.sched.kBlocks * BK;

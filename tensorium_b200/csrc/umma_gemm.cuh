@@ -325,7 +325,7 @@ inline Plan make_gemm_plan(tnn_context *ctx, int64_t M, int64_t N, int64_t K, bo
 template <bool AMN, bool BMN, int KB>
 int gemm_tma_one(tnn_context *ctx, int64_t M, int64_t N, int64_t K, float alpha, const float *A, int64_t lda,
                  const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
-  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  const bool split = tnn_math_is_split(ctx);
   const bool zeroFirst = beta == 0.0f && ldc == N;
   Plan p = make_gemm_plan(ctx, M, N, K, split, BMN, beta == 1.0f || zeroFirst, KB);
   alignas(64) CUtensorMap tmA, tmB;
@@ -354,7 +354,7 @@ inline int gemm_tma(tnn_context *ctx, bool tA, bool tB, int64_t M, int64_t N, in
   if (!ok(A, lda, sA) || !ok(B, ldb, sB) || K < BK || M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31))
     return kNotTaken;
   // 3xTF32 stages are twice as large: half-depth stages keep four of them in flight (ctx->tma_gemm == 2 forces 32)
-  const bool kb16 = ctx->tma_gemm == 3 || (ctx->tma_gemm == 1 && ctx->math_mode == TNN_MATH_3XTF32);
+  const bool kb16 = ctx->tma_gemm == 3 || (ctx->tma_gemm == 1 && tnn_math_is_split(ctx));
   for (int z = 0; z < batch; ++z) {
     const float *Az = A + z * sA, *Bz = B + z * sB;
     float *Cz = C + z * sC;

@@ -369,7 +369,7 @@ inline int conv_halo(tnn_context *ctx, const simt::ConvGeom &v, int batch, const
   const int HR = kPatchH + saMax - saMin, HC = kPatchW + sbMax - sbMin;
   const int NP = s * s * HR * HC;
   if (HR > 255 || HC > 255) return kNotTaken;
-  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  const bool split = tnn_math_is_split(ctx);
   // channels per staged halo: 32 unless two stages of it do not fit next to the weight ring
   int CH = 32;
   if ((size_t)NP * 32 * 4 * (split ? 2 : 1) * 2 > 150 * 1024) CH = 16;

@@ -297,7 +297,7 @@ inline int conv_wgrad_tiles(tnn_context *ctx, const simt::ConvGeom &g, int batch
   const int TH = kWgKT / TW, CPL = TW / 4;
   const int HL = TH + (g.kh - 1) * g.dy;
   if (g.kw * HL * CPL * kWgBRows > kWgMaxB * kProducerThreads || HL > 255 || g.pw > 60) return kNotTaken;
-  const bool split = ctx->math_mode == TNN_MATH_3XTF32;
+  const bool split = tnn_math_is_split(ctx);
   const int aBytes = (kWgKT / 4) * kWgLboA, bBytes = g.kw * HL * CPL * kWgLboB;
   const size_t stageBytes = (size_t)(aBytes + bBytes) * (split ? 2 : 1);
   const size_t smemBytes = kWgStages * stageBytes + 128;

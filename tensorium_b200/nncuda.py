@@ -22,7 +22,7 @@ acLOGISTIC, acRELU, acRELU6, acRELIE, acLINEAR, acRAMP, acTANH, acPLSE, acREVLEA
     acSTAIR, acHARDTAN, acLHTAN, acSELU, acSOFTMAX, acGELU, acSWISH, acMISH, acHARD_MISH, acNORM_CHAN, \
     acNORM_CHAN_SOFTMAX, acNORM_CHAN_SOFTMAX_MAXVAL = range(24)
 
-MATH_FP32, MATH_3XTF32, MATH_TF32 = 0, 1, 2
+MATH_FP32, MATH_3XTF32, MATH_TF32, MATH_BF16X3 = 0, 1, 2, 3
 
 
 class CudaError(RuntimeError):

@@ -8,7 +8,7 @@ import pytest
 from util import TOL_3XTF32, TOL_TF32, Dev, rel_elem, rel_max
 
 pytestmark = pytest.mark.gpu
-FP32, X3, TF32 = 0, 1, 2
+FP32, X3, TF32, BF3 = 0, 1, 2, 3
 NCHW, NHWC = 0, 1
 
 
@@ -49,7 +49,7 @@ GEOMS = [
 ]
 
 
-@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32)])
+@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32), (BF3, TOL_3XTF32)])
 @pytest.mark.parametrize("geom", GEOMS)
 def test_conv_forward_nhwc(cuda_backend, oracle, mode, tol, geom):
     cu = cuda_backend
@@ -81,7 +81,7 @@ def test_conv_forward_nhwc(cuda_backend, oracle, mode, tol, geom):
         assert np.all(raw[..., F:] == 777.0)  # the neighbouring slice of the concat buffer is untouched
 
 
-@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32)])
+@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32), (BF3, TOL_3XTF32)])
 def test_conv_forward_nhwc_planar_output(cuda_backend, oracle, mode, tol):
     """Head layers: channels-innermost input, NCHW output planes (255 filters, linear, bias only)."""
     cu = cuda_backend

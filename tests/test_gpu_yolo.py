@@ -64,14 +64,29 @@ def check_conv_layers(cu, net, probe, x, batch, tol, expect_kernel=None):
     return worst
 
 
-def pick_threshold(want, batch):
-    """A threshold in a gap of the oracle's objectness values near their 90 % quantile: a few dozen boxes pass and
-    none sits within the arithmetic tolerance of the threshold."""
-    objs = np.sort(np.concatenate([w.reshape(batch, 3, 85, -1)[:, :, 4, :].ravel() for w in want]))
-    idx = int(0.9 * objs.size)
-    while objs[idx] - objs[idx - 1] < 1e-3:
+def detection_values(want, batch):
+    """Every value getDetections compares with the threshold: objectness, and objectness * class score."""
+    vals = []
+    for w in want:
+        y = w.reshape(batch, 3, 85, -1)
+        vals.append(y[:, :, 4, :].ravel())
+        vals.append((y[:, :, 4:5, :] * y[:, :, 5:, :]).ravel())
+    return vals
+
+
+def pick_threshold(want, batch, outs=None, q=0.999, start=None):
+    """A detection threshold no compared value sits close to: the GPU outputs differ from the oracle's by
+    d = max|g - r| (measured here), so a value within 2d of the threshold could legitimately fall on either side; the
+    threshold is moved up from the q-quantile of the products (or from `start`) to the first gap wider than 6d."""
+    d = max(float(np.abs(g - r).max()) for g, r in zip(outs, want)) if outs is not None else 1e-4
+    vals = detection_values(want, batch)
+    v = np.sort(np.concatenate(vals))
+    prods = np.sort(np.concatenate(vals[1::2]))
+    target = prods[int(q * prods.size)] if start is None else start
+    idx = max(1, int(np.searchsorted(v, target)))
+    while idx < v.size - 1 and v[idx] - v[idx - 1] < 6 * d + 1e-7:
         idx += 1
-    return float((objs[idx] + objs[idx - 1]) / 2)
+    return float((v[idx] + v[idx - 1]) / 2)
 
 
 def check_detections(net, outs, want, batch, thresh, nms=0.45):
@@ -98,7 +113,7 @@ def check_detections(net, outs, want, batch, thresh, nms=0.45):
             assert c1 == c2 and abs(p1 - p2) < 2e-3 * max(p1, 1e-3)
             assert rd.box_iou(b1, b2) >= 0.99
         total += len(ref)
-    return total
+    return total  # class scores that survived NMS, over the batch
 
 
 @pytest.mark.parametrize("variant", ["fused", "unfused", "channels_last"])
@@ -122,7 +137,7 @@ def test_yolov3_small_against_oracle(cuda_backend, oracle, variant):
     for g, r in zip(outs, want):
         assert rel_max(g, r) < 2e-3
     # (3) detections + NMS: product on GPU outputs vs the oracle's restatement on oracle outputs
-    assert check_detections(net, outs, want, batch, pick_threshold(want, batch)) > 0  # not vacuous
+    assert check_detections(net, outs, want, batch, pick_threshold(want, batch, outs)) > 0  # not vacuous
 
 
 @pytest.mark.parametrize("math,tol", [("3xtf32", TOL_3XTF32), ("tf32", 5e-3)])
@@ -152,13 +167,15 @@ def test_yolov3_416_bench_configuration(cuda_backend, oracle, math, tol):
         assert rel_max(g, r) < (2e-3 if math == "3xtf32" else 5e-2)
     if math == "3xtf32":
         # thresh 0.45 / nms 0.45 as in the sample; skip boxes whose objectness sits within 1e-3 of the threshold
-        objs = np.concatenate([w.reshape(batch, 3, 85, -1)[:, :, 4, :].ravel() for w in want])
-        thresh = 0.45
-        while np.any(np.abs(objs - thresh) < 1e-3):
-            thresh += 2e-3
+        # thresh / nms 0.45 as in the sample (MSCOCOYolo.pas:252-253), nudged to the nearest gap in the compared values
+        thresh = pick_threshold(want, batch, outs, start=0.45)
         n = check_detections(net, outs, want, batch, thresh)
-        print(f"post-NMS class scores compared at thresh {thresh:.3f}: {n}")
-        assert n > 0
+        print(f"post-NMS class scores compared at thresh {thresh:.4f}: {n}")
+        # random-init heads give few confident class scores at 0.45: repeat where a few dozen survive
+        t2 = pick_threshold(want, batch, outs)
+        n2 = check_detections(net, outs, want, batch, t2)
+        print(f"post-NMS class scores compared at thresh {t2:.4f}: {n2}")
+        assert n2 > 0
 
 
 def test_shortcut_fusion_is_bit_identical(cuda_backend):

@@ -26,3 +26,20 @@ for K in (32, 64, 256, 1024, 2048, 4608, 8192):
         bias = float(np.mean(err * np.sign(truth)) / np.sqrt(np.mean(truth ** 2)))
         print(f"{name:7s} {K:5d}  {rel_max(got, truth):.3e}  {bias:+.3e}  {rel_max(cpu, truth):.3e}")
 cu.set_math_mode(1)
+
+# ---- the channels-innermost convolution kernel (a 1x1 convolution over 256 pixels is the same GEMM), all tensor modes
+print("\nnhwc conv 1x1 (M = 256 pixels, F = 256):  mode K  rel_max_vs_fp64  signed_bias/rms")
+for K in (32, 256, 1024, 2048, 4608, 8192):
+    A = rng.uniform(-1, 1, (M, K)).astype(np.float32)       # [pixel][channel]  (NHWC rows)
+    B = rng.uniform(-1, 1, (N, K)).astype(np.float32)       # [filter][channel]
+    truth = A.astype(np.float64) @ B.astype(np.float64).T   # [pixel][filter]
+    dA, dB, dC = Dev(cu, A), Dev(cu, B), Dev(cu, n=M * N)
+    desc = cu.conv_desc(1, K, 16, 16, N, 1, 1, 0, 0, 1, 1)
+    for mode, name in ((1, "3xtf32"), (2, "tf32"), (3, "bf16x3")):
+        cu.set_math_mode(mode)
+        cu.conv2dForwardNhwc(desc, dA.ptr, 0, K, 1, dB.ptr, None, None, 4, dC.ptr, 0, N, 1)
+        got = dC.read((M, N)).astype(np.float64)
+        err = got - truth
+        bias = float(np.mean(err * np.sign(truth)) / np.sqrt(np.mean(truth ** 2)))
+        print(f"{name:7s} {K:5d}  {rel_max(got, truth):.3e}  {bias:+.3e}")
+cu.set_math_mode(1)

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from tensorium_b200 import tensor  # noqa: E402
 from tensorium_b200.nnet import layer_channels, yolov3_spec  # noqa: E402
 
-MATH = {"3xtf32": 1, "tf32": 2}
+MATH = {"3xtf32": 1, "tf32": 2, "bf16x3": 3}
 
 
 def shapes(size=416):
