@@ -391,6 +391,37 @@ TNN_API int32_t tnn_upsample_nhwc(tnn_context *ctx, int64_t batch, int64_t chann
                                   int64_t stride, float scale, const float *in, int64_t inPitch, float *out,
                                   int64_t outPitch);
 
+/* ------------------------------------------------------------------ multi-GPU exchange (data-parallel training)
+ * New with this backend: the reference is single-device ("todo ... multi GPU", nConvolutionLayer.pas:472,498).  The
+ * path shards along the batch; its ONE exchange step is the sum of the update buffers (weight_updates / bias_updates /
+ * scale_updates of every layer, laid out in one flat device buffer) over the replicas, between TNNet.backward and
+ * TNNet.update (nnet.pas:371-403).  One process (or one TNNCuda instance + host thread) per GPU; NCCL over NVLink.
+ * Rank 0 creates the 128-byte id and ships it to the other ranks by whatever means the host has. */
+typedef struct tnn_comm tnn_comm;
+TNN_API int32_t tnn_comm_unique_id(void *id, int64_t bytes);                 /* bytes >= 128 */
+TNN_API int32_t tnn_comm_init_rank(tnn_context *ctx, int32_t nranks, int32_t rank, const void *id, tnn_comm **comm);
+TNN_API int32_t tnn_comm_destroy(tnn_comm *comm);
+TNN_API int32_t tnn_comm_info(tnn_comm *comm, int32_t *nranks, int32_t *rank, int32_t *nccl_version);
+/* buf[offset .. offset+n) := sum over ranks, in place, enqueued on the context's stream (capturable in a tnn_graph) */
+TNN_API int32_t tnn_allreduce_sum(tnn_context *ctx, tnn_comm *comm, float *buf, int64_t offset, int64_t n);
+/* buf[offset .. offset+n) := rank `root`'s values (replicas start from the same weights) */
+TNN_API int32_t tnn_broadcast(tnn_context *ctx, tnn_comm *comm, float *buf, int64_t offset, int64_t n, int32_t root);
+/* batch-norm over a batch that is sharded across replicas (SyncBN): the statistics of the GLOBAL mini-batch, as the
+ * single-device reference computes them (nbaselayer.pas:352; two-pass MeansAndVars ntensors.pas:9102-9177), by
+ * exchanging the per-channel sums on the context's stream.  comm may be NULL (single device: the same two-pass
+ * arithmetic).  After backward, mean_delta / variance_delta hold the exchanged raw sums (not the reference's scaled
+ * values); scale_updates receives the LOCAL sum (the update bucket is summed over the replicas afterwards). */
+TNN_API int32_t tnn_batchnorm_forward_training_sync(tnn_context *ctx, tnn_comm *comm, int64_t globalBatch, int64_t batch,
+                                                    int64_t channels, int64_t blockSize, float *out, float *x,
+                                                    float *x_norm, float *mean, float *variance, float *rolling_mean,
+                                                    float *rolling_variance, float bn_momentum, const float *scales,
+                                                    const float *biases, int32_t activation);
+TNN_API int32_t tnn_batchnorm_backward_sync(tnn_context *ctx, tnn_comm *comm, int64_t globalBatch, int64_t batch,
+                                            int64_t channels, int64_t blockSize, const float *out, int32_t activation,
+                                            float *delta, const float *x, const float *x_norm, const float *mean,
+                                            const float *variance, const float *scales, float *scale_updates,
+                                            float *mean_delta, float *variance_delta);
+
 #ifdef __cplusplus
 }
 #endif

@@ -122,6 +122,16 @@ SIGNATURES = {
     "tnn_rows_copy": (i32, [ctxp, i64, i64, fptr, i64, fptr, i64]),
     "tnn_rows_add": (i32, [ctxp, i64, i64, fptr, i64, fptr, i64, fptr, i64]),
     "tnn_upsample_nhwc": (i32, [ctxp, i64, i64, i64, i64, i64, f32, fptr, i64, fptr, i64]),
+    "tnn_comm_unique_id": (i32, [vp, i64]),
+    "tnn_comm_init_rank": (i32, [ctxp, i32, i32, vp, C.POINTER(vp)]),
+    "tnn_comm_destroy": (i32, [vp]),
+    "tnn_comm_info": (i32, [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
+    "tnn_allreduce_sum": (i32, [ctxp, vp, fptr, i64, i64]),
+    "tnn_broadcast": (i32, [ctxp, vp, fptr, i64, i64, i32]),
+    "tnn_batchnorm_forward_training_sync": (i32, [ctxp, vp, i64, i64, i64, i64, fptr, fptr, fptr, fptr, fptr, fptr, fptr, f32,
+                                                  fptr, fptr, i32]),
+    "tnn_batchnorm_backward_sync": (i32, [ctxp, vp, i64, i64, i64, i64, fptr, i32, fptr, fptr, fptr, fptr, fptr, fptr, fptr,
+                                          fptr, fptr]),
 }
 
 _lib = None

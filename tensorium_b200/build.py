@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libtensorium_b200.so")
-SOURCES = ["api_core.cu", "elementwise.cu", "reduce.cu", "misc.cu", "contract.cu", "conv_nhwc.cu"]
+SOURCES = ["api_core.cu", "elementwise.cu", "reduce.cu", "misc.cu", "contract.cu", "conv_nhwc.cu", "comm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--extended-lambda", "-std=c++17",
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError(f"nvcc not found at {NVCC}; cannot build libtensorium_b200.so")
     with cf.ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(_compile, SOURCES))
-    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-Xlinker", "--no-undefined"]
+    cmd = [NVCC, "-shared", "-o", LIB, *objs, "-cudart", "static", "-ldl", "-Xlinker", "--no-undefined"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

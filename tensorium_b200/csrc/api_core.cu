@@ -88,6 +88,8 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     ctx->patch_kb16 = (pk && pk[0] == '1') ? 1 : 0;  // measured: no difference (97.3 vs 96.6 TFLOP/s), so the 32-k path stays
     const char *ts = getenv("TNN_TAIL_SPLIT");
     ctx->tail_split = (ts && ts[0] == '0') ? 0 : 1;
+    const char *np_ = getenv("TNN_NHWC_PAIR");
+    ctx->nhwc_pair = (np_ && np_[0] == '0') ? 0 : 1;
     const char *nk = getenv("TNN_NHWC_KB");
     ctx->nhwc_kb = (nk && atoi(nk) == 32) ? 32 : (nk && atoi(nk) == 16) ? 16 : 0;
   }
@@ -102,6 +104,7 @@ int32_t tnn_destroy(tnn_context *ctx) {
   if (ctx->red_partials) cudaFree(ctx->red_partials);
   if (ctx->red_counters) cudaFree(ctx->red_counters);
   if (ctx->work) cudaFree(ctx->work);
+  for (int i = 0; i < ctx->n_retired; ++i) cudaFree(ctx->retired[i]);
   tnn_wcache_destroy(ctx);
   if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -233,6 +236,7 @@ struct tnn_graph {
   cudaGraph_t graph;
   cudaGraphExec_t exec;
   int64_t launches;  // kernel launches captured (tnn_launch_count advances by this much per replay)
+  tnn_context *ctx;
 };
 
 int32_t tnn_graph_begin_capture(tnn_context *ctx) {
@@ -259,6 +263,8 @@ int32_t tnn_graph_end_capture(tnn_context *ctx, tnn_graph **graph) {
     tnn_set_error("graph capture failed: %s", cudaGetErrorString(e));
     return 2;
   }
+  g->ctx = ctx;
+  ctx->live_graphs++;
   *graph = g;
   return 0;
 }
@@ -273,6 +279,7 @@ int32_t tnn_graph_launch(tnn_context *ctx, tnn_graph *graph) {
 
 int32_t tnn_graph_destroy(tnn_graph *graph) {
   if (graph) {
+    if (graph->ctx && graph->ctx->live_graphs > 0) graph->ctx->live_graphs--;
     cudaGraphExecDestroy(graph->exec);
     cudaGraphDestroy(graph->graph);
     delete graph;
@@ -312,13 +319,28 @@ int32_t tnn_finish(tnn_context *ctx) {
 
 }  // extern "C"
 
+int tnn_release_scratch(tnn_context *ctx, void *p) {
+  if (ctx->live_graphs > 0) {
+    // an instantiated graph may replay kernels that read or write this buffer: keep it alive
+    TNN_REQUIRE(ctx->n_retired < (int)(sizeof(ctx->retired) / sizeof(ctx->retired[0])),
+                "too many scratch buffers retired while CUDA graphs are alive: destroy the graphs first");
+    ctx->retired[ctx->n_retired++] = p;
+    return 0;
+  }
+  TNN_CUDA(cudaFree(p));
+  return 0;
+}
+
 int tnn_reserve_reduction(tnn_context *ctx, size_t partial_floats, size_t counters) {
   TNN_REQUIRE(!ctx->capturing || (ctx->red_partials_bytes >= partial_floats * sizeof(float) && ctx->red_counters_n >= counters),
               "scratch buffer would grow during graph capture: run the step once eagerly first");
   if (ctx->red_partials_bytes < partial_floats * sizeof(float)) {
     // the old buffer may still be in use by kernels queued on the stream
     TNN_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->red_partials) TNN_CUDA(cudaFree(ctx->red_partials));
+    if (ctx->red_partials) {
+      int rc = tnn_release_scratch(ctx, ctx->red_partials);
+      if (rc) return rc;
+    }
     ctx->red_partials = nullptr;
     size_t bytes = partial_floats * sizeof(float) * 2;
     TNN_CUDA(cudaMalloc((void **)&ctx->red_partials, bytes));
@@ -326,7 +348,10 @@ int tnn_reserve_reduction(tnn_context *ctx, size_t partial_floats, size_t counte
   }
   if (ctx->red_counters_n < counters) {
     TNN_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->red_counters) TNN_CUDA(cudaFree(ctx->red_counters));
+    if (ctx->red_counters) {
+      int rc = tnn_release_scratch(ctx, ctx->red_counters);
+      if (rc) return rc;
+    }
     ctx->red_counters = nullptr;
     size_t n = counters * 2;
     TNN_CUDA(cudaMalloc((void **)&ctx->red_counters, n * sizeof(unsigned int)));
@@ -409,7 +434,10 @@ int tnn_reserve_work(tnn_context *ctx, size_t bytes) {
   if (ctx->work_bytes < bytes) {
     TNN_REQUIRE(!ctx->capturing, "scratch buffer would grow during graph capture: run the step once eagerly first");
     TNN_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (ctx->work) TNN_CUDA(cudaFree(ctx->work));
+    if (ctx->work) {
+      int rc = tnn_release_scratch(ctx, ctx->work);
+      if (rc) return rc;
+    }
     ctx->work = nullptr;
     TNN_CUDA(cudaMalloc((void **)&ctx->work, bytes));
     ctx->work_bytes = bytes;

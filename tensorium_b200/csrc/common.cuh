@@ -18,6 +18,7 @@ struct tnn_context {
   int gather_kb16;      // 1: the gathering 3xTF32 convolution runs 16-k pipeline stages (TNN_GATHER_KB16=1; slower, kept for A/B runs)
   int patch_kb16;       // 1: TMA-activation convolutions run 16-channel pipeline stages in 3xTF32 mode (TNN_PATCH_KB16=1; no measurable gain, opt-in)
   int tail_split;       // 1: a last wave that fills <= half of the SMs runs as half-width tiles (default; TNN_TAIL_SPLIT=0)
+  int nhwc_pair;        // 1: the NHWC convolution runs wide tiles on CTA pairs (tcgen05.mma.cta_group::2); TNN_NHWC_PAIR=0 turns it off
   int nhwc_kb;          // channels per pipeline stage of the NHWC convolution in 3xTF32 mode: 0 = default (16), 16 or 32 (TNN_NHWC_KB)
   int last_conv_kernel; // which kernel the last tnn_conv2d_forward took (TNN_CONV_KERNEL_*), for measurement tools
   int64_t launches;
@@ -33,6 +34,11 @@ struct tnn_context {
   size_t work_bytes;
   // prepared copies of weight tensors the caller declared immutable (tnn_set_weights_static)
   struct tnn_wcache *wcache;
+  // instantiated CUDA graphs bake the scratch pointers into their kernel nodes: while any graph is alive a scratch
+  // buffer that must grow is RETIRED (kept allocated until tnn_destroy) instead of freed
+  int live_graphs;
+  void *retired[64];
+  int n_retired;
 };
 
 // Buffer for the prepared (re-ordered, TF32-split) copy of `weights`: hi plane then lo plane, `count` floats each.
@@ -86,6 +92,8 @@ static inline bool tnn_math_is_split(const tnn_context *ctx) {
 
 int tnn_reserve_reduction(tnn_context *ctx, size_t partial_floats, size_t counters);
 int tnn_reserve_work(tnn_context *ctx, size_t bytes);
+// free a scratch buffer, or park it until tnn_destroy when a live CUDA graph may still reference it
+int tnn_release_scratch(tnn_context *ctx, void *p);
 
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -140,6 +140,119 @@ struct Ctl {
 constexpr int kStageTile = 32 * 32 * 4;  // one epilogue staging tile: 32 pixels x 32 filters
 constexpr int kStageBufs = 2;            // per epilogue warp
 
+// ---- device pieces shared by the single-CTA kernel and the CTA-pair kernel
+// producers: derive the second operand plane(s) of the landed fp32 A tile `sa` (aBytes = 128 rows x KB floats)
+template <int MODE, int KB>
+__device__ __forceinline__ void convert_stage(uint8_t *sa, int tid) {
+  constexpr bool BF = MODE == MODE_BF16X3;
+  constexpr int aBytes = BM * KB * 4;
+  if constexpr (BF) {
+    // One unit = 8 consecutive k of one row: two 16-byte fp32 chunks in, one 16-byte bf16 chunk out per plane.
+    // KB = 32: raw rows of 128 bytes, chunk c at c ^ (r & 7) (SWIZZLE_128B); bf16 rows of 64 bytes, chunk j at
+    //          j ^ ((r >> 1) & 3) (SWIZZLE_64B).
+    // KB = 16: raw rows of 64 bytes, chunk c at c ^ ((r >> 1) & 3) (SWIZZLE_64B); bf16 rows of 32 bytes, chunk j
+    //          at j ^ ((r >> 2) & 1) (SWIZZLE_32B).
+    uint8_t *shi = sa + aBytes, *slo = shi + aBytes / 2;
+    constexpr int UPR = KB / 8;  // units per row
+#pragma unroll
+    for (int i = 0; i < (BM * UPR) / kProducerThreads; ++i) {
+      const int u = i * kProducerThreads + tid;
+      const int r = u / UPR, j = u % UPR;
+      const int rsw = KB == 32 ? (r & 7) : ((r >> 1) & 3);
+      const uint8_t *rowp = sa + r * (KB * 4);
+      const float4 a = *reinterpret_cast<const float4 *>(rowp + (((2 * j) ^ rsw) << 4));
+      const float4 b = *reinterpret_cast<const float4 *>(rowp + (((2 * j + 1) ^ rsw) << 4));
+      uint4 hi, lo;
+      split_bf16x8(a, b, hi, lo);
+      const int osw = KB == 32 ? ((r >> 1) & 3) : ((r >> 2) & 1);
+      const int o = r * (KB * 2) + ((j ^ osw) << 4);
+      *reinterpret_cast<uint4 *>(shi + o) = hi;
+      *reinterpret_cast<uint4 *>(slo + o) = lo;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < aBytes / (16 * kProducerThreads); ++i) {
+      const int off = (i * kProducerThreads + tid) * 16;
+      const float4 v = *reinterpret_cast<const float4 *>(sa + off);
+      *reinterpret_cast<float4 *>(sa + aBytes + off) =
+          make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
+    }
+  }
+}
+
+// epilogue of one tile for one warp (32 accumulator rows): TMEM -> scale/bias/activation -> TMA store (channels-innermost
+// rows) or per-plane stores (NCHW).  `release()` is called by lane 0 once the warp's last TMEM read has completed.
+template <typename EPI, typename RELEASE>
+__device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int bn, int64_t n0, int row0, float *scratch,
+                                           uint8_t *stg, int &sbuf, const CUtensorMap *tmOut, RELEASE release) {
+  const int lane = threadIdx.x & 31;
+  const int nChunks = (bn + 31) >> 5;
+  if constexpr (EPI::kTmaStore) {
+    const bool leaky = epi.act == TNN_ACT_LEAKY || epi.act == TNN_ACT_REVLEAKY;
+    const bool simple = leaky || epi.act == TNN_ACT_LINEAR;
+    const float neg = leaky ? 0.1f : 1.0f;
+    for (int ci = 0; ci < nChunks; ++ci) {
+      const int c0 = ci * 32;
+      uint32_t r[32];
+      tmem_ld32(tmem_d + (uint32_t)c0, r);
+      if (ci == nChunks - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release();
+      }
+      int64_t cnt = min((int64_t)(bn - c0), epi.cols - (n0 + c0));  // warp-uniform
+      if (cnt > 32) cnt = 32;
+      if (cnt <= 0 || row0 >= epi.rows) continue;
+      const int64_t n = n0 + c0;
+      __syncwarp();
+      scratch[lane] = (epi.scale && lane < cnt) ? __ldg(epi.scale + n + lane) : 1.0f;
+      scratch[32 + lane] = (epi.bias && lane < cnt) ? __ldg(epi.bias + n + lane) : 0.0f;
+      if (lane == 0) bulk_wait_read<kStageBufs - 1>();  // the staging tile written two chunks ago has been read
+      __syncwarp();
+      uint8_t *tile = stg + sbuf * kStageTile;
+      uint8_t *rowp = tile + lane * 128;
+#pragma unroll
+      for (int j4 = 0; j4 < 32; j4 += 4) {
+        const float4 s4 = *reinterpret_cast<const float4 *>(scratch + j4);
+        const float4 b4 = *reinterpret_cast<const float4 *>(scratch + 32 + j4);
+        const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+        float o[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float v = __fadd_rn(__fmul_rn(__uint_as_float(r[j4 + u]), s[u]), b[u]);
+          o[u] = simple ? fmaxf(v, __fmul_rn(neg, v)) : act_out_of_line(v, epi.act);
+        }
+        // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) — conflict-free and what the TMA store expects
+        *reinterpret_cast<float4 *>(rowp + ((((j4 >> 2) ^ (lane & 7))) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(tmOut, smem_u32(tile), (int)n, row0);
+        bulk_commit();
+      }
+      sbuf ^= 1;
+    }
+  } else {
+    const int64_t m = (int64_t)row0 + lane;
+    bool mvalid;
+    typename EPI::Row rc = epi.row(m, mvalid);
+    for (int ci = 0; ci < nChunks; ++ci) {
+      const int c0 = ci * 32;
+      uint32_t r[32];
+      tmem_ld32(tmem_d + (uint32_t)c0, r);
+      if (ci == nChunks - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release();
+      }
+      int64_t cnt = min((int64_t)(bn - c0), epi.cols - (n0 + c0));
+      if (cnt > 32) cnt = 32;
+      if (cnt > 0) epi.store_chunk(rc, n0 + c0, r, (int)cnt, mvalid, scratch);
+    }
+  }
+}
+
 template <int MODE, int KB, typename EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCols,
@@ -150,7 +263,7 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr bool SPLIT = MODE != MODE_TF32;   // producers touch the landed A tile; two B planes
   constexpr bool BF = MODE == MODE_BF16X3;
-  static_assert(!BF || KB == 32, "bf16 stages are 32 channels deep (64-byte bf16 rows)");
+  static_assert(KB == 32 || KB == 16, "stages are 32 or 16 channels deep");
   constexpr int aBytes = BM * KB * 4;                 // the landed fp32 A tile
   const int bBytes = BN * KB * (BF ? 2 : 4);          // one weight plane of the stage
   // stage layout: 3xTF32  A(=hi) | A_lo | B_hi | B_lo;   TF32  A | B;   BF16x3  A raw | A_hi | A_lo | B_hi | B_lo (bf16 tiles)
@@ -198,32 +311,7 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
       for (; remaining > 0; --remaining) {
         mbar_wait_warp(&ctl.araw[stage], phase);
         uint8_t *sa = smem + (size_t)stage * stageBytes;
-        if constexpr (BF) {
-          // raw tile: row r = 128 bytes, 16-byte chunk c at c ^ (r & 7) (SWIZZLE_128B).  bf16 tiles: row r = 64 bytes,
-          // 16-byte chunk j (8 k) at j ^ ((r >> 1) & 3) (SWIZZLE_64B).  One unit = 8 consecutive k of one row.
-          uint8_t *shi = sa + aBytes, *slo = shi + aBytes / 2;
-#pragma unroll
-          for (int i = 0; i < (BM * 4) / kProducerThreads; ++i) {
-            const int u = i * kProducerThreads + tid;
-            const int r = u >> 2, j = u & 3;
-            const uint8_t *rowp = sa + r * 128;
-            const float4 a = *reinterpret_cast<const float4 *>(rowp + (((2 * j) ^ (r & 7)) << 4));
-            const float4 b = *reinterpret_cast<const float4 *>(rowp + (((2 * j + 1) ^ (r & 7)) << 4));
-            uint4 hi, lo;
-            split_bf16x8(a, b, hi, lo);
-            const int o = r * 64 + ((j ^ ((r >> 1) & 3)) << 4);
-            *reinterpret_cast<uint4 *>(shi + o) = hi;
-            *reinterpret_cast<uint4 *>(slo + o) = lo;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < aBytes / (16 * kProducerThreads); ++i) {
-            const int off = (i * kProducerThreads + tid) * 16;
-            const float4 v = *reinterpret_cast<const float4 *>(sa + off);
-            *reinterpret_cast<float4 *>(sa + aBytes + off) =
-                make_float4(v.x - tf32_hi(v.x), v.y - tf32_hi(v.y), v.z - tf32_hi(v.z), v.w - tf32_hi(v.w));
-          }
-        }
+        convert_stage<MODE, KB>(sa, tid);
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(&ctl.full[stage]);
@@ -255,12 +343,14 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
           // K-major rows of KB floats: 8-row groups are 8*KB*4 bytes apart, one UMMA_K = 8 step = +32 bytes
           constexpr uint32_t kSbo = KB == 32 ? 1024 : 512, kLt = KB == 32 ? 2u : 4u;
           if constexpr (BF) {
-            // bf16 tiles: 64-byte rows (32 k), SWIZZLE_64B, 8-row groups 512 bytes apart; UMMA_K = 16 -> +32 bytes
+            // bf16 tiles: rows of KB*2 bytes (SWIZZLE_64B for 32 k, SWIZZLE_32B for 16 k), 8-row groups KB*16 bytes apart;
+            // UMMA_K = 16 -> +32 bytes per step
             const uint32_t shi = sa + aBytes, slo = shi + aBytes / 2;
+            constexpr uint32_t bSbo = KB * 16, bLt = KB == 32 ? 4u : 6u;
 #pragma unroll
             for (int ks = 0; ks < KB / 16; ++ks) {
-              const uint64_t ah = make_desc(shi + ks * 32, 16, 512, 4u), al = make_desc(slo + ks * 32, 16, 512, 4u);
-              const uint64_t bh = make_desc(sb + ks * 32, 16, 512, 4u), bl = make_desc(sb + bBytes + ks * 32, 16, 512, 4u);
+              const uint64_t ah = make_desc(shi + ks * 32, 16, bSbo, bLt), al = make_desc(slo + ks * 32, 16, bSbo, bLt);
+              const uint64_t bh = make_desc(sb + ks * 32, 16, bSbo, bLt), bl = make_desc(sb + bBytes + ks * 32, 16, bSbo, bLt);
               const uint32_t acc = (kb != kb0 || ks != 0) ? 1u : 0u;
               mma_bf16(tmem_d, al, bh, idesc, acc);  // small terms first
               mma_bf16(tmem_d, ah, bl, idesc, 1u);
@@ -343,75 +433,9 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
       const int64_t n0 = (int64_t)nt * BN + (hf == 2 ? BN >> 1 : 0);
       const int row0 = mt * BM + quad * 32;  // first pixel row of this warp
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
-      const int nChunks = (bn + 31) >> 5;
-      if constexpr (EPI::kTmaStore) {
-        mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
-        tc_fence_after();
-        const bool leaky = epi.act == TNN_ACT_LEAKY || epi.act == TNN_ACT_REVLEAKY;
-        const bool simple = leaky || epi.act == TNN_ACT_LINEAR;
-        const float neg = leaky ? 0.1f : 1.0f;
-        for (int ci = 0; ci < nChunks; ++ci) {
-          const int c0 = ci * 32;
-          uint32_t r[32];
-          tmem_ld32(tmem_d + (uint32_t)c0, r);
-          if (ci == nChunks - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl.tmem_empty[as]);
-          }
-          int64_t cnt = min((int64_t)(bn - c0), epi.cols - (n0 + c0));  // warp-uniform
-          if (cnt > 32) cnt = 32;
-          if (cnt <= 0 || row0 >= epi.rows) continue;
-          const int64_t n = n0 + c0;
-          __syncwarp();
-          scratch[lane] = (epi.scale && lane < cnt) ? __ldg(epi.scale + n + lane) : 1.0f;
-          scratch[32 + lane] = (epi.bias && lane < cnt) ? __ldg(epi.bias + n + lane) : 0.0f;
-          if (lane == 0) bulk_wait_read<kStageBufs - 1>();  // the staging tile written two chunks ago has been read
-          __syncwarp();
-          uint8_t *tile = stg + sbuf * kStageTile;
-          uint8_t *rowp = tile + lane * 128;
-#pragma unroll
-          for (int j4 = 0; j4 < 32; j4 += 4) {
-            const float4 s4 = *reinterpret_cast<const float4 *>(scratch + j4);
-            const float4 b4 = *reinterpret_cast<const float4 *>(scratch + 32 + j4);
-            const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
-            float o[4];
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float v = __fadd_rn(__fmul_rn(__uint_as_float(r[j4 + u]), s[u]), b[u]);
-              o[u] = simple ? fmaxf(v, __fmul_rn(neg, v)) : act_out_of_line(v, epi.act);
-            }
-            // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) — conflict-free and what the TMA store expects
-            *reinterpret_cast<float4 *>(rowp + ((((j4 >> 2) ^ (lane & 7))) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
-          }
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmOut, smem_u32(tile), (int)n, row0);
-            bulk_commit();
-          }
-          sbuf ^= 1;
-        }
-      } else {
-        const int64_t m = (int64_t)row0 + lane;
-        bool mvalid;
-        typename EPI::Row rc = epi.row(m, mvalid);
-        mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
-        tc_fence_after();
-        for (int ci = 0; ci < nChunks; ++ci) {
-          const int c0 = ci * 32;
-          uint32_t r[32];
-          tmem_ld32(tmem_d + (uint32_t)c0, r);
-          if (ci == nChunks - 1) {
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&ctl.tmem_empty[as]);
-          }
-          int64_t cnt = min((int64_t)(bn - c0), epi.cols - (n0 + c0));
-          if (cnt > 32) cnt = 32;
-          if (cnt > 0) epi.store_chunk(rc, n0 + c0, r, (int)cnt, mvalid, scratch);
-        }
-      }
+      mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
+      tc_fence_after();
+      drain_tile(epi, tmem_d, bn, n0, row0, scratch, stg, sbuf, &tmOut, [&] { mbar_arrive(&ctl.tmem_empty[as]); });
     }
     if (EPI::kTmaStore && lane == 0) bulk_wait_all();  // the staging tiles must outlive their stores
   }
@@ -419,6 +443,288 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) tmem_dealloc(tmem_base, accCols * 2);
+}
+
+// =====================================================================================================================
+// CTA-pair version (tcgen05.mma.cta_group::2).  The single-CTA kernel is bound by shared-memory bandwidth, not by the
+// tensor pipe: per 32-deep k-block in TF32 mode the TMA unit writes 48 KB (16 A + 32 B) and the MMAs read 48 KB —
+// 96 KB against the ~64 KB the SM moves in the 512 cycles four 128x256x8 MMAs take.  Two CTAs of one cluster (the two
+// SMs of a TPC) compute a 256-pixel x BN-filter tile together: each CTA lands the A rows of ITS 128 pixels and only
+// HALF of the weight tile (BN/2 filter rows); the pair's tensor cores read both B halves.  Per CTA and k-block the
+// weight fill and the weight reads halve: 32 + 32 KB in TF32 mode — the tensor pipe becomes the bound.
+//
+// Protocol (rank = %cluster_ctarank, leader = rank 0):
+//   araw[s]   (split modes) per CTA: its fp32 A tile has landed; the producer warps derive the second plane(s)
+//   full[s]   the LEADER's barrier: every TMA load of both CTAs that the MMA reads directly signals it
+//             (cp.async.bulk.tensor ... cta_group::2 — the completion goes to the barrier at the same offset in the
+//             leader CTA), plus 8 local + 8 remote producer-warp arrivals in the split modes
+//   empty[s]  one per CTA, released together by the leader's multicast tcgen05.commit
+//   tmem_full[a] per CTA (multicast commit); tmem_empty[a] the leader's: 4 local + 4 remote epilogue-warp arrivals
+//   The leader's elected thread issues every MMA (M = 256 over the pair); each CTA's epilogue drains its own 128 lanes.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster.  Default (CTA-scope release)
+// semantics: the data the peer's tensor core will read was made visible by fence.proxy.async before this arrive; a
+// cluster-scope release here costs ~0.9 us per stage and serialises the producer warps (measured: 155 vs 330 TFLOP/s).
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) {
+  asm volatile(
+      "{\n.reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [ra];\n}\n" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t *dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+template <bool BF>
+__device__ __forceinline__ void mma2(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  const uint32_t z = 0;
+  if (BF)
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+  else
+    asm volatile(
+        "{\n.reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(z)
+        : "memory");
+}
+// when the MMAs issued so far complete: arrive on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void mma2_commit(uint64_t *bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+// tile -> local smem, completion bytes on the LEADER's barrier (the peer bit of the barrier address cleared)
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst_smem, const CUtensorMap *tmap, int c0, int c1, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], "
+      "[%4];" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar) & 0xFEFFFFFFu)
+      : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col(uint32_t dst_smem, const CUtensorMap *tmap, int c, int w, int h, int n,
+                                                 uint32_t offw, uint32_t offh, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], "
+      "[%1, {%2, %3, %4, %5}], [%6], {%7, %8};" ::"r"(dst_smem),
+      "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c), "r"(w), "r"(h), "r"(n), "r"(smem_u32(bar) & 0xFEFFFFFFu),
+      "h"((uint16_t)offw), "h"((uint16_t)offh)
+      : "memory");
+}
+
+// BN = filters per pair tile (multiple of 32, <= 256): each CTA holds BN/2 weight rows.  mTiles counts 128-pixel tiles.
+template <int MODE, int KB, typename EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, int stages,
+                 const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+                 const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ Ctl ctl;
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr bool SPLIT = MODE != MODE_TF32;
+  constexpr bool BF = MODE == MODE_BF16X3;
+  constexpr int aBytes = BM * KB * 4;
+  const int bBytes = (BN >> 1) * KB * (BF ? 2 : 4);   // this CTA's half of one weight plane
+  const int bOff = BF ? 2 * aBytes : (SPLIT ? 2 : 1) * aBytes;
+  const int stageBytes = bOff + bBytes * (SPLIT ? 2 : 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int pair = blockIdx.x >> 1, numPairs = gridDim.x >> 1;
+  const int mPairs = (mTiles + 1) >> 1;
+  const int numTiles = mPairs * nTiles;   // pair tiles: 256 pixels x BN filters, pixel-pair index fastest
+  constexpr uint32_t kAccStride = 256;    // TMEM columns between the two accumulator buffers
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(&ctl.full[s], SPLIT ? 2 * kProducerWarps + 1 : 1);
+      mbar_init(&ctl.empty[s], 1);
+      mbar_init(&ctl.araw[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ctl.tmem_full[s], 1);
+      mbar_init(&ctl.tmem_empty[s], 2 * kEpilogueWarps);
+    }
+    fence_barrier_init();
+  }
+  if (warp == kMmaWarp) tmem_alloc2(&ctl.tmem_base, 512);
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmBhi);
+    if (SPLIT) tma_prefetch_desc(&tmBlo);
+    if (EPI::kTmaStore) tma_prefetch_desc(&tmOut);
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // both CTAs' barriers exist before anyone signals across the pair
+  tc_fence_after();
+  const uint32_t tmem_base = ctl.tmem_base;
+
+  if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
+    // ===================== split modes: second plane(s) of this CTA's A tile =====================
+    if (SPLIT) {
+      const int tid = threadIdx.x - kFirstProducerWarp * 32;
+      int64_t remaining = 0;
+      for (int t = pair; t < numTiles; t += numPairs) remaining += kBlocks;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (; remaining > 0; --remaining) {
+        mbar_wait_warp(&ctl.araw[stage], phase);
+        convert_stage<MODE, KB>(smem + (size_t)stage * stageBytes, tid);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(&ctl.full[stage]);
+          else mbar_arrive_cluster(&ctl.full[stage], 0);
+        }
+        if (++stage == stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer: the leader's elected thread drives both tensor cores =====================
+    if (rank == 0) {
+      // D = F32, K-major operands, N = BN, M = 256 over the pair
+      const uint32_t idesc = (1u << 4) | ((BF ? 1u : 2u) << 7) | ((BF ? 1u : 2u) << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(256 >> 4) << 24);
+      const uint32_t smem_base = smem_u32(smem);
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      for (int t = pair; t < numTiles; t += numPairs, ++it) {
+        const int as = it & 1;
+        const uint32_t use = (uint32_t)(it >> 1);
+        mbar_wait_warp(&ctl.tmem_empty[as], (use & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * kAccStride;
+        for (int kb = 0; kb < kBlocks; ++kb) {
+          mbar_wait_warp(&ctl.full[stage], phase);
+          tc_fence_after();
+          if (elect_one_sync()) {
+            const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
+            const uint32_t sb = sa + bOff;
+            if constexpr (BF) {
+              const uint32_t shi = sa + aBytes, slo = shi + aBytes / 2;
+              constexpr uint32_t bSbo = KB * 16, bLt = KB == 32 ? 4u : 6u;
+#pragma unroll
+              for (int ks = 0; ks < KB / 16; ++ks) {
+                const uint64_t ah = make_desc(shi + ks * 32, 16, bSbo, bLt), al = make_desc(slo + ks * 32, 16, bSbo, bLt);
+                const uint64_t bh = make_desc(sb + ks * 32, 16, bSbo, bLt), bl = make_desc(sb + bBytes + ks * 32, 16, bSbo, bLt);
+                const uint32_t acc = (kb != 0 || ks != 0) ? 1u : 0u;
+                mma2<true>(tmem_d, al, bh, idesc, acc);
+                mma2<true>(tmem_d, ah, bl, idesc, 1u);
+                mma2<true>(tmem_d, ah, bh, idesc, 1u);
+              }
+            } else {
+              constexpr uint32_t kSbo = KB == 32 ? 1024 : 512, kLt = KB == 32 ? 2u : 4u;
+#pragma unroll
+              for (int ks = 0; ks < KB / 8; ++ks) {
+                const uint64_t ah = make_desc(sa + ks * 32, 16, kSbo, kLt);
+                const uint64_t bh = make_desc(sb + ks * 32, 16, kSbo, kLt);
+                const uint32_t acc = (kb != 0 || ks != 0) ? 1u : 0u;
+                if (SPLIT) {
+                  const uint64_t al = make_desc(sa + aBytes + ks * 32, 16, kSbo, kLt);
+                  const uint64_t bl = make_desc(sb + bBytes + ks * 32, 16, kSbo, kLt);
+                  mma2<false>(tmem_d, al, bh, idesc, acc);
+                  mma2<false>(tmem_d, ah, bl, idesc, 1u);
+                  mma2<false>(tmem_d, ah, bh, idesc, 1u);
+                } else {
+                  mma2<false>(tmem_d, ah, bh, idesc, acc);
+                }
+              }
+            }
+            mma2_commit(&ctl.empty[stage]);
+            if (kb == kBlocks - 1) mma2_commit(&ctl.tmem_full[as]);
+          }
+          __syncwarp();
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kTmaWarp) {
+    // ===================== TMA: this CTA's A tile and its half of the weight tile =====================
+    if (lane == 0) {
+      const uint32_t smem_base = smem_u32(smem);
+      int stage = 0;
+      uint32_t phase = 0;
+      // bytes the leader's full[] barrier expects per stage: the loads of BOTH CTAs that signal it
+      const uint32_t fullTx = 2u * (uint32_t)(bBytes * (SPLIT ? 2 : 1) + (SPLIT ? 0 : aBytes));
+      for (int t = pair; t < numTiles; t += numPairs) {
+        const int mp = t % mPairs, nt = t / mPairs;
+        const int n0 = nt * BN + (int)rank * (BN >> 1);
+        const int m0 = (mp * 2 + (int)rank) * BM;   // past the last pixel for the odd tile out: the TMA zero-fills
+        const int img = m0 / g.OHW;
+        const int rem = m0 - img * g.OHW;
+        const int oh0 = rem / g.OW;
+        const int ow0 = rem - oh0 * g.OW;
+        const int cw = ow0 * g.sx - g.pw, ch = oh0 * g.sy - g.ph;
+        int cb = 0, kr = 0, kc = 0;
+        for (int kb = 0; kb < kBlocks; ++kb) {
+          mbar_wait(&ctl.empty[stage], phase ^ 1);
+          const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
+          const uint32_t sb = sa + bOff;
+          if (rank == 0) mbar_arrive_expect_tx(&ctl.full[stage], fullTx);
+          if (SPLIT) {
+            mbar_arrive_expect_tx(&ctl.araw[stage], (uint32_t)aBytes);
+            tma_load_im2col(sa, &tmA, cb * KB, cw, ch, img, (uint32_t)(kc * g.dx), (uint32_t)(kr * g.dy), &ctl.araw[stage]);
+          } else {
+            tma2_load_im2col(sa, &tmA, cb * KB, cw, ch, img, (uint32_t)(kc * g.dx), (uint32_t)(kr * g.dy), &ctl.full[stage]);
+          }
+          tma2_load_2d(sb, &tmBhi, kb * KB, n0, &ctl.full[stage]);
+          if (SPLIT) tma2_load_2d(sb + bBytes, &tmBlo, kb * KB, n0, &ctl.full[stage]);
+          if (++cb == g.cBlocks) {
+            cb = 0;
+            if (++kc == g.kw) { kc = 0; ++kr; }
+          }
+          if (++stage == stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue: each CTA drains its own 128 TMEM lanes =====================
+    const int quad = warp;
+    int it = 0;
+    uint8_t *stg = smem + (size_t)stages * stageBytes + (size_t)quad * (kStageBufs * kStageTile);
+    int sbuf = 0;
+    float *scratch = ctl.epi_sb[quad];
+    for (int t = pair; t < numTiles; t += numPairs, ++it) {
+      const int mp = t % mPairs, nt = t / mPairs;
+      const int as = it & 1;
+      const uint32_t use = (uint32_t)(it >> 1);
+      const int64_t n0 = (int64_t)nt * BN;
+      const int row0 = (mp * 2 + (int)rank) * BM + quad * 32;
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * kAccStride + ((uint32_t)(quad * 32) << 16);
+      mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
+      tc_fence_after();
+      drain_tile(epi, tmem_d, BN, n0, row0, scratch, stg, sbuf, &tmOut, [&] {
+        if (rank == 0) mbar_arrive(&ctl.tmem_empty[as]);
+        else mbar_arrive_cluster(&ctl.tmem_empty[as], 0);
+      });
+    }
+    if (EPI::kTmaStore && lane == 0) bulk_wait_all();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer may still be reading this CTA's shared memory / signalling its barriers
+  if (warp == kMmaWarp) tmem_dealloc2(tmem_base, 512);
 }
 
 // bf16 big/small planes of the weights in the kernel's k order:  k = (tap*CB + cb)*32 + ci,  channel = cb*32 + ci
@@ -444,15 +750,16 @@ static __global__ void __launch_bounds__(256) k_prepare_weights_bf16(const float
 }
 
 // bf16 matrix [rows][Kpad] (k contiguous) -> tiles of 32 k x boxRows rows, 64-byte rows: SWIZZLE_64B
-static int encode_weights_map_bf16(CUtensorMap *tm, const uint16_t *base, int64_t rows, int64_t Kpad, int boxRows) {
+static int encode_weights_map_bf16(CUtensorMap *tm, const uint16_t *base, int64_t rows, int64_t Kpad, int boxRows, int kb) {
   EncodeTiledFn enc = get_encode_tiled();
   TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
-  cuuint32_t box[2] = {32, (cuuint32_t)boxRows};
+  cuuint32_t box[2] = {(cuuint32_t)kb, (cuuint32_t)boxRows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     tnn_set_error("cuTensorMapEncodeTiled (bf16 weights) failed with CUresult %d", (int)r);
@@ -510,6 +817,17 @@ static int launch_nhwc(tnn_context *ctx, const Plan &p, const Geo &geo, EPI epi,
   return 0;
 }
 
+template <int MODE, int KB, typename EPI>
+static int launch_nhwc_pair(tnn_context *ctx, int grid, size_t smemBytes, int mTiles, int nTiles, int kBlocks, const Geo &geo,
+                            int BN, int stages, EPI epi, const CUtensorMap &tmA, const CUtensorMap &tmHi,
+                            const CUtensorMap &tmLo, const CUtensorMap &tmOut) {
+  auto kern = k_conv_nhwc_pair<MODE, KB, EPI>;
+  TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+  kern<<<grid, kThreads, smemBytes, ctx->stream>>>(epi, mTiles, nTiles, kBlocks, geo, BN, stages, tmA, tmHi, tmLo, tmOut);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
 static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, int64_t inPitch,
                         const float *weights, const float *scale, const float *bias, int act, float *out,
                         int64_t outPitch, bool outNchw) {
@@ -526,12 +844,20 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   const int CB = (g.C + 31) / 32;       // 32-channel blocks per tap (the weight copy's k order)
   const int64_t K = (int64_t)kk * CB * 32;
   // 3xTF32 stages carry four fp32 tiles: half-depth (16-channel) stages keep four of them in flight
-  const int KB = bf ? 32 : split ? (ctx->nhwc_kb ? ctx->nhwc_kb : 16) : 32;
+  // (bf16 stages are half the bytes per channel: 32-channel stages measured 13.5 vs 15.3 ms over the YOLOv3 layers)
+  const int KB = split ? (ctx->nhwc_kb ? ctx->nhwc_kb : (bf ? 32 : 16)) : 32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
   // half-width tail tiles: the TMA store writes whole 32-filter boxes, so a half tile must be a multiple of 32 wide
-  if (outNchw || (p.BN % 64) == 0) split_tail_wave(ctx, p);
-  const size_t stageBytes = bf ? (size_t)BM * KB * 8 + (size_t)p.BN * KB * 4
-                               : (size_t)(BM + p.BN) * KB * 4 * (split ? 2 : 1);
+  // CTA pairs (cta_group::2) halve the weight traffic through shared memory — the bound of the single-CTA kernel.
+  // Taken when the tile is wide enough to split (each CTA holds BN/2 >= 32 weight rows) and there are pair tiles for
+  // every TPC; TNN_NHWC_PAIR=0 keeps the single-CTA kernel (A/B runs).
+  const int sms = ctx->prop.multiProcessorCount;
+  const int64_t pairTiles = (int64_t)((p.sched.mTiles + 1) / 2) * p.sched.nTiles;
+  const bool pairMode = ctx->nhwc_pair && (p.BN % 32) == 0 && p.BN >= 64 && pairTiles >= sms / 2;
+  const int bnCta = pairMode ? p.BN / 2 : p.BN;   // weight rows a CTA stages
+  if (!pairMode && (outNchw || (p.BN % 64) == 0)) split_tail_wave(ctx, p);
+  const size_t stageBytes = bf ? (size_t)BM * KB * 8 + (size_t)bnCta * KB * 4
+                               : (size_t)(BM + bnCta) * KB * 4 * (split ? 2 : 1);
   const size_t epiBytes = outNchw ? 0 : (size_t)kEpilogueWarps * kStageBufs * kStageTile;
   int st = (int)((225 * 1024 - epiBytes) / stageBytes);
   p.stages = st > kMaxStages ? kMaxStages : st;
@@ -556,19 +882,30 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   rc = encode_im2col_map(&tmA, in, g, batch, inPitch, KB);
   if (rc) return rc;
   if (bf) {
-    rc = encode_weights_map_bf16(&tmHi, (const uint16_t *)whi, N, K, p.BN);
+    rc = encode_weights_map_bf16(&tmHi, (const uint16_t *)whi, N, K, bnCta, KB);
     if (rc) return rc;
-    rc = encode_weights_map_bf16(&tmLo, (const uint16_t *)wlo, N, K, p.BN);
+    rc = encode_weights_map_bf16(&tmLo, (const uint16_t *)wlo, N, K, bnCta, KB);
   } else {
-    rc = KB == 16 ? encode_weights_map16(&tmHi, whi, N, K, p.BN) : encode_weights_map(&tmHi, whi, N, K, p.BN);
+    rc = KB == 16 ? encode_weights_map16(&tmHi, whi, N, K, bnCta) : encode_weights_map(&tmHi, whi, N, K, bnCta);
     if (rc) return rc;
-    rc = KB == 16 ? encode_weights_map16(&tmLo, split ? wlo : whi, N, K, p.BN)
-                  : encode_weights_map(&tmLo, split ? wlo : whi, N, K, p.BN);
+    rc = KB == 16 ? encode_weights_map16(&tmLo, split ? wlo : whi, N, K, bnCta)
+                  : encode_weights_map(&tmLo, split ? wlo : whi, N, K, bnCta);
   }
   if (rc) return rc;
   Geo geo{g.OW, g.OH * g.OW, g.sx, g.sy, g.pw, g.ph, g.dx, g.dy, g.kw, CB * 32 / KB, (int)M};
   auto go = [&](auto epi) -> int {
-    if (bf) return launch_nhwc<MODE_BF16X3, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+    if (pairMode) {
+      const int grid = (int)(2 * (pairTiles < sms / 2 ? pairTiles : sms / 2));
+      const int kBlocks = (int)(K / KB);
+#define TNN_PAIR_GO(MODE, KBV) \
+  launch_nhwc_pair<MODE, KBV>(ctx, grid, p.smemBytes, p.sched.mTiles, p.sched.nTiles, kBlocks, geo, p.BN, p.stages, epi, tmA, tmHi, tmLo, tmOut)
+      if (bf) return KB == 16 ? TNN_PAIR_GO(MODE_BF16X3, 16) : TNN_PAIR_GO(MODE_BF16X3, 32);
+      if (!split) return TNN_PAIR_GO(MODE_TF32, 32);
+      return KB == 16 ? TNN_PAIR_GO(MODE_3X, 16) : TNN_PAIR_GO(MODE_3X, 32);
+#undef TNN_PAIR_GO
+    }
+    if (bf) return KB == 16 ? launch_nhwc<MODE_BF16X3, 16>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut)
+                            : launch_nhwc<MODE_BF16X3, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
     if (!split) return launch_nhwc<MODE_TF32, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
     return KB == 16 ? launch_nhwc<MODE_3X, 16>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut)
                     : launch_nhwc<MODE_3X, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);

@@ -392,4 +392,124 @@ int32_t tnn_batchnorm_backward(tnn_context *ctx, int64_t batch, int64_t channels
       });
 }
 
+// ---- batch-norm under batch sharding (SyncBN).  The reference computes the statistics over the whole mini-batch
+// (nbaselayer.pas:352, MeansAndVars ntensors.pas:9102-9177); with the batch split over replicas the per-channel sums
+// are exchanged (tnn_allreduce_sum on the context's stream) so that every replica normalises with the statistics of
+// the GLOBAL batch: the reference's two-pass formula — mean = sum(x)/S, variance = sum((x-mean)^2)/(S-1) with
+// S = globalBatch*blockSize — and, backward, the two sums mean_delta / variance_delta are built from.
+// comm == NULL (or one rank) degenerates to the single-device two-pass computation.
+int32_t tnn_batchnorm_forward_training_sync(tnn_context *ctx, tnn_comm *comm, int64_t globalBatch, int64_t batch,
+                                            int64_t channels, int64_t blockSize, float *out, float *x, float *x_norm,
+                                            float *mean, float *variance, float *rolling_mean, float *rolling_variance,
+                                            float bn_momentum, const float *scales, const float *biases,
+                                            int32_t activation) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(activation == TNN_ACT_LINEAR || tnn_act_is_elementwise(activation), "activation not elementwise");
+  TNN_REQUIRE(globalBatch >= batch, "the global batch is the sum of the replicas' batches");
+  const int64_t total = batch * channels * blockSize;
+  const float *src = out;
+  const double S = (double)(globalBatch * blockSize);
+  // pass 1: local sum(x) -> mean[] ; exchanged ; mean = sum / S
+  int rc = launch_reduce<1>(
+      ctx, channels, batch, blockSize, [src] __device__(int64_t i, int, float(&acc)[1]) { acc[0] += src[i]; },
+      [mean] __device__(int c, const float(&t)[1]) { mean[c] = t[0]; });
+  if (rc) return rc;
+  if (comm) {
+    rc = tnn_allreduce_sum(ctx, comm, mean, 0, channels);
+    if (rc) return rc;
+  }
+  rc = tnn_scale(ctx, channels, (float)(1.0 / S), mean, 1);
+  if (rc) return rc;
+  // pass 2: local sum((x - mean)^2) -> variance[] ; exchanged ; variance = sum / (S-1) ; rolling averages
+  rc = launch_reduce<1>(
+      ctx, channels, batch, blockSize,
+      [src, mean] __device__(int64_t i, int c, float(&acc)[1]) {
+        const float d = src[i] - __ldg(mean + c);
+        acc[0] = fmaf(d, d, acc[0]);
+      },
+      [variance] __device__(int c, const float(&t)[1]) { variance[c] = t[0]; });
+  if (rc) return rc;
+  if (comm) {
+    rc = tnn_allreduce_sum(ctx, comm, variance, 0, channels);
+    if (rc) return rc;
+  }
+  const float m = bn_momentum;
+  const float inv = (float)(1.0 / (S - 1.0));
+  rc = planemap::launch<0, 0>(
+      ctx, variance, nullptr, nullptr, nullptr, nullptr, channels, channels, 1,
+      [mean, rolling_mean, rolling_variance, m, inv] __device__(float &v, float, float, float &, float &, int c) {
+        v = __fmul_rn(v, inv);
+        rolling_mean[c] = __fadd_rn(__fmul_rn(m, mean[c]), __fmul_rn(1 - m, rolling_mean[c]));
+        rolling_variance[c] = __fadd_rn(__fmul_rn(m, v), __fmul_rn(1 - m, rolling_variance[c]));
+      });
+  if (rc) return rc;
+  const int a = activation;
+  const bool block1 = blockSize == 1;
+  return planemap::launch<0, 2>(
+      ctx, out, nullptr, nullptr, x, x_norm, total, channels, batch,
+      [mean, variance, scales, biases, a, block1] __device__(float &v, float, float, float &xo, float &xn, int c) {
+        const float var = __ldg(variance + c);
+        const float d = block1 ? sqrtf(fmaxf(var, TNN_EPS)) : fmaxf(sqrtf(var), TNN_EPS);
+        xo = v;
+        float t = (v - __ldg(mean + c)) / d;
+        xn = t;
+        t = __fmul_rn(t, __ldg(scales + c));
+        t = __fadd_rn(t, __ldg(biases + c));
+        v = tnn_act(t, a);
+      });
+}
+
+int32_t tnn_batchnorm_backward_sync(tnn_context *ctx, tnn_comm *comm, int64_t globalBatch, int64_t batch,
+                                    int64_t channels, int64_t blockSize, const float *out, int32_t activation,
+                                    float *delta, const float *x, const float *x_norm, const float *mean,
+                                    const float *variance, const float *scales, float *scale_updates, float *mean_delta,
+                                    float *variance_delta) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(activation == TNN_ACT_LINEAR || (tnn_act_is_elementwise(activation) && activation != TNN_ACT_SWISH),
+              "activation gradient not implemented");
+  TNN_REQUIRE(globalBatch >= batch, "the global batch is the sum of the replicas' batches");
+  const int a = activation;
+  const float *dl = delta;
+  // local sums; scale_updates keeps the LOCAL sum (the gradient bucket sums it over the replicas later), the two
+  // sums behind mean_delta / variance_delta are exchanged now because every replica's delta needs the global ones
+  int rc = launch_reduce<3>(
+      ctx, channels, batch, blockSize,
+      [dl, out, x, x_norm, mean, a] __device__(int64_t i, int c, float(&s)[3]) {
+        const float g = (a == TNN_ACT_LINEAR) ? dl[i] : dl[i] * tnn_grad(out[i], a);
+        s[0] = fmaf(x_norm[i], g, s[0]);
+        s[1] += g;
+        s[2] = fmaf(g, x[i] - __ldg(mean + c), s[2]);
+      },
+      [scale_updates, mean_delta, variance_delta] __device__(int c, const float(&t)[3]) {
+        scale_updates[c] = scale_updates[c] + t[0];
+        mean_delta[c] = t[1];
+        variance_delta[c] = t[2];
+      });
+  if (rc) return rc;
+  if (comm) {
+    rc = tnn_allreduce_sum(ctx, comm, mean_delta, 0, channels);
+    if (rc) return rc;
+    rc = tnn_allreduce_sum(ctx, comm, variance_delta, 0, channels);
+    if (rc) return rc;
+  }
+  const float batchSize = (float)(blockSize * globalBatch);
+  // delta = d/sqrt(max(var,eps)) + (2*variance_delta*(x-mean) + mean_delta)/(globalBatch*blockSize), the per-channel
+  // factors of sMeanAndVarianceDelta (ntensors.pas:8831-8899) applied to the exchanged sums on the fly
+  return planemap::launch<2, 0>(
+      ctx, delta, out, x, nullptr, nullptr, batch * channels * blockSize, channels, batch,
+      [mean, variance, mean_delta, variance_delta, scales, batchSize, a] __device__(float &d, float ov, float xv,
+                                                                                    float &, float &, int c) {
+        float g = (a == TNN_ACT_LINEAR) ? d : d * tnn_grad(ov, a);
+        const float sc = __ldg(scales + c);
+        g = g * sc;
+        const double v = (double)fmaxf(__ldg(variance + c), TNN_EPS);
+        const float mdelta = (float)((double)(__ldg(mean_delta + c) * sc) * (-1.0 / sqrt(v)));
+        const float vdelta = (float)((double)(__ldg(variance_delta + c) * sc) * -0.5 * pow(v, -1.5));
+        const float md = mdelta / batchSize;
+        const float vd = 2 * vdelta / batchSize;
+        const float sd = sqrtf((float)v);
+        d = __fadd_rn(g / sd, __fadd_rn(__fmul_rn(vd, xv - __ldg(mean + c)), md));
+      });
+}
+
 }  // extern "C"

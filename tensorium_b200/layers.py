@@ -190,6 +190,19 @@ class TConvolutionalLayer:
         elif not self.isBatchNormalized:
             cu.conv2dForward(self._desc, state.input.devData, 0, self.weights.devData, None, self.biases.devData,
                              self.ActivationType, self.output.devData, 0)
+        elif training_bn and getattr(self, "sync_stats", None) is not None:
+            # data-parallel replicas with SyncBN: statistics of the GLOBAL mini-batch (dataparallel.attach(sync_bn=True))
+            ss = self.sync_stats
+            cu.conv2dForward(self._desc, state.input.devData, 0, self.weights.devData, None, None, nn.acLINEAR,
+                             self.output.devData, 0)
+            cu.batchNormForwardTrainingSync(ss.comm, self.batch * ss.world, self.batch, self.filters,
+                                            self.outH * self.outW, self.output.devData, self.x.devData,
+                                            self.x_norm.devData, self.mean.devData, self.variance.devData,
+                                            self.rolling_mean.devData, self.rolling_variance.devData, self.bnMomentum,
+                                            self.scales.devData, self.biases.devData, self.ActivationType)
+            for t in (self.x, self.x_norm, self.mean, self.variance, self.rolling_mean, self.rolling_variance):
+                t.setCUDA()
+            self._bn_fold = None
         elif training_bn:
             # raw conv output, then the fused training batch-norm (+ activation)
             cu.conv2dForward(self._desc, state.input.devData, 0, self.weights.devData, None, None, nn.acLINEAR,
@@ -304,7 +317,15 @@ class TConvolutionalLayer:
         if self.isBatchNormalized:
             if not self.scale_updates.wasGPU():
                 self.scale_updates.pushToDevice()
-            cu.batchNormBackward(self.batch, self.filters, self.outH * self.outW, self.output.devData,
+            ss = getattr(self, "sync_stats", None)
+            if ss is not None:
+                cu.batchNormBackwardSync(ss.comm, self.batch * ss.world, self.batch, self.filters, self.outH * self.outW,
+                                         self.output.devData, self.ActivationType, self.delta.devData, self.x.devData,
+                                         self.x_norm.devData, self.mean.devData, self.variance.devData,
+                                         self.scales.devData, self.scale_updates.devData, self.mean_delta.devData,
+                                         self.variance_delta.devData)
+            else:
+                cu.batchNormBackward(self.batch, self.filters, self.outH * self.outW, self.output.devData,
                                  self.ActivationType, self.delta.devData, self.x.devData, self.x_norm.devData,
                                  self.mean.devData, self.variance.devData, self.scales.devData,
                                  self.scale_updates.devData, self.mean_delta.devData, self.variance_delta.devData)

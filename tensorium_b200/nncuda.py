@@ -438,3 +438,45 @@ class TNNCuda:
     def upSampleNhwc(self, batch, channels, inHeight, inWidth, stride, scale, in_, inPitch, out, outPitch):
         self._ck(self._l.tnn_upsample_nhwc(self._h, batch, channels, inHeight, inWidth, stride, scale, _addr(in_),
                                            inPitch, _addr(out), outPitch))
+
+    # ---- multi-GPU exchange (include/tensorium_b200.h, last section): NCCL behind the C ABI
+    @staticmethod
+    def commUniqueId() -> bytes:
+        buf = C.create_string_buffer(128)
+        lib = _lib.load()
+        if lib.tnn_comm_unique_id(buf, 128):
+            raise CudaError(lib.tnn_last_error().decode())
+        return buf.raw
+
+    def commInitRank(self, nranks: int, rank: int, uid: bytes):
+        comm = C.c_void_p()
+        self._ck(self._l.tnn_comm_init_rank(self._h, nranks, rank, C.c_char_p(uid), C.byref(comm)))
+        return comm
+
+    def commDestroy(self, comm):
+        self._ck(self._l.tnn_comm_destroy(comm))
+
+    def commInfo(self, comm):
+        n, r, v = C.c_int32(), C.c_int32(), C.c_int32()
+        self._ck(self._l.tnn_comm_info(comm, C.byref(n), C.byref(r), C.byref(v)))
+        return n.value, r.value, v.value
+
+    def allreduceSum(self, comm, buf, offset, n):
+        self._ck(self._l.tnn_allreduce_sum(self._h, comm, _addr(buf), offset, n))
+
+    def broadcast(self, comm, buf, offset, n, root=0):
+        self._ck(self._l.tnn_broadcast(self._h, comm, _addr(buf), offset, n, root))
+
+    def batchNormForwardTrainingSync(self, comm, globalBatch, batch, channels, blockSize, out, x, x_norm, mean, variance,
+                                     rolling_mean, rolling_variance, bn_momentum, scales, biases, activation):
+        self._ck(self._l.tnn_batchnorm_forward_training_sync(
+            self._h, comm, globalBatch, batch, channels, blockSize, _addr(out), _addr(x), _addr(x_norm), _addr(mean),
+            _addr(variance), _addr(rolling_mean), _addr(rolling_variance), bn_momentum, _addr(scales), _addr(biases),
+            int(activation)))
+
+    def batchNormBackwardSync(self, comm, globalBatch, batch, channels, blockSize, out, activation, delta, x, x_norm, mean,
+                              variance, scales, scale_updates, mean_delta, variance_delta):
+        self._ck(self._l.tnn_batchnorm_backward_sync(
+            self._h, comm, globalBatch, batch, channels, blockSize, _addr(out), int(activation), _addr(delta), _addr(x),
+            _addr(x_norm), _addr(mean), _addr(variance), _addr(scales), _addr(scale_updates), _addr(mean_delta),
+            _addr(variance_delta)))

@@ -314,7 +314,9 @@ class TNNet:
         """Capture forward+backward (and update) of ONE training step into CUDA graphs and replay them from then on.
         Call after at least one eager trainBatch (scratch buffers must have their final size, every parameter must be
         on the device).  Dropout seeds move to a device counter: layer i, step t uses seed + t*GRAPH_SEED_STEP +
-        (i+1)*2^40.  With a gradient bucket attached the all-reduce stays eager between the two graphs."""
+        (i+1)*2^40.  A native gradient bucket (dataparallel.NativeBucket: the library's NCCL entry point) is captured
+        with the step — forward + backward + all-reduce + update are ONE graph; with a torch bucket (gloo tests) the
+        all-reduce stays eager between a forward/backward graph and an update graph."""
         assert self.subdivisions == 1, "graph mode updates every step"
         cu = cuda()
         self._seed_ctr = TSingleTensor((1,), groups=1, host=True, dtype=np.int64)
@@ -328,7 +330,8 @@ class TNNet:
         cu.beginCapture()
         self.Propagate()
         cu.counterAdd(self._seed_ctr.devData, self.GRAPH_SEED_STEP)
-        if self.bucket is None:
+        if self.bucket is None or getattr(self.bucket, "capturable", False):
+            # (a native bucket's all-reduce is an operator on the backend's stream: it is captured with the step)
             self.update()
             self._graphs = (cu.endCapture(), None)
         else:

@@ -46,6 +46,10 @@ GEOMS = [
     (2, 32, 14, 14, 64, 3, 2, 1, 0, 0),      # padding 2 with a 3x3 kernel (output larger than input)
     (1, 32, 31, 29, 48, 3, 1, 2, 0, 64),     # stride 2 on odd sizes, output slice of a 64-wide concat buffer
     (4, 256, 13, 13, 512, 3, 1, 1, 0, 0),    # the YOLO 13x13 shape (K = 2304), 6 tiles x 2 filter tiles
+    # enough 128-pixel tiles for every TPC: these run on CTA PAIRS (tcgen05.mma.cta_group::2, half a weight tile per CTA)
+    (8, 64, 52, 52, 128, 3, 1, 1, 0, 0),     # 169 tiles (odd: the last pair has one empty half), BN = 128
+    (7, 32, 52, 52, 64, 3, 1, 2, 0, 0),      # stride 2, BN = 64 (32 weight rows per CTA), 37 pair tiles x ... single n tile
+    (10, 96, 40, 40, 288, 1, 0, 1, 0, 320),  # 1x1, two filter tiles (256 + 32), output slice of a 320-wide buffer
 ]
 
 
@@ -82,10 +86,11 @@ def test_conv_forward_nhwc(cuda_backend, oracle, mode, tol, geom):
 
 
 @pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32), (BF3, TOL_3XTF32)])
-def test_conv_forward_nhwc_planar_output(cuda_backend, oracle, mode, tol):
+@pytest.mark.parametrize("B,H", [(3, 13), (10, 52)])   # (10, 52): 212 tiles -> CTA pairs
+def test_conv_forward_nhwc_planar_output(cuda_backend, oracle, mode, tol, B, H):
     """Head layers: channels-innermost input, NCHW output planes (255 filters, linear, bias only)."""
     cu = cuda_backend
-    B, C, H, W, F, k, p, s = 3, 64, 13, 13, 255, 1, 0, 1
+    C, W, F, k, p, s = 64, H, 255, 1, 0, 1
     rng = np.random.default_rng(77)
     x, w, b = conv_case(rng, B, C, H, W, F, k)
     want = oracle.conv2d(x, w, p, s, s, 1, k, k)

@@ -5,7 +5,7 @@ seeded inputs, parameters and dropout masks — for the fused entry points and f
 import numpy as np
 import pytest
 
-from util import rel_max
+from util import Dev, rel_max
 
 pytestmark = pytest.mark.gpu
 FP32, X3, TF32 = 0, 1, 2
@@ -265,3 +265,30 @@ def test_graph_replay_matches_eager_training(cuda_backend):
                 assert np.array_equal(lg.rand.pullFromDevice(), le.rand.pullFromDevice())  # same masks
                 le.rand.setCUDA()
                 lg.rand.setCUDA()
+
+
+def test_native_nccl_entry_points_single_rank(cuda_backend):
+    """tnn_comm_* / tnn_allreduce_sum / tnn_broadcast (the C-ABI exchange step a FreePascal host would call): a
+    one-rank communicator really goes through NCCL (dlopen'ed libnccl.so.2) on the backend's stream, eagerly and
+    captured into a CUDA graph; the multi-rank run is tools/cifar_train.py under torchrun (profiles/)."""
+    cu = cuda_backend
+    comm = cu.commInitRank(1, 0, cu.commUniqueId())
+    try:
+        nranks, rank, version = cu.commInfo(comm)
+        assert (nranks, rank) == (1, 0) and version >= 20000
+        x = np.random.default_rng(0).uniform(-1, 1, 5000).astype(np.float32)
+        d = Dev(cu, x, pad_front=3)
+        cu.allreduceSum(comm, d._base, 3, x.size)
+        cu.broadcast(comm, d._base, 3, x.size, 0)
+        assert np.array_equal(d.read(), x)
+        cu.finish()
+        cu.beginCapture()
+        cu.scale(x.size, 2.0, d.ptr + 12, 1)
+        cu.allreduceSum(comm, d._base, 3, x.size)
+        g = cu.endCapture()
+        cu.launchGraph(g)
+        cu.launchGraph(g)
+        assert np.array_equal(d.read(), 4 * x)
+        cu.destroyGraph(g)
+    finally:
+        cu.commDestroy(comm)

@@ -84,6 +84,8 @@ def pick_threshold(want, batch, outs=None, q=0.999, start=None):
     prods = np.sort(np.concatenate(vals[1::2]))
     target = prods[int(q * prods.size)] if start is None else start
     idx = max(1, int(np.searchsorted(v, target)))
+    if idx >= v.size:          # nothing reaches the starting threshold (random-init heads): any value above works
+        return float(max(target, v[-1] + 12 * d + 1e-6))
     while idx < v.size - 1 and v[idx] - v[idx - 1] < 6 * d + 1e-7:
         idx += 1
     return float((v[idx] + v[idx - 1]) / 2)
