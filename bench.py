@@ -5,13 +5,21 @@ Workload = BASELINE.json configs[3]: YOLOv3 416x416 inference, batch 64 per GPU,
 (BN folded like MSCOCOYolo.pas:327-340), synthetic U[0,1) images; batch-sharded across GPUs with no collective
 (weak scaling: every rank runs its own batch of 64).  One "step" = one forward pass of the 107-layer net.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math 3xtf32|tf32|fp32]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--math bf16x3|3xtf32|tf32|fp32]
 
 Prints ONE JSON line (rank 0).  `value` is device-resident throughput, `e2e` includes the pinned-host H2D copy of
 the batch and the D2H read of the three yolo outputs every step.  `roofline` is for the dominant kernel (the
 tcgen05 implicit-GEMM conv): algorithmic FLOPs (2*B*F*OH*OW*C*k*k summed over the 75 convs) / summed CUDA-event
 durations of those launches.  `cpu_baseline` / `--impl reference` time the reference's CPU algorithm (oracle/, the
 C restatement — FreePascal is not available to build the reference itself) on the host cores.
+
+Default arithmetic: bf16x3 — every fp32 operand split into two bf16 numbers, three tensor-core MMAs per product,
+fp32 accumulation; the same 1e-4 per-layer gate as 3xTF32 (tests/test_gpu_nhwc.py, test_gpu_yolo.py; measured error
+vs fp64 is LOWER than 3xTF32's at K >= 1024, profiles/r02_accuracy_vs_k.txt).  The line also carries, as secondary
+objects measured in the same run: `modes` (the step in 3xtf32 and tf32 arithmetic), `cifar10_train` (BASELINE
+configs[2]: deepCIFAR10 training with the NCCL all-reduce of the update bucket captured in the step graph, global
+batch 128 split over the GPUs and 128 per GPU) and `roofline_membound` (the HBM-bound kernels against the measured
+copy bandwidth).
 """
 from __future__ import annotations
 
@@ -33,6 +41,7 @@ BATCH = 64
 SIZE = 416
 METRIC = "YOLOv3-416 inference images/sec"
 MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16x3": 3}
+MMA_PER_PRODUCT = {"fp32": 1, "3xtf32": 3, "tf32": 1, "bf16x3": 3}
 
 
 def load_peaks():
@@ -144,7 +153,7 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     rates = []
-    for _ in range(args.warmup if args.warmup < 1 else 1):
+    for _ in range(args.warmup):      # every warm-up pass is a full single-image forward (about 1 s each)
         cpu_forward_rate(1)
     t_all = 0.0
     for _ in range(args.steps):
@@ -157,7 +166,10 @@ def run_reference(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"YOLOv3-{SIZE} inference (107 layers, BN fused), reference CPU algorithm "
                                f"(C restatement of ntensors.pas cblas_sgemm+sim2Col), 1 image per step",
-                   "global_batch": 1, "image": SIZE},
+                   "global_batch": 1, "image": SIZE,
+                   "same_config": "same net, weights and image size as the GPU arm; the step is ONE image instead of 64 "
+                                  "(the reference's CPU path loops per image - Conv2D ntensors.pas:8326-8333 - so images/s "
+                                  "does not depend on the batch); a bounded sample so that the run ends within minutes"},
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"{args.steps} x 1 image full forward ({cpu_model()})"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -167,6 +179,64 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------------ GPU arm
+def membound_roofline(cu, stream, hbm_gbs):
+    """The HBM-bound kernels of the path against the measured copy bandwidth: algorithmic bytes per element (DESIGN.md
+    §4) x elements / CUDA-event time on tensors far larger than the 126 MB L2."""
+    import torch
+    out = {}
+
+    def timed(fn, reps=10):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def entry(name, kernel, bytes_per_elem, n, ms, what):
+        gbs = bytes_per_elem * n / (ms * 1e-3) / 1e9
+        out[name] = {"kernel": kernel, "elements": n, "bytes_per_element": bytes_per_elem, "ms": round(ms, 4),
+                     "achieved": round(gbs, 1), "peak": hbm_gbs, "unit": "GB/s", "frac": round(gbs / hbm_gbs, 3), "what": what}
+
+    B, C, HW = 64, 64, 208 * 208                      # the YOLOv3 64-channel 208x208 tensor at batch 64: 709 MB
+    n = B * C * HW
+    a, b_, c_ = (torch.rand(n, device="cuda") for _ in range(3))
+    rows = B * HW
+    entry("shortcut_add", "nhwc::k_rows<true> (tnn_rows_add)", 12, n,
+          timed(lambda: cu.rowsAdd(rows, C, a.data_ptr(), C, b_.data_ptr(), C, c_.data_ptr(), C)),
+          "TAddLayer.forwardGPU (naddlayer.pas:891-910) on channels-innermost rows: 2 reads + 1 write")
+    entry("leaky_activate", "k_map_vec (tnn_activate_array)", 8, n, timed(lambda: cu.ActivateArray(n, a.data_ptr(), 0, 9)),
+          "ActivateArray(leaky) in place (nncuda.pas:524-542): 1 read + 1 write")
+    entry("axpy", "k_map_vec (tnn_axpy)", 12, n, timed(lambda: cu.axpy(n, 0.5, a.data_ptr(), 0, 1, b_.data_ptr(), 0, 1)),
+          "y += a*x (nncuda.pas:945-964): 2 reads + 1 write")
+    del c_
+    # batch-norm, training: deepCIFAR10's 32-channel 32x32 layer scaled to batch 2048 (268 MB per tensor)
+    Bb, Cb, HWb = 2048, 32, 32 * 32
+    nb = Bb * Cb * HWb
+    x, xn = torch.empty(nb, device="cuda"), torch.empty(nb, device="cuda")
+    o = a[:nb]
+    dl = b_[:nb]
+    vec = [torch.ones(Cb, device="cuda") for _ in range(9)]
+    p = [v.data_ptr() for v in vec]
+    entry("batchnorm_forward_training", "k_channel_reduce<2> + planemap::k_plane<0,2> (tnn_batchnorm_forward_training)", 20, nb,
+          timed(lambda: cu.batchNormForwardTraining(Bb, Cb, HWb, o.data_ptr(), x.data_ptr(), xn.data_ptr(), p[0], p[1], p[2],
+                                                    p[3], 0.1, p[4], p[5], 1)),
+          "batchNormGPU training (nbaselayer.pas:583-643) fused: 1 statistics read + 1 read / 3 writes (out, x, x_norm)")
+    entry("batchnorm_backward", "k_channel_reduce<3> + planemap::k_plane<2,0> (tnn_batchnorm_backward)", 32, nb,
+          timed(lambda: cu.batchNormBackward(Bb, Cb, HWb, o.data_ptr(), 1, dl.data_ptr(), x.data_ptr(), xn.data_ptr(), p[0],
+                                             p[1], p[4], p[6], p[7], p[8])),
+          "DeriveArray + batchNormBackGPU (nbaselayer.pas:662-714) in two passes: reads delta, out, x, x_norm, then "
+          "reads delta, out, x and writes delta")
+    np_ = 1 << 27                                       # 134 M parameters (512 MB per tensor)
+    entry("sgd_update", "k_sgd (tnn_sgd_update)", 16, np_,
+          timed(lambda: cu.sgdUpdate(np_, a.data_ptr(), b_.data_ptr(), 1e-6, 0.9, -1e-6)),
+          "updateGPU (nConvolutionLayer.pas:1309-1322) fused: read+write params and updates")
+    return out
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -318,18 +388,57 @@ def run_ours(args, rank, world, local_rank):
     for b in by_kernel.values():
         b["tflops"] = b["flops"] / b["ms"] / 1e9
         b["share_of_step"] = b["ms"] / (ms / args.steps)
+    # bf16x3 issues kind::f16 MMAs: its bound is the bf16 dense peak (driver-measured, sustained); the tf32 modes are
+    # bounded by the TF32 peak measured with tools/measure_peaks.py
+    if args.math == "bf16x3":
+        pipe_peak, pipe_src = float(peaks["bf16_tflops_sustained"]), f"bf16_tflops_sustained of {which} MEASURED_PEAKS.json"
+    else:
+        pipe_peak, pipe_src = tf32_peak, tf32_src
+    issue = MMA_PER_PRODUCT[args.math]
     dom_name = max(by_kernel, key=lambda k: by_kernel[k]["ms"])
     dom = by_kernel[dom_name]
     achieved = dom["tflops"]
     # DRAM traffic of the dominant kernel's launches, from a separate `ncu` capture (never measured under the timed run)
     traffic, traffic_src = None, None
-    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if os.path.exists(tpath) and args.math == "3xtf32":
+    tpath = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.exists(tpath):
         tj = json.load(open(tpath))
-        ent = tj.get("by_kernel", {}).get(dom_name)
+        ent = tj.get(args.math, {}).get("by_kernel", {}).get(dom_name)
         if ent:
             traffic = ent["dram_bytes_total"] / max(ent["launches"], 1)
-            traffic_src = f"profiles/r01_traffic.json (ncu dram__bytes_read+write, mean of {ent['launches']} launches)"
+            traffic_src = (f"profiles/r02_traffic.json (ncu dram__bytes_read+write, mean of {ent['launches']} launches, "
+                           f"{args.math})")
+
+    # ---- secondary objects, measured after the headline regions (all ranks take part: the training run has a collective)
+    modes, cifar, membound = None, None, None
+    if not args.no_secondary:
+        modes = {}
+        for m in ("bf16x3", "3xtf32", "tf32"):
+            if m == args.math:
+                continue
+            cu.set_math_mode(MATH[m])
+            for _ in range(3):
+                step_resident()
+            ms_m = timed(step_resident, 5)
+            modes[m] = {"images_per_s": aggregate_images_per_s(world, 5, ms_m), "ms_per_step": ms_m / 5, "steps": 5,
+                        "gate": "5e-3" if m == "tf32" else "1e-4"}
+        cu.set_math_mode(MATH[args.math])
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import cifar_train
+        cu.set_math_mode(MATH["3xtf32"])   # the training kernels (wgrad, dgrad, connected layers) are the planar tf32 ones
+        cifar = {"workload": "deepCIFAR10 (nmodels.pas:82-111) training step: host batch in, forward, backward, NCCL "
+                             "all-reduce of the update bucket (tnn_allreduce_sum, captured in the step's CUDA graph), SGD; "
+                             "synthetic 32x32 images, 3xtf32", "math": "3xtf32"}
+        if world == 1:
+            cifar["batch128"] = cifar_train.train_throughput(cu, stream, 128, 100, 5, rank, world)
+        else:
+            cifar["global_batch_128_split"] = cifar_train.train_throughput(cu, stream, max(128 // world, 1), 100, 5, rank, world)
+            cifar["batch128_per_gpu"] = cifar_train.train_throughput(cu, stream, 128, 100, 5, rank, world)
+            cifar["global_batch_128_split_syncbn"] = cifar_train.train_throughput(cu, stream, max(128 // world, 1), 100, 5,
+                                                                                 rank, world, sync_bn=True)
+        cu.set_math_mode(MATH[args.math])
+        if rank == 0:
+            membound = membound_roofline(cu, stream, float(peaks["hbm_gbs"]))
 
     if rank == 0:
         if args.layers_out:
@@ -346,6 +455,9 @@ def run_ours(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32" if args.math != "tf32" else "tf32",
+            "dtype_note": {"bf16x3": "fp32 tensors and accumulation; every product as 3 bf16 MMAs on hi/lo halves (1e-4 gate)",
+                           "3xtf32": "fp32 tensors and accumulation; every product as 3 TF32 MMAs on hi/lo halves (1e-4 gate)",
+                           "tf32": "fp32 tensors, TF32 products (5e-3 gate)", "fp32": "fp32 CUDA-core FMA"}[args.math],
             "data": "synthetic",
             "config": {"workload": f"YOLOv3-{SIZE} inference, 107 layers (75 conv), BN folded, random-init weights",
                        "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": SIZE,
@@ -354,16 +466,21 @@ def run_ours(args, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes_in,
                     "d2h_bytes_per_step": nbytes_out, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": tf32_peak, "unit": "TFLOP/s",
-                         "frac": achieved / tf32_peak, "traffic": traffic, "traffic_unit": "bytes per launch",
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": pipe_peak, "unit": "TFLOP/s",
+                         "frac": achieved / pipe_peak, "traffic": traffic, "traffic_unit": "bytes per launch",
                          "traffic_source": traffic_src,
                          "compulsory_bytes": dom["compulsory_bytes"] / dom["launches"],
-                         "kernel": f"{dom_name}: tcgen05 kind::tf32 implicit-GEMM conv, {dom['launches']} launches/step",
+                         "kernel": f"{dom_name}: tcgen05 kind::{'f16 (bf16 operands)' if args.math == 'bf16x3' else 'tf32'} "
+                                   f"implicit-GEMM conv, {dom['launches']} launches/step",
                          "avg_launch_ms": dom["ms"] / dom["launches"],
-                         "peak_source": tf32_src,
+                         "peak_source": pipe_src,
+                         "achieved_note": "ALGORITHMIC FLOPs (2*B*F*OH*OW*C*k*k, counted once) / CUDA-event time; the "
+                                          f"kernel issues {issue} MMA(s) per product, so the tensor pipe itself runs at "
+                                          "issued_frac of its peak",
+                         "frac_of_tf32_peak": achieved / tf32_peak, "tf32_peak": tf32_peak, "tf32_peak_source": tf32_src,
                          "kernel_ms_per_step": dom["ms"], "share_of_step": dom["share_of_step"],
-                         "mma_issue_factor": 3 if args.math == "3xtf32" else 1,
-                         "issued_frac": achieved * (3 if args.math == "3xtf32" else 1) / tf32_peak,
+                         "mma_issue_factor": issue,
+                         "issued_frac": achieved * issue / pipe_peak,
                          "all_conv": {"launches": len(per_layer), "ms": conv_ms, "tflops": conv_flops / conv_ms / 1e9,
                                       "share_of_step": conv_ms / (ms / args.steps)},
                          "by_kernel": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()
@@ -371,6 +488,9 @@ def run_ours(args, rank, world, local_rank):
                                        for k, v in by_kernel.items()}},
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "modes": modes,
+            "cifar10_train": cifar,
+            "roofline_membound": membound,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -384,7 +504,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--math", default="3xtf32", choices=list(MATH))
+    ap.add_argument("--math", default="bf16x3", choices=list(MATH))
+    ap.add_argument("--no-secondary", action="store_true", help="skip the modes / cifar10_train / roofline_membound objects")
     ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"],
                     help="internal activation layout of the graph: channels-innermost (TMA im2col kernels) or planar")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -64,45 +64,38 @@ def check_conv_layers(cu, net, probe, x, batch, tol, expect_kernel=None):
     return worst
 
 
-def detection_values(want, batch):
-    """Every value getDetections compares with the threshold: objectness, and objectness * class score."""
-    vals = []
-    for w in want:
-        y = w.reshape(batch, 3, 85, -1)
-        vals.append(y[:, :, 4, :].ravel())
-        vals.append((y[:, :, 4:5, :] * y[:, :, 5:, :]).ravel())
-    return vals
+def detection_products(want, batch):
+    """objectness * class score of every candidate — what getDetections compares with the threshold."""
+    return np.concatenate([(w.reshape(batch, 3, 85, -1)[:, :, 4:5, :] * w.reshape(batch, 3, 85, -1)[:, :, 5:, :]).ravel()
+                           for w in want])
 
 
-def pick_threshold(want, batch, outs=None, q=0.999, start=None):
-    """A detection threshold no compared value sits close to: the GPU outputs differ from the oracle's by
-    d = max|g - r| (measured here), so a value within 2d of the threshold could legitimately fall on either side; the
-    threshold is moved up from the q-quantile of the products (or from `start`) to the first gap wider than 6d."""
-    d = max(float(np.abs(g - r).max()) for g, r in zip(outs, want)) if outs is not None else 1e-4
-    vals = detection_values(want, batch)
-    v = np.sort(np.concatenate(vals))
-    prods = np.sort(np.concatenate(vals[1::2]))
-    target = prods[int(q * prods.size)] if start is None else start
-    idx = max(1, int(np.searchsorted(v, target)))
-    if idx >= v.size:          # nothing reaches the starting threshold (random-init heads): any value above works
-        return float(max(target, v[-1] + 12 * d + 1e-6))
-    while idx < v.size - 1 and v[idx] - v[idx - 1] < 6 * d + 1e-7:
-        idx += 1
-    return float((v[idx] + v[idx - 1]) / 2)
+def pick_threshold(want, batch, q=0.9995):
+    """A detection threshold at the q-quantile of the products: a few dozen class scores per image survive."""
+    prods = np.sort(detection_products(want, batch))
+    return float(prods[int(q * prods.size)])
 
 
-def check_detections(net, outs, want, batch, thresh, nms=0.45):
+def check_detections(net, outs, want, batch, thresh, nms=0.45, images=None):
     """Product decode + NMS on the GPU outputs (tensorium_b200/nnet.py) vs the ORACLE's restatement of
     getDetections / correctBoxes / doNMSSort with the reference's own QuickSort (oracle/ref_detect.py) on the oracle's
-    outputs: same count, same classes, IoU >= 0.99 (BASELINE.json)."""
+    outputs: same class scores, boxes with IoU >= 0.99 (BASELINE.json).
+
+    The GPU outputs differ from the oracle's by d = max|g - r| (measured here), so a score within `margin` = 8d of the
+    threshold may legitimately be kept on one side and dropped on the other.  Such a borderline score is the LOWEST of
+    its class, so it can be suppressed but never suppresses a non-borderline one (NMS walks scores downward): every
+    score farther than `margin` from the threshold must match one to one; borderline ones may be unmatched."""
     from oracle import ref_detect as rd
+    d = max(float(np.abs(g - r).max()) for g, r in zip(outs, want))
+    margin = 8 * d + 1e-7
     total = 0
     yl = net.yolo_layers()
-    for b in range(batch):
+    for b in (images if images is not None else range(batch)):
         db, do, dp = net.Detections(thresh, nms, b, host_outputs=outs)
         dets = rd.net_detections([dict(output=w, w=l.w, h=l.h, n=l.n, classes=l.classes, mask=l.mask, biases=l.biases)
                                   for l, w in zip(yl, want)], net.w, net.h, net.w, net.h, thresh, True, False, b)
-        assert len(dets) == len(db)
+        objs = np.concatenate([w[b].reshape(3, 85, -1)[:, 4, :].ravel() for w in want])
+        assert abs(len(dets) - len(db)) <= int((np.abs(objs - thresh) < margin).sum())
         rd.do_nms_sort(dets, yl[0].classes, nms)
         ref = rd.surviving(dets)
         got = []
@@ -110,12 +103,18 @@ def check_detections(net, outs, want, batch, thresh, nms=0.45):
             for c in np.nonzero(dp[i])[0]:
                 got.append((int(c), float(dp[i, c]), [float(v) for v in db[i]]))
         got.sort(key=lambda t: (t[0], -t[1]))
-        assert len(ref) == len(got)
-        for (c1, p1, b1), (c2, p2, b2) in zip(ref, got):
-            assert c1 == c2 and abs(p1 - p2) < 2e-3 * max(p1, 1e-3)
-            assert rd.box_iou(b1, b2) >= 0.99
-        total += len(ref)
-    return total  # class scores that survived NMS, over the batch
+        # every score farther than `margin` above the threshold on one side has its twin on the other side
+        firm = lambda lst: [e for e in lst if e[1] > thresh + margin]
+        fr = firm(ref)
+
+        def twin(e, lst):
+            return any(c == e[0] and abs(p - e[1]) <= margin and rd.box_iou(bx, e[2]) >= 0.99 for c, p, bx in lst)
+        for e in fr:
+            assert twin(e, got), ("oracle score without a product twin", e)
+        for e in firm(got):
+            assert twin(e, ref), ("product score without an oracle twin", e)
+        total += len(fr)
+    return total  # class scores that survived NMS (and were compared), over the images
 
 
 @pytest.mark.parametrize("variant", ["fused", "unfused", "channels_last"])
@@ -139,7 +138,7 @@ def test_yolov3_small_against_oracle(cuda_backend, oracle, variant):
     for g, r in zip(outs, want):
         assert rel_max(g, r) < 2e-3
     # (3) detections + NMS: product on GPU outputs vs the oracle's restatement on oracle outputs
-    assert check_detections(net, outs, want, batch, pick_threshold(want, batch, outs)) > 0  # not vacuous
+    assert check_detections(net, outs, want, batch, pick_threshold(want, batch, q=0.99)) > 0  # not vacuous
 
 
 @pytest.mark.parametrize("math,tol", [("3xtf32", TOL_3XTF32), ("tf32", 5e-3)])
@@ -169,13 +168,13 @@ def test_yolov3_416_bench_configuration(cuda_backend, oracle, math, tol):
         assert rel_max(g, r) < (2e-3 if math == "3xtf32" else 5e-2)
     if math == "3xtf32":
         # thresh 0.45 / nms 0.45 as in the sample; skip boxes whose objectness sits within 1e-3 of the threshold
-        # thresh / nms 0.45 as in the sample (MSCOCOYolo.pas:252-253), nudged to the nearest gap in the compared values
-        thresh = pick_threshold(want, batch, outs, start=0.45)
-        n = check_detections(net, outs, want, batch, thresh)
-        print(f"post-NMS class scores compared at thresh {thresh:.4f}: {n}")
-        # random-init heads give few confident class scores at 0.45: repeat where a few dozen survive
-        t2 = pick_threshold(want, batch, outs)
-        n2 = check_detections(net, outs, want, batch, t2)
+        # thresh / nms 0.45 as in the sample (MSCOCOYolo.pas:252-253)
+        n = check_detections(net, outs, want, batch, 0.45)
+        print(f"post-NMS class scores compared at thresh 0.45: {n}")
+        # random-init heads (objectness bias -4) give hardly any confident class score at 0.45: repeat at the
+        # 99.95 % quantile of the scores, where a few dozen per image survive (two images keep the O(n^2) NMS short)
+        t2 = pick_threshold(want, batch)
+        n2 = check_detections(net, outs, want, batch, t2, images=(0, batch - 1))
         print(f"post-NMS class scores compared at thresh {t2:.4f}: {n2}")
         assert n2 > 0
 
