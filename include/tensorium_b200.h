@@ -238,6 +238,16 @@ TNN_API int32_t tnn_forward_dropout_dev(tnn_context *ctx, int64_t N, const float
 TNN_API int32_t tnn_lstm_gates(tnn_context *ctx, int64_t batch, int64_t hidden, const float *wz, const float *bw,
                                const float *uz, int64_t uzOffset, float *c, float *h, float *cell_out, float *h_out,
                                int64_t outOffset);
+/* One launch for the element-wise part of an LSTM step of back-propagation through time (TLSTMLayer.backward,
+ * source/nlstmlayer.pas:661-812, plus the sub-layers' delta.Clamp(-1,1), nconnectedlayer.pas:262).  wz / uz hold the gate
+ * pre-activations of ALL steps ([steps*batch][4*hidden], gate order f|i|g|o; wz without bias, uz with the input-side
+ * bias) and zOffset selects the step; cell holds c of all steps (cellOffset = this step, prevCellOffset = the step
+ * before, or -1 at the first step); dh + dhOffset = dL/dh of this step; dc [batch][hidden] is the carried dL/dc
+ * (updated in place); dz + dzOffset receives the four pre-activation deltas [batch][4*hidden]. */
+TNN_API int32_t tnn_lstm_gates_backward(tnn_context *ctx, int64_t batch, int64_t hidden, const float *wz, const float *bw,
+                                        const float *uz, int64_t zOffset, const float *cell, int64_t cellOffset,
+                                        int64_t prevCellOffset, const float *dh, int64_t dhOffset, float *dc, float *dz,
+                                        int64_t dzOffset);
 TNN_API int32_t tnn_backward_dropout(tnn_context *ctx, int64_t N, const float *src, float probability, float scale,
                                      const float *rnd, float *dst);
 

@@ -243,6 +243,16 @@ class RefLSTM:
         self.cell = np.zeros((batch_total, outputs), f32)
         self.c = np.zeros((self.batch, outputs), f32)
         self.h = np.zeros((self.batch, outputs), f32)
+        # training state: the sub-layers' linear outputs per step (wf.output ... uo.output), their update buffers,
+        # the layer's delta (filled by the caller before backward) and the carried dc
+        self.wout = {g: np.zeros((batch_total, outputs), f32) for g in self.GATES}
+        self.uout = {g: np.zeros((batch_total, outputs), f32) for g in self.GATES}
+        self.w_updates = {g: np.zeros_like(self.w[g]) for g in self.GATES}
+        self.u_updates = {g: np.zeros_like(self.u[g]) for g in self.GATES}
+        self.bw_updates = {g: np.zeros_like(self.bw[g]) for g in self.GATES}
+        self.bu_updates = {g: np.zeros_like(self.bu[g]) for g in self.GATES}
+        self.delta = np.zeros((batch_total, outputs), f32)
+        self.dc = np.zeros((self.batch, outputs), f32)
 
     def _connected(self, x, w, b, n_in):
         out = np.zeros((self.batch, self.outputs), f32)
@@ -260,6 +270,8 @@ class RefLSTM:
             for g in self.GATES:
                 wo = self._connected(self.h, self.w[g], self.bw[g], self.outputs)
                 uo = self._connected(xt, self.u[g], self.bu[g], self.inputs)
+                self.wout[g][t * B:(t + 1) * B] = wo
+                self.uout[g][t * B:(t + 1) * B] = uo
                 gate[g] = (wo + uo).astype(f32)  # addvv
                 orc.activate_array(gate[g], A["TANH"] if g == "g" else A["LOGISTIC"])
             temp = (gate["i"] * gate["g"]).astype(f32)           # mulvv
@@ -270,7 +282,87 @@ class RefLSTM:
             self.h = (self.h * gate["o"]).astype(f32)
             self.cell[t * B:(t + 1) * B] = self.c
             self.output[t * B:(t + 1) * B] = self.h
+        self.input = x
         return self.output
+
+    def _connected_backward(self, d, inp, w, w_updates, b_updates, upstream, n_in):
+        """TConnectedLayer.backward (nconnectedlayer.pas:244-322) of one linear sub-layer at one step: clamp, bias
+        sums, weight_updates += d^T inp, upstream += d W."""
+        orc.clamp(d, -1.0, 1.0)
+        orc.add_sums(b_updates, d, self.batch)
+        orc.sgemm(True, False, self.outputs, n_in, self.batch, 1.0, d, self.outputs, inp, n_in, 1.0, w_updates, n_in)
+        if upstream is not None:
+            orc.sgemm(False, False, self.batch, n_in, self.outputs, 1.0, d, self.outputs, w, n_in, 1.0, upstream, n_in)
+
+    def backward(self, upstream_delta=None, stale_first_step=True):
+        """TLSTMLayer.backward (source/nlstmlayer.pas:621-841): back-propagation through time, last step first.  self.delta
+        holds dL/dh of every step on entry; the hidden-side sub-layers add W^T d into the PREVIOUS step's delta, the
+        input-side ones into `upstream_delta` rows of the step.
+
+        stale_first_step=True restates the reference literally: prevCell / prevState are only refreshed `if i <> 0`
+        (:664-669), so at step 0 they still hold what the step-1 iteration copied — cell[0] and output[0] — not the
+        state before the sequence.  (darknet's backward_lstm_layer has the same behaviour.)  False gives the textbook
+        recurrence (zeros before the sequence), which tests check against finite differences."""
+        A = orc.ACT
+        B, H = self.batch, self.outputs
+        x = self.input
+        up = None if upstream_delta is None else upstream_delta.reshape(self.steps * B, self.inputs)
+        for t in range(self.steps - 1, -1, -1):
+            sl = slice(t * B, (t + 1) * B)
+            if t:
+                prev_cell, prev_state = self.cell[(t - 1) * B:t * B].copy(), self.output[(t - 1) * B:t * B].copy()
+            elif stale_first_step and self.steps > 1:
+                prev_cell, prev_state = self.cell[0:B].copy(), self.output[0:B].copy()   # left over from the t = 1 pass
+            else:
+                prev_cell, prev_state = np.zeros((B, H), f32), np.zeros((B, H), f32)      # fresh tensors are zero
+            c = self.cell[sl].copy()
+            gate = {}
+            for g in self.GATES:
+                gate[g] = (self.wout[g][sl] + self.uout[g][sl]).astype(f32)
+                orc.activate_array(gate[g], A["TANH"] if g == "g" else A["LOGISTIC"])
+            temp3 = self.delta[sl].copy()
+            temp = c.copy()
+            orc.activate_array(temp, A["TANH"])
+            temp2 = (temp3 * gate["o"]).astype(f32)
+            orc.gradient_array(temp, A["TANH"], temp2)
+            temp2 = (temp2 + self.dc).astype(f32)
+            temp = c.copy()
+            orc.activate_array(temp, A["TANH"])
+            temp = (temp * temp3).astype(f32)
+            orc.gradient_array(gate["o"], A["LOGISTIC"], temp)
+            dh = self.delta[(t - 1) * B:t * B] if t else None
+            xt = np.ascontiguousarray(x[sl])
+            upt = None if up is None else up[sl]
+
+            def both(g, d):
+                dw = d.copy()
+                self._connected_backward(dw, prev_state, self.w[g], self.w_updates[g], self.bw_updates[g], dh, H)
+                du = d.copy()
+                self._connected_backward(du, xt, self.u[g], self.u_updates[g], self.bu_updates[g], upt, self.inputs)
+
+            both("o", temp)
+            temp = (temp2 * gate["i"]).astype(f32)
+            orc.gradient_array(gate["g"], A["TANH"], temp)
+            both("g", temp)
+            temp = (temp2 * gate["g"]).astype(f32)
+            orc.gradient_array(gate["i"], A["LOGISTIC"], temp)
+            both("i", temp)
+            temp = (temp2 * prev_cell).astype(f32)
+            orc.gradient_array(gate["f"], A["LOGISTIC"], temp)
+            both("f", temp)
+            self.dc = (temp2 * gate["f"]).astype(f32)
+
+    def update(self, learning_rate, momentum, decay, batch):
+        """TLSTMLayer.update (nlstmlayer.pas:843-861): the eight sub-layers' TConnectedLayer.update (nconnectedlayer.pas:324-359)."""
+        lr_b = f32(f32(learning_rate) / f32(batch))
+        for g in self.GATES:
+            for w, wu, b, bu in ((self.w[g], self.w_updates[g], self.bw[g], self.bw_updates[g]),
+                                 (self.u[g], self.u_updates[g], self.bu[g], self.bu_updates[g])):
+                orc.axpy(lr_b, bu, b)
+                orc.scal(momentum, bu)
+                orc.axpy(f32(f32(-decay) * f32(batch)), w, wu)
+                orc.axpy(lr_b, wu, w)
+                orc.scal(momentum, wu)
 
 
 def lstm_params(inputs, outputs, seed=0):

@@ -56,6 +56,7 @@ SIGNATURES = {
     "tnn_counter_add": (i32, [ctxp, vp, C.c_uint64]),
     "tnn_forward_dropout_dev": (i32, [ctxp, i64, fptr, f32, f32, fptr, fptr, vp, C.c_uint64]),
     "tnn_lstm_gates": (i32, [ctxp, i64, i64, fptr, fptr, fptr, i64, fptr, fptr, fptr, fptr, i64]),
+    "tnn_lstm_gates_backward": (i32, [ctxp, i64, i64, fptr, fptr, fptr, i64, fptr, i64, i64, fptr, i64, fptr, fptr, i64]),
     "tnn_host_alloc": (i32, [ctxp, i64, C.POINTER(vp)]),
     "tnn_host_free": (i32, [ctxp, vp]),
     "tnn_activate_array": (i32, [ctxp, i64, fptr, i64, i32]),

@@ -845,7 +845,8 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   const int64_t K = (int64_t)kk * CB * 32;
   // 3xTF32 stages carry four fp32 tiles: half-depth (16-channel) stages keep four of them in flight
   // (bf16 stages are half the bytes per channel: 32-channel stages measured 13.5 vs 15.3 ms over the YOLOv3 layers)
-  const int KB = split ? (ctx->nhwc_kb ? ctx->nhwc_kb : (bf ? 32 : 16)) : 32;
+  // a layer with at most 16 channels (the image layer) moves half the zero padding per tap with 16-channel stages
+  const int KB = split ? (ctx->nhwc_kb ? ctx->nhwc_kb : ((bf && g.C > 16) ? 32 : 16)) : 32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
   // half-width tail tiles: the TMA store writes whole 32-filter boxes, so a half tile must be a multiple of 32 wide
   // CTA pairs (cta_group::2) halve the weight traffic through shared memory — the bound of the single-CTA kernel.

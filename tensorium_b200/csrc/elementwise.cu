@@ -494,6 +494,64 @@ int32_t tnn_lstm_gates(tnn_context *ctx, int64_t batch, int64_t hidden, const fl
   return 0;
 }
 
+// ---- LSTM step, backward (TLSTMLayer.backward, nlstmlayer.pas:661-812: per step 4 addvv + 6 activate + 7 mulvv +
+// 5 gradient_array + add + 10 copies, then the eight sub-layers' delta.Clamp(-1,1) nconnectedlayer.pas:262) in ONE
+// launch.  Gate pre-activations are re-formed as in the forward kernel; per element, in the reference's order:
+//   t2 = dh*o ; t2 *= tanh'(tanh c) ; t2 += dc                 (dL/dc of this step)
+//   d_o = tanh(c)*dh * o(1-o) ; d_g = t2*i * (1-g^2) ; d_i = t2*g * i(1-i) ; d_f = t2*c_prev * f(1-f) ; dc = t2*f
+// dz[b][gate*hidden + j] (gate order f|i|g|o) receives the four pre-activation deltas clamped to [-1, 1].
+__global__ void k_lstm_gates_backward(int64_t n, int hidden, const float *__restrict__ wz, const float *__restrict__ bw,
+                                      const float *__restrict__ uz, const float *__restrict__ cell,
+                                      const float *__restrict__ prev_cell, const float *__restrict__ dh,
+                                      float *__restrict__ dc, float *__restrict__ dz) {
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += nthreads) {
+    const int64_t b = e / hidden;
+    const int j = (int)(e - b * hidden);
+    const int64_t row = b * 4 * hidden;
+    float z[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int64_t k = row + (int64_t)g * hidden + j;
+      z[g] = __fadd_rn(__fadd_rn(wz[k], __ldg(bw + g * hidden + j)), uz[k]);
+    }
+    const float f = tnn_act(z[0], TNN_ACT_LOGISTIC), i = tnn_act(z[1], TNN_ACT_LOGISTIC);
+    const float g = tnn_act(z[2], TNN_ACT_TANH), o = tnn_act(z[3], TNN_ACT_LOGISTIC);
+    const float t3 = dh[e];
+    const float th = tnn_act(cell[e], TNN_ACT_TANH);
+    float t2 = __fmul_rn(t3, o);
+    t2 = __fmul_rn(t2, tnn_grad(th, TNN_ACT_TANH));
+    t2 = __fadd_rn(t2, dc[e]);
+    const float d_o = __fmul_rn(__fmul_rn(th, t3), tnn_grad(o, TNN_ACT_LOGISTIC));
+    const float d_g = __fmul_rn(__fmul_rn(t2, i), tnn_grad(g, TNN_ACT_TANH));
+    const float d_i = __fmul_rn(__fmul_rn(t2, g), tnn_grad(i, TNN_ACT_LOGISTIC));
+    const float cp = prev_cell ? prev_cell[e] : 0.0f;
+    const float d_f = __fmul_rn(__fmul_rn(t2, cp), tnn_grad(f, TNN_ACT_LOGISTIC));
+    dc[e] = __fmul_rn(t2, f);
+    auto clamp1 = [](float v) { return fminf(fmaxf(v, -1.0f), 1.0f); };
+    dz[row + j] = clamp1(d_f);
+    dz[row + hidden + j] = clamp1(d_i);
+    dz[row + 2 * (int64_t)hidden + j] = clamp1(d_g);
+    dz[row + 3 * (int64_t)hidden + j] = clamp1(d_o);
+  }
+}
+
+int32_t tnn_lstm_gates_backward(tnn_context *ctx, int64_t batch, int64_t hidden, const float *wz, const float *bw,
+                                const float *uz, int64_t zOffset, const float *cell, int64_t cellOffset,
+                                int64_t prevCellOffset, const float *dh, int64_t dhOffset, float *dc, float *dz,
+                                int64_t dzOffset) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(wz && bw && uz && cell && dh && dc && dz, "null pointer");
+  const int64_t n = batch * hidden;
+  if (n <= 0) return 0;
+  TNN_REQUIRE(hidden < (1ll << 29), "hidden size too large");
+  k_lstm_gates_backward<<<grid_for(n, kThreads), kThreads, 0, ctx->stream>>>(
+      n, (int)hidden, wz + zOffset, bw, uz + zOffset, cell + cellOffset, prevCellOffset >= 0 ? cell + prevCellOffset : nullptr,
+      dh + dhOffset, dc, dz + dzOffset);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
 // ---- fused SGD update (nConvolutionLayer.pas:1309-1322: 3 launches -> 1; 16 B/param) -----------------
 int32_t tnn_sgd_update(tnn_context *ctx, int64_t N, float *params, float *updates, float rate, float momentum,
                        float decay_term) {

@@ -480,3 +480,9 @@ class TNNCuda:
             self._h, comm, globalBatch, batch, channels, blockSize, _addr(out), int(activation), _addr(delta), _addr(x),
             _addr(x_norm), _addr(mean), _addr(variance), _addr(scales), _addr(scale_updates), _addr(mean_delta),
             _addr(variance_delta)))
+
+    def lstmGatesBackward(self, batch, hidden, wz, bw, uz, zOffset, cell, cellOffset, prevCellOffset, dh, dhOffset, dc,
+                          dz, dzOffset):
+        self._ck(self._l.tnn_lstm_gates_backward(self._h, batch, hidden, _addr(wz), _addr(bw), _addr(uz), zOffset,
+                                                 _addr(cell), cellOffset, prevCellOffset, _addr(dh), dhOffset, _addr(dc),
+                                                 _addr(dz), dzOffset))

@@ -292,3 +292,36 @@ def test_native_nccl_entry_points_single_rank(cuda_backend):
         cu.destroyGraph(g)
     finally:
         cu.commDestroy(comm)
+
+
+@pytest.mark.parametrize("blockSize,act", [(49, 1), (1, 4)])
+def test_syncbn_entry_points_match_the_fused_single_device_ones(cuda_backend, blockSize, act):
+    """tnn_batchnorm_forward_training_sync / _backward_sync with no communicator (one replica) compute the reference's
+    two-pass statistics over the whole batch — the same numbers as the fused single-device entry points (whose
+    one-pass shifted formula finishes in double) to rounding; the multi-replica exchange itself is exercised by
+    tools/syncbn_check.py under torchrun (profiles/r02_syncbn_check.json)."""
+    cu = cuda_backend
+    rng = np.random.default_rng(3)
+    B, C = 16, 12
+    shape = (B, C, blockSize)
+    y = rng.normal(0.3, 1.2, shape).astype(np.float32)
+    scales, biases = rng.uniform(0.5, 1.5, C).astype(np.float32), rng.uniform(-0.3, 0.3, C).astype(np.float32)
+    delta = rng.uniform(-1, 1, shape).astype(np.float32)
+    outs = []
+    for sync in (False, True):
+        d = {k: Dev(cu, v) for k, v in dict(out=y, x=np.zeros(shape), xn=np.zeros(shape), mean=np.zeros(C), var=np.zeros(C),
+                                            rm=np.full(C, 0.1), rv=np.full(C, 0.9), sc=scales, bi=biases, delta=delta,
+                                            su=np.zeros(C), md=np.zeros(C), vd=np.zeros(C)).items()}
+        if sync:
+            cu.batchNormForwardTrainingSync(None, B, B, C, blockSize, d["out"].ptr, d["x"].ptr, d["xn"].ptr, d["mean"].ptr,
+                                            d["var"].ptr, d["rm"].ptr, d["rv"].ptr, 0.1, d["sc"].ptr, d["bi"].ptr, act)
+            cu.batchNormBackwardSync(None, B, B, C, blockSize, d["out"].ptr, act, d["delta"].ptr, d["x"].ptr, d["xn"].ptr,
+                                     d["mean"].ptr, d["var"].ptr, d["sc"].ptr, d["su"].ptr, d["md"].ptr, d["vd"].ptr)
+        else:
+            cu.batchNormForwardTraining(B, C, blockSize, d["out"].ptr, d["x"].ptr, d["xn"].ptr, d["mean"].ptr, d["var"].ptr,
+                                        d["rm"].ptr, d["rv"].ptr, 0.1, d["sc"].ptr, d["bi"].ptr, act)
+            cu.batchNormBackward(B, C, blockSize, d["out"].ptr, act, d["delta"].ptr, d["x"].ptr, d["xn"].ptr, d["mean"].ptr,
+                                 d["var"].ptr, d["sc"].ptr, d["su"].ptr, d["md"].ptr, d["vd"].ptr)
+        outs.append({k: d[k].read() for k in ("out", "x", "xn", "mean", "var", "rm", "rv", "delta", "su")})
+    for k in outs[0]:
+        assert rel_max(outs[1][k], outs[0][k]) < 5e-6, k

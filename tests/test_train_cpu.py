@@ -193,3 +193,55 @@ def test_oracle_lstm_matches_float64_formula(oracle):
         h = np.tanh(c) * sig(z["o"])
         want[t * B:(t + 1) * B] = h
     assert np.abs(got - want).max() <= 2e-6
+
+
+def test_oracle_lstm_backward_matches_finite_differences(oracle):
+    """RefLSTM.backward (nlstmlayer.pas:621-841 restated sub-layer by sub-layer) with the textbook initial state
+    (stale_first_step=False) against central differences of the float64 recurrence; the reference-literal variant
+    differs from it only through step 0's stale prevCell / prevState."""
+    from oracle import ref_train as rt
+    steps, B, n_in, H = 3, 2, 4, 5
+    P = rt.lstm_params(n_in, H, seed=4)
+    rng = np.random.default_rng(1)
+    x = rng.uniform(-1, 1, (steps * B, n_in)).astype(np.float32)
+    gout = rng.uniform(-0.5, 0.5, (steps * B, H)).astype(np.float32)
+
+    def loss(P64, x64):
+        sig = lambda v: 1 / (1 + np.exp(-v))
+        h = np.zeros((B, H)); c = np.zeros((B, H)); L = 0.0
+        for t in range(steps):
+            xt = x64[t * B:(t + 1) * B]
+            z = {g: h @ P64["w" + g]["w"].T + P64["w" + g]["b"] + xt @ P64["u" + g]["w"].T + P64["u" + g]["b"] for g in "figo"}
+            c = c * sig(z["f"]) + sig(z["i"]) * np.tanh(z["g"])
+            h = np.tanh(c) * sig(z["o"])
+            L += (gout[t * B:(t + 1) * B].astype(np.float64) * h).sum()
+        return L
+    P64 = {k: {kk: vv.astype(np.float64) for kk, vv in v.items()} for k, v in P.items()}
+    net = rt.RefLSTM(steps * B, n_in, H, steps, P)
+    net.forward(x)
+    net.delta[...] = gout
+    up = np.zeros((steps * B, n_in), np.float32)
+    net.backward(up, stale_first_step=False)
+    eps = 1e-5
+    for kind, upd, bupd in (("w", net.w_updates, net.bw_updates), ("u", net.u_updates, net.bu_updates)):
+        for g in "figo":
+            for field, got, idx in (("w", upd[g], (1, 2)), ("b", bupd[g], (3,))):
+                Pp = {k: {kk: vv.copy() for kk, vv in v.items()} for k, v in P64.items()}
+                Pp[kind + g][field][idx] += eps
+                a = loss(Pp, x.astype(np.float64))
+                Pp[kind + g][field][idx] -= 2 * eps
+                b = loss(Pp, x.astype(np.float64))
+                assert abs(float(got[idx]) - (a - b) / (2 * eps)) < 2e-6, (kind, g, field)
+    x64 = x.astype(np.float64)
+    for idx in ((0, 1), (3, 2), (5, 0)):
+        xp = x64.copy(); xp[idx] += eps; a = loss(P64, xp)
+        xp[idx] -= 2 * eps; b = loss(P64, xp)
+        assert abs(float(up[idx]) - (a - b) / (2 * eps)) < 2e-6
+    # the literal restatement: only the hidden-side updates see step 0's stale prevState / prevCell
+    net2 = rt.RefLSTM(steps * B, n_in, H, steps, P)
+    net2.forward(x)
+    net2.delta[...] = gout
+    up2 = np.zeros_like(up)
+    net2.backward(up2)
+    assert all(np.allclose(net2.u_updates[g], net.u_updates[g], atol=1e-6) for g in "igo")
+    assert any(not np.allclose(net2.w_updates[g], net.w_updates[g], atol=1e-6) for g in "figo")

@@ -1,5 +1,6 @@
 """Run single conv configurations through tnn_conv2d_forward (for ncu / timing).  usage: conv_one.py [math] [cfg ...]
-cfg = B,C,H,F,k,s"""
+cfg = B,C,H,F,k,s      TNN_NHWC=1: the channels-innermost entry point (tnn_conv2d_forward_nhwc; random data, so the planar
+input buffer is simply read as rows of channels)"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -7,7 +8,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from tensorium_b200 import tensor
 from util import Dev
 
-MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16x3": 3}
+NHWC = os.environ.get("TNN_NHWC", "0") == "1"
 math = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
 cfgs = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]] or [(64, 256, 26, 512, 3, 1)]
 cu = tensor.initCUDART(0)
@@ -21,17 +23,21 @@ for (B, C, H, F, k, s) in cfgs:
     b = np.zeros(F, np.float32)
     dx, dw, db, do = Dev(cu, x), Dev(cu, w), Dev(cu, b), Dev(cu, n=B * F * oh * oh)
     desc = cu.conv_desc(B, C, H, H, F, k, k, p, p, s, s)
+    if NHWC:
+        run = lambda: cu.conv2dForwardNhwc(desc, dx.ptr, 0, C, 1, dw.ptr, None, db.ptr, 9, do.ptr, 0, F, 1)
+    else:
+        run = lambda: cu.conv2dForward(desc, dx.ptr, 0, dw.ptr, None, db.ptr, 9, do.ptr, 0)
     for _ in range(2):
-        cu.conv2dForward(desc, dx.ptr, 0, dw.ptr, None, db.ptr, 9, do.ptr, 0)
+        run()
     cu.finish()
     t0 = time.perf_counter()
     n = 5
     for _ in range(n):
-        cu.conv2dForward(desc, dx.ptr, 0, dw.ptr, None, db.ptr, 9, do.ptr, 0)
+        run()
     cu.finish()
     dt = (time.perf_counter() - t0) / n
     fl = 2.0 * B * F * oh * oh * C * k * k
-    print(f"B{B} C{C} H{H} F{F} k{k} s{s}: {dt*1e3:.3f} ms  {fl/dt/1e12:.1f} TFLOP/s ({math})", flush=True)
+    print(f"B{B} C{C} H{H} F{F} k{k} s{s}: {dt*1e3:.3f} ms  {fl/dt/1e12:.1f} TFLOP/s ({math}, {cu.lastConvKernel()})", flush=True)
     if os.environ.get("TNN_BWD"):
         dd, dwu, ddx = Dev(cu, rng.uniform(-1, 1, (B, F, oh, oh)).astype(np.float32)), Dev(cu, n=w.size), Dev(cu, n=x.size)
         for name, fn in (("wgrad", lambda: cu.conv2dBackwardFilter(desc, dx.ptr, 0, dd.ptr, 0, dwu.ptr)),
