@@ -252,7 +252,10 @@ def run_ours(args, rank, world, local_rank):
     cu = tensor.initCUDART(local_rank)  # raises if libtensorium_b200.so / a B200 is missing: no fallback
     cu.set_stream(stream.cuda_stream)
     cu.set_math_mode(MATH[args.math])
-    net = build_yolov3(BATCH, SIZE, seed=1234, channels_last=args.layout == "nhwc")
+    # channels-innermost graph: the 23 shortcut adds are folded into the preceding convolution's epilogue
+    # (tnn_conv2d_forward_nhwc_residual; bit-identical to the separate layers, tests/test_gpu_yolo.py)
+    net = build_yolov3(BATCH, SIZE, seed=1234, channels_last=args.layout == "nhwc",
+                       fuse_shortcuts=args.layout == "nhwc" and not args.no_fuse)
     # shortcut fusion into the conv epilogue: "" (off, default), "gather" or "all".  Measured (B200, batch 64): 27.7 ms
     # un-fused, 28.0 ms with the MMA-bound gathering layers fused, 28.9 ms with all 23 fused — the residual read in
     # the four epilogue warps costs what the separate add kernels cost, so it stays off.
@@ -326,7 +329,7 @@ def run_ours(args, rank, world, local_rank):
         cu_copy.finish()
 
     step_resident()  # first pass: every conv layer learns which kernel it dispatches to
-    if FUSE:
+    if FUSE and args.layout != "nhwc":
         nf = net.fuseShortcuts(None if FUSE == "all" else (FUSE,))
     for _ in range(max(args.warmup, 3)):
         step_resident()
@@ -461,7 +464,9 @@ def run_ours(args, rank, world, local_rank):
             "data": "synthetic",
             "config": {"workload": f"YOLOv3-{SIZE} inference, 107 layers (75 conv), BN folded, random-init weights",
                        "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": SIZE,
-                       "math": args.math, "layout": args.layout, "parallelism": f"batch-sharded x{world}, no collective",
+                       "math": args.math, "layout": args.layout,
+                       "shortcuts_fused_into_conv": sum(bool(getattr(l, "_fused_into_conv", False)) for l in net.layers),
+                       "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "activations streamed per step = 14.6 GB per GPU, far larger than the 126 MB L2 (no flush needed)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes_in,
                     "d2h_bytes_per_step": nbytes_out, "ms_per_step": ms_e2e / args.steps},
@@ -508,6 +513,7 @@ def main():
     ap.add_argument("--no-secondary", action="store_true", help="skip the modes / cifar10_train / roofline_membound objects")
     ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"],
                     help="internal activation layout of the graph: channels-innermost (TMA im2col kernels) or planar")
+    ap.add_argument("--no-fuse", action="store_true", help="keep the shortcut adds as separate kernels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-images", type=int, default=2)
     ap.add_argument("--layers-out", default="", help="write the per-conv-layer timing table (JSON) here")

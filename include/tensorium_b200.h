@@ -385,6 +385,15 @@ TNN_API int32_t tnn_conv2d_forward_nhwc(tnn_context *ctx, const tnn_conv_desc *d
                                         int64_t inPitch, int32_t inLayout, const float *weights, const float *scale,
                                         const float *bias, int32_t activation, float *out, int64_t outOffset,
                                         int64_t outPitch, int32_t outLayout);
+/* The same with the following shortcut layer folded in (TAddLayer.forwardGPU naddlayer.pas:885-910, linear activation):
+ *   out = act( conv(in, weights) * scale[f] + bias[f] ) + residual,   residual rows of residualPitch floats
+ * (channels-innermost in and out; filters a multiple of 4).  The add kernel and one round trip of the tensor through
+ * HBM disappear; the arithmetic is the separate layers' (one fp32 add after the activation). */
+TNN_API int32_t tnn_conv2d_forward_nhwc_residual(tnn_context *ctx, const tnn_conv_desc *d, const float *in,
+                                                 int64_t inOffset, int64_t inPitch, int32_t inLayout, const float *weights,
+                                                 const float *scale, const float *bias, int32_t activation,
+                                                 const float *residual, int64_t residualOffset, int64_t residualPitch,
+                                                 float *out, int64_t outOffset, int64_t outPitch, int32_t outLayout);
 /* [batch][channels][blockSize] -> [batch][blockSize][outPitch] and back */
 TNN_API int32_t tnn_nchw_to_nhwc(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize, const float *in,
                                  float *out, int64_t outPitch);

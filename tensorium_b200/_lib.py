@@ -118,6 +118,8 @@ SIGNATURES = {
     "tnn_concat_channels": (i32, [ctxp, i64, i64, i64, fptr, i64, i64, fptr]),
     "tnn_conv2d_forward_nhwc": (i32, [ctxp, C.POINTER(ConvDesc), fptr, i64, i64, i32, fptr, fptr, fptr, i32, fptr, i64,
                                       i64, i32]),
+    "tnn_conv2d_forward_nhwc_residual": (i32, [ctxp, C.POINTER(ConvDesc), fptr, i64, i64, i32, fptr, fptr, fptr, i32, fptr,
+                                               i64, i64, fptr, i64, i64, i32]),
     "tnn_nchw_to_nhwc": (i32, [ctxp, i64, i64, i64, fptr, fptr, i64]),
     "tnn_nhwc_to_nchw": (i32, [ctxp, i64, i64, i64, fptr, i64, fptr]),
     "tnn_rows_copy": (i32, [ctxp, i64, i64, fptr, i64, fptr, i64]),

@@ -121,6 +121,10 @@ struct NhwcEpilogue {
   const float *scale, *bias;
   int act;
   int64_t rows, cols;  // M, F
+  // optional: the shortcut layer that follows (TAddLayer.forwardGPU naddlayer.pas:885-910, linear activation):
+  // value + residual[row][filter], rows of `resPitch` floats — one fp32 add after the activation, like the separate layer
+  const float *residual;
+  int64_t resPitch;
 };
 // NCHW planes (head layers): the epilogue of the NCHW kernels
 struct NchwEpilogue : ConvEpilogueT<false> {
@@ -204,6 +208,17 @@ __device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int 
       if (cnt > 32) cnt = 32;
       if (cnt <= 0 || row0 >= epi.rows) continue;
       const int64_t n = n0 + c0;
+      // the shortcut's other operand: this thread's 32 consecutive filters of its pixel row, fetched before the staging
+      // wait so that the loads are in flight while the scale / bias scratch is filled
+      float4 res[8];
+      const bool addRes = epi.residual != nullptr;
+      if (addRes) {
+        const int64_t row = (int64_t)row0 + lane;
+        const float4 *rq = reinterpret_cast<const float4 *>(epi.residual + (row < epi.rows ? row : 0) * epi.resPitch + n);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          res[j] = (row < epi.rows && 4 * j < cnt) ? __ldg(rq + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
       __syncwarp();
       scratch[lane] = (epi.scale && lane < cnt) ? __ldg(epi.scale + n + lane) : 1.0f;
       scratch[32 + lane] = (epi.bias && lane < cnt) ? __ldg(epi.bias + n + lane) : 0.0f;
@@ -221,6 +236,10 @@ __device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int 
         for (int u = 0; u < 4; ++u) {
           const float v = __fadd_rn(__fmul_rn(__uint_as_float(r[j4 + u]), s[u]), b[u]);
           o[u] = simple ? fmaxf(v, __fmul_rn(neg, v)) : act_out_of_line(v, epi.act);
+        }
+        if (addRes) {
+          const float4 rr = res[j4 >> 2];
+          o[0] = __fadd_rn(o[0], rr.x); o[1] = __fadd_rn(o[1], rr.y); o[2] = __fadd_rn(o[2], rr.z); o[3] = __fadd_rn(o[3], rr.w);
         }
         // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) — conflict-free and what the TMA store expects
         *reinterpret_cast<float4 *>(rowp + ((((j4 >> 2) ^ (lane & 7))) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
@@ -830,7 +849,7 @@ static int launch_nhwc_pair(tnn_context *ctx, int grid, size_t smemBytes, int mT
 
 static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, int64_t inPitch,
                         const float *weights, const float *scale, const float *bias, int act, float *out,
-                        int64_t outPitch, bool outNchw) {
+                        int64_t outPitch, bool outNchw, const float *residual = nullptr, int64_t resPitch = 0) {
   const int kk = g.kh * g.kw;
   TNN_REQUIRE((inPitch % 4) == 0 && inPitch >= g.C && (((uintptr_t)in) & 15) == 0,
               "NHWC input needs a pixel pitch that is a multiple of 4 floats and a 16-byte aligned base");
@@ -920,7 +939,10 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
               "NHWC output needs a pixel pitch that is a multiple of 4 floats and a 16-byte aligned base");
   rc = encode_out_map(&tmOut, out, M, N, outPitch);
   if (rc) return rc;
-  NhwcEpilogue epi{scale, bias, act, M, N};
+  if (residual)
+    TNN_REQUIRE((resPitch % 4) == 0 && resPitch >= N && (N % 4) == 0 && (((uintptr_t)residual) & 15) == 0,
+                "the residual needs 16-byte aligned rows and a filter count that is a multiple of 4");
+  NhwcEpilogue epi{scale, bias, act, M, N, residual, resPitch};
   return go(epi);
 }
 
@@ -1041,6 +1063,15 @@ int32_t tnn_conv2d_forward_nhwc(tnn_context *ctx, const tnn_conv_desc *d, const 
                                 int64_t inPitch, int32_t inLayout, const float *weights, const float *scale,
                                 const float *bias, int32_t activation, float *out, int64_t outOffset, int64_t outPitch,
                                 int32_t outLayout) {
+  return tnn_conv2d_forward_nhwc_residual(ctx, d, in, inOffset, inPitch, inLayout, weights, scale, bias, activation,
+                                          nullptr, 0, 0, out, outOffset, outPitch, outLayout);
+}
+
+int32_t tnn_conv2d_forward_nhwc_residual(tnn_context *ctx, const tnn_conv_desc *d, const float *in, int64_t inOffset,
+                                         int64_t inPitch, int32_t inLayout, const float *weights, const float *scale,
+                                         const float *bias, int32_t activation, const float *residual,
+                                         int64_t residualOffset, int64_t residualPitch, float *out, int64_t outOffset,
+                                         int64_t outPitch, int32_t outLayout) {
   TNN_CHECK_CTX(ctx);
   simt::ConvGeom g;
   int rc = fill_geom_nhwc(d, g);
@@ -1051,6 +1082,10 @@ int32_t tnn_conv2d_forward_nhwc(tnn_context *ctx, const tnn_conv_desc *d, const 
   TNN_REQUIRE(ctx->math_mode != TNN_MATH_FP32, "the channels-innermost path runs on the tensor cores (3xTF32 / TF32 mode)");
   in += inOffset;
   out += outOffset;
+  if (residual) {
+    residual += residualOffset;
+    TNN_REQUIRE(inLayout == TNN_LAYOUT_NHWC && outLayout == TNN_LAYOUT_NHWC, "the residual add is fused for channels-innermost tensors");
+  }
   if (inLayout == TNN_LAYOUT_NCHW) {
     // planar input (the image fed to the first layer): direct fp32 convolution writing channels-innermost rows
     TNN_REQUIRE(outLayout == TNN_LAYOUT_NHWC && direct::supported(g),
@@ -1060,7 +1095,7 @@ int32_t tnn_conv2d_forward_nhwc(tnn_context *ctx, const tnn_conv_desc *d, const 
   }
   ctx->last_conv_kernel = 7;
   return nhwc::conv_forward(ctx, g, (int)d->batch, in, inPitch, weights, scale, bias, activation, out, outPitch,
-                            outLayout == TNN_LAYOUT_NCHW);
+                            outLayout == TNN_LAYOUT_NCHW, residual, residualPitch);
 }
 
 int32_t tnn_nchw_to_nhwc(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize, const float *in,

@@ -174,6 +174,14 @@ class TConvolutionalLayer:
                     self._in_nhwc.pitch = pitch
                 cu.nchwToNhwc(self.batch, self.c, self.h * self.w, src.devData, self._in_nhwc.devData, self._in_nhwc.pitch)
                 src, in_layout, in_pitch = self._in_nhwc, NHWC, self._in_nhwc.pitch
+            if self._residual is not None and in_layout == NHWC and self.out_layout == NHWC:
+                # the shortcut that follows, folded into the epilogue (TNNet.fuseShortcuts): writes the shortcut's output
+                self._fused_out.setCUDA()
+                cu.conv2dForwardNhwcResidual(self._desc, src.devData, 0, in_pitch, in_layout, self.weights.devData,
+                                             sc.devData if sc is not None else None, bi.devData, self.ActivationType,
+                                             self._residual.devData, 0, getattr(self._residual, "pitch", 0) or self.filters,
+                                             self._fused_out.devData, 0, self.filters, self.out_layout)
+                return
             cu.conv2dForwardNhwc(self._desc, src.devData, 0, in_pitch, in_layout, self.weights.devData,
                                  sc.devData if sc is not None else None, bi.devData, self.ActivationType,
                                  self.output.devData, 0, self.out_pitch or self.filters, self.out_layout)

@@ -422,6 +422,13 @@ class TNNCuda:
                                                  _addr(weights), _addr(scale), _addr(bias), int(activation),
                                                  _addr(out), outOffset, outPitch, int(outLayout)))
 
+    def conv2dForwardNhwcResidual(self, desc, in_, inOffset, inPitch, inLayout, weights, scale, bias, activation, residual,
+                                  residualOffset, residualPitch, out, outOffset, outPitch, outLayout):
+        self._ck(self._l.tnn_conv2d_forward_nhwc_residual(
+            self._h, C.byref(desc), _addr(in_), inOffset, inPitch, int(inLayout), _addr(weights), _addr(scale),
+            _addr(bias), int(activation), _addr(residual), residualOffset, residualPitch, _addr(out), outOffset, outPitch,
+            int(outLayout)))
+
     def nchwToNhwc(self, batch, channels, blockSize, in_, out, outPitch):
         self._ck(self._l.tnn_nchw_to_nhwc(self._h, batch, channels, blockSize, _addr(in_), _addr(out), outPitch))
 

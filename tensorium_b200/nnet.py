@@ -567,6 +567,6 @@ def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=12
     net = TNNet(layers, batch, 3, size, size)
     if channels_last:
         net.setChannelsLast()
-    elif fuse_shortcuts and fused:
+    if fuse_shortcuts and fused:
         net.fuseShortcuts()
     return net

@@ -179,8 +179,10 @@ def test_yolov3_416_bench_configuration(cuda_backend, oracle, math, tol):
         assert n2 > 0
 
 
-def test_shortcut_fusion_is_bit_identical(cuda_backend):
-    """tnn_conv2d_forward_residual: conv epilogue + the following shortcut's add == the two separate layers."""
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_shortcut_fusion_is_bit_identical(cuda_backend, channels_last):
+    """tnn_conv2d_forward_residual / tnn_conv2d_forward_nhwc_residual: conv epilogue + the following shortcut's add ==
+    the two separate layers, bit for bit (one fp32 add after the activation either way)."""
     from tensorium_b200.nnet import build_yolov3, init_yolov3_params, yolov3_spec
     cu = cuda_backend
     size, batch = 64, 2
@@ -188,12 +190,12 @@ def test_shortcut_fusion_is_bit_identical(cuda_backend):
     x = np.random.default_rng(2).random((batch, 3, size, size), dtype=np.float32)
     outs = []
     for fuse in (False, True):
-        net = build_yolov3(batch, size, params=params, fuse_shortcuts=fuse)
+        net = build_yolov3(batch, size, params=params, fuse_shortcuts=fuse, channels_last=channels_last)
         if fuse:
             assert sum(getattr(l, "_fused_into_conv", False) for l in net.layers) == 23
         cu.writeBuffer(net.input.devData, x.nbytes, x)
         net.predict()
-        outs.append([net.layers[i].output.pullFromDevice().copy() for i in (4, 36, 61, 74)] +
+        outs.append([net.output_nchw(i) for i in (4, 36, 61, 74)] +
                     [l.output.pullFromDevice().copy() for l in net.yolo_layers()])
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
