@@ -256,6 +256,10 @@ def run_ours(args, rank, world, local_rank):
     # (tnn_conv2d_forward_nhwc_residual; bit-identical to the separate layers, tests/test_gpu_yolo.py)
     net = build_yolov3(BATCH, SIZE, seed=1234, channels_last=args.layout == "nhwc",
                        fuse_shortcuts=args.layout == "nhwc" and not args.no_fuse)
+    # BF16x3: activations that only convolutions read stay as pre-split bf16 hi/lo planes (tnn_conv2d_forward_split) —
+    # the planes the kernel would otherwise derive in shared memory for every tap; same bits out
+    can_split = args.layout == "nhwc" and not args.no_fuse and not args.no_split
+    net.setSplitActivations(can_split and args.math == "bf16x3")
     # shortcut fusion into the conv epilogue: "" (off, default), "gather" or "all".  Measured (B200, batch 64): 27.7 ms
     # un-fused, 28.0 ms with the MMA-bound gathering layers fused, 28.9 ms with all 23 fused — the residual read in
     # the four epilogue warps costs what the separate add kernels cost, so it stays off.
@@ -420,12 +424,14 @@ def run_ours(args, rank, world, local_rank):
             if m == args.math:
                 continue
             cu.set_math_mode(MATH[m])
+            net.setSplitActivations(can_split and m == "bf16x3")
             for _ in range(3):
                 step_resident()
             ms_m = timed(step_resident, 5)
             modes[m] = {"images_per_s": aggregate_images_per_s(world, 5, ms_m), "ms_per_step": ms_m / 5, "steps": 5,
                         "gate": "5e-3" if m == "tf32" else "1e-4"}
         cu.set_math_mode(MATH[args.math])
+        net.setSplitActivations(can_split and args.math == "bf16x3")
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import cifar_train
         cu.set_math_mode(MATH["3xtf32"])   # the training kernels (wgrad, dgrad, connected layers) are the planar tf32 ones
@@ -465,6 +471,9 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"YOLOv3-{SIZE} inference, 107 layers (75 conv), BN folded, random-init weights",
                        "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": SIZE,
                        "math": args.math, "layout": args.layout,
+                       "activations": ("pre-split bf16 hi/lo planes between convolutions (4 B/element, the operands BF16x3 "
+                                       "multiplies); fp32 rows where a shortcut / yolo layer reads"
+                                       if getattr(net, "split_activations", False) else "fp32"),
                        "shortcuts_fused_into_conv": sum(bool(getattr(l, "_fused_into_conv", False)) for l in net.layers),
                        "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "activations streamed per step = 14.6 GB per GPU, far larger than the 126 MB L2 (no flush needed)"},
@@ -514,6 +523,7 @@ def main():
     ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"],
                     help="internal activation layout of the graph: channels-innermost (TMA im2col kernels) or planar")
     ap.add_argument("--no-fuse", action="store_true", help="keep the shortcut adds as separate kernels")
+    ap.add_argument("--no-split", action="store_true", help="bf16x3: fp32 activations between all layers (no pre-split planes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-images", type=int, default=2)
     ap.add_argument("--layers-out", default="", help="write the per-conv-layer timing table (JSON) here")

@@ -375,7 +375,7 @@ TNN_API int32_t tnn_concat_channels(tnn_context *ctx, int64_t batch, int64_t c, 
  * (pitch > C lets a layer write straight into its slice of a route/concat buffer), and convert at the graph edges:
  * the first layer reads the planar image, the head layers write planar outputs for the yolo layer / host decode.
  * Same arithmetic as tnn_conv2d_forward (same products, fp32 accumulation, scale/bias/activation epilogue). */
-typedef enum { TNN_LAYOUT_NCHW = 0, TNN_LAYOUT_NHWC = 1 } tnn_layout;
+typedef enum { TNN_LAYOUT_NCHW = 0, TNN_LAYOUT_NHWC = 1, TNN_LAYOUT_NHWC_SPLIT = 2 } tnn_layout;
 /* forwardGPU steps 2-5 (nConvolutionLayer.pas:1040-1122) on channels-innermost activations:
  *   out = act( conv(in, weights) * scale[f] + bias[f] ),  weights [filters][c*kh*kw] as always.
  * inLayout NHWC: inPitch a multiple of 4 floats, 16-byte aligned base (channels past c read as zero) — tcgen05 implicit GEMM, activations and
@@ -394,6 +394,28 @@ TNN_API int32_t tnn_conv2d_forward_nhwc_residual(tnn_context *ctx, const tnn_con
                                                  const float *scale, const float *bias, int32_t activation,
                                                  const float *residual, int64_t residualOffset, int64_t residualPitch,
                                                  float *out, int64_t outOffset, int64_t outPitch, int32_t outLayout);
+/* Pre-split activations (TNN_MATH_BF16X3).  The BF16x3 arithmetic multiplies bf16 halves of every fp32 operand,
+ *   hi = bf16_rn(x), lo = bf16_rn(x - hi)   (x = hi + lo to 2^-18 relative),
+ * which the kernel above derives from the fp32 tile inside shared memory for every kernel tap.  A graph may instead keep
+ * an INTERNAL activation as those two bf16 planes (TNN_LAYOUT_NHWC_SPLIT: rows of channels, `pitch` bf16 elements
+ * between pixels, the lo plane `plane` elements after the hi plane; 4 bytes per element like fp32): the producing
+ * layer's epilogue writes them (`outSplit`), the consuming convolution's TMA lands them directly in the tensor-core
+ * layout and nothing converts — the same products and the same fp32 accumulation as the fp32-input form, bit for bit.
+ * `out` (fp32 rows or planes) and `outSplit` may both be given (a tensor that is also a later shortcut's operand or a
+ * graph output); either may be NULL.  in: const float* for NCHW / NHWC, the hi plane for NHWC_SPLIT (inPitch, inPlane in
+ * bf16 elements, multiples of 8).  residual: fp32 rows as in tnn_conv2d_forward_nhwc_residual, or NULL. */
+TNN_API int32_t tnn_conv2d_forward_split(tnn_context *ctx, const tnn_conv_desc *d, const void *in, int64_t inOffset,
+                                         int64_t inPitch, int32_t inLayout, int64_t inPlane, const float *weights,
+                                         const float *scale, const float *bias, int32_t activation,
+                                         const float *residual, int64_t residualOffset, int64_t residualPitch,
+                                         float *out, int64_t outOffset, int64_t outPitch, int32_t outLayout,
+                                         void *outSplit, int64_t outSplitOffset, int64_t outSplitPitch,
+                                         int64_t outSplitPlane);
+/* fp32 rows of channels <-> the pre-split planes (the way back is hi + lo, exact in fp32); channels a multiple of 8 */
+TNN_API int32_t tnn_nhwc_to_split(tnn_context *ctx, int64_t rows, int64_t channels, const float *in, int64_t inPitch,
+                                  void *outSplit, int64_t outPitch, int64_t outPlane);
+TNN_API int32_t tnn_split_to_nhwc(tnn_context *ctx, int64_t rows, int64_t channels, const void *inSplit, int64_t inPitch,
+                                  int64_t inPlane, float *out, int64_t outPitch);
 /* [batch][channels][blockSize] -> [batch][blockSize][outPitch] and back */
 TNN_API int32_t tnn_nchw_to_nhwc(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize, const float *in,
                                  float *out, int64_t outPitch);

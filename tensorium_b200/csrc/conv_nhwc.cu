@@ -125,6 +125,9 @@ struct NhwcEpilogue {
   // value + residual[row][filter], rows of `resPitch` floats — one fp32 add after the activation, like the separate layer
   const float *residual;
   int64_t resPitch;
+  // what to write: fp32 rows (tmOut) and / or the pre-split bf16 planes the next convolution's TMA reads directly
+  // (tmOutHi / tmOutLo: hi = bf16_rn(v), lo = bf16_rn(v - hi) — the very split the converter warps would derive)
+  bool f32Out, splitOut;
 };
 // NCHW planes (head layers): the epilogue of the NCHW kernels
 struct NchwEpilogue : ConvEpilogueT<false> {
@@ -198,9 +201,14 @@ __device__ __forceinline__ void convert_stage(uint8_t *sa, int tid) {
 
 // epilogue of one tile for one warp (32 accumulator rows): TMEM -> scale/bias/activation -> TMA store (channels-innermost
 // rows) or per-plane stores (NCHW).  `release()` is called by lane 0 once the warp's last TMEM read has completed.
-template <typename EPI, typename RELEASE>
+struct StoreRows {   // the default store: 32 consecutive pixel rows of the 2-D {F, M} map
+  int row0;
+  __device__ __forceinline__ void operator()(const CUtensorMap *tm, uint32_t src, int n) const { tma_store_2d(tm, src, n, row0); }
+};
+template <typename EPI, typename RELEASE, typename STORE>
 __device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int bn, int64_t n0, int row0, float *scratch,
-                                           uint8_t *stg, int &sbuf, const CUtensorMap *tmOut, RELEASE release) {
+                                           uint8_t *stg, int &sbuf, const CUtensorMap *tmOut, const CUtensorMap *tmOutHi,
+                                           const CUtensorMap *tmOutLo, RELEASE release, STORE store) {
   const int lane = threadIdx.x & 31;
   const int nChunks = (bn + 31) >> 5;
   if constexpr (EPI::kTmaStore) {
@@ -234,32 +242,59 @@ __device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int 
       __syncwarp();
       scratch[lane] = (epi.scale && lane < cnt) ? __ldg(epi.scale + n + lane) : 1.0f;
       scratch[32 + lane] = (epi.bias && lane < cnt) ? __ldg(epi.bias + n + lane) : 0.0f;
-      if (lane == 0) bulk_wait_read<kStageBufs - 1>();  // the staging tile written two chunks ago has been read
+      // staging: fp32 rows take one 4 KB tile (SWIZZLE_128B), the two bf16 planes half a tile each (64-byte rows,
+      // SWIZZLE_64B).  One of the two -> the warp's two tiles alternate; both -> they are used together.
+      const bool both = epi.f32Out && epi.splitOut;
+      if (lane == 0) {
+        if (both) bulk_wait_read<0>();
+        else bulk_wait_read<kStageBufs - 1>();  // the staging tile written two chunks ago has been read
+      }
       __syncwarp();
-      uint8_t *tile = stg + sbuf * kStageTile;
+      uint8_t *tile = both ? stg : stg + sbuf * kStageTile;
+      uint8_t *tileHi = both ? stg + kStageTile : tile;
+      uint8_t *tileLo = tileHi + kStageTile / 2;
       uint8_t *rowp = tile + lane * 128;
 #pragma unroll
-      for (int j4 = 0; j4 < 32; j4 += 4) {
-        const float4 s4 = *reinterpret_cast<const float4 *>(scratch + j4);
-        const float4 b4 = *reinterpret_cast<const float4 *>(scratch + 32 + j4);
-        const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
-        float o[4];
+      for (int j8 = 0; j8 < 32; j8 += 8) {
+        float o[8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const float v = __fadd_rn(__fmul_rn(__uint_as_float(r[j4 + u]), s[u]), b[u]);
-          o[u] = simple ? fmaxf(v, __fmul_rn(neg, v)) : act_out_of_line(v, epi.act);
+        for (int h = 0; h < 2; ++h) {
+          const float4 s4 = *reinterpret_cast<const float4 *>(scratch + j8 + 4 * h);
+          const float4 b4 = *reinterpret_cast<const float4 *>(scratch + 32 + j8 + 4 * h);
+          const float s[4] = {s4.x, s4.y, s4.z, s4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float v = __fadd_rn(__fmul_rn(__uint_as_float(r[j8 + 4 * h + u]), s[u]), b[u]);
+            o[4 * h + u] = simple ? fmaxf(v, __fmul_rn(neg, v)) : act_out_of_line(v, epi.act);
+          }
+          if (addRes) {
+            const float4 rr = res[(j8 >> 2) + h];
+            o[4 * h + 0] = __fadd_rn(o[4 * h + 0], rr.x); o[4 * h + 1] = __fadd_rn(o[4 * h + 1], rr.y);
+            o[4 * h + 2] = __fadd_rn(o[4 * h + 2], rr.z); o[4 * h + 3] = __fadd_rn(o[4 * h + 3], rr.w);
+          }
         }
-        if (addRes) {
-          const float4 rr = res[j4 >> 2];
-          o[0] = __fadd_rn(o[0], rr.x); o[1] = __fadd_rn(o[1], rr.y); o[2] = __fadd_rn(o[2], rr.z); o[3] = __fadd_rn(o[3], rr.w);
+        const float4 oa = make_float4(o[0], o[1], o[2], o[3]), ob = make_float4(o[4], o[5], o[6], o[7]);
+        if (epi.f32Out) {
+          // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) — conflict-free and what the TMA store expects
+          *reinterpret_cast<float4 *>(rowp + ((((j8 >> 2) ^ (lane & 7))) << 4)) = oa;
+          *reinterpret_cast<float4 *>(rowp + (((((j8 >> 2) + 1) ^ (lane & 7))) << 4)) = ob;
         }
-        // SWIZZLE_128B staging: 16-byte chunk index XOR (row & 7) — conflict-free and what the TMA store expects
-        *reinterpret_cast<float4 *>(rowp + ((((j4 >> 2) ^ (lane & 7))) << 4)) = make_float4(o[0], o[1], o[2], o[3]);
+        if (epi.splitOut) {
+          uint4 hi, lo;
+          split_bf16x8(oa, ob, hi, lo);
+          const int o16 = lane * 64 + (((j8 >> 3) ^ ((lane >> 1) & 3)) << 4);  // SWIZZLE_64B
+          *reinterpret_cast<uint4 *>(tileHi + o16) = hi;
+          *reinterpret_cast<uint4 *>(tileLo + o16) = lo;
+        }
       }
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(tmOut, smem_u32(tile), (int)n, row0);
+        if (epi.f32Out) store(tmOut, smem_u32(tile), (int)n);
+        if (epi.splitOut) {
+          store(tmOutHi, smem_u32(tileHi), (int)n);
+          store(tmOutLo, smem_u32(tileLo), (int)n);
+        }
         bulk_commit();
       }
       sbuf ^= 1;
@@ -284,21 +319,29 @@ __device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int 
   }
 }
 
-template <int MODE, int KB, typename EPI>
+// ASPLIT (BF16x3 only): the activations arrive PRE-SPLIT — two bf16 planes (hi, lo) written by the producing layer's
+// epilogue — so both A tiles land by TMA in the tensor-core layout and nobody converts: the TF32-mode pipeline
+// (TMA -> mbarrier -> MMA) with the BF16x3 arithmetic.  tmA = hi plane, tmA2 = lo plane.
+template <int MODE, int KB, bool ASPLIT, typename EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCols,
-            const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-            const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut) {
+            const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+            const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+            const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutHi,
+            const __grid_constant__ CUtensorMap tmOutLo) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ Ctl ctl;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  constexpr bool SPLIT = MODE != MODE_TF32;   // producers touch the landed A tile; two B planes
+  constexpr bool SPLIT = MODE != MODE_TF32;   // two B planes
   constexpr bool BF = MODE == MODE_BF16X3;
+  constexpr bool CONVERT = SPLIT && !ASPLIT;  // producers derive the second plane(s) of the landed A tile
   static_assert(KB == 32 || KB == 16, "stages are 32 or 16 channels deep");
-  constexpr int aBytes = BM * KB * 4;                 // the landed fp32 A tile
+  static_assert(!ASPLIT || (BF && KB == 32), "pre-split activations: BF16x3, 32-channel stages");
+  constexpr int aBytes = BM * KB * 4;                 // the landed fp32 A tile (= the two landed bf16 tiles of ASPLIT)
   const int bBytes = BN * KB * (BF ? 2 : 4);          // one weight plane of the stage
   // stage layout: 3xTF32  A(=hi) | A_lo | B_hi | B_lo;   TF32  A | B;   BF16x3  A raw | A_hi | A_lo | B_hi | B_lo (bf16 tiles)
-  const int bOff = BF ? 2 * aBytes : (SPLIT ? 2 : 1) * aBytes;
+  //               BF16x3 pre-split  A_hi | A_lo | B_hi | B_lo
+  const int bOff = BF ? (ASPLIT ? 1 : 2) * aBytes : (SPLIT ? 2 : 1) * aBytes;
   const int stageBytes = bOff + bBytes * (SPLIT ? 2 : 1);
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -318,6 +361,7 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
   if (warp == kMmaWarp) tmem_alloc(&ctl.tmem_base, accCols * 2);
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
+    if (ASPLIT) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmBhi);
     if (SPLIT) tma_prefetch_desc(&tmBlo);
     if (EPI::kTmaStore) tma_prefetch_desc(&tmOut);
@@ -328,8 +372,8 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
   const uint32_t tmem_base = ctl.tmem_base;
 
   if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
-    // ===================== 3xTF32 only: low half of the landed A tile =====================
-    if (SPLIT) {
+    // ===================== split modes on fp32 activations: second plane(s) of the landed A tile =====================
+    if (CONVERT) {
       constexpr int kConvGroups = ConvGroups<MODE>::kGroups, kConvGroupWarps = ConvGroups<MODE>::kWarps;
       const int group = (warp - kFirstProducerWarp) / kConvGroupWarps;
       const int tid = threadIdx.x - (kFirstProducerWarp + group * kConvGroupWarps) * 32;
@@ -367,7 +411,7 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols;
       for (int kb = kb0; kb < kb1; ++kb) {
-        mbar_wait_warp(SPLIT ? &ctl.full[stage] : &ctl.araw[stage], phase);
+        mbar_wait_warp(CONVERT ? &ctl.full[stage] : &ctl.araw[stage], phase);
         tc_fence_after();
         if (elect_one_sync()) {
           const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
@@ -377,7 +421,7 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
           if constexpr (BF) {
             // bf16 tiles: rows of KB*2 bytes (SWIZZLE_64B for 32 k, SWIZZLE_32B for 16 k), 8-row groups KB*16 bytes apart;
             // UMMA_K = 16 -> +32 bytes per step
-            const uint32_t shi = sa + aBytes, slo = shi + aBytes / 2;
+            const uint32_t shi = ASPLIT ? sa : sa + aBytes, slo = shi + aBytes / 2;
             constexpr uint32_t bSbo = KB * 16, bLt = KB == 32 ? 4u : 6u;
 #pragma unroll
             for (int ks = 0; ks < KB / 16; ++ks) {
@@ -438,6 +482,9 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
           const uint32_t sb = sa + bOff;
           mbar_arrive_expect_tx(&ctl.araw[stage], (uint32_t)(aBytes + bBytes * (SPLIT ? 2 : 1)));
           tma_load_im2col(sa, &tmA, cb * KB, cw, ch, img, (uint32_t)(kc * g.dx), (uint32_t)(kr * g.dy), &ctl.araw[stage]);
+          if (ASPLIT)
+            tma_load_im2col(sa + aBytes / 2, &tmA2, cb * KB, cw, ch, img, (uint32_t)(kc * g.dx), (uint32_t)(kr * g.dy),
+                            &ctl.araw[stage]);
           tma_load_2d(sb, &tmBhi, kb * KB, n0, &ctl.araw[stage]);
           if (SPLIT) tma_load_2d(sb + bBytes, &tmBlo, kb * KB, n0, &ctl.araw[stage]);
           if (++cb == g.cBlocks) {
@@ -467,7 +514,8 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
       mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
       tc_fence_after();
-      drain_tile(epi, tmem_d, bn, n0, row0, scratch, stg, sbuf, &tmOut, [&] { mbar_arrive(&ctl.tmem_empty[as]); });
+      drain_tile(epi, tmem_d, bn, n0, row0, scratch, stg, sbuf, &tmOut, &tmOutHi, &tmOutLo,
+                 [&] { mbar_arrive(&ctl.tmem_empty[as]); }, StoreRows{row0});
     }
     if (EPI::kTmaStore && lane == 0) bulk_wait_all();  // the staging tiles must outlive their stores
   }
@@ -565,19 +613,23 @@ __device__ __forceinline__ void tma2_load_im2col(uint32_t dst_smem, const CUtens
 }
 
 // BN = filters per pair tile (multiple of 32, <= 256): each CTA holds BN/2 weight rows.  mTiles counts 128-pixel tiles.
-template <int MODE, int KB, typename EPI>
+template <int MODE, int KB, bool ASPLIT, typename EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, int stages,
-                 const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-                 const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmOut) {
+                 const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+                 const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutHi,
+                 const __grid_constant__ CUtensorMap tmOutLo) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ Ctl ctl;
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr bool SPLIT = MODE != MODE_TF32;
   constexpr bool BF = MODE == MODE_BF16X3;
+  constexpr bool CONVERT = SPLIT && !ASPLIT;
+  static_assert(!ASPLIT || (BF && KB == 32), "pre-split activations: BF16x3, 32-channel stages");
   constexpr int aBytes = BM * KB * 4;
   const int bBytes = (BN >> 1) * KB * (BF ? 2 : 4);   // this CTA's half of one weight plane
-  const int bOff = BF ? 2 * aBytes : (SPLIT ? 2 : 1) * aBytes;
+  const int bOff = BF ? (ASPLIT ? 1 : 2) * aBytes : (SPLIT ? 2 : 1) * aBytes;
   const int stageBytes = bOff + bBytes * (SPLIT ? 2 : 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -588,7 +640,7 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) {
-      mbar_init(&ctl.full[s], SPLIT ? 2 * ConvGroups<MODE>::kWarps + 1 : 1);
+      mbar_init(&ctl.full[s], CONVERT ? 2 * ConvGroups<MODE>::kWarps + 1 : 1);
       mbar_init(&ctl.empty[s], 1);
       mbar_init(&ctl.araw[s], 1);
     }
@@ -601,6 +653,7 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
   if (warp == kMmaWarp) tmem_alloc2(&ctl.tmem_base, 512);
   if (warp == kTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmA);
+    if (ASPLIT) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmBhi);
     if (SPLIT) tma_prefetch_desc(&tmBlo);
     if (EPI::kTmaStore) tma_prefetch_desc(&tmOut);
@@ -612,8 +665,8 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
   const uint32_t tmem_base = ctl.tmem_base;
 
   if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
-    // ===================== split modes: second plane(s) of this CTA's A tile =====================
-    if (SPLIT) {
+    // ===================== split modes on fp32 activations: second plane(s) of this CTA's A tile =====================
+    if (CONVERT) {
       constexpr int kConvGroups = ConvGroups<MODE>::kGroups, kConvGroupWarps = ConvGroups<MODE>::kWarps;
       const int group = (warp - kFirstProducerWarp) / kConvGroupWarps;
       const int tid = threadIdx.x - (kFirstProducerWarp + group * kConvGroupWarps) * 32;
@@ -654,7 +707,7 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
             const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
             const uint32_t sb = sa + bOff;
             if constexpr (BF) {
-              const uint32_t shi = sa + aBytes, slo = shi + aBytes / 2;
+              const uint32_t shi = ASPLIT ? sa : sa + aBytes, slo = shi + aBytes / 2;
               constexpr uint32_t bSbo = KB * 16, bLt = KB == 32 ? 4u : 6u;
 #pragma unroll
               for (int ks = 0; ks < KB / 16; ++ks) {
@@ -698,7 +751,7 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
       int stage = 0;
       uint32_t phase = 0;
       // bytes the leader's full[] barrier expects per stage: the loads of BOTH CTAs that signal it
-      const uint32_t fullTx = 2u * (uint32_t)(bBytes * (SPLIT ? 2 : 1) + (SPLIT ? 0 : aBytes));
+      const uint32_t fullTx = 2u * (uint32_t)(bBytes * (SPLIT ? 2 : 1) + (CONVERT ? 0 : aBytes));
       for (int t = pair; t < numTiles; t += numPairs) {
         const int mp = t % mPairs, nt = t / mPairs;
         const int n0 = nt * BN + (int)rank * (BN >> 1);
@@ -714,11 +767,14 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
           const uint32_t sa = smem_base + (uint32_t)stage * stageBytes;
           const uint32_t sb = sa + bOff;
           if (rank == 0) mbar_arrive_expect_tx(&ctl.full[stage], fullTx);
-          if (SPLIT) {
+          if (CONVERT) {
             mbar_arrive_expect_tx(&ctl.araw[stage], (uint32_t)aBytes);
             tma_load_im2col(sa, &tmA, cb * KB, cw, ch, img, (uint32_t)(kc * g.dx), (uint32_t)(kr * g.dy), &ctl.araw[stage]);
           } else {
             tma2_load_im2col(sa, &tmA, cb * KB, cw, ch, img, (uint32_t)(kc * g.dx), (uint32_t)(kr * g.dy), &ctl.full[stage]);
+            if (ASPLIT)
+              tma2_load_im2col(sa + aBytes / 2, &tmA2, cb * KB, cw, ch, img, (uint32_t)(kc * g.dx), (uint32_t)(kr * g.dy),
+                               &ctl.full[stage]);
           }
           tma2_load_2d(sb, &tmBhi, kb * KB, n0, &ctl.full[stage]);
           if (SPLIT) tma2_load_2d(sb + bBytes, &tmBlo, kb * KB, n0, &ctl.full[stage]);
@@ -746,10 +802,10 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
       const uint32_t tmem_d = tmem_base + (uint32_t)as * kAccStride + ((uint32_t)(quad * 32) << 16);
       mbar_wait_warp_relaxed(&ctl.tmem_full[as], use & 1, 64);
       tc_fence_after();
-      drain_tile(epi, tmem_d, BN, n0, row0, scratch, stg, sbuf, &tmOut, [&] {
+      drain_tile(epi, tmem_d, BN, n0, row0, scratch, stg, sbuf, &tmOut, &tmOutHi, &tmOutLo, [&] {
         if (rank == 0) mbar_arrive(&ctl.tmem_empty[as]);
         else mbar_arrive_cluster(&ctl.tmem_empty[as], 0);
-      });
+      }, StoreRows{row0});
     }
     if (EPI::kTmaStore && lane == 0) bulk_wait_all();
   }
@@ -802,18 +858,22 @@ static int encode_weights_map_bf16(CUtensorMap *tm, const uint16_t *base, int64_
 }
 
 // activations [B][H][W][pitch] as the im2col-mode tensor {C, W, H, N}: box = 128 pixels x kb channels of one tap
-static int encode_im2col_map(CUtensorMap *tm, const float *base, const simt::ConvGeom &g, int batch, int64_t pitch, int kb) {
+// (bf16 = one plane of a pre-split tensor: 2-byte elements, 64-byte rows for 32 channels -> SWIZZLE_64B)
+static int encode_im2col_map(CUtensorMap *tm, const void *base, const simt::ConvGeom &g, int batch, int64_t pitch, int kb,
+                             bool bf16 = false) {
   EncodeIm2colFn enc = get_encode_im2col();
   TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeIm2col is not available from the driver");
+  const cuuint64_t es = bf16 ? 2 : 4;
   cuuint64_t dims[4] = {(cuuint64_t)g.C, (cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)batch};
-  cuuint64_t strides[3] = {(cuuint64_t)pitch * 4, (cuuint64_t)pitch * g.W * 4, (cuuint64_t)pitch * g.W * g.H * 4};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * g.W * es, (cuuint64_t)pitch * g.W * g.H * es};
   // bounding box of the tap-(0,0) position of an output pixel (the convention of the im2col mode: lower corner
   // = -padding, upper corner = padding - (k-1)*dilation, measured from the far edge)
   int lower[2] = {-g.pw, -g.ph};
   int upper[2] = {g.pw - (g.kw - 1) * g.dx, g.ph - (g.kh - 1) * g.dy};
   cuuint32_t estr[4] = {1, (cuuint32_t)g.sx, (cuuint32_t)g.sy, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims, strides, lower, upper, (cuuint32_t)kb, BM,
-                   estr, CU_TENSOR_MAP_INTERLEAVE_NONE, kb == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+  CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)base, dims,
+                   strides, lower, upper, (cuuint32_t)kb, BM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   kb * es == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     tnn_set_error("cuTensorMapEncodeIm2col failed with CUresult %d", (int)r);
@@ -823,16 +883,17 @@ static int encode_im2col_map(CUtensorMap *tm, const float *base, const simt::Con
 }
 
 // output rows [M][pitch] (channels innermost): 32 x 32 store boxes, SWIZZLE_128B staging
-static int encode_out_map(CUtensorMap *tm, float *base, int64_t M, int64_t F, int64_t pitch) {
+// (bf16 = one plane of a pre-split tensor: the same boxes with 64-byte rows, SWIZZLE_64B staging)
+static int encode_out_map(CUtensorMap *tm, void *base, int64_t M, int64_t F, int64_t pitch, bool bf16 = false) {
   EncodeTiledFn enc = get_encode_tiled();
   TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t dims[2] = {(cuuint64_t)F, (cuuint64_t)M};
-  cuuint64_t strides[1] = {(cuuint64_t)pitch * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch * (bf16 ? 2 : 4)};
   cuuint32_t box[2] = {32, 32};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *)base, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, base, dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     tnn_set_error("cuTensorMapEncodeTiled (NHWC output) failed with CUresult %d", (int)r);
     return 6;
@@ -840,33 +901,54 @@ static int encode_out_map(CUtensorMap *tm, float *base, int64_t M, int64_t F, in
   return 0;
 }
 
-template <int MODE, int KB, typename EPI>
-static int launch_nhwc(tnn_context *ctx, const Plan &p, const Geo &geo, EPI epi, const CUtensorMap &tmA,
-                       const CUtensorMap &tmHi, const CUtensorMap &tmLo, const CUtensorMap &tmOut) {
-  auto kern = k_conv_nhwc<MODE, KB, EPI>;
+struct Maps {
+  alignas(64) CUtensorMap a, a2, bhi, blo, out, outHi, outLo;
+};
+
+template <int MODE, int KB, bool ASPLIT, typename EPI>
+static int launch_nhwc(tnn_context *ctx, const Plan &p, const Geo &geo, EPI epi, const Maps &m) {
+  auto kern = k_conv_nhwc<MODE, KB, ASPLIT, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
-  kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(epi, p.sched, geo, p.BN, p.stages, p.accCols, tmA, tmHi, tmLo, tmOut);
+  kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(epi, p.sched, geo, p.BN, p.stages, p.accCols, m.a, m.a2, m.bhi, m.blo,
+                                                       m.out, m.outHi, m.outLo);
   TNN_LAUNCHED(ctx);
   return 0;
 }
 
-template <int MODE, int KB, typename EPI>
+template <int MODE, int KB, bool ASPLIT, typename EPI>
 static int launch_nhwc_pair(tnn_context *ctx, int grid, size_t smemBytes, int mTiles, int nTiles, int kBlocks, const Geo &geo,
-                            int BN, int stages, EPI epi, const CUtensorMap &tmA, const CUtensorMap &tmHi,
-                            const CUtensorMap &tmLo, const CUtensorMap &tmOut) {
-  auto kern = k_conv_nhwc_pair<MODE, KB, EPI>;
+                            int BN, int stages, EPI epi, const Maps &m) {
+  auto kern = k_conv_nhwc_pair<MODE, KB, ASPLIT, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-  kern<<<grid, kThreads, smemBytes, ctx->stream>>>(epi, mTiles, nTiles, kBlocks, geo, BN, stages, tmA, tmHi, tmLo, tmOut);
+  kern<<<grid, kThreads, smemBytes, ctx->stream>>>(epi, mTiles, nTiles, kBlocks, geo, BN, stages, m.a, m.a2, m.bhi, m.blo,
+                                                   m.out, m.outHi, m.outLo);
   TNN_LAUNCHED(ctx);
   return 0;
 }
 
+// One tensor of the convolution: fp32 (rows of channels or planes) and / or the pre-split bf16 planes.
+struct SplitRef {
+  const uint16_t *hi;       // nullptr: not present
+  int64_t pitch, plane;     // bf16 elements between pixels / between the hi and the lo plane
+};
+
+// in: fp32 rows (inSplit.hi == nullptr) or pre-split planes.  Outputs: `out` fp32 (rows of channels, or planes when
+// outNchw) and / or outSplit (pre-split planes, rows of channels only).
 static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, int64_t inPitch,
-                        const float *weights, const float *scale, const float *bias, int act, float *out,
-                        int64_t outPitch, bool outNchw, const float *residual = nullptr, int64_t resPitch = 0) {
+                        SplitRef inSplit, const float *weights, const float *scale, const float *bias, int act, float *out,
+                        int64_t outPitch, bool outNchw, SplitRef outSplit, const float *residual = nullptr,
+                        int64_t resPitch = 0) {
   const int kk = g.kh * g.kw;
-  TNN_REQUIRE((inPitch % 4) == 0 && inPitch >= g.C && (((uintptr_t)in) & 15) == 0,
-              "NHWC input needs a pixel pitch that is a multiple of 4 floats and a 16-byte aligned base");
+  const bool aSplit = inSplit.hi != nullptr;
+  if (aSplit) {
+    TNN_REQUIRE(ctx->math_mode == TNN_MATH_BF16X3, "pre-split (bf16 hi/lo) activations are the BF16x3 mode's operands");
+    TNN_REQUIRE((inSplit.pitch % 8) == 0 && inSplit.pitch >= g.C && (inSplit.plane % 8) == 0 &&
+                    (((uintptr_t)inSplit.hi) & 15) == 0,
+                "pre-split input needs a pixel pitch and a plane stride that are multiples of 8 and a 16-byte aligned base");
+  } else {
+    TNN_REQUIRE((inPitch % 4) == 0 && inPitch >= g.C && (((uintptr_t)in) & 15) == 0,
+                "NHWC input needs a pixel pitch that is a multiple of 4 floats and a 16-byte aligned base");
+  }
   TNN_REQUIRE(g.sx <= 8 && g.sy <= 8 && g.pw <= 128 && g.ph <= 128 && (g.kw - 1) * g.dx - g.pw <= 128 &&
                   (g.kh - 1) * g.dy - g.ph <= 128, "geometry outside the TMA im2col limits");
   const int64_t M = (int64_t)batch * g.OH * g.OW;
@@ -879,7 +961,7 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   // 3xTF32 stages carry four fp32 tiles: half-depth (16-channel) stages keep four of them in flight
   // (bf16 stages are half the bytes per channel: 32-channel stages measured 13.5 vs 15.3 ms over the YOLOv3 layers)
   // a layer with at most 16 channels (the image layer) moves half the zero padding per tap with 16-channel stages
-  const int KB = split ? (ctx->nhwc_kb ? ctx->nhwc_kb : ((bf && g.C > 16) ? 32 : 16)) : 32;
+  const int KB = aSplit ? 32 : split ? (ctx->nhwc_kb ? ctx->nhwc_kb : ((bf && g.C > 16) ? 32 : 16)) : 32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
   // half-width tail tiles: the TMA store writes whole 32-filter boxes, so a half tile must be a multiple of 32 wide
   // CTA pairs (cta_group::2) halve the weight traffic through shared memory — the bound of the single-CTA kernel.
@@ -890,7 +972,7 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   const bool pairMode = ctx->nhwc_pair && (p.BN % 32) == 0 && p.BN >= 64 && pairTiles >= sms / 2;
   const int bnCta = pairMode ? p.BN / 2 : p.BN;   // weight rows a CTA stages
   if (!pairMode && (outNchw || (p.BN % 64) == 0)) split_tail_wave(ctx, p);
-  const size_t stageBytes = bf ? (size_t)BM * KB * 8 + (size_t)bnCta * KB * 4
+  const size_t stageBytes = bf ? (size_t)BM * KB * (aSplit ? 4 : 8) + (size_t)bnCta * KB * 4
                                : (size_t)(BM + bnCta) * KB * 4 * (split ? 2 : 1);
   const size_t epiBytes = outNchw ? 0 : (size_t)kEpilogueWarps * kStageBufs * kStageTile;
   int st = (int)((225 * 1024 - epiBytes) / stageBytes);
@@ -912,18 +994,25 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
       k_prepare_weights_patch<<<(int)blocks, 256, 0, ctx->stream>>>(weights, (int)N, g.C, kk, CB, 0, whi, wlo, split ? 1 : 0);
     TNN_LAUNCHED(ctx);
   }
-  alignas(64) CUtensorMap tmA, tmHi, tmLo, tmOut;
-  rc = encode_im2col_map(&tmA, in, g, batch, inPitch, KB);
+  Maps m;
+  memset(&m, 0, sizeof(m));
+  if (aSplit) {
+    rc = encode_im2col_map(&m.a, inSplit.hi, g, batch, inSplit.pitch, KB, true);
+    if (rc) return rc;
+    rc = encode_im2col_map(&m.a2, inSplit.hi + inSplit.plane, g, batch, inSplit.pitch, KB, true);
+  } else {
+    rc = encode_im2col_map(&m.a, in, g, batch, inPitch, KB);
+  }
   if (rc) return rc;
   if (bf) {
-    rc = encode_weights_map_bf16(&tmHi, (const uint16_t *)whi, N, K, bnCta, KB);
+    rc = encode_weights_map_bf16(&m.bhi, (const uint16_t *)whi, N, K, bnCta, KB);
     if (rc) return rc;
-    rc = encode_weights_map_bf16(&tmLo, (const uint16_t *)wlo, N, K, bnCta, KB);
+    rc = encode_weights_map_bf16(&m.blo, (const uint16_t *)wlo, N, K, bnCta, KB);
   } else {
-    rc = KB == 16 ? encode_weights_map16(&tmHi, whi, N, K, bnCta) : encode_weights_map(&tmHi, whi, N, K, bnCta);
+    rc = KB == 16 ? encode_weights_map16(&m.bhi, whi, N, K, bnCta) : encode_weights_map(&m.bhi, whi, N, K, bnCta);
     if (rc) return rc;
-    rc = KB == 16 ? encode_weights_map16(&tmLo, split ? wlo : whi, N, K, bnCta)
-                  : encode_weights_map(&tmLo, split ? wlo : whi, N, K, bnCta);
+    rc = KB == 16 ? encode_weights_map16(&m.blo, split ? wlo : whi, N, K, bnCta)
+                  : encode_weights_map(&m.blo, split ? wlo : whi, N, K, bnCta);
   }
   if (rc) return rc;
   Geo geo{g.OW, g.OH * g.OW, g.sx, g.sy, g.pw, g.ph, g.dx, g.dy, g.kw, CB * 32 / KB, (int)M};
@@ -931,33 +1020,354 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
     if (pairMode) {
       const int grid = (int)(2 * (pairTiles < sms / 2 ? pairTiles : sms / 2));
       const int kBlocks = (int)(K / KB);
-#define TNN_PAIR_GO(MODE, KBV) \
-  launch_nhwc_pair<MODE, KBV>(ctx, grid, p.smemBytes, p.sched.mTiles, p.sched.nTiles, kBlocks, geo, p.BN, p.stages, epi, tmA, tmHi, tmLo, tmOut)
-      if (bf) return KB == 16 ? TNN_PAIR_GO(MODE_BF16X3, 16) : TNN_PAIR_GO(MODE_BF16X3, 32);
-      if (!split) return TNN_PAIR_GO(MODE_TF32, 32);
-      return KB == 16 ? TNN_PAIR_GO(MODE_3X, 16) : TNN_PAIR_GO(MODE_3X, 32);
+#define TNN_PAIR_GO(MODE, KBV, AS) \
+  launch_nhwc_pair<MODE, KBV, AS>(ctx, grid, p.smemBytes, p.sched.mTiles, p.sched.nTiles, kBlocks, geo, p.BN, p.stages, epi, m)
+      if (aSplit) return TNN_PAIR_GO(MODE_BF16X3, 32, true);
+      if (bf) return KB == 16 ? TNN_PAIR_GO(MODE_BF16X3, 16, false) : TNN_PAIR_GO(MODE_BF16X3, 32, false);
+      if (!split) return TNN_PAIR_GO(MODE_TF32, 32, false);
+      return KB == 16 ? TNN_PAIR_GO(MODE_3X, 16, false) : TNN_PAIR_GO(MODE_3X, 32, false);
 #undef TNN_PAIR_GO
     }
-    if (bf) return KB == 16 ? launch_nhwc<MODE_BF16X3, 16>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut)
-                            : launch_nhwc<MODE_BF16X3, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
-    if (!split) return launch_nhwc<MODE_TF32, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
-    return KB == 16 ? launch_nhwc<MODE_3X, 16>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut)
-                    : launch_nhwc<MODE_3X, 32>(ctx, p, geo, epi, tmA, tmHi, tmLo, tmOut);
+    if (aSplit) return launch_nhwc<MODE_BF16X3, 32, true>(ctx, p, geo, epi, m);
+    if (bf) return KB == 16 ? launch_nhwc<MODE_BF16X3, 16, false>(ctx, p, geo, epi, m)
+                            : launch_nhwc<MODE_BF16X3, 32, false>(ctx, p, geo, epi, m);
+    if (!split) return launch_nhwc<MODE_TF32, 32, false>(ctx, p, geo, epi, m);
+    return KB == 16 ? launch_nhwc<MODE_3X, 16, false>(ctx, p, geo, epi, m) : launch_nhwc<MODE_3X, 32, false>(ctx, p, geo, epi, m);
   };
   if (outNchw) {
-    memset(&tmOut, 0, sizeof(tmOut));
+    TNN_REQUIRE(out != nullptr && outSplit.hi == nullptr, "planar output is fp32 only");
     NchwEpilogue epi{{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, nullptr}};
     return go(epi);
   }
-  TNN_REQUIRE((outPitch % 4) == 0 && outPitch >= N && (((uintptr_t)out) & 15) == 0,
-              "NHWC output needs a pixel pitch that is a multiple of 4 floats and a 16-byte aligned base");
-  rc = encode_out_map(&tmOut, out, M, N, outPitch);
-  if (rc) return rc;
+  TNN_REQUIRE(out != nullptr || outSplit.hi != nullptr, "no output tensor");
+  if (out) {
+    TNN_REQUIRE((outPitch % 4) == 0 && outPitch >= N && (((uintptr_t)out) & 15) == 0,
+                "NHWC output needs a pixel pitch that is a multiple of 4 floats and a 16-byte aligned base");
+    rc = encode_out_map(&m.out, out, M, N, outPitch);
+    if (rc) return rc;
+  }
+  if (outSplit.hi) {
+    TNN_REQUIRE((outSplit.pitch % 8) == 0 && outSplit.pitch >= N && (outSplit.plane % 8) == 0 &&
+                    (((uintptr_t)outSplit.hi) & 15) == 0,
+                "pre-split output needs a pixel pitch and a plane stride that are multiples of 8 and a 16-byte aligned base");
+    rc = encode_out_map(&m.outHi, (void *)outSplit.hi, M, N, outSplit.pitch, true);
+    if (rc) return rc;
+    rc = encode_out_map(&m.outLo, (void *)(outSplit.hi + outSplit.plane), M, N, outSplit.pitch, true);
+    if (rc) return rc;
+  }
   if (residual)
     TNN_REQUIRE((resPitch % 4) == 0 && resPitch >= N && (N % 4) == 0 && (((uintptr_t)residual) & 15) == 0,
                 "the residual needs 16-byte aligned rows and a filter count that is a multiple of 4");
-  NhwcEpilogue epi{scale, bias, act, M, N, residual, resPitch};
+  NhwcEpilogue epi{scale, bias, act, M, N, residual, resPitch, out != nullptr, outSplit.hi != nullptr};
   return go(epi);
+}
+
+// =====================================================================================================================
+// The image layer (planar NCHW input, C*kh*kw <= 32: 3 channels x 3x3 = 27) on the tensor cores.
+// Its contraction is ONE 32-deep k-block, k = (c, kr, kc) in the weights' own order.  A tile is a patch of 8 x 16 output
+// pixels of one image:
+//   TMA     one tiled 4-D load fetches the patch's input HALO from the planes ({W, H, C, N} box, columns from a 16-byte
+//           aligned start, padding / image edges zero-filled by the TMA unit) — a few KB of fp32
+//   gather  thread = one pixel: 27 shared-memory reads at fixed offsets (no address arithmetic, no bounds checks),
+//           split to bf16 hi/lo, four 16-byte stores per plane into the K-major SWIZZLE_64B tile
+//   MMA     six 128 x F x 16 MMAs (BF16x3) into one slot of a ring of up to eight TMEM accumulators
+//   out     the usual epilogue; stores are 4-D ({F, OW, OH, N} boxes of 32 filters x 16 columns x 2 rows), so ragged
+//           patches are clipped by the TMA unit
+// The work per tile is tiny, so everything is about keeping many tiles in flight: the eight gather warps form two groups
+// that take alternate tiles, halos / operand tiles / accumulators are rings, and the weights (F x 32 bf16 x 2 planes) stay
+// in shared memory for the whole kernel.  The CUDA-core direct kernel needs 1.2 ms for YOLOv3's first layer at batch 64
+// (864 FMAs per pixel); a first tensor-core version that gathered from global memory needed 1.0 ms (5700 warp
+// instructions per tile, most of them address arithmetic and edge tests, ncu).
+constexpr int kImgStages = 6;      // operand tiles
+constexpr int kImgHalos = 4;       // halo ring
+constexpr int kImgHaloBytes = 8192;
+constexpr int kImgGroups = 2;
+constexpr int kImgGroupWarps = kProducerWarps / kImgGroups;   // 4 warps = 128 threads = one pixel each
+constexpr int kImgMaxAcc = 8;
+constexpr int kImgTW = 16, kImgTH = 8;   // output patch
+
+struct ImgCtl {
+  uint64_t h_full[kImgHalos], h_empty[kImgHalos];
+  uint64_t a_full[kImgStages], a_empty[kImgStages];
+  uint64_t tmem_full[kImgMaxAcc], tmem_empty[kImgMaxAcc];
+  uint32_t tmem_base;
+  alignas(16) float epi_sb[kEpilogueWarps][64];
+};
+struct ImgGeo {
+  int tilesX, tilesY;     // patches per image row / column
+  int PC, PR;             // halo box: columns (multiple of 4), rows
+  int delta;              // columns between the aligned box start and the first tap column
+  int haloBytes;
+};
+
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap *tmap, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(tmap)),
+               "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+k_conv_image(NhwcEpilogue epi, simt::ConvGeom g, ImgGeo ig, const float *__restrict__ w, int BN, int nAcc, uint32_t accCols,
+             int numTiles, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
+             const __grid_constant__ CUtensorMap tmOutHi, const __grid_constant__ CUtensorMap tmOutLo) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ ImgCtl ctl;
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int aPlane = BM * 64;                 // one bf16 plane of a tile: 128 rows x 64 bytes
+  constexpr int aStage = 2 * aPlane;
+  const int bPlane = BN * 64;
+  uint8_t *sB = smem + kImgStages * aStage;       // B_hi | B_lo
+  uint8_t *sStg = sB + 2 * bPlane;                // epilogue staging (1024-aligned: BN is a multiple of 16)
+  uint8_t *sHalo = sStg + kEpilogueWarps * kStageBufs * kStageTile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int K = g.C * g.kh * g.kw, kk = g.kh * g.kw;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kImgHalos; ++s) {
+      mbar_init(&ctl.h_full[s], 1);
+      mbar_init(&ctl.h_empty[s], kImgGroupWarps);
+    }
+    for (int s = 0; s < kImgStages; ++s) {
+      mbar_init(&ctl.a_full[s], kImgGroupWarps);
+      mbar_init(&ctl.a_empty[s], 1);
+    }
+    for (int s = 0; s < kImgMaxAcc; ++s) {
+      mbar_init(&ctl.tmem_full[s], 1);
+      mbar_init(&ctl.tmem_empty[s], kEpilogueWarps);
+    }
+    fence_barrier_init();
+  }
+  // weights -> bf16 hi / lo K-major SWIZZLE_64B tiles (row n = filter, 64 bytes = 32 k; rows >= F and k >= K zero)
+  for (int u = threadIdx.x; u < BN * 4; u += kThreads) {
+    const int n = u >> 2, j = u & 3;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = j * 8 + e;
+      v[e] = (n < g.F && k < K) ? __ldg(w + (int64_t)n * K + k) : 0.f;
+    }
+    uint4 hi, lo;
+    split_bf16x8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+    const int o = n * 64 + ((j ^ ((n >> 1) & 3)) << 4);
+    *reinterpret_cast<uint4 *>(sB + o) = hi;
+    *reinterpret_cast<uint4 *>(sB + bPlane + o) = lo;
+  }
+  if (warp == kMmaWarp) tmem_alloc(&ctl.tmem_base, 512);
+  if (warp == kTmaWarp && lane == 0) {
+    tma_prefetch_desc(&tmIn);
+    if (epi.f32Out) tma_prefetch_desc(&tmOut);
+    if (epi.splitOut) { tma_prefetch_desc(&tmOutHi); tma_prefetch_desc(&tmOutLo); }
+  }
+  fence_proxy_async();   // the weight tiles are read by the tensor core (async proxy)
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = ctl.tmem_base;
+  const int tilesPerImg = ig.tilesX * ig.tilesY;
+
+  if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
+    // ===================== gather: thread = one pixel of the patch, all 32 k =====================
+    const int group = (warp - kFirstProducerWarp) / kImgGroupWarps;
+    const int p = threadIdx.x - (kFirstProducerWarp + group * kImgGroupWarps) * 32;   // row of the operand tile
+    const int pr = p / kImgTW, pc = p - pr * kImgTW;
+    // halo [c][row][column] fp32: this pixel's tap (c, kr, kc) sits at koff[k] floats after its own corner
+    const int corner = (pr * g.sy) * ig.PC + pc * g.sx + ig.delta;
+    int koff[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) {
+      const int c = k / kk, tap = k - c * kk, kr = tap / g.kw, kc = tap - kr * g.kw;
+      koff[k] = k < K ? ((c * ig.PR + kr * g.dy) * ig.PC + kc * g.dx + corner) * 4 : -1;
+    }
+    const int sw = (p >> 1) & 3;
+    int it = group;
+    for (int t = blockIdx.x + group * gridDim.x; t < numTiles; t += kImgGroups * gridDim.x, it += kImgGroups) {
+      const int stage = it % kImgStages, hs = it % kImgHalos;
+      mbar_wait_warp(&ctl.h_full[hs], (uint32_t)((it / kImgHalos) & 1));
+      const uint8_t *halo = sHalo + hs * kImgHaloBytes;
+      float x[32];
+#pragma unroll
+      for (int k = 0; k < 32; ++k) x[k] = koff[k] >= 0 ? *reinterpret_cast<const float *>(halo + koff[k]) : 0.f;
+      uint4 hi[4], lo[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        split_bf16x8(make_float4(x[8 * j], x[8 * j + 1], x[8 * j + 2], x[8 * j + 3]),
+                     make_float4(x[8 * j + 4], x[8 * j + 5], x[8 * j + 6], x[8 * j + 7]), hi[j], lo[j]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl.h_empty[hs]);   // the halo is in registers
+      mbar_wait_warp(&ctl.a_empty[stage], (uint32_t)(((it / kImgStages) & 1) ^ 1));
+      uint8_t *shi = smem + stage * aStage, *slo = shi + aPlane;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = p * 64 + ((j ^ sw) << 4);
+        *reinterpret_cast<uint4 *>(shi + o) = hi[j];
+        *reinterpret_cast<uint4 *>(slo + o) = lo[j];
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ctl.a_full[stage]);
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer: six MMAs per tile, accumulator ring =====================
+    const uint32_t idesc = make_idesc_bf16(BN);
+    const uint32_t sb = smem_u32(sB);
+    int it = 0;
+    for (int t = blockIdx.x; t < numTiles; t += gridDim.x, ++it) {
+      const int stage = it % kImgStages;
+      const uint32_t phase = (uint32_t)((it / kImgStages) & 1);
+      const int as = it % nAcc;
+      const uint32_t use = (uint32_t)(it / nAcc);
+      mbar_wait_warp(&ctl.tmem_empty[as], (use & 1) ^ 1);
+      mbar_wait_warp(&ctl.a_full[stage], phase);
+      tc_fence_after();
+      if (elect_one_sync()) {
+        const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols;
+        const uint32_t shi = smem_u32(smem) + (uint32_t)stage * aStage, slo = shi + aPlane;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint64_t ah = make_desc(shi + ks * 32, 16, 512, 4u), al = make_desc(slo + ks * 32, 16, 512, 4u);
+          const uint64_t bh = make_desc(sb + ks * 32, 16, 512, 4u), bl = make_desc(sb + bPlane + ks * 32, 16, 512, 4u);
+          mma_bf16(tmem_d, al, bh, idesc, ks ? 1u : 0u);
+          mma_bf16(tmem_d, ah, bl, idesc, 1u);
+          mma_bf16(tmem_d, ah, bh, idesc, 1u);
+        }
+        mma_commit(&ctl.a_empty[stage]);
+        mma_commit(&ctl.tmem_full[as]);
+      }
+      __syncwarp();
+    }
+  } else if (warp == kTmaWarp) {
+    // ===================== TMA: one halo per tile =====================
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < numTiles; t += gridDim.x, ++it) {
+        const int hs = it % kImgHalos;
+        mbar_wait(&ctl.h_empty[hs], (uint32_t)(((it / kImgHalos) & 1) ^ 1));
+        const int b = t / tilesPerImg, rem = t - b * tilesPerImg, ty = rem / ig.tilesX, tx = rem - ty * ig.tilesX;
+        mbar_arrive_expect_tx(&ctl.h_full[hs], (uint32_t)ig.haloBytes);
+        tma_load_4d(smem_u32(sHalo + hs * kImgHaloBytes), &tmIn, tx * kImgTW * g.sx - g.pw - ig.delta,
+                    ty * kImgTH * g.sy - g.ph, 0, b, &ctl.h_full[hs]);
+      }
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int quad = warp;
+    uint8_t *stg = sStg + (size_t)quad * (kStageBufs * kStageTile);
+    int sbuf = 0, it = 0;
+    float *scratch = ctl.epi_sb[quad];
+    for (int t = blockIdx.x; t < numTiles; t += gridDim.x, ++it) {
+      const int as = it % nAcc;
+      const uint32_t use = (uint32_t)(it / nAcc);
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
+      const int b = t / tilesPerImg, rem = t - b * tilesPerImg, ty = rem / ig.tilesX, tx = rem - ty * ig.tilesX;
+      const int ow0 = tx * kImgTW, oh0 = ty * kImgTH + quad * 2;   // this warp's two patch rows
+      mbar_wait_warp(&ctl.tmem_full[as], use & 1);
+      tc_fence_after();
+      drain_tile(epi, tmem_d, BN, 0, 0, scratch, stg, sbuf, &tmOut, &tmOutHi, &tmOutLo,
+                 [&] { mbar_arrive(&ctl.tmem_empty[as]); },
+                 [&](const CUtensorMap *tm, uint32_t src, int n) { tma_store_4d(tm, src, n, ow0, oh0, b); });
+    }
+    if (lane == 0) bulk_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+}
+
+static bool image_geo(const simt::ConvGeom &g, ImgGeo &ig) {
+  // first tap column of a patch = X - pw with X a multiple of 16; the box starts `delta` columns earlier on a multiple
+  // of 4 (tiled TMA wants a 16-byte aligned start):  (X - pw - delta) % 4 == 0  <=>  delta = (-pw) mod 4
+  ig.delta = ((-g.pw) % 4 + 4) % 4;
+  const int cols = (kImgTW - 1) * g.sx + (g.kw - 1) * g.dx + 1 + ig.delta;
+  ig.PC = (cols + 3) / 4 * 4;
+  ig.PR = (kImgTH - 1) * g.sy + (g.kh - 1) * g.dy + 1;
+  ig.haloBytes = ig.PC * ig.PR * g.C * 4;
+  ig.tilesX = (g.OW + kImgTW - 1) / kImgTW;
+  ig.tilesY = (g.OH + kImgTH - 1) / kImgTH;
+  return ig.PC <= 256 && ig.PR <= 256 && g.C <= 256 && ig.haloBytes <= kImgHaloBytes;
+}
+
+static bool image_supported(const simt::ConvGeom &g, const float *in) {
+  ImgGeo ig;
+  return g.C * g.kh * g.kw <= 32 && g.F <= 256 && (g.W % 4) == 0 && (((uintptr_t)in) & 15) == 0 && image_geo(g, ig);
+}
+
+// 4-D output map {F, OW, OH, N} over rows of channels: boxes of 32 filters x 16 columns x 2 rows (= 32 staged pixel rows)
+static int encode_out_map4(CUtensorMap *tm, void *base, const simt::ConvGeom &g, int batch, int64_t pitch, bool bf16) {
+  EncodeTiledFn enc = get_encode_tiled();
+  TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t es = bf16 ? 2 : 4;
+  cuuint64_t dims[4] = {(cuuint64_t)g.F, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)batch};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * g.OW * es, (cuuint64_t)pitch * g.OW * g.OH * es};
+  cuuint32_t box[4] = {32, kImgTW, 2, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    tnn_set_error("cuTensorMapEncodeTiled (image layer output) failed with CUresult %d", (int)r);
+    return 6;
+  }
+  return 0;
+}
+
+static int conv_image(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, const float *weights,
+                      const float *scale, const float *bias, int act, float *out, int64_t outPitch, SplitRef outSplit) {
+  const int64_t N = g.F;
+  TNN_REQUIRE(out != nullptr || outSplit.hi != nullptr, "no output tensor");
+  ImgGeo ig;
+  TNN_REQUIRE(image_geo(g, ig), "image layer geometry outside the halo limits");
+  const int BN = (int)((N + 15) / 16 * 16);
+  const uint32_t accCols = pow2_cols(BN);
+  int nAcc = (int)(512 / accCols);
+  if (nAcc > kImgMaxAcc) nAcc = kImgMaxAcc;
+  Maps m;
+  memset(&m, 0, sizeof(m));
+  int rc;
+  {
+    EncodeTiledFn enc = get_encode_tiled();
+    TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+    cuuint64_t dims[4] = {(cuuint64_t)g.W, (cuuint64_t)g.H, (cuuint64_t)g.C, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {(cuuint64_t)g.W * 4, (cuuint64_t)g.W * g.H * 4, (cuuint64_t)g.inImg * 4};
+    cuuint32_t box[4] = {(cuuint32_t)ig.PC, (cuuint32_t)ig.PR, (cuuint32_t)g.C, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&m.a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void *)in, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      tnn_set_error("cuTensorMapEncodeTiled (image planes) failed with CUresult %d", (int)r);
+      return 6;
+    }
+  }
+  if (out) {
+    TNN_REQUIRE((outPitch % 4) == 0 && outPitch >= N && (((uintptr_t)out) & 15) == 0,
+                "NHWC output needs a pixel pitch that is a multiple of 4 floats and a 16-byte aligned base");
+    rc = encode_out_map4(&m.out, out, g, batch, outPitch, false);
+    if (rc) return rc;
+  }
+  if (outSplit.hi) {
+    TNN_REQUIRE((outSplit.pitch % 8) == 0 && outSplit.pitch >= N && (outSplit.plane % 8) == 0 &&
+                    (((uintptr_t)outSplit.hi) & 15) == 0,
+                "pre-split output needs a pixel pitch and a plane stride that are multiples of 8 and a 16-byte aligned base");
+    rc = encode_out_map4(&m.outHi, (void *)outSplit.hi, g, batch, outSplit.pitch, true);
+    if (rc) return rc;
+    rc = encode_out_map4(&m.outLo, (void *)(outSplit.hi + outSplit.plane), g, batch, outSplit.pitch, true);
+    if (rc) return rc;
+  }
+  // rows = 1 / row0 = 0: the 4-D stores clip ragged patches themselves
+  NhwcEpilogue epi{scale, bias, act, 1, N, nullptr, 0, out != nullptr, outSplit.hi != nullptr};
+  const int64_t tiles = (int64_t)batch * ig.tilesX * ig.tilesY;
+  TNN_REQUIRE(tiles < (1ll << 30), "too many patches");
+  const int numTiles = (int)tiles;
+  const int sms = ctx->prop.multiProcessorCount;
+  const int grid = numTiles < sms ? numTiles : sms;
+  const size_t smemBytes = (size_t)kImgStages * 2 * BM * 64 + (size_t)2 * BN * 64 +
+                           (size_t)kEpilogueWarps * kStageBufs * kStageTile + (size_t)kImgHalos * kImgHaloBytes + 1024;
+  TNN_CUDA(cudaFuncSetAttribute(k_conv_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
+  k_conv_image<<<grid, kThreads, smemBytes, ctx->stream>>>(epi, g, ig, weights, BN, nAcc, accCols, numTiles, m.a, m.out,
+                                                           m.outHi, m.outLo);
+  TNN_LAUNCHED(ctx);
+  return 0;
 }
 
 // ------------------------------------------------------------------ layout companions (HBM-bound)
@@ -1040,6 +1450,43 @@ __global__ void __launch_bounds__(256) k_upsample_nhwc(int64_t total, int C4, in
   }
 }
 
+// fp32 rows -> the pre-split planes (hi = bf16_rn(x), lo = bf16_rn(x - hi)) and back (hi + lo, exact in fp32);
+// 8 channels per thread: two 16-byte loads, one 16-byte store per plane
+__global__ void __launch_bounds__(256) k_rows_to_split(int64_t rows, int C8, const float4 *__restrict__ in, int64_t ldi4,
+                                                       uint4 *__restrict__ hi, uint4 *__restrict__ lo, int64_t ldo8) {
+  const int64_t total = rows * C8;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const int64_t r = i / C8;
+    const int c = (int)(i - r * C8);
+    const float4 a = __ldg(in + r * ldi4 + 2 * c), b = __ldg(in + r * ldi4 + 2 * c + 1);
+    uint4 h, l;
+    split_bf16x8(a, b, h, l);
+    hi[r * ldo8 + c] = h;
+    lo[r * ldo8 + c] = l;
+  }
+}
+__global__ void __launch_bounds__(256) k_split_to_rows(int64_t rows, int C8, const uint4 *__restrict__ hi,
+                                                       const uint4 *__restrict__ lo, int64_t ldi8, float4 *__restrict__ out,
+                                                       int64_t ldo4) {
+  const int64_t total = rows * C8;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    const int64_t r = i / C8;
+    const int c = (int)(i - r * C8);
+    const uint4 h = __ldg(hi + r * ldi8 + c), l = __ldg(lo + r * ldi8 + c);
+    const uint32_t hh[4] = {h.x, h.y, h.z, h.w}, ll[4] = {l.x, l.y, l.z, l.w};
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[2 * j] = __fadd_rn(__uint_as_float(hh[j] << 16), __uint_as_float(ll[j] << 16));
+      v[2 * j + 1] = __fadd_rn(__uint_as_float(hh[j] & 0xFFFF0000u), __uint_as_float(ll[j] & 0xFFFF0000u));
+    }
+    out[r * ldo4 + 2 * c] = make_float4(v[0], v[1], v[2], v[3]);
+    out[r * ldo4 + 2 * c + 1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+}
+
 static int grid_for(int64_t total) {
   int64_t blocks = cdiv64(total, 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
@@ -1086,30 +1533,83 @@ int32_t tnn_conv2d_forward_nhwc_residual(tnn_context *ctx, const tnn_conv_desc *
                                          const float *bias, int32_t activation, const float *residual,
                                          int64_t residualOffset, int64_t residualPitch, float *out, int64_t outOffset,
                                          int64_t outPitch, int32_t outLayout) {
+  return tnn_conv2d_forward_split(ctx, d, in, inOffset, inPitch, inLayout, 0, weights, scale, bias, activation, residual,
+                                  residualOffset, residualPitch, out, outOffset, outPitch, outLayout, nullptr, 0, 0, 0);
+}
+
+int32_t tnn_conv2d_forward_split(tnn_context *ctx, const tnn_conv_desc *d, const void *in, int64_t inOffset, int64_t inPitch,
+                                 int32_t inLayout, int64_t inPlane, const float *weights, const float *scale,
+                                 const float *bias, int32_t activation, const float *residual, int64_t residualOffset,
+                                 int64_t residualPitch, float *out, int64_t outOffset, int64_t outPitch, int32_t outLayout,
+                                 void *outSplit, int64_t outSplitOffset, int64_t outSplitPitch, int64_t outSplitPlane) {
   TNN_CHECK_CTX(ctx);
   simt::ConvGeom g;
   int rc = fill_geom_nhwc(d, g);
   if (rc) return rc;
   TNN_REQUIRE(activation == TNN_ACT_LINEAR || tnn_act_is_elementwise(activation), "activation not elementwise");
-  TNN_REQUIRE((inLayout == TNN_LAYOUT_NCHW || inLayout == TNN_LAYOUT_NHWC) &&
+  TNN_REQUIRE((inLayout == TNN_LAYOUT_NCHW || inLayout == TNN_LAYOUT_NHWC || inLayout == TNN_LAYOUT_NHWC_SPLIT) &&
                   (outLayout == TNN_LAYOUT_NCHW || outLayout == TNN_LAYOUT_NHWC), "unknown layout");
   TNN_REQUIRE(ctx->math_mode != TNN_MATH_FP32, "the channels-innermost path runs on the tensor cores (3xTF32 / TF32 mode)");
-  in += inOffset;
-  out += outOffset;
+  TNN_REQUIRE(in != nullptr, "null input");
+  if (out) out += outOffset;
+  nhwc::SplitRef os{outSplit ? (const uint16_t *)outSplit + outSplitOffset : nullptr, outSplitPitch, outSplitPlane};
   if (residual) {
     residual += residualOffset;
-    TNN_REQUIRE(inLayout == TNN_LAYOUT_NHWC && outLayout == TNN_LAYOUT_NHWC, "the residual add is fused for channels-innermost tensors");
+    TNN_REQUIRE(inLayout != TNN_LAYOUT_NCHW && outLayout == TNN_LAYOUT_NHWC,
+                "the residual add is fused for channels-innermost tensors");
   }
   if (inLayout == TNN_LAYOUT_NCHW) {
     // planar input (the image fed to the first layer): direct fp32 convolution writing channels-innermost rows
+    const float *inf = (const float *)in + inOffset;
     TNN_REQUIRE(outLayout == TNN_LAYOUT_NHWC && direct::supported(g),
-                "NCHW input is only taken by the small-contraction direct kernel (C*kh*kw <= 64) writing NHWC");
+                "NCHW input is only taken by the small-contraction kernels (C*kh*kw <= 64) writing NHWC");
+    if ((ctx->math_mode == TNN_MATH_BF16X3 || ctx->math_mode == TNN_MATH_TF32) && nhwc::image_supported(g, inf) && ctx->nhwc_image) {
+      // tensor cores, BF16x3 arithmetic (in TF32 mode too: it is the tighter of the two)
+      ctx->last_conv_kernel = 9;
+      return nhwc::conv_image(ctx, g, (int)d->batch, inf, weights, scale, bias, activation, out, outPitch, os);
+    }
     ctx->last_conv_kernel = 8;
-    return direct::conv_forward(ctx, g, (int)d->batch, in, weights, scale, bias, activation, out, outPitch);
+    rc = direct::conv_forward(ctx, g, (int)d->batch, inf, weights, scale, bias, activation, out, outPitch);
+    if (rc || !os.hi) return rc;
+    return tnn_nhwc_to_split(ctx, d->batch * g.OH * g.OW, g.F, out, outPitch, (void *)os.hi, os.pitch, os.plane);
   }
   ctx->last_conv_kernel = 7;
-  return nhwc::conv_forward(ctx, g, (int)d->batch, in, inPitch, weights, scale, bias, activation, out, outPitch,
-                            outLayout == TNN_LAYOUT_NCHW, residual, residualPitch);
+  nhwc::SplitRef is{nullptr, 0, 0};
+  const float *inf = nullptr;
+  if (inLayout == TNN_LAYOUT_NHWC_SPLIT) is = nhwc::SplitRef{(const uint16_t *)in + inOffset, inPitch, inPlane};
+  else inf = (const float *)in + inOffset;
+  return nhwc::conv_forward(ctx, g, (int)d->batch, inf, inPitch, is, weights, scale, bias, activation, out, outPitch,
+                            outLayout == TNN_LAYOUT_NCHW, os, residual, residualPitch);
+}
+
+int32_t tnn_nhwc_to_split(tnn_context *ctx, int64_t rows, int64_t channels, const float *in, int64_t inPitch, void *outSplit,
+                          int64_t outPitch, int64_t outPlane) {
+  TNN_CHECK_CTX(ctx);
+  if (rows <= 0 || channels <= 0) return 0;
+  TNN_REQUIRE((channels % 8) == 0 && (inPitch % 4) == 0 && (outPitch % 8) == 0 && (outPlane % 8) == 0 &&
+                  ((((uintptr_t)in) | ((uintptr_t)outSplit)) & 15) == 0,
+              "pre-split rows: channels, pitches and the plane stride multiples of 8, 16-byte aligned bases");
+  uint16_t *hi = (uint16_t *)outSplit;
+  nhwc::k_rows_to_split<<<nhwc::grid_for(rows * channels / 8), 256, 0, ctx->stream>>>(
+      rows, (int)(channels / 8), reinterpret_cast<const float4 *>(in), inPitch / 4, reinterpret_cast<uint4 *>(hi),
+      reinterpret_cast<uint4 *>(hi + outPlane), outPitch / 8);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
+int32_t tnn_split_to_nhwc(tnn_context *ctx, int64_t rows, int64_t channels, const void *inSplit, int64_t inPitch,
+                          int64_t inPlane, float *out, int64_t outPitch) {
+  TNN_CHECK_CTX(ctx);
+  if (rows <= 0 || channels <= 0) return 0;
+  TNN_REQUIRE((channels % 8) == 0 && (inPitch % 8) == 0 && (inPlane % 8) == 0 && (outPitch % 4) == 0 &&
+                  ((((uintptr_t)inSplit) | ((uintptr_t)out)) & 15) == 0,
+              "pre-split rows: channels, pitches and the plane stride multiples of 8, 16-byte aligned bases");
+  const uint16_t *hi = (const uint16_t *)inSplit;
+  nhwc::k_split_to_rows<<<nhwc::grid_for(rows * channels / 8), 256, 0, ctx->stream>>>(
+      rows, (int)(channels / 8), reinterpret_cast<const uint4 *>(hi), reinterpret_cast<const uint4 *>(hi + inPlane),
+      inPitch / 8, reinterpret_cast<float4 *>(out), outPitch / 4);
+  TNN_LAUNCHED(ctx);
+  return 0;
 }
 
 int32_t tnn_nchw_to_nhwc(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize, const float *in,

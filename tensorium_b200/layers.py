@@ -111,6 +111,8 @@ class TConvolutionalLayer:
         self.in_layout = self.out_layout = nn.TNNCuda.LAYOUT_NCHW
         self.out_pitch = 0   # 0 = dense (filters floats per pixel)
         self._in_nhwc = None  # private channels-innermost copy of a planar input the direct kernel cannot take
+        self.in_split = self.out_split = False  # pre-split bf16 planes in / out (TNNet.setSplitActivations)
+        self.out_f32 = True
         self._desc = nn.TNNCuda.conv_desc(batch, c, h, w, filters, kernelSize, kernelSize, padding, padding, stride,
                                           stride, dilation, dilation)
 
@@ -174,6 +176,25 @@ class TConvolutionalLayer:
                     self._in_nhwc.pitch = pitch
                 cu.nchwToNhwc(self.batch, self.c, self.h * self.w, src.devData, self._in_nhwc.devData, self._in_nhwc.pitch)
                 src, in_layout, in_pitch = self._in_nhwc, NHWC, self._in_nhwc.pitch
+            if self.in_split or self.out_split:
+                # pre-split (bf16 hi / lo planes) activations in and / or out (TNNet.setSplitActivations; BF16x3 mode)
+                SPLIT = nn.TNNCuda.LAYOUT_NHWC_SPLIT
+                tgt = self._fused_out if self._residual is not None else self.output
+                tgt.setCUDA()
+                if self.in_split:
+                    n_in = self.batch * self.h * self.w * self.c
+                    in_ptr, in_layout, in_pitch, in_plane = src.split.devData, SPLIT, self.c, n_in
+                else:
+                    in_ptr, in_plane = src.devData, 0
+                res = self._residual
+                cu.conv2dForwardSplit(self._desc, in_ptr, 0, in_pitch, in_layout, in_plane, self.weights.devData,
+                                      sc.devData if sc is not None else None, bi.devData, self.ActivationType,
+                                      res.devData if res is not None else None, 0,
+                                      (getattr(res, "pitch", 0) or self.filters) if res is not None else 0,
+                                      tgt.devData if self.out_f32 else None, 0, self.out_pitch or self.filters,
+                                      self.out_layout, tgt.split.devData if self.out_split else None, 0, self.filters,
+                                      tgt.Size())
+                return
             if self._residual is not None and in_layout == NHWC and self.out_layout == NHWC:
                 # the shortcut that follows, folded into the epilogue (TNNet.fuseShortcuts): writes the shortcut's output
                 self._fused_out.setCUDA()

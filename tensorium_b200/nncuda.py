@@ -360,7 +360,8 @@ class TNNCuda:
     CONV_KERNELS = {0: "none", 1: "direct::k_conv_direct", 2: "umma::k_umma<Im2colPixelLoader> (gather)",
                     3: "umma::k_umma<TmaPatchLoader> (TMA activations)", 4: "umma::k_umma_halo", 5: "simt::k_gemm",
                     6: "umma::k_umma_pair (gather, CTA pairs)",
-                    7: "nhwc::k_conv_nhwc (TMA im2col activations, TMA store)", 8: "direct::k_conv_direct (NHWC out)"}
+                    7: "nhwc::k_conv_nhwc (TMA im2col activations, TMA store)", 8: "direct::k_conv_direct (NHWC out)",
+                    9: "nhwc::k_conv_image (planar image in, tensor cores, TMA store)"}
 
     def setWeightsStatic(self, weights, is_static: bool = True):
         """The backend may keep its re-ordered / TF32-split copy of `weights` across calls (inference)."""
@@ -414,7 +415,7 @@ class TNNCuda:
                                              _addr(out)))
 
     # ---- channels-innermost (NHWC) inference graph (include/tensorium_b200.h, last section)
-    LAYOUT_NCHW, LAYOUT_NHWC = 0, 1
+    LAYOUT_NCHW, LAYOUT_NHWC, LAYOUT_NHWC_SPLIT = 0, 1, 2
 
     def conv2dForwardNhwc(self, desc, in_, inOffset, inPitch, inLayout, weights, scale, bias, activation, out,
                           outOffset, outPitch, outLayout):
@@ -428,6 +429,21 @@ class TNNCuda:
             self._h, C.byref(desc), _addr(in_), inOffset, inPitch, int(inLayout), _addr(weights), _addr(scale),
             _addr(bias), int(activation), _addr(residual), residualOffset, residualPitch, _addr(out), outOffset, outPitch,
             int(outLayout)))
+
+    def conv2dForwardSplit(self, desc, in_, inOffset, inPitch, inLayout, inPlane, weights, scale, bias, activation, residual,
+                           residualOffset, residualPitch, out, outOffset, outPitch, outLayout, outSplit, outSplitOffset,
+                           outSplitPitch, outSplitPlane):
+        """Pre-split (bf16 hi/lo planes) activations in and / or out — BF16x3 mode (include/tensorium_b200.h)."""
+        self._ck(self._l.tnn_conv2d_forward_split(
+            self._h, C.byref(desc), _addr(in_), inOffset, inPitch, int(inLayout), inPlane, _addr(weights), _addr(scale),
+            _addr(bias), int(activation), _addr(residual), residualOffset, residualPitch, _addr(out), outOffset, outPitch,
+            int(outLayout), _addr(outSplit), outSplitOffset, outSplitPitch, outSplitPlane))
+
+    def nhwcToSplit(self, rows, channels, in_, inPitch, outSplit, outPitch, outPlane):
+        self._ck(self._l.tnn_nhwc_to_split(self._h, rows, channels, _addr(in_), inPitch, _addr(outSplit), outPitch, outPlane))
+
+    def splitToNhwc(self, rows, channels, inSplit, inPitch, inPlane, out, outPitch):
+        self._ck(self._l.tnn_split_to_nhwc(self._h, rows, channels, _addr(inSplit), inPitch, inPlane, _addr(out), outPitch))
 
     def nchwToNhwc(self, batch, channels, blockSize, in_, out, outPitch):
         self._ck(self._l.tnn_nchw_to_nhwc(self._h, batch, channels, blockSize, _addr(in_), _addr(out), outPitch))

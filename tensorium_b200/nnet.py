@@ -57,8 +57,15 @@ class TConcatLayer:
             src = net.layers[li].output
             if getattr(self, "layout", "NCHW") == "NHWC":
                 # channels-innermost: every source is a column slice of the output rows
-                cu.rowsCopy(self.batch * self.h * self.w, c, src.devData, getattr(src, "pitch", 0) or c,
-                            self.output.devData + 4 * off, self.outC)
+                rows = self.batch * self.h * self.w
+                if getattr(self, "f32_rows", True):
+                    cu.rowsCopy(rows, c, src.devData, getattr(src, "pitch", 0) or c, self.output.devData + 4 * off, self.outC)
+                if getattr(self, "split_planes", False):
+                    # pre-split tensors (TNNet.setSplitActivations): the same slice copy on the hi and the lo plane —
+                    # rows of c bf16 = c/2 floats, planes rows*C bf16 elements apart
+                    for plane in (0, 1):
+                        cu.rowsCopy(rows, c // 2, src.split.devData + 2 * plane * rows * c, c // 2,
+                                    self.output.split.devData + 2 * (plane * rows * self.outC + off), self.outC // 2)
             elif self.batch == 1 or len(self.inputLayers) == 1:
                 cu.copy(src.Size(), src.devData, 0, 1, self.output.devData, off * self.h * self.w, 1)
             else:
@@ -78,8 +85,16 @@ class TUpsampleLayer:
     def forwardGPU(self, state: TNNetState, net: "TNNet"):
         self.output.setCUDA()
         if getattr(self, "layout", "NCHW") == "NHWC":
-            cuda().upSampleNhwc(self.batch, self.c, self.h, self.w, self.stride, self.scale, state.input.devData,
-                                getattr(state.input, "pitch", 0) or self.c, self.output.devData, self.c)
+            if getattr(self, "f32_rows", True):
+                cuda().upSampleNhwc(self.batch, self.c, self.h, self.w, self.stride, self.scale, state.input.devData,
+                                    getattr(state.input, "pitch", 0) or self.c, self.output.devData, self.c)
+            if getattr(self, "split_planes", False):
+                assert self.scale == 1.0, "pre-split planes are repeated, not rescaled"
+                n_in, n_out = self.batch * self.h * self.w * self.c, self.output.Size()
+                for plane in (0, 1):  # bf16 rows seen as rows of c/2 floats
+                    cuda().upSampleNhwc(self.batch, self.c // 2, self.h, self.w, self.stride, 1.0,
+                                        state.input.split.devData + 2 * plane * n_in, self.c // 2,
+                                        self.output.split.devData + 2 * plane * n_out, self.c // 2)
             return
         cuda().upSample(self.batch, self.c, self.h, self.w, state.input.devData, self.stride, 1, self.scale,
                         self.output.devData)
@@ -423,9 +438,74 @@ class TNNet:
         self.channels_last = bool(on)
         return self
 
+    def setSplitActivations(self, on: bool = True):
+        """BF16x3 graphs: keep every activation that a convolution reads as PRE-SPLIT bf16 planes
+        (TNN_LAYOUT_NHWC_SPLIT, include/tensorium_b200.h): the producing epilogue writes hi = bf16(x), lo = bf16(x - hi),
+        the consuming convolution's TMA lands them as tensor-core operands and nothing converts — the same products
+        and fp32 accumulation as the fp32-input kernel, bit for bit.  fp32 rows are written only where something other
+        than a convolution reads the tensor: the operand of a later shortcut, a yolo layer, the graph's last layer.
+        Call after setChannelsLast() and fuseShortcuts()."""
+        n = len(self.layers)
+        if not on:
+            for l in self.layers:
+                for a in ("in_split", "out_split", "split_planes"):
+                    if hasattr(l, a):
+                        setattr(l, a, False)
+                for a in ("out_f32", "f32_rows"):
+                    if hasattr(l, a):
+                        setattr(l, a, True)
+                l.output.f32_valid = True
+            self.split_activations = False
+            return self
+        assert getattr(self, "channels_last", False), "pre-split activations live in the channels-innermost graph"
+        need_split, need_f32 = [False] * n, [False] * n
+        need_f32[n - 1] = True
+        for j in range(n - 1, -1, -1):
+            l = self.layers[j]
+            if isinstance(l, TConvolutionalLayer):
+                if j > 0:
+                    need_split[j - 1] = True
+            elif isinstance(l, TShortcutLayer):
+                assert getattr(l, "_fused_into_conv", False), "pre-split graphs need the shortcuts folded into the convolutions"
+                need_f32[l.inputLayers[0]] = True
+            elif isinstance(l, TConcatLayer):
+                for idx in l.inputLayers:
+                    need_split[idx] |= need_split[j]
+                    need_f32[idx] |= need_f32[j]
+            elif isinstance(l, TUpsampleLayer):
+                need_split[j - 1] |= need_split[j]
+                need_f32[j - 1] |= need_f32[j]
+            elif isinstance(l, TYoloLayer):
+                need_f32[j - 1] = True
+        for j, l in enumerate(self.layers):
+            if isinstance(l, TConvolutionalLayer):
+                t = j + 1 if l._residual is not None else j     # the tensor this convolution writes
+                tgt = self.layers[t].output
+                l.in_split = j > 0
+                l.out_split = need_split[t]
+                # (an image layer too deep for the tensor-core image kernel runs the direct kernel, which writes rows first)
+                l.out_f32 = need_f32[t] or not need_split[t] or (j == 0 and l.c * l.kernelSize ** 2 > 32)
+                assert not (l.out_split and l.out_layout != nn.TNNCuda.LAYOUT_NHWC), "planes are fp32 only"
+                assert l.c % 8 == 0 or j == 0, "pre-split rows need a channel count that is a multiple of 8"
+            elif isinstance(l, (TConcatLayer, TUpsampleLayer)):
+                t, tgt = j, l.output
+                l.split_planes = need_split[j]
+                l.f32_rows = need_f32[j] or not need_split[j]
+            else:
+                continue
+            tgt.f32_valid = getattr(l, "out_f32", False) or getattr(l, "f32_rows", False)
+            if need_split[t] and getattr(tgt, "split", None) is None:
+                tgt.split = TSingleTensor(tgt.FShape, groups=self.batch, host=False)   # hi plane | lo plane, 4 B/element
+        self.split_activations = True
+        return self
+
     def output_nchw(self, i: int) -> np.ndarray:
         """Host copy of layer i's output in the reference's planar order, whatever the internal layout."""
         l = self.layers[i]
+        if not getattr(l.output, "f32_valid", True):
+            # only the pre-split planes were written: fp32 = hi + lo (exact) into the tensor's idle fp32 twin
+            b, c, h, w = l.output.FShape
+            cuda().splitToNhwc(b * h * w, c, l.output.split.devData, c, b * h * w * c, l.output.devData, c)
         data = l.output.pullFromDevice()
         l.output.setCUDA()
         if getattr(l.output, "layout", "NCHW") == "NHWC":
@@ -530,7 +610,7 @@ def init_yolov3_params(spec, c_in=3, seed=1234, objectness_bias=-4.0):
 
 
 def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=1234, fuse_shortcuts=False,
-                 channels_last=False):
+                 channels_last=False, split_activations=False):
     """Builds the 107-layer net on the current `cuda` backend.  fuse_bn=True mirrors MSCOCOYolo.pas:327-340
     (Neural.fuseBatchNorm before predict)."""
     spec = yolov3_spec()
@@ -569,4 +649,6 @@ def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=12
         net.setChannelsLast()
     if fuse_shortcuts and fused:
         net.fuseShortcuts()
+    if split_activations:
+        net.setSplitActivations()
     return net

@@ -196,6 +196,12 @@ meth("procedure concatChannels(const batch, c, blockSize: SizeInt; const inp: TC
      "tnn_concat_channels", "batch, c, blockSize, inp, outChannels, cOffset, outp")
 meth("procedure setWeightsStatic(const weights: TCUMem; const isStatic: boolean)", "tnn_set_weights_static", "weights, ord(isStatic)", False)
 meth("procedure setMathMode(const mode: longint)", "tnn_set_math_mode", "mode", False)
+meth("procedure conv2dForwardSplit(const d: TNNConvDesc; const inp: TCUMem; const inOffset, inPitch: SizeInt; const inLayout: longint; const inPlane: SizeInt; const weights, scale, bias: TCUMem; const activation: longint; const residual: TCUMem; const residualOffset, residualPitch: SizeInt; const outp: TCUMem; const outOffset, outPitch: SizeInt; const outLayout: longint; const outSplit: TCUMem; const outSplitOffset, outSplitPitch, outSplitPlane: SizeInt)",
+     "tnn_conv2d_forward_split", "@d, inp, inOffset, inPitch, inLayout, inPlane, weights, scale, bias, activation, residual, residualOffset, residualPitch, outp, outOffset, outPitch, outLayout, outSplit, outSplitOffset, outSplitPitch, outSplitPlane")
+meth("procedure nhwcToSplit(const rows, channels: SizeInt; const inp: TCUMem; const inPitch: SizeInt; const outSplit: TCUMem; const outPitch, outPlane: SizeInt)",
+     "tnn_nhwc_to_split", "rows, channels, inp, inPitch, outSplit, outPitch, outPlane")
+meth("procedure splitToNhwc(const rows, channels: SizeInt; const inSplit: TCUMem; const inPitch, inPlane: SizeInt; const outp: TCUMem; const outPitch: SizeInt)",
+     "tnn_split_to_nhwc", "rows, channels, inSplit, inPitch, inPlane, outp, outPitch")
 meth("procedure nchwToNhwc(const batch, channels, blockSize: SizeInt; const inp, outp: TCUMem; const outPitch: SizeInt)",
      "tnn_nchw_to_nhwc", "batch, channels, blockSize, inp, outp, outPitch")
 meth("procedure nhwcToNchw(const batch, channels, blockSize: SizeInt; const inp: TCUMem; const inPitch: SizeInt; const outp: TCUMem)",
