@@ -331,7 +331,9 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
             const __grid_constant__ CUtensorMap tmOutLo) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ Ctl ctl;
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared address space
+  // and emits LDS / STS instead of generic LD / ST for every access below)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr bool SPLIT = MODE != MODE_TF32;   // two B planes
   constexpr bool BF = MODE == MODE_BF16X3;
   constexpr bool CONVERT = SPLIT && !ASPLIT;  // producers derive the second plane(s) of the landed A tile
@@ -622,7 +624,9 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
                  const __grid_constant__ CUtensorMap tmOutLo) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ Ctl ctl;
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared address space
+  // and emits LDS / STS instead of generic LD / ST for every access below)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr bool SPLIT = MODE != MODE_TF32;
   constexpr bool BF = MODE == MODE_BF16X3;
   constexpr bool CONVERT = SPLIT && !ASPLIT;
@@ -1073,16 +1077,24 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
 //   MMA     six 128 x F x 16 MMAs (BF16x3) into one slot of a ring of up to eight TMEM accumulators
 //   out     the usual epilogue; stores are 4-D ({F, OW, OH, N} boxes of 32 filters x 16 columns x 2 rows), so ragged
 //           patches are clipped by the TMA unit
-// The work per tile is tiny, so everything is about keeping many tiles in flight: the eight gather warps form two groups
-// that take alternate tiles, halos / operand tiles / accumulators are rings, and the weights (F x 32 bf16 x 2 planes) stay
-// in shared memory for the whole kernel.  The CUDA-core direct kernel needs 1.2 ms for YOLOv3's first layer at batch 64
+// The work per tile is tiny and every role's per-tile instruction chain is latency bound, so everything is about keeping
+// many tiles in flight: the twelve worker warps form three sets of four (one warp per TMEM lane quadrant); a set gathers
+// tile i, then drains tile i - 3 (whose MMAs have finished meanwhile), then gathers tile i + 3, ... — all twelve warps
+// always have independent work.  Halos / operand tiles / accumulators are rings, and the weights (F x 32 bf16 x 2
+// planes) stay in shared memory for the whole kernel.  The CUDA-core direct kernel needs 1.2 ms for YOLOv3's first layer at batch 64
 // (864 FMAs per pixel); a first tensor-core version that gathered from global memory needed 1.0 ms (5700 warp
 // instructions per tile, most of them address arithmetic and edge tests, ncu).
-constexpr int kImgStages = 6;      // operand tiles
+constexpr int kImgStages = 4;      // operand tiles
 constexpr int kImgHalos = 4;       // halo ring
 constexpr int kImgHaloBytes = 8192;
-constexpr int kImgGroups = 2;
-constexpr int kImgGroupWarps = kProducerWarps / kImgGroups;   // 4 warps = 128 threads = one pixel each
+#ifndef TNN_IMG_SETS
+#define TNN_IMG_SETS 3
+#endif
+constexpr int kImgSets = TNN_IMG_SETS;   // worker sets
+constexpr int kImgSetWarps = 4;    // 4 warps = 128 threads = one pixel each = the four TMEM lane quadrants
+constexpr int kImgWorkers = kImgSets * kImgSetWarps;   // then one MMA warp and one TMA warp
+constexpr int kImgMmaWarp = kImgWorkers, kImgTmaWarp = kImgWorkers + 1;
+constexpr int kImgThreads = (kImgWorkers + 2) * 32;
 constexpr int kImgMaxAcc = 8;
 constexpr int kImgTW = 16, kImgTH = 8;   // output patch
 
@@ -1091,13 +1103,15 @@ struct ImgCtl {
   uint64_t a_full[kImgStages], a_empty[kImgStages];
   uint64_t tmem_full[kImgMaxAcc], tmem_empty[kImgMaxAcc];
   uint32_t tmem_base;
-  alignas(16) float epi_sb[kEpilogueWarps][64];
+  alignas(16) int ktab[32];   // k -> byte offset of tap (c, kr, kc) from a pixel's corner in the halo; k >= K: -1
+  alignas(16) float epi_sb[kImgWorkers][64];
 };
 struct ImgGeo {
   int tilesX, tilesY;     // patches per image row / column
   int PC, PR;             // halo box: columns (multiple of 4), rows
   int delta;              // columns between the aligned box start and the first tap column
   int haloBytes;
+  int haloSlot;           // bytes between the halos of the ring (haloBytes rounded up to 128)
 };
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap *tmap, uint32_t src_smem, int c0, int c1, int c2, int c3) {
@@ -1107,39 +1121,46 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap *tmap, uint32_t s
                : "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kImgThreads, 1)
 k_conv_image(NhwcEpilogue epi, simt::ConvGeom g, ImgGeo ig, const float *__restrict__ w, int BN, int nAcc, uint32_t accCols,
              int numTiles, const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmOut,
              const __grid_constant__ CUtensorMap tmOutHi, const __grid_constant__ CUtensorMap tmOutLo) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ ImgCtl ctl;
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared address space
+  // and emits LDS / STS instead of generic LD / ST for every access below)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int aPlane = BM * 64;                 // one bf16 plane of a tile: 128 rows x 64 bytes
   constexpr int aStage = 2 * aPlane;
   const int bPlane = BN * 64;
   uint8_t *sB = smem + kImgStages * aStage;       // B_hi | B_lo
   uint8_t *sStg = sB + 2 * bPlane;                // epilogue staging (1024-aligned: BN is a multiple of 16)
-  uint8_t *sHalo = sStg + kEpilogueWarps * kStageBufs * kStageTile;
+  uint8_t *sHalo = sStg + kImgWorkers * kStageBufs * kStageTile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int K = g.C * g.kh * g.kw, kk = g.kh * g.kw;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kImgHalos; ++s) {
       mbar_init(&ctl.h_full[s], 1);
-      mbar_init(&ctl.h_empty[s], kImgGroupWarps);
+      mbar_init(&ctl.h_empty[s], kImgSetWarps);
     }
     for (int s = 0; s < kImgStages; ++s) {
-      mbar_init(&ctl.a_full[s], kImgGroupWarps);
+      mbar_init(&ctl.a_full[s], kImgSetWarps);
       mbar_init(&ctl.a_empty[s], 1);
     }
     for (int s = 0; s < kImgMaxAcc; ++s) {
       mbar_init(&ctl.tmem_full[s], 1);
-      mbar_init(&ctl.tmem_empty[s], kEpilogueWarps);
+      mbar_init(&ctl.tmem_empty[s], kImgSetWarps);
     }
     fence_barrier_init();
   }
+  if (threadIdx.x < 32) {
+    const int k = threadIdx.x;
+    const int c = k / kk, tap = k - c * kk, kr = tap / g.kw, kc = tap - kr * g.kw;
+    ctl.ktab[k] = k < K ? ((c * ig.PR + kr * g.dy) * ig.PC + kc * g.dx) * 4 : -1;
+  }
   // weights -> bf16 hi / lo K-major SWIZZLE_64B tiles (row n = filter, 64 bytes = 32 k; rows >= F and k >= K zero)
-  for (int u = threadIdx.x; u < BN * 4; u += kThreads) {
+  for (int u = threadIdx.x; u < BN * 4; u += kImgThreads) {
     const int n = u >> 2, j = u & 3;
     float v[8];
 #pragma unroll
@@ -1153,8 +1174,8 @@ k_conv_image(NhwcEpilogue epi, simt::ConvGeom g, ImgGeo ig, const float *__restr
     *reinterpret_cast<uint4 *>(sB + o) = hi;
     *reinterpret_cast<uint4 *>(sB + bPlane + o) = lo;
   }
-  if (warp == kMmaWarp) tmem_alloc(&ctl.tmem_base, 512);
-  if (warp == kTmaWarp && lane == 0) {
+  if (warp == kImgMmaWarp) tmem_alloc(&ctl.tmem_base, 512);
+  if (warp == kImgTmaWarp && lane == 0) {
     tma_prefetch_desc(&tmIn);
     if (epi.f32Out) tma_prefetch_desc(&tmOut);
     if (epi.splitOut) { tma_prefetch_desc(&tmOutHi); tma_prefetch_desc(&tmOutLo); }
@@ -1166,33 +1187,35 @@ k_conv_image(NhwcEpilogue epi, simt::ConvGeom g, ImgGeo ig, const float *__restr
   const uint32_t tmem_base = ctl.tmem_base;
   const int tilesPerImg = ig.tilesX * ig.tilesY;
 
-  if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
-    // ===================== gather: thread = one pixel of the patch, all 32 k =====================
-    const int group = (warp - kFirstProducerWarp) / kImgGroupWarps;
-    const int p = threadIdx.x - (kFirstProducerWarp + group * kImgGroupWarps) * 32;   // row of the operand tile
+  if (warp < kImgWorkers) {
+    // ===================== workers: gather tile i, drain tile i - 3 =====================
+    const int set = warp / kImgSetWarps, quad = warp & 3;
+    const int p = threadIdx.x - set * kImgSetWarps * 32;   // row of the operand tile = pixel of the patch
     const int pr = p / kImgTW, pc = p - pr * kImgTW;
-    // halo [c][row][column] fp32: this pixel's tap (c, kr, kc) sits at koff[k] floats after its own corner
-    const int corner = (pr * g.sy) * ig.PC + pc * g.sx + ig.delta;
-    int koff[32];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const int c = k / kk, tap = k - c * kk, kr = tap / g.kw, kc = tap - kr * g.kw;
-      koff[k] = k < K ? ((c * ig.PR + kr * g.dy) * ig.PC + kc * g.dx + corner) * 4 : -1;
-    }
+    const int corner = ((pr * g.sy) * ig.PC + pc * g.sx + ig.delta) * 4;   // this pixel's tap (0, 0, 0) in the halo, bytes
     const int sw = (p >> 1) & 3;
-    int it = group;
-    for (int t = blockIdx.x + group * gridDim.x; t < numTiles; t += kImgGroups * gridDim.x, it += kImgGroups) {
+    uint8_t *stg = sStg + (size_t)warp * (kStageBufs * kStageTile);
+    float *scratch = ctl.epi_sb[warp];
+    int sbuf = 0;
+
+    auto gather = [&](int it) {
       const int stage = it % kImgStages, hs = it % kImgHalos;
       mbar_wait_warp(&ctl.h_full[hs], (uint32_t)((it / kImgHalos) & 1));
-      const uint8_t *halo = sHalo + hs * kImgHaloBytes;
-      float x[32];
-#pragma unroll
-      for (int k = 0; k < 32; ++k) x[k] = koff[k] >= 0 ? *reinterpret_cast<const float *>(halo + koff[k]) : 0.f;
+      const uint8_t *halo = sHalo + hs * ig.haloSlot + corner;
       uint4 hi[4], lo[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        split_bf16x8(make_float4(x[8 * j], x[8 * j + 1], x[8 * j + 2], x[8 * j + 3]),
-                     make_float4(x[8 * j + 4], x[8 * j + 5], x[8 * j + 6], x[8 * j + 7]), hi[j], lo[j]);
+      for (int j = 0; j < 4; ++j) {
+        float x[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int4 o = *reinterpret_cast<const int4 *>(&ctl.ktab[8 * j + 4 * q]);
+          x[4 * q + 0] = o.x >= 0 ? *reinterpret_cast<const float *>(halo + o.x) : 0.f;
+          x[4 * q + 1] = o.y >= 0 ? *reinterpret_cast<const float *>(halo + o.y) : 0.f;
+          x[4 * q + 2] = o.z >= 0 ? *reinterpret_cast<const float *>(halo + o.z) : 0.f;
+          x[4 * q + 3] = o.w >= 0 ? *reinterpret_cast<const float *>(halo + o.w) : 0.f;
+        }
+        split_bf16x8(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), hi[j], lo[j]);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl.h_empty[hs]);   // the halo is in registers
       mbar_wait_warp(&ctl.a_empty[stage], (uint32_t)(((it / kImgStages) & 1) ^ 1));
@@ -1206,8 +1229,30 @@ k_conv_image(NhwcEpilogue epi, simt::ConvGeom g, ImgGeo ig, const float *__restr
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ctl.a_full[stage]);
+    };
+    auto drain = [&](int it) {
+      const int t = blockIdx.x + it * gridDim.x;
+      const int as = it % nAcc;
+      const uint32_t use = (uint32_t)(it / nAcc);
+      const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
+      const int b = t / tilesPerImg, rem = t - b * tilesPerImg, ty = rem / ig.tilesX, tx = rem - ty * ig.tilesX;
+      const int ow0 = tx * kImgTW, oh0 = ty * kImgTH + quad * 2;   // this warp's two patch rows
+      mbar_wait_warp(&ctl.tmem_full[as], use & 1);
+      tc_fence_after();
+      drain_tile(epi, tmem_d, BN, 0, 0, scratch, stg, sbuf, &tmOut, &tmOutHi, &tmOutLo,
+                 [&] { mbar_arrive(&ctl.tmem_empty[as]); },
+                 [&](const CUtensorMap *tm, uint32_t src, int n) { tma_store_4d(tm, src, n, ow0, oh0, b); });
+    };
+    const int nIt = (numTiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // this CTA's tiles
+    int prev = -1;
+    for (int it = set; it < nIt; it += kImgSets) {
+      gather(it);
+      if (prev >= 0) drain(prev);
+      prev = it;
     }
-  } else if (warp == kMmaWarp) {
+    if (prev >= 0) drain(prev);
+    if (lane == 0) bulk_wait_all();
+  } else if (warp == kImgMmaWarp) {
     // ===================== MMA issuer: six MMAs per tile, accumulator ring =====================
     const uint32_t idesc = make_idesc_bf16(BN);
     const uint32_t sb = smem_u32(sB);
@@ -1236,7 +1281,7 @@ k_conv_image(NhwcEpilogue epi, simt::ConvGeom g, ImgGeo ig, const float *__restr
       }
       __syncwarp();
     }
-  } else if (warp == kTmaWarp) {
+  } else if (warp == kImgTmaWarp) {
     // ===================== TMA: one halo per tile =====================
     if (lane == 0) {
       int it = 0;
@@ -1245,33 +1290,14 @@ k_conv_image(NhwcEpilogue epi, simt::ConvGeom g, ImgGeo ig, const float *__restr
         mbar_wait(&ctl.h_empty[hs], (uint32_t)(((it / kImgHalos) & 1) ^ 1));
         const int b = t / tilesPerImg, rem = t - b * tilesPerImg, ty = rem / ig.tilesX, tx = rem - ty * ig.tilesX;
         mbar_arrive_expect_tx(&ctl.h_full[hs], (uint32_t)ig.haloBytes);
-        tma_load_4d(smem_u32(sHalo + hs * kImgHaloBytes), &tmIn, tx * kImgTW * g.sx - g.pw - ig.delta,
+        tma_load_4d(smem_u32(sHalo + hs * ig.haloSlot), &tmIn, tx * kImgTW * g.sx - g.pw - ig.delta,
                     ty * kImgTH * g.sy - g.ph, 0, b, &ctl.h_full[hs]);
       }
     }
-  } else {
-    // ===================== epilogue =====================
-    const int quad = warp;
-    uint8_t *stg = sStg + (size_t)quad * (kStageBufs * kStageTile);
-    int sbuf = 0, it = 0;
-    float *scratch = ctl.epi_sb[quad];
-    for (int t = blockIdx.x; t < numTiles; t += gridDim.x, ++it) {
-      const int as = it % nAcc;
-      const uint32_t use = (uint32_t)(it / nAcc);
-      const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
-      const int b = t / tilesPerImg, rem = t - b * tilesPerImg, ty = rem / ig.tilesX, tx = rem - ty * ig.tilesX;
-      const int ow0 = tx * kImgTW, oh0 = ty * kImgTH + quad * 2;   // this warp's two patch rows
-      mbar_wait_warp(&ctl.tmem_full[as], use & 1);
-      tc_fence_after();
-      drain_tile(epi, tmem_d, BN, 0, 0, scratch, stg, sbuf, &tmOut, &tmOutHi, &tmOutLo,
-                 [&] { mbar_arrive(&ctl.tmem_empty[as]); },
-                 [&](const CUtensorMap *tm, uint32_t src, int n) { tma_store_4d(tm, src, n, ow0, oh0, b); });
-    }
-    if (lane == 0) bulk_wait_all();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == kMmaWarp) tmem_dealloc(tmem_base, 512);
+  if (warp == kImgMmaWarp) tmem_dealloc(tmem_base, 512);
 }
 
 static bool image_geo(const simt::ConvGeom &g, ImgGeo &ig) {
@@ -1282,6 +1308,7 @@ static bool image_geo(const simt::ConvGeom &g, ImgGeo &ig) {
   ig.PC = (cols + 3) / 4 * 4;
   ig.PR = (kImgTH - 1) * g.sy + (g.kh - 1) * g.dy + 1;
   ig.haloBytes = ig.PC * ig.PR * g.C * 4;
+  ig.haloSlot = (ig.haloBytes + 127) / 128 * 128;
   ig.tilesX = (g.OW + kImgTW - 1) / kImgTW;
   ig.tilesY = (g.OH + kImgTH - 1) / kImgTH;
   return ig.PC <= 256 && ig.PR <= 256 && g.C <= 256 && ig.haloBytes <= kImgHaloBytes;
@@ -1362,9 +1389,9 @@ static int conv_image(tnn_context *ctx, const simt::ConvGeom &g, int batch, cons
   const int sms = ctx->prop.multiProcessorCount;
   const int grid = numTiles < sms ? numTiles : sms;
   const size_t smemBytes = (size_t)kImgStages * 2 * BM * 64 + (size_t)2 * BN * 64 +
-                           (size_t)kEpilogueWarps * kStageBufs * kStageTile + (size_t)kImgHalos * kImgHaloBytes + 1024;
+                           (size_t)kImgWorkers * kStageBufs * kStageTile + (size_t)kImgHalos * ig.haloSlot + 1024;
   TNN_CUDA(cudaFuncSetAttribute(k_conv_image, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-  k_conv_image<<<grid, kThreads, smemBytes, ctx->stream>>>(epi, g, ig, weights, BN, nAcc, accCols, numTiles, m.a, m.out,
+  k_conv_image<<<grid, kImgThreads, smemBytes, ctx->stream>>>(epi, g, ig, weights, BN, nAcc, accCols, numTiles, m.a, m.out,
                                                            m.outHi, m.outLo);
   TNN_LAUNCHED(ctx);
   return 0;

@@ -782,7 +782,9 @@ k_umma(LA la, LB lb, EPI epi, TileSched sched, int BN, int stages, uint32_t accC
   extern __shared__ uint8_t smem_raw[];
   __shared__ SharedCtl ctl;
   // 1024B-aligned operand ring
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared address space
+  // and emits LDS / STS instead of generic LD / ST for every access below)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int KB = StageK<LA>::v;
   static_assert(KB == BK || (LB::kTma && LA::kMnMajor), "16-k stages: MN-major A (gathered or TMA patches) + TMA weights only");
   const int aBytes = BM * KB * 4;

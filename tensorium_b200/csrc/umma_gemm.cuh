@@ -67,7 +67,9 @@ k_umma_gemm(EPI epi, TileSched sched, int BN, int stages, uint32_t accCols, cons
             const __grid_constant__ CUtensorMap tmB) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ SharedCtl ctl;
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared address space
+  // and emits LDS / STS instead of generic LD / ST for every access below)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   constexpr int aBytes = BM * KB * 4;
   const int bBytes = BN * KB * 4;
   const int stageBytes = (aBytes + bBytes) * (SPLIT ? 2 : 1);

@@ -55,7 +55,9 @@ k_umma_halo(HaloGeom g, ConvEpilogueT<EXTRA> epi, int mTiles, int nTiles, int BN
             const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ HaloCtl ctl;
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // (pointer arithmetic on the __shared__ array, not an integer round trip: the compiler keeps the shared address space
+  // and emits LDS / STS instead of generic LD / ST for every access below)
+  uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int Q = g.CH >> 2;            // 16-byte channel chunks per pixel
   const int plane = g.NP * 16;        // one chunk (4 channels) of every halo pixel
   const int haloBytes = plane * Q;    // one precision copy

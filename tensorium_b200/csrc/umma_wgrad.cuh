@@ -51,7 +51,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(kThreads, 1) k_umma_wgrad(WgradGeom g) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ WgradCtl ctl;
-  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~(uintptr_t)127);
+  uint8_t *smem = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);   // keeps the shared address space (LDS / STS)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int aBytes = (kWgKT / 4) * kWgLboA;             // one precision copy of the delta tile
   const int bCopy = g.HL * g.CPL * kWgLboB;             // one pre-shifted input copy, one precision
