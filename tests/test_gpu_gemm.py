@@ -111,3 +111,33 @@ def test_gemm_empty_and_degenerate(cuda_backend):
     cu.gemm(False, False, 0, 4, 4, 1.0, d.ptr, 0, 4, d.ptr, 0, 4, 0.0, d.ptr, 0, 4)  # M = 0: no-op
     cu.gemm(False, False, 4, 4, 0, 1.0, d.ptr, 0, 4, d.ptr, 0, 4, 1.0, d.ptr, 0, 4)  # K = 0: C unchanged (beta=1)
     assert np.array_equal(d.read(), np.ones(16, np.float32))
+
+
+@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32)])
+@pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0)])
+def test_gemm_8192_against_the_oracle_on_a_row_sample(cuda_backend, oracle, mode, tol, ta, tb):
+    """BASELINE configs[1] at its largest size, M = N = K = 8192, NN / NT / TN: the GPU computes the whole product, the
+    oracle (same cblas_sgemm routine, same transpose flags) the 24 rows of a sample — 3.2 GFLOP of CPU work."""
+    cu = cuda_backend
+    n = 8192
+    rng = np.random.default_rng(8192 + 2 * ta + tb)
+    A = rng.uniform(-1, 1, (n, n)).astype(np.float32)   # [M][K], or [K][M] when ta
+    B = rng.uniform(-1, 1, (n, n)).astype(np.float32)   # [K][N], or [N][K] when tb
+    dA, dB, dC = Dev(cu, A), Dev(cu, B), Dev(cu, n=n * n)
+    cu.set_math_mode(mode)
+    try:
+        cu.gemm(ta, tb, n, n, n, 1.0, dA.ptr, 0, n, dB.ptr, 0, n, 0.0, dC.ptr, 0, n)
+    finally:
+        cu.set_math_mode(X3)
+    got = dC.read((n, n))
+    rows = np.sort(rng.choice(n, 24, replace=False))
+    # the sampled rows of op(A) as a matrix with the SAME storage order (so the oracle runs the same routine)
+    Asub = np.ascontiguousarray(A[:, rows]) if ta else np.ascontiguousarray(A[rows, :])
+    want = np.zeros((rows.size, n), np.float32)
+    oracle.sgemm(ta, tb, rows.size, n, n, 1.0, Asub, rows.size if ta else n, B, n, 0.0, want, n)
+    e1, e2 = rel_max(got[rows], want), rel_elem(got[rows], want, floor=1.0)
+    # north-star metric (max|g-r| / max|r|) inside the gate; the stricter element metric (error over max(|r|, rms)) is
+    # reported with a 4x allowance: the tensor core's truncating fp32 accumulate gives an error that grows with K
+    # (profiles/r02_accuracy_vs_k.txt: 5.7e-5 of max|r| at K = 8192), and max|r| is ~3.5 rms here
+    print(f"K=8192 ta={ta} tb={tb} mode={mode}: rel_max {e1:.2e}, rel_elem {e2:.2e}")
+    assert e1 < tol and e2 < 4 * tol, (e1, e2)
