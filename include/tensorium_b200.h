@@ -358,6 +358,12 @@ TNN_API int32_t tnn_batchnorm_backward(tnn_context *ctx, int64_t batch, int64_t 
  * with decay_term = -decay*batch for weights, 0 for biases/scales; rate = learning_rate/batch. */
 TNN_API int32_t tnn_sgd_update(tnn_context *ctx, int64_t N, float *params, float *updates, float rate,
                                float momentum, float decay_term);
+/* The same update for `count` parameter tensors in one launch per 32 tensors (TNNet.update, nnet.pas:378-403, walks the
+ * layers and each updateGPU touches two or three tensors): params[i], updates[i], sizes[i], rates[i], decay_terms[i] are
+ * HOST arrays of device pointers / element counts / per-tensor rate and decay term. */
+TNN_API int32_t tnn_sgd_update_multi(tnn_context *ctx, int32_t count, float *const *params, float *const *updates,
+                                     const uint64_t *sizes, const float *rates, const float *decay_terms,
+                                     float momentum);
 /* TYoloLayer.forwardGPU's per-(image, anchor) ActivateArray / fmavss loop (nyololayer.pas:1081-1099) in one
  * launch: logistic on the x, y, objectness and class planes of out[batch][n*(5+classes)][wh]; x,y are then
  * mapped v*scale_xy + 0.5*(1-scale_xy) when scale_xy != 1. */

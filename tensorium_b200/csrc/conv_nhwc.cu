@@ -1068,14 +1068,14 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
 
 // =====================================================================================================================
 // The image layer (planar NCHW input, C*kh*kw <= 32: 3 channels x 3x3 = 27) on the tensor cores.
-// Its contraction is ONE 32-deep k-block, k = (c, kr, kc) in the weights' own order.  A tile is a patch of 8 x 16 output
+// Its contraction is ONE 32-deep k-block, k = (c, kr, kc) in the weights' own order.  A tile is a patch of 4 x 32 output
 // pixels of one image:
 //   TMA     one tiled 4-D load fetches the patch's input HALO from the planes ({W, H, C, N} box, columns from a 16-byte
 //           aligned start, padding / image edges zero-filled by the TMA unit) — a few KB of fp32
 //   gather  thread = one pixel: 27 shared-memory reads at fixed offsets (no address arithmetic, no bounds checks),
 //           split to bf16 hi/lo, four 16-byte stores per plane into the K-major SWIZZLE_64B tile
 //   MMA     six 128 x F x 16 MMAs (BF16x3) into one slot of a ring of up to eight TMEM accumulators
-//   out     the usual epilogue; stores are 4-D ({F, OW, OH, N} boxes of 32 filters x 16 columns x 2 rows), so ragged
+//   out     the usual epilogue; stores are 4-D ({F, OW, OH, N} boxes of 32 filters x 32 columns x 1 row), so ragged
 //           patches are clipped by the TMA unit
 // The work per tile is tiny and every role's per-tile instruction chain is latency bound, so everything is about keeping
 // many tiles in flight: the twelve worker warps form three sets of four (one warp per TMEM lane quadrant); a set gathers
@@ -1096,7 +1096,7 @@ constexpr int kImgWorkers = kImgSets * kImgSetWarps;   // then one MMA warp and 
 constexpr int kImgMmaWarp = kImgWorkers, kImgTmaWarp = kImgWorkers + 1;
 constexpr int kImgThreads = (kImgWorkers + 2) * 32;
 constexpr int kImgMaxAcc = 8;
-constexpr int kImgTW = 16, kImgTH = 8;   // output patch
+constexpr int kImgTW = 32, kImgTH = 4;   // output patch: one warp = one patch row, so its halo reads are 32 consecutive floats
 
 struct ImgCtl {
   uint64_t h_full[kImgHalos], h_empty[kImgHalos];
@@ -1236,7 +1236,7 @@ k_conv_image(NhwcEpilogue epi, simt::ConvGeom g, ImgGeo ig, const float *__restr
       const uint32_t use = (uint32_t)(it / nAcc);
       const uint32_t tmem_d = tmem_base + (uint32_t)as * accCols + ((uint32_t)(quad * 32) << 16);
       const int b = t / tilesPerImg, rem = t - b * tilesPerImg, ty = rem / ig.tilesX, tx = rem - ty * ig.tilesX;
-      const int ow0 = tx * kImgTW, oh0 = ty * kImgTH + quad * 2;   // this warp's two patch rows
+      const int ow0 = tx * kImgTW, oh0 = ty * kImgTH + quad;   // this warp's patch row
       mbar_wait_warp(&ctl.tmem_full[as], use & 1);
       tc_fence_after();
       drain_tile(epi, tmem_d, BN, 0, 0, scratch, stg, sbuf, &tmOut, &tmOutHi, &tmOutLo,
@@ -1319,14 +1319,14 @@ static bool image_supported(const simt::ConvGeom &g, const float *in) {
   return g.C * g.kh * g.kw <= 32 && g.F <= 256 && (g.W % 4) == 0 && (((uintptr_t)in) & 15) == 0 && image_geo(g, ig);
 }
 
-// 4-D output map {F, OW, OH, N} over rows of channels: boxes of 32 filters x 16 columns x 2 rows (= 32 staged pixel rows)
+// 4-D output map {F, OW, OH, N} over rows of channels: boxes of 32 filters x 32 columns x 1 row (= 32 staged pixel rows)
 static int encode_out_map4(CUtensorMap *tm, void *base, const simt::ConvGeom &g, int batch, int64_t pitch, bool bf16) {
   EncodeTiledFn enc = get_encode_tiled();
   TNN_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t es = bf16 ? 2 : 4;
   cuuint64_t dims[4] = {(cuuint64_t)g.F, (cuuint64_t)g.OW, (cuuint64_t)g.OH, (cuuint64_t)batch};
   cuuint64_t strides[3] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * g.OW * es, (cuuint64_t)pitch * g.OW * g.OH * es};
-  cuuint32_t box[4] = {32, kImgTW, 2, 1};
+  cuuint32_t box[4] = {32, kImgTW, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(tm, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, bf16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,

@@ -110,6 +110,44 @@ __global__ void __launch_bounds__(kThreads) k_sgd(int64_t n, float *__restrict__
   }
 }
 
+// the same update for up to kSgdMulti parameter tensors in ONE launch (blockIdx.y = tensor): a training step of a small
+// net is bound by its launch count, and updateGPU contributes two or three launches per layer
+constexpr int kSgdMulti = 32;
+struct SgdItems {
+  float *w[kSgdMulti];
+  float *u[kSgdMulti];
+  int64_t n[kSgdMulti];
+  float rate[kSgdMulti];
+  float decay[kSgdMulti];
+};
+__global__ void __launch_bounds__(kThreads) k_sgd_multi(const __grid_constant__ SgdItems it, float momentum) {
+  const int t = blockIdx.y;
+  const int64_t n = it.n[t];
+  float *__restrict__ w = it.w[t];
+  float *__restrict__ u = it.u[t];
+  const float rate = it.rate[t], decay_term = it.decay[t];
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+  auto step = [&](float &wv, float &uv) {
+    if (decay_term != 0.f) uv = __fadd_rn(__fmul_rn(decay_term, wv), uv);
+    wv = __fadd_rn(__fmul_rn(rate, uv), wv);
+    uv = momentum * uv;
+  };
+  if (((((uintptr_t)w) | ((uintptr_t)u)) & 15) == 0) {
+    const int64_t nvec = n >> 2;
+    float4 *w4 = reinterpret_cast<float4 *>(w), *u4 = reinterpret_cast<float4 *>(u);
+    for (int64_t i = tid; i < nvec; i += nthreads) {
+      float4 wv = w4[i], uv = u4[i];
+      step(wv.x, uv.x); step(wv.y, uv.y); step(wv.z, uv.z); step(wv.w, uv.w);
+      w4[i] = wv; u4[i] = uv;
+    }
+    const int64_t i = (nvec << 2) + tid;
+    if (i < n) { float wv = w[i], uv = u[i]; step(wv, uv); w[i] = wv; u[i] = uv; }
+  } else {
+    for (int64_t i = tid; i < n; i += nthreads) { float wv = w[i], uv = u[i]; step(wv, uv); w[i] = wv; u[i] = uv; }
+  }
+}
+
 int tnn_sgd_launch(tnn_context *ctx, int64_t N, float *params, float *updates, float rate, float momentum,
                    float decay_term) {
   const int vec_ok = ((((uintptr_t)params) | ((uintptr_t)updates)) & 15) == 0;
@@ -558,6 +596,33 @@ int32_t tnn_sgd_update(tnn_context *ctx, int64_t N, float *params, float *update
   TNN_CHECK_CTX(ctx);
   if (N <= 0) return 0;
   return tnn_sgd_launch(ctx, N, params, updates, rate, momentum, decay_term);
+}
+
+int32_t tnn_sgd_update_multi(tnn_context *ctx, int32_t count, float *const *params, float *const *updates,
+                             const uint64_t *sizes, const float *rates, const float *decay_terms, float momentum) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(count >= 0 && (count == 0 || (params && updates && sizes && rates && decay_terms)), "null table");
+  for (int32_t base = 0; base < count; base += kSgdMulti) {
+    SgdItems it;
+    memset(&it, 0, sizeof(it));
+    int m = 0;
+    int64_t largest = 0;
+    for (int32_t i = base; i < count && m < kSgdMulti; ++i) {
+      if (sizes[i] == 0) continue;
+      it.w[m] = params[i];
+      it.u[m] = updates[i];
+      it.n[m] = (int64_t)sizes[i];
+      it.rate[m] = rates[i];
+      it.decay[m] = decay_terms[i];
+      if (it.n[m] > largest) largest = it.n[m];
+      ++m;
+    }
+    if (!m) continue;
+    dim3 grid((unsigned)grid_for(cdiv64(largest, 4), kThreads), (unsigned)m);
+    k_sgd_multi<<<grid, kThreads, 0, ctx->stream>>>(it, momentum);
+    TNN_LAUNCHED(ctx);
+  }
+  return 0;
 }
 
 }  // extern "C"

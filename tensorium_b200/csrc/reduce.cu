@@ -122,6 +122,137 @@ int launch_reduce(tnn_context *ctx, int64_t channels, int64_t groups, int64_t bl
   return 0;
 }
 
+// The same reduction with the inputs handed over as pointers: when every plane is 16-byte aligned the kernel reads them
+// with 128-bit loads, two independent quads per input and trip in flight (BASELINE north star: "128-bit vectorised
+// coalesced loads with warp-shuffle reductions").  The index-functor kernel above reads 4 bytes per load and thread:
+// ncu on a 268 MB tensor showed the batch-norm backward sums at 14 % of the DRAM peak.
+// AccV: void acc(const float (&v)[NIN], int c, float (&a)[NACC])     v[j] = in[j][element]
+template <int NIN>
+struct Inputs {
+  const float *p[NIN];
+};
+template <int NACC, int NIN, bool VEC, typename AccV, typename Fin>
+__global__ void __launch_bounds__(kRT) k_channel_reduce_v(int64_t channels, int64_t groups, int64_t blockSize, Split sp,
+                                                          float *partials, unsigned int *counters, Inputs<NIN> in, AccV acc,
+                                                          Fin fin) {
+  const int item = blockIdx.x;
+  const int c = blockIdx.y;
+  const int pg = item / sp.partsPerPlane;
+  const int part = item - pg * sp.partsPerPlane;
+  const int64_t b0 = (int64_t)pg * sp.planesPerItem;
+  const int64_t b1 = min(groups, b0 + sp.planesPerItem);
+  const int64_t r0 = (int64_t)part * sp.partLen;
+  const int64_t r1 = min(blockSize, r0 + sp.partLen);
+  float a[NACC];
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) a[k] = 0.f;
+  auto one = [&](const float4 (&q)[NIN]) {
+    float v[NIN];
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) v[j] = q[j].x;
+    acc(v, c, a);
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) v[j] = q[j].y;
+    acc(v, c, a);
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) v[j] = q[j].z;
+    acc(v, c, a);
+#pragma unroll
+    for (int j = 0; j < NIN; ++j) v[j] = q[j].w;
+    acc(v, c, a);
+  };
+  for (int64_t b = b0; b < b1; ++b) {
+    const int64_t base = (b * channels + c) * blockSize;
+    if (VEC) {   // r0, r1 - r0 and base are multiples of 4 (checked by the launcher)
+      int64_t r = r0 + 4 * threadIdx.x;
+      for (; r + 4 * kRT < r1; r += 8 * kRT) {
+        float4 q0[NIN], q1[NIN];
+#pragma unroll
+        for (int j = 0; j < NIN; ++j) {
+          q0[j] = __ldg(reinterpret_cast<const float4 *>(in.p[j] + base + r));
+          q1[j] = __ldg(reinterpret_cast<const float4 *>(in.p[j] + base + r + 4 * kRT));
+        }
+        one(q0);
+        one(q1);
+      }
+      for (; r < r1; r += 4 * kRT) {
+        float4 q0[NIN];
+#pragma unroll
+        for (int j = 0; j < NIN; ++j) q0[j] = __ldg(reinterpret_cast<const float4 *>(in.p[j] + base + r));
+        one(q0);
+      }
+    } else {
+      for (int64_t r = r0 + threadIdx.x; r < r1; r += kRT) {
+        float v[NIN];
+#pragma unroll
+        for (int j = 0; j < NIN; ++j) v[j] = __ldg(in.p[j] + base + r);
+        acc(v, c, a);
+      }
+    }
+  }
+  __shared__ float sm[NACC][kRT / 32];
+  __shared__ bool is_last;
+#pragma unroll
+  for (int k = 0; k < NACC; ++k) {
+    float v = warp_sum(a[k]);
+    if ((threadIdx.x & 31) == 0) sm[k][threadIdx.x >> 5] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot[NACC];
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) {
+      float v = 0.f;
+      for (int w = 0; w < kRT / 32; ++w) v += sm[k][w];
+      tot[k] = v;
+    }
+    if (sp.items == 1) {
+      fin(c, tot);
+      is_last = false;
+    } else {
+      float *p = partials + ((int64_t)c * sp.items + item) * NACC;
+#pragma unroll
+      for (int k = 0; k < NACC; ++k) p[k] = tot[k];
+      __threadfence();
+      const unsigned int prev = atomicAdd(&counters[c], 1u);
+      is_last = (prev == (unsigned int)sp.items - 1);
+      if (is_last) {
+        __threadfence();
+        float s[NACC];
+#pragma unroll
+        for (int k = 0; k < NACC; ++k) s[k] = 0.f;
+        const volatile float *q = partials + (int64_t)c * sp.items * NACC;
+        for (int i = 0; i < sp.items; ++i)
+#pragma unroll
+          for (int k = 0; k < NACC; ++k) s[k] += q[i * NACC + k];
+        fin(c, s);
+        counters[c] = 0;
+      }
+    }
+  }
+}
+
+template <int NACC, int NIN, typename AccV, typename Fin>
+int launch_reduce_v(tnn_context *ctx, int64_t channels, int64_t groups, int64_t blockSize, Inputs<NIN> in, AccV acc, Fin fin) {
+  if (channels <= 0) return 0;
+  TNN_REQUIRE(groups > 0 && blockSize > 0, "tensor sizes do not align");
+  TNN_REQUIRE(channels <= 65535, "too many channels for one launch");
+  Split sp = make_split(channels, groups, blockSize);
+  int rc = tnn_reserve_reduction(ctx, (size_t)channels * sp.items * NACC, (size_t)channels);
+  if (rc) return rc;
+  bool vec = (blockSize % 4) == 0;
+  for (int j = 0; j < NIN; ++j) vec = vec && (((uintptr_t)in.p[j]) & 15) == 0;
+  dim3 grid(sp.items, (unsigned)channels);
+  if (vec)
+    k_channel_reduce_v<NACC, NIN, true, AccV, Fin><<<grid, kRT, 0, ctx->stream>>>(channels, groups, blockSize, sp, ctx->red_partials,
+                                                                                 ctx->red_counters, in, acc, fin);
+  else
+    k_channel_reduce_v<NACC, NIN, false, AccV, Fin><<<grid, kRT, 0, ctx->stream>>>(channels, groups, blockSize, sp, ctx->red_partials,
+                                                                                  ctx->red_counters, in, acc, fin);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
 inline int64_t block_size(int64_t total, int64_t channels, int64_t groups) {
   if (channels <= 0 || groups <= 0) return 0;
   int64_t bs = total / (channels * groups);
@@ -129,6 +260,92 @@ inline int64_t block_size(int64_t total, int64_t channels, int64_t groups) {
 }
 
 }  // namespace
+
+// kA: the activation as a compile-time constant (the gradient switch folds away), -1 = decided per element at run time
+template <int kA>
+static int bn_backward_impl(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize, const float *out,
+                            int activation, float *delta, const float *x, const float *x_norm, const float *mean,
+                            const float *variance, const float *scales, float *scale_updates, float *mean_delta,
+                            float *variance_delta) {
+  const float *dl = delta;
+  const float batchSize = (float)(blockSize * batch);
+  const int a = activation;
+  int rc = launch_reduce_v<3, 4>(
+      ctx, channels, batch, blockSize, Inputs<4>{{dl, out, x, x_norm}},
+      [mean, a] __device__(const float(&v)[4], int c, float(&s)[3]) {
+        const int act = kA >= 0 ? kA : a;
+        const float g = (act == TNN_ACT_LINEAR) ? v[0] : v[0] * tnn_grad(v[1], act);
+        s[0] = fmaf(v[3], g, s[0]);
+        s[1] += g;
+        s[2] = fmaf(g, v[2] - __ldg(mean + c), s[2]);
+      },
+      [scales, scale_updates, variance, mean_delta, variance_delta] __device__(int c, const float(&t)[3]) {
+        scale_updates[c] = scale_updates[c] + t[0];
+        const double v = (double)fmaxf(variance[c], TNN_EPS);
+        const float sc = scales[c];
+        mean_delta[c] = (float)((double)(t[1] * sc) * (-1.0 / sqrt(v)));
+        variance_delta[c] = (float)((double)(t[2] * sc) * -0.5 * pow(v, -1.5));
+      });
+  if (rc) return rc;
+  return planemap::launch<2, 0>(
+      ctx, delta, out, x, nullptr, nullptr, batch * channels * blockSize, channels, batch,
+      [mean, variance, mean_delta, variance_delta, scales, batchSize, a] __device__(float &d, float ov, float xv, float &,
+                                                                                    float &, int c) {
+        const int act = kA >= 0 ? kA : a;
+        float g = (act == TNN_ACT_LINEAR) ? d : d * tnn_grad(ov, act);
+        g = g * __ldg(scales + c);
+        const float md = __ldg(mean_delta + c) / batchSize;
+        const float vd = 2 * __ldg(variance_delta + c) / batchSize;
+        const float sd = sqrtf(fmaxf(__ldg(variance + c), TNN_EPS));
+        d = __fadd_rn(g / sd, __fadd_rn(__fmul_rn(vd, xv - __ldg(mean + c)), md));
+      });
+}
+
+template <int kA>
+static int bn_forward_training_impl(tnn_context *ctx, int64_t batch, int64_t channels, int64_t blockSize, float *out, float *x,
+                                    float *x_norm, float *mean, float *variance, float *rolling_mean,
+                                    float *rolling_variance, float bn_momentum, const float *scales, const float *biases,
+                                    int32_t activation) {
+  const int64_t total = batch * channels * blockSize;
+  // Statistics in ONE read: sums of d = x - s and d*d, with s = the channel's first element as the shift (so the
+  // subtraction in  var = (sum d^2 - (sum d)^2/N)/(N-1)  cancels little), finished in double; the rolling averages
+  // are updated by the same finaliser.  (The reference reads the tensor twice: MeansAndVars ntensors.pas:9102-9177.)
+  const float *src = out;
+  const double S = (double)(batch * blockSize);
+  const float m = bn_momentum;
+  int rc = launch_reduce_v<2, 1>(
+      ctx, channels, batch, blockSize, Inputs<1>{{src}},
+      [src, blockSize] __device__(const float(&v)[1], int c, float(&acc)[2]) {
+        const float d = v[0] - __ldg(src + (int64_t)c * blockSize);
+        acc[0] += d;
+        acc[1] = fmaf(d, d, acc[1]);
+      },
+      [src, blockSize, mean, variance, rolling_mean, rolling_variance, S, m] __device__(int c, const float(&t)[2]) {
+        const double sd = (double)t[0], sq = (double)t[1];
+        const float mu = (float)((double)src[(int64_t)c * blockSize] + sd / S);
+        double var = (sq - sd * sd / S) / (S - 1.0);
+        const float v = (float)(var > 0.0 ? var : 0.0);
+        mean[c] = mu;
+        variance[c] = v;
+        rolling_mean[c] = __fadd_rn(__fmul_rn(m, mu), __fmul_rn(1 - m, rolling_mean[c]));
+        rolling_variance[c] = __fadd_rn(__fmul_rn(m, v), __fmul_rn(1 - m, rolling_variance[c]));
+      });
+  if (rc) return rc;
+  const int a = activation;
+  const bool block1 = blockSize == 1;
+  return planemap::launch<0, 2>(
+      ctx, out, nullptr, nullptr, x, x_norm, total, channels, batch,
+      [mean, variance, scales, biases, a, block1] __device__(float &v, float, float, float &xo, float &xn, int c) {
+        const float var = __ldg(variance + c);
+        const float d = block1 ? sqrtf(fmaxf(var, TNN_EPS)) : fmaxf(sqrtf(var), TNN_EPS);
+        xo = v;
+        float t = (v - __ldg(mean + c)) / d;
+        xn = t;
+        t = __fmul_rn(t, __ldg(scales + c));
+        t = __fadd_rn(t, __ldg(biases + c));
+        v = tnn_act(t, kA >= 0 ? kA : a);
+      });
+}
 
 extern "C" {
 
@@ -308,45 +525,15 @@ int32_t tnn_batchnorm_forward_training(tnn_context *ctx, int64_t batch, int64_t 
                                        const float *scales, const float *biases, int32_t activation) {
   TNN_CHECK_CTX(ctx);
   TNN_REQUIRE(activation == TNN_ACT_LINEAR || tnn_act_is_elementwise(activation), "activation not elementwise");
-  const int64_t total = batch * channels * blockSize;
-  // Statistics in ONE read: sums of d = x - s and d*d, with s = the channel's first element as the shift (so the
-  // subtraction in  var = (sum d^2 - (sum d)^2/N)/(N-1)  cancels little), finished in double; the rolling averages
-  // are updated by the same finaliser.  (The reference reads the tensor twice: MeansAndVars ntensors.pas:9102-9177.)
-  const float *src = out;
-  const double S = (double)(batch * blockSize);
-  const float m = bn_momentum;
-  int rc = launch_reduce<2>(
-      ctx, channels, batch, blockSize,
-      [src, blockSize] __device__(int64_t i, int c, float(&acc)[2]) {
-        const float d = src[i] - __ldg(src + (int64_t)c * blockSize);
-        acc[0] += d;
-        acc[1] = fmaf(d, d, acc[1]);
-      },
-      [src, blockSize, mean, variance, rolling_mean, rolling_variance, S, m] __device__(int c, const float(&t)[2]) {
-        const double sd = (double)t[0], sq = (double)t[1];
-        const float mu = (float)((double)src[(int64_t)c * blockSize] + sd / S);
-        double var = (sq - sd * sd / S) / (S - 1.0);
-        const float v = (float)(var > 0.0 ? var : 0.0);
-        mean[c] = mu;
-        variance[c] = v;
-        rolling_mean[c] = __fadd_rn(__fmul_rn(m, mu), __fmul_rn(1 - m, rolling_mean[c]));
-        rolling_variance[c] = __fadd_rn(__fmul_rn(m, v), __fmul_rn(1 - m, rolling_variance[c]));
-      });
-  if (rc) return rc;
-  const int a = activation;
-  const bool block1 = blockSize == 1;
-  return planemap::launch<0, 2>(
-      ctx, out, nullptr, nullptr, x, x_norm, total, channels, batch,
-      [mean, variance, scales, biases, a, block1] __device__(float &v, float, float, float &xo, float &xn, int c) {
-        const float var = __ldg(variance + c);
-        const float d = block1 ? sqrtf(fmaxf(var, TNN_EPS)) : fmaxf(sqrtf(var), TNN_EPS);
-        xo = v;
-        float t = (v - __ldg(mean + c)) / d;
-        xn = t;
-        t = __fmul_rn(t, __ldg(scales + c));
-        t = __fadd_rn(t, __ldg(biases + c));
-        v = tnn_act(t, a);
-      });
+  switch (activation) {   // the common activations as compile-time constants: the per-element switch folds away
+#define TNN_BNF(A) bn_forward_training_impl<A>(ctx, batch, channels, blockSize, out, x, x_norm, mean, variance, rolling_mean, \
+                                            rolling_variance, bn_momentum, scales, biases, activation)
+    case TNN_ACT_LINEAR: return TNN_BNF(TNN_ACT_LINEAR);
+    case TNN_ACT_RELU: return TNN_BNF(TNN_ACT_RELU);
+    case TNN_ACT_LEAKY: return TNN_BNF(TNN_ACT_LEAKY);
+    default: return TNN_BNF(-1);
+#undef TNN_BNF
+  }
 }
 
 // DeriveArray + batchNormBackGPU (nConvolutionLayer.pas:1186; nbaselayer.pas:662-714) in two passes.
@@ -360,36 +547,15 @@ int32_t tnn_batchnorm_backward(tnn_context *ctx, int64_t batch, int64_t channels
   TNN_CHECK_CTX(ctx);
   TNN_REQUIRE(activation == TNN_ACT_LINEAR || (tnn_act_is_elementwise(activation) && activation != TNN_ACT_SWISH),
               "activation gradient not implemented");
-  const int a = activation;
-  const float *dl = delta;
-  int rc = launch_reduce<3>(
-      ctx, channels, batch, blockSize,
-      [dl, out, x, x_norm, mean, a] __device__(int64_t i, int c, float(&s)[3]) {
-        const float g = (a == TNN_ACT_LINEAR) ? dl[i] : dl[i] * tnn_grad(out[i], a);
-        s[0] = fmaf(x_norm[i], g, s[0]);
-        s[1] += g;
-        s[2] = fmaf(g, x[i] - __ldg(mean + c), s[2]);
-      },
-      [scales, scale_updates, variance, mean_delta, variance_delta] __device__(int c, const float(&t)[3]) {
-        scale_updates[c] = scale_updates[c] + t[0];
-        const double v = (double)fmaxf(variance[c], TNN_EPS);
-        const float sc = scales[c];
-        mean_delta[c] = (float)((double)(t[1] * sc) * (-1.0 / sqrt(v)));
-        variance_delta[c] = (float)((double)(t[2] * sc) * -0.5 * pow(v, -1.5));
-      });
-  if (rc) return rc;
-  const float batchSize = (float)(blockSize * batch);
-  return planemap::launch<2, 0>(
-      ctx, delta, out, x, nullptr, nullptr, batch * channels * blockSize, channels, batch,
-      [mean, variance, mean_delta, variance_delta, scales, batchSize, a] __device__(float &d, float ov, float xv,
-                                                                                    float &, float &, int c) {
-        float g = (a == TNN_ACT_LINEAR) ? d : d * tnn_grad(ov, a);
-        g = g * __ldg(scales + c);
-        const float md = __ldg(mean_delta + c) / batchSize;
-        const float vd = 2 * __ldg(variance_delta + c) / batchSize;
-        const float sd = sqrtf(fmaxf(__ldg(variance + c), TNN_EPS));
-        d = __fadd_rn(g / sd, __fadd_rn(__fmul_rn(vd, xv - __ldg(mean + c)), md));
-      });
+  switch (activation) {
+#define TNN_BNB(A) bn_backward_impl<A>(ctx, batch, channels, blockSize, out, activation, delta, x, x_norm, mean, variance, \
+                                    scales, scale_updates, mean_delta, variance_delta)
+    case TNN_ACT_LINEAR: return TNN_BNB(TNN_ACT_LINEAR);
+    case TNN_ACT_RELU: return TNN_BNB(TNN_ACT_RELU);
+    case TNN_ACT_LEAKY: return TNN_BNB(TNN_ACT_LEAKY);
+    default: return TNN_BNB(-1);
+#undef TNN_BNB
+  }
 }
 
 // ---- batch-norm under batch sharding (SyncBN).  The reference computes the statistics over the whole mini-batch

@@ -447,6 +447,23 @@ class TConvolutionalLayer:
         for t in (self.biases, self.bias_updates, self.weights, self.weight_updates):
             t.setCUDA()
 
+    def sgdItems(self, args: TUpdateArgs):
+        """The tensors updateGPU touches, for ONE multi-tensor launch over the whole net (TNNet._update_layers): the same
+        per-tensor rate / decay term / arithmetic as the fused branch of updateGPU."""
+        for t in (self.biases, self.bias_updates, self.weights, self.weight_updates):
+            if not t.wasGPU():
+                t.pushToDevice()
+        f32 = np.float32
+        rate = float(f32(f32(args.learningRate) * f32(self.learningRateScale) / f32(args.batch)))
+        decay_term = float(f32(f32(-args.decay) * f32(args.batch)))
+        items = [(self.biases.devData, self.bias_updates.devData, self.biases.Size(), rate, 0.0),
+                 (self.weights.devData, self.weight_updates.devData, self.weights.Size(), rate, decay_term)]
+        if self.isBatchNormalized:
+            items.append((self.scales.devData, self.scale_updates.devData, self.scales.Size(), rate, 0.0))
+        for t in (self.biases, self.bias_updates, self.weights, self.weight_updates):
+            t.setCUDA()
+        return items
+
     def gradients(self):
         """The update buffers a data-parallel run sums across replicas before updateGPU."""
         g = [self.weight_updates, self.bias_updates]

@@ -407,6 +407,18 @@ class TNNCuda:
     def sgdUpdate(self, N, params, updates, rate, momentum, decay_term):
         self._ck(self._l.tnn_sgd_update(self._h, N, _addr(params), _addr(updates), rate, momentum, decay_term))
 
+    def sgdUpdateMulti(self, items, momentum):
+        """items: [(params devptr, updates devptr, n, rate, decay_term)] — one launch per 32 tensors."""
+        n = len(items)
+        if not n:
+            return
+        P = (C.c_void_p * n)(*[int(i[0]) for i in items])
+        U = (C.c_void_p * n)(*[int(i[1]) for i in items])
+        S = (C.c_uint64 * n)(*[int(i[2]) for i in items])
+        R = (C.c_float * n)(*[float(i[3]) for i in items])
+        D = (C.c_float * n)(*[float(i[4]) for i in items])
+        self._ck(self._l.tnn_sgd_update_multi(self._h, n, P, U, S, R, D, float(momentum)))
+
     def yoloActivate(self, batch, n, classes, wh, out, scale_xy=1.0):
         self._ck(self._l.tnn_yolo_activate(self._h, batch, n, classes, wh, _addr(out), scale_xy))
 

@@ -271,9 +271,15 @@ class TNNet:
     def _update_layers(self):
         arg = TUpdateArgs(batch=self.batch * self.subdivisions * self.replicas, learningRate=self.learningRate,
                           momentum=self.momentum, decay=self.decay, replicas=self.replicas)
-        for l in self.layers[:-1]:
-            if getattr(l, "trainable", False) and l.train:
-                l.updateGPU(arg)
+        todo = [l for l in self.layers[:-1] if getattr(l, "trainable", False) and l.train]
+        if todo and all(getattr(l, "fused", True) and hasattr(l, "sgdItems") for l in todo):
+            # fused entry points: every parameter tensor of the net in one launch (tnn_sgd_update_multi) instead of two
+            # or three launches per layer; same arithmetic per tensor as updateGPU
+            items = [it for l in todo for it in l.sgdItems(arg)]
+            cuda().sgdUpdateMulti(items, arg.momentum / arg.replicas)
+            return
+        for l in todo:
+            l.updateGPU(arg)
 
     def Propagate(self):
         """nnet.pas:404-432; `input` and `truth` must already hold the batch (host or device side)."""

@@ -168,6 +168,17 @@ class TConnectedLayer:
         for t in (self.biases, self.bias_updates, self.weights, self.weight_updates):
             t.setCUDA()
 
+    def sgdItems(self, args: TUpdateArgs):
+        """See TConvolutionalLayer.sgdItems."""
+        self._push(self.biases, self.bias_updates, self.weights, self.weight_updates)
+        f32 = np.float32
+        rate = float(f32(f32(args.learningRate) * f32(self.learningRateScale) / f32(args.batch)))
+        decay_term = float(f32(f32(-args.decay) * f32(args.batch)))
+        for t in (self.biases, self.bias_updates, self.weights, self.weight_updates):
+            t.setCUDA()
+        return [(self.biases.devData, self.bias_updates.devData, self.biases.Size(), rate, 0.0),
+                (self.weights.devData, self.weight_updates.devData, self.weights.Size(), rate, decay_term)]
+
     def gradients(self):
         return [self.weight_updates, self.bias_updates]
 

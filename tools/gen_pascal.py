@@ -190,6 +190,8 @@ meth("procedure batchNormBackward(const batch, channels, blockSize: SizeInt; con
      "tnn_batchnorm_backward", "batch, channels, blockSize, outp, activation, delta, x, x_norm, mean, variance, scales, scale_updates, mean_delta, variance_delta")
 meth("procedure sgdUpdate(const N: SizeInt; const params, updates: TCUMem; const rate, momentum, decayTerm: T)",
      "tnn_sgd_update", "N, params, updates, rate, momentum, decayTerm")
+meth("procedure sgdUpdateMulti(const count: longint; const params, updates: PPointer; const sizes: PQWord; const rates, decayTerms: pointer; const momentum: T)",
+     "tnn_sgd_update_multi", "count, params, updates, sizes, rates, decayTerms, momentum")
 meth("procedure yoloActivate(const batch, n, classes, wh: SizeInt; const outp: TCUMem; const scaleXY: T)",
      "tnn_yolo_activate", "batch, n, classes, wh, outp, scaleXY")
 meth("procedure concatChannels(const batch, c, blockSize: SizeInt; const inp: TCUMem; const outChannels, cOffset: SizeInt; const outp: TCUMem)",

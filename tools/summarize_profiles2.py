@@ -26,6 +26,8 @@ def kernel_key(name):
         return "nhwc::k_conv_nhwc_pair (CTA pairs, TMA im2col activations, TMA store)"
     if "k_conv_nhwc" in name:
         return "nhwc::k_conv_nhwc (TMA im2col activations, TMA store)"
+    if "k_conv_image" in name:
+        return "nhwc::k_conv_image (planar image in, tensor cores, TMA store)"
     if "k_conv_direct" in name:
         return "direct::k_conv_direct (NHWC out)"
     name = re.sub(r"\[lambda.*", "[lambda]", name)
@@ -59,7 +61,7 @@ def launch_list(mode):
         a["dram"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
         tot += d.get("gpu__time_duration.sum", 0.0)
     with open(os.path.join(DST, f"r02_launch_list_summary_{mode}.txt"), "w") as f:
-        f.write(f"# YOLOv3-416 batch 64, channels-innermost graph, {mode}: {len(per)} consecutive launches (about two steps)\n")
+        f.write(f"# YOLOv3-416 batch 64, channels-innermost graph, {mode}: {len(per)} consecutive launches (about four steps)\n")
         f.write("# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none\n")
         f.write("# (cold-cache, serialised per-launch times: compare SHARES with bench.py's CUDA-event shares, not absolutes)\n")
         f.write(f"# total {tot / 1e6:.3f} ms\nshare%  launches   total_ms   dram_MB/launch  kernel\n")
@@ -79,12 +81,15 @@ RAW_KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write
 
 
 def full_capture(rep):
-    name = os.path.basename(rep).replace(".ncu-rep", "")
-    try:
-        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, timeout=600).stdout
-    except Exception as e:
-        print("ncu failed for", rep, e)
-        return
+    name = os.path.basename(rep).replace(".ncu-rep", "").replace(".raw.csv", "")
+    if rep.endswith(".raw.csv"):
+        out = open(rep).read()
+    else:
+        try:
+            out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True, timeout=600).stdout
+        except Exception as e:
+            print("ncu failed for", rep, e)
+            return
     rows = list(csv.reader(out.splitlines()))
     if len(rows) < 3:
         return
@@ -109,7 +114,7 @@ def main():
             traffic[mode] = {"by_kernel": t, "source": f"ncu launch list of bench.py --math {mode} (tools/profile_round2.sh yolo)"}
     if traffic:
         json.dump(traffic, open(os.path.join(DST, "r02_traffic.json"), "w"), indent=1)
-    for rep in sorted(glob.glob(os.path.join(SRC, "*.ncu-rep"))):
+    for rep in sorted(glob.glob(os.path.join(SRC, "*.ncu-rep")) + glob.glob(os.path.join(SRC, "*.raw.csv"))):
         full_capture(rep)
     print(sorted(os.listdir(DST)))
 
