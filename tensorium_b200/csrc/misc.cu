@@ -98,8 +98,12 @@ __global__ void __launch_bounds__(kT) k_maxpool_fwd(int64_t total, int outH, int
 __global__ void __launch_bounds__(kT) k_maxpool_bwd(int64_t total, float *out, const unsigned long long *idx,
                                                     const float *__restrict__ delta) {
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads)
-    atomicAdd(out + idx[i], delta[i]);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += nthreads) {
+    // a window that held no value greater than -FLT_MAX (all NaN, all padding) has no arg-max: the forward pass stored
+    // index -1; such an output routes no gradient instead of writing out of bounds
+    const unsigned long long j = idx[i];
+    if (j != ~0ull) atomicAdd(out + j, delta[i]);
+  }
 }
 
 // upsample cuda_sgemm.cu:1274-1296: N = batch*channels planes, out is (h*stride) x (w*stride)

@@ -63,6 +63,11 @@ def cfg_to_spec(sections):
     net = dict(batch=_int(o, "batch", 1), subdivisions=_int(o, "subdivisions", 1), width=_int(o, "width", 0),
                height=_int(o, "height", 0), channels=_int(o, "channels", 0), momentum=_float(o, "momentum", 0.9),
                decay=_float(o, "decay", 0.0001), learning_rate=_float(o, "learning_rate", 0.001))
+    # keys that change the numerics and that this mirror does not implement are refused, not ignored
+    policy = o.get("policy", "constant").strip().lower()
+    if policy != "constant":
+        raise ValueError(f"[net] policy={policy}: only the constant learning-rate policy is mirrored (steps / scales / "
+                         "burn_in schedules are outside the path)")
     spec = []
     for name, o in sections[1:]:
         if name == "convolutional":
@@ -83,12 +88,18 @@ def cfg_to_spec(sections):
         elif name == "softmax":
             spec.append(("softmax",))
         elif name == "shortcut":
+            if o.get("activation", "linear").strip().lower() != "linear":
+                raise ValueError("[shortcut] activation other than linear is not mirrored")
             spec.append(("shortcut", _ints(o["from"])[0]))
         elif name == "route":
             spec.append(("route", _ints(o["layers"])))
         elif name == "upsample":
+            if _float(o, "scale", 1.0) != 1.0:
+                raise ValueError("[upsample] scale other than 1 is not mirrored")
             spec.append(("upsample", _int(o, "stride", 2)))
         elif name == "yolo":
+            if _float(o, "scale_x_y", 1.0) != 1.0:
+                raise ValueError("[yolo] scale_x_y other than 1 (YOLOv4-style heads) is not mirrored")
             spec.append(("yolo", _ints(o.get("mask", "")), _ints(o["anchors"]), _int(o, "classes", 20)))
         else:
             raise ValueError(f"[{name}] is outside the convolution path")
@@ -209,9 +220,13 @@ def write_weights(params, spec, c, h, w, seen=0, version=(0, 2, 5)):
     out = io.BytesIO()
     out.write(struct.pack("<3i", *version))
     out.write(struct.pack("<Q", seen) if version[0] * 10 + version[1] >= 2 else struct.pack("<I", seen))
+    transpose = version[0] > 1000 or version[1] > 1000   # the same flag read_weights honours (nparser.pas:1140-1182)
     for i, fields in param_layout(spec, c, h, w):
         for name, n in fields:
-            a = np.ascontiguousarray(params[i][name], dtype="<f4").reshape(-1)
+            a = np.asarray(params[i][name], dtype="<f4")
+            if transpose and spec[i][0] == "connected" and name == "w":
+                a = a.reshape(spec[i][1], -1).T   # stored [inputs][outputs] in transposed files
+            a = np.ascontiguousarray(a).reshape(-1)
             assert a.size == n, (i, name, a.size, n)
             out.write(a.tobytes())
     return out.getvalue()
@@ -225,6 +240,11 @@ def build_from_spec(spec, batch, c, h, w, params=None, train=False, fused=True, 
     from .nnet import YOLOV3_ANCHORS, TConcatLayer, TNNet, TShortcutLayer, TUpsampleLayer, TYoloLayer
     from .train_layers import TConnectedLayer, TDropoutLayer, TMaxPoolLayer, TSoftmaxLayer
     act = {"leaky": nn.acLEAKY, "linear": nn.acLINEAR, "relu": nn.acRELU, "logistic": nn.acLOGISTIC}
+    if train:
+        graph = sorted({it[0] for it in spec if it[0] in ("shortcut", "route", "upsample", "yolo")})
+        if graph:
+            raise ValueError(f"training is mirrored for sequential nets only; this spec has {', '.join(graph)} layers "
+                             "(their backward passes are outside the path, DESIGN.md section 7)")
     rng = np.random.default_rng(seed)
     layers = []
     c0, h0, w0 = c, h, w

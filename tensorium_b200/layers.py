@@ -446,6 +446,7 @@ class TConvolutionalLayer:
                 cu.scale(self.scale_updates.Size(), args.momentum, self.scale_updates.devData, 1)
         for t in (self.biases, self.bias_updates, self.weights, self.weight_updates):
             t.setCUDA()
+        self._bn_fold = None  # biases / scales changed: the inference fold is stale
 
     def sgdItems(self, args: TUpdateArgs):
         """The tensors updateGPU touches, for ONE multi-tensor launch over the whole net (TNNet._update_layers): the same
@@ -462,6 +463,7 @@ class TConvolutionalLayer:
             items.append((self.scales.devData, self.scale_updates.devData, self.scales.Size(), rate, 0.0))
         for t in (self.biases, self.bias_updates, self.weights, self.weight_updates):
             t.setCUDA()
+        self._bn_fold = None
         return items
 
     def gradients(self):

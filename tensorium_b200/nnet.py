@@ -374,6 +374,8 @@ class TNNet:
         for l in self.layers:  # the loss tensor is new after every replay
             if hasattr(l, "_cost_stale"):
                 l._cost_stale = True
+            if hasattr(l, "_bn_fold"):
+                l._bn_fold = None  # scales / rolling statistics / biases moved on the device: a later predict() folds anew
         if g2 is not None:
             self.bucket.all_reduce()
             cu.launchGraph(g2)

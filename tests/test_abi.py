@@ -55,6 +55,14 @@ def test_activation_enum_matches_reference_ordinals():
     assert (nn.acLOGISTIC, nn.acRELU, nn.acLINEAR, nn.acLEAKY, nn.acSWISH) == (0, 1, 4, 9, 18)
     src = open(HEADER).read()
     assert "TNN_ACT_LEAKY = 9" in src and "TNN_ACT_LINEAR = 4" in src and "TNN_ACT_LOGISTIC = 0" in src
+    # every ordinal of TActivationType (source/ntypes.pas:66-71), in the reference's order
+    import re
+    names = ["LOGISTIC", "RELU", "RELU6", "RELIE", "LINEAR", "RAMP", "TANH", "PLSE", "REVLEAKY", "LEAKY", "ELU", "LOGGY",
+             "STAIR", "HARDTAN", "LHTAN", "SELU", "SOFTMAX", "GELU", "SWISH", "MISH", "HARD_MISH", "NORM_CHAN",
+             "NORM_CHAN_SOFTMAX", "NORM_CHAN_SOFTMAX_MAXVAL"]
+    enum = dict((m.group(1), int(m.group(2))) for m in re.finditer(r"TNN_ACT_(\w+) = (\d+)", src))
+    for i, n in enumerate(names):
+        assert enum.get(n) == i, (n, enum.get(n), i)
 
 
 def test_product_does_not_import_oracle():

@@ -118,3 +118,40 @@ def test_yolov3_weights_file_round_trip_small_input():
     back, _ = dn.read_weights(blob, spec, 3, 64, 64)
     for i in [j for j, it in enumerate(spec) if it[0] == "conv"][::9]:
         assert all(np.array_equal(params[i][k].reshape(-1), back[i][k].reshape(-1)) for k in params[i])
+
+
+def test_transposed_connected_weights_round_trip():
+    """Files whose header carries major or minor > 1000 store connected weights transposed (nparser.pas:1140-1182):
+    write_weights honours the flag like read_weights does."""
+    from tensorium_b200 import darknet as dn
+    spec = [("conv", 4, 3, 1, 1, "relu", 1), ("connected", 5, "linear"), ("softmax",)]
+    rng = np.random.default_rng(1)
+    params = [dict(w=rng.standard_normal((4, 27)).astype(np.float32), b=rng.standard_normal(4).astype(np.float32),
+                   scales=rng.standard_normal(4).astype(np.float32), rm=rng.standard_normal(4).astype(np.float32),
+                   rv=rng.uniform(0.5, 1.5, 4).astype(np.float32)),
+              dict(w=rng.standard_normal((5, 4 * 6 * 6)).astype(np.float32), b=rng.standard_normal(5).astype(np.float32)),
+              None]
+    plain = dn.write_weights(params, spec, 3, 6, 6, seen=7, version=(0, 2, 5))
+    transposed = dn.write_weights(params, spec, 3, 6, 6, seen=7, version=(0, 1001, 0))
+    assert len(plain) == len(transposed) and plain[20:] != transposed[20:]
+    for blob in (plain, transposed):
+        back, hdr = dn.read_weights(blob, spec, 3, 6, 6)
+        assert hdr["seen"] == 7
+        assert np.array_equal(back[1]["w"], params[1]["w"]) and np.array_equal(back[0]["w"].reshape(4, 27), params[0]["w"])
+
+
+@pytest.mark.parametrize("bad", ["[net]\nwidth=8\nheight=8\nchannels=3\npolicy=steps\nsteps=100\nscales=.1\n[softmax]\n",
+                                 "[net]\nwidth=8\nheight=8\nchannels=3\n[yolo]\nmask=0\nanchors=1,2\nclasses=1\nscale_x_y=1.05\n",
+                                 "[net]\nwidth=8\nheight=8\nchannels=3\n[upsample]\nstride=2\nscale=2\n",
+                                 "[net]\nwidth=8\nheight=8\nchannels=3\n[convolutional]\nfilters=3\n[shortcut]\nfrom=-1\nactivation=leaky\n"])
+def test_cfg_keys_that_change_the_numerics_are_refused(bad):
+    from tensorium_b200 import darknet as dn
+    with pytest.raises(ValueError):
+        dn.cfg_to_spec(dn.parse_cfg(bad))
+
+
+def test_training_a_graph_net_is_refused_up_front():
+    from tensorium_b200 import darknet as dn
+    spec = [("conv", 8, 3, 1, 1, "leaky", 1), ("conv", 8, 3, 1, 1, "leaky", 1), ("shortcut", -2)]
+    with pytest.raises(ValueError, match="sequential nets only"):
+        dn.build_from_spec(spec, 2, 3, 8, 8, train=True)

@@ -270,6 +270,53 @@ def test_graph_replay_matches_eager_training(cuda_backend):
                 lg.rand.setCUDA()
 
 
+def test_predict_between_graph_replays_sees_the_trained_parameters(cuda_backend):
+    """Validation between replayed training steps: the inference-time batch-norm fold is cached on the
+    host side, and a CUDA-graph replay moves scales / rolling statistics / biases on the device without running the
+    Python forward.  A predict() after more replays must fold the CURRENT device values (and must not push stale host
+    copies over them): it has to agree with an eager twin that went through the same steps."""
+    from tensorium_b200 import models
+    from tensorium_b200.layers import TNNetState
+    from tensorium_b200.train_layers import TDropoutLayer
+    B = 16
+    nets = [models.deepCIFAR10(B, seed=33, learningRate=0.01) for _ in range(2)]
+    eager, graph = nets
+    batches = [_batch(B, 500 + i) for i in range(6)]
+    xv, _ = _batch(B, 999)
+    for net in nets:
+        for i in range(2):
+            for li, l in enumerate(net.layers):
+                if isinstance(l, TDropoutLayer):
+                    l.seed = 1000 * i + li
+            net.trainBatch(*batches[i])
+    graph.enableGraph(seed=0x5EED)
+
+    def predict(net):
+        net.input.Data[...] = xv
+        net.input.pushToDevice()
+        net.forward(TNNetState(input=net.input, isTraining=False))
+        out = net.layers[-1].output.pullFromDevice().copy()
+        net.layers[-1].output.setCUDA()
+        return out
+
+    for rnd in range(2):
+        for step in range(2):
+            _copy_training_state(eager, graph)
+            x, t = batches[2 + 2 * rnd + step]
+            for li, l in enumerate(eager.layers):
+                if isinstance(l, TDropoutLayer):
+                    l.seed = graph.dropout_seed(li, 2 * rnd + step)
+            eager.trainBatch(x, t)
+            graph.trainBatch(x, t)
+        pe, pg = predict(eager), predict(graph)
+        assert rel_max(pg, pe) <= 1e-3, (rnd, rel_max(pg, pe))   # fp32-atomic noise of the steps, not a stale fold (which is percent-level)
+    # and the replays after a predict() still train from the device values (nothing was pushed back over them)
+    for le, lg in zip(_trainables(eager), _trainables(graph)):
+        if hasattr(le, "rolling_mean"):
+            assert rel_max(lg.rolling_mean.pullFromDevice(), le.rolling_mean.pullFromDevice()) <= 1e-4
+            assert rel_max(lg.scales.pullFromDevice(), le.scales.pullFromDevice()) <= 1e-4
+
+
 def test_native_nccl_entry_points_single_rank(cuda_backend):
     """tnn_comm_* / tnn_allreduce_sum / tnn_broadcast (the C-ABI exchange step a FreePascal host would call): a
     one-rank communicator really goes through NCCL (dlopen'ed libnccl.so.2) on the backend's stream, eagerly and
