@@ -90,6 +90,8 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     ctx->tail_split = (ts && ts[0] == '0') ? 0 : 1;
     const char *np_ = getenv("TNN_NHWC_PAIR");
     ctx->nhwc_pair = (np_ && np_[0] == '0') ? 0 : 1;
+    const char *gn = getenv("TNN_GEMM_NHWC");
+    ctx->gemm_nhwc = (gn && gn[0] == '0') ? 0 : 1;
     const char *ni = getenv("TNN_NHWC_IMAGE");
     ctx->nhwc_image = (ni && ni[0] == '0') ? 0 : 1;
     const char *nk = getenv("TNN_NHWC_KB");
@@ -105,6 +107,7 @@ int32_t tnn_destroy(tnn_context *ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->red_partials) cudaFree(ctx->red_partials);
   if (ctx->red_counters) cudaFree(ctx->red_counters);
+  if (ctx->gemm_scratch) cudaFree(ctx->gemm_scratch);
   if (ctx->work) cudaFree(ctx->work);
   for (int i = 0; i < ctx->n_retired; ++i) cudaFree(ctx->retired[i]);
   tnn_wcache_destroy(ctx);

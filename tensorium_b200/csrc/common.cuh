@@ -30,6 +30,9 @@ struct tnn_context {
   size_t red_partials_bytes;
   unsigned int *red_counters;
   size_t red_counters_n;
+  float *gemm_scratch;          // operand copies of the SGEMM that runs on the channels-innermost convolution kernel (conv_nhwc.cu)
+  size_t gemm_scratch_bytes;
+  int gemm_nhwc;                // 1: large SGEMMs run as 1x1 convolutions on the CTA-pair kernel (default; TNN_GEMM_NHWC=0)
   // scratch for the contraction kernels (pre-split / transposed weight copies, split-K partials)
   float *work;
   size_t work_bytes;

@@ -130,6 +130,9 @@ int gemm_simt_fold(tnn_context *ctx, bool tA, bool tB, int64_t M, int64_t N, int
 
 }  // namespace
 
+int tnn_gemm_on_conv(tnn_context *ctx, bool tA, bool tB, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                     int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc);   // conv_nhwc.cu
+
 extern "C" {
 
 int32_t tnn_gemm_strided_batched(tnn_context *ctx, int32_t transA, int32_t transB, int64_t M, int64_t N, int64_t K,
@@ -158,6 +161,11 @@ int32_t tnn_gemm_strided_batched(tnn_context *ctx, int32_t transA, int32_t trans
       if (rc) return rc;
     }
     return 0;
+  }
+  if (ctx->math_mode != TNN_MATH_FP32 && batchCount == 1) {
+    // large products: a 1x1 convolution on the CTA-pair kernel of conv_nhwc.cu
+    int rc = tnn_gemm_on_conv(ctx, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (rc != umma::kNotTaken) return rc;
   }
   if (ctx->math_mode != TNN_MATH_FP32 && umma::gemm_supported(ctx, M, N, K)) {
     int rc = ctx->tma_gemm ? umma::gemm_tma(ctx, tA, tB, M, N, K, alpha, A, lda, strideA, B, ldb, strideB, beta, C, ldc,

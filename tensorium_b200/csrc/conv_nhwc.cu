@@ -1520,7 +1520,120 @@ static int grid_for(int64_t total) {
   return (int)(blocks < 1 ? 1 : blocks);
 }
 
+// ------------------------------------------------------------------ SGEMM on the convolution kernel
+// C[M][N] = alpha * op(A) op(B) + beta * C is a 1x1 convolution: pixels = the M rows of op(A) (K "channels" each, K
+// contiguous), filters = the N rows of op(B)^T, fused epilogue = *alpha (+ C).  Large products therefore run on the
+// CTA-pair kernel above — TMA im2col rows, half a weight tile per CTA, TMA store — in all three tensor modes: the
+// TMA-fed single-CTA SGEMM of umma_gemm.cuh tops out at 332 TFLOP/s in TF32 mode (shared-memory bandwidth, §4.3 of
+// DESIGN.md), the pair kernel reaches the cuBLAS rate.  Operands that are not already K-contiguous are transposed into a
+// scratch copy first (one pass over the operand, < 5 % of the product for the sizes taken); in BF16x3 mode the rows
+// of op(A) are pre-split into the bf16 planes the kernel multiplies.
+__global__ void __launch_bounds__(256) k_transpose(const float *__restrict__ src, int64_t lds, int64_t rows, int64_t cols,
+                                                   float *__restrict__ dst, int64_t ldd) {   // dst[c][r] = src[r][c]
+  __shared__ float t[32][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 32, c0 = (int64_t)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t r = r0 + j, c = c0 + tx;
+    t[j][tx] = (r < rows && c < cols) ? __ldg(src + r * lds + c) : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t c = c0 + j, r = r0 + tx;
+    if (c < cols && r < rows) dst[c * ldd + r] = t[tx][j];
+  }
+}
+__global__ void __launch_bounds__(256) k_fill1(float *p, int64_t n, float v) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+constexpr int kGemmNotTaken = umma::kNotTaken;
+
+static int gemm_on_conv(tnn_context *ctx, bool tA, bool tB, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                        int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
+  if (!ctx->gemm_nhwc || ctx->capturing || ctx->math_mode == TNN_MATH_FP32) return kGemmNotTaken;
+  if (!(beta == 0.0f || beta == 1.0f)) return kGemmNotTaken;
+  const int sms = ctx->prop.multiProcessorCount;
+  // enough 256 x 256 pair tiles for every TPC and a contraction worth the operand passes
+  if (((M + 255) / 256) * ((N + 255) / 256) < sms / 2 || K < 256 || (K % 8) != 0 || M >= (1ll << 31) - 256 || N > 65535 * 16)
+    return kGemmNotTaken;
+  if ((ldc % 4) != 0 || (((uintptr_t)C) & 15) != 0 || (beta == 1.0f && (N % 4) != 0)) return kGemmNotTaken;
+  const bool bf = ctx->math_mode == TNN_MATH_BF16X3;
+  const bool aAligned = (lda % 4) == 0 && (((uintptr_t)A) & 15) == 0;
+  const bool bDirect = tB && ldb == K;
+  // rows that are read in place (fp32 rows by TMA, or by the 128-bit split / copy kernels) must be 16-byte aligned
+  if (!tA && !aAligned) return kGemmNotTaken;
+  if (tB && !bDirect && ((ldb % 4) != 0 || (((uintptr_t)B) & 15) != 0)) return kGemmNotTaken;
+  // scratch: [A rows M x K fp32 (transposed A)] [A planes M x K x 4 bytes (bf16x3)] [B rows N x K] [alpha vector N]
+  const size_t aRows = (tA ? (size_t)M * K : 0), aPlanes = bf ? (size_t)M * K : 0, bRows = bDirect ? 0 : (size_t)N * K;
+  const size_t floats = aRows + aPlanes + bRows + (size_t)N + 64;
+  if (ctx->gemm_scratch_bytes < floats * sizeof(float)) {
+    TNN_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->gemm_scratch) {
+      int rc = tnn_release_scratch(ctx, ctx->gemm_scratch);
+      if (rc) return rc;
+    }
+    ctx->gemm_scratch = nullptr;
+    ctx->gemm_scratch_bytes = 0;
+    TNN_CUDA(cudaMalloc((void **)&ctx->gemm_scratch, floats * sizeof(float)));
+    ctx->gemm_scratch_bytes = floats * sizeof(float);
+  }
+  float *sA = ctx->gemm_scratch, *sP = sA + ((aRows + 3) & ~(size_t)3), *sB = sP + ((aPlanes + 3) & ~(size_t)3),
+        *sAlpha = sB + ((bRows + 3) & ~(size_t)3);
+  const float *rowsA = A;
+  int64_t pitchA = lda;
+  if (tA) {   // A is [K][M]: op(A) rows [M][K]
+    dim3 grid((unsigned)cdiv64(M, 32), (unsigned)cdiv64(K, 32));
+    k_transpose<<<grid, 256, 0, ctx->stream>>>(A, lda, K, M, sA, K);
+    TNN_LAUNCHED(ctx);
+    rowsA = sA;
+    pitchA = K;
+  }
+  SplitRef in{nullptr, 0, 0};
+  if (bf) {
+    int rc = tnn_nhwc_to_split(ctx, M, K, rowsA, pitchA, sP, K, M * K);
+    if (rc) return rc;
+    in = SplitRef{reinterpret_cast<const uint16_t *>(sP), K, M * K};
+  }
+  const float *w = B;
+  if (!bDirect) {
+    if (tB) {   // [N][K] with padded rows: dense copy
+      k_rows<false><<<grid_for(N * (K / 4)), 256, 0, ctx->stream>>>(N, (int)(K / 4), reinterpret_cast<const float4 *>(B),
+                                                                 ldb / 4, nullptr, 0, reinterpret_cast<float4 *>(sB), K / 4);
+    } else {    // B is [K][N]: op(B)^T rows [N][K]
+      dim3 grid((unsigned)cdiv64(N, 32), (unsigned)cdiv64(K, 32));
+      k_transpose<<<grid, 256, 0, ctx->stream>>>(B, ldb, K, N, sB, K);
+    }
+    TNN_LAUNCHED(ctx);
+    w = sB;
+  }
+  const float *scale = nullptr;
+  if (alpha != 1.0f) {
+    k_fill1<<<(unsigned)cdiv64(N, 256), 256, 0, ctx->stream>>>(sAlpha, N, alpha);
+    TNN_LAUNCHED(ctx);
+    scale = sAlpha;
+  }
+  simt::ConvGeom g;
+  g.C = (int)K; g.H = 1; g.W = (int)M; g.F = (int)N;
+  g.kh = g.kw = 1; g.ph = g.pw = 0; g.sy = g.sx = 1; g.dy = g.dx = 1;
+  g.OH = 1; g.OW = (int)M;
+  g.inImg = K * M;
+  g.outImg = N * M;
+  ctx->last_conv_kernel = 7;
+  return conv_forward(ctx, g, 1, bf ? nullptr : rowsA, pitchA, in, w, scale, nullptr, TNN_ACT_LINEAR, C, ldc, false,
+                      SplitRef{nullptr, 0, 0}, beta == 1.0f ? C : nullptr, ldc);
+}
+
 }  // namespace nhwc
+
+// (called by tnn_gemm's dispatch in contract.cu; umma::kNotTaken when the product stays on the SGEMM kernels)
+int tnn_gemm_on_conv(tnn_context *ctx, bool tA, bool tB, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
+                     int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
+  return nhwc::gemm_on_conv(ctx, tA, tB, M, N, K, alpha, A, lda, B, ldb, beta, C, ldc);
+}
 
 // ------------------------------------------------------------------ C ABI
 namespace {

@@ -113,7 +113,7 @@ def test_gemm_empty_and_degenerate(cuda_backend):
     assert np.array_equal(d.read(), np.ones(16, np.float32))
 
 
-@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32)])
+@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32), (3, TOL_3XTF32)])   # 3 = BF16x3
 @pytest.mark.parametrize("ta,tb", [(0, 0), (0, 1), (1, 0)])
 def test_gemm_8192_against_the_oracle_on_a_row_sample(cuda_backend, oracle, mode, tol, ta, tb):
     """BASELINE configs[1] at its largest size, M = N = K = 8192, NN / NT / TN: the GPU computes the whole product, the
@@ -141,3 +141,17 @@ def test_gemm_8192_against_the_oracle_on_a_row_sample(cuda_backend, oracle, mode
     # (profiles/r02_accuracy_vs_k.txt: 5.7e-5 of max|r| at K = 8192), and max|r| is ~3.5 rms here
     print(f"K=8192 ta={ta} tb={tb} mode={mode}: rel_max {e1:.2e}, rel_elem {e2:.2e}")
     assert e1 < tol and e2 < 4 * tol, (e1, e2)
+
+
+@pytest.mark.parametrize("mode,tol", [(X3, TOL_3XTF32), (TF32, TOL_TF32), (3, TOL_3XTF32)])
+@pytest.mark.parametrize("ta,tb,alpha,beta", [(0, 0, 1.0, 0.0), (0, 1, 0.5, 1.0), (1, 0, 1.0, 1.0), (1, 1, 2.0, 0.0)])
+def test_large_gemm_on_the_convolution_kernel(cuda_backend, oracle, mode, tol, ta, tb, alpha, beta):
+    """Products with a pair tile for every TPC run as a 1x1 convolution on the CTA-pair kernel (conv_nhwc.cu,
+    gemm_on_conv): all four transposes, alpha, beta in {0, 1}, a padded C, against the oracle's cblas_sgemm."""
+    cu = cuda_backend
+    M, N, K = 2304, 2112, 512       # 9 x 9 pair tiles (ragged in N: 2112 = 8 x 256 + 64)
+    got, want, C0 = run_gemm(cu, oracle, mode, ta, tb, M, N, K, alpha, beta, seed=77 + ta + 2 * tb, ldpad=4)
+    assert "k_conv_nhwc" in cu.lastConvKernel()
+    e1, e2 = rel_max(got[:, :N], want[:, :N]), rel_elem(got[:, :N], want[:, :N], floor=1.0)
+    assert e1 < tol and e2 < tol, (e1, e2)
+    assert np.array_equal(got[:, N:], C0[:, N:])   # the padding columns of C are untouched

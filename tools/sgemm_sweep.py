@@ -7,7 +7,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 from tensorium_b200 import tensor
 from util import Dev
-MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2}
+MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16x3": 3}
 math = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
 cu = tensor.initCUDART(0)
 cu.set_math_mode(MATH[math])
