@@ -259,7 +259,7 @@ def run_ours(args, rank, world, local_rank):
     # BF16x3: activations that only convolutions read stay as pre-split bf16 hi/lo planes (tnn_conv2d_forward_split) —
     # the planes the kernel would otherwise derive in shared memory for every tap; same bits out
     can_split = args.layout == "nhwc" and not args.no_fuse and not args.no_split
-    net.setSplitActivations(can_split and args.math == "bf16x3")
+    net.setSplitActivations(can_split and args.math == "bf16x3", split_into_1x1=args.split_1x1)
     # shortcut fusion into the conv epilogue: "" (off, default), "gather" or "all".  Measured (B200, batch 64): 27.7 ms
     # un-fused, 28.0 ms with the MMA-bound gathering layers fused, 28.9 ms with all 23 fused — the residual read in
     # the four epilogue warps costs what the separate add kernels cost, so it stays off.
@@ -424,14 +424,14 @@ def run_ours(args, rank, world, local_rank):
             if m == args.math:
                 continue
             cu.set_math_mode(MATH[m])
-            net.setSplitActivations(can_split and m == "bf16x3")
+            net.setSplitActivations(can_split and m == "bf16x3", split_into_1x1=args.split_1x1)
             for _ in range(3):
                 step_resident()
             ms_m = timed(step_resident, 5)
             modes[m] = {"images_per_s": aggregate_images_per_s(world, 5, ms_m), "ms_per_step": ms_m / 5, "steps": 5,
                         "gate": "5e-3" if m == "tf32" else "1e-4"}
         cu.set_math_mode(MATH[args.math])
-        net.setSplitActivations(can_split and args.math == "bf16x3")
+        net.setSplitActivations(can_split and args.math == "bf16x3", split_into_1x1=args.split_1x1)
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import cifar_train
         cu.set_math_mode(MATH["3xtf32"])   # the training kernels (wgrad, dgrad, connected layers) are the planar tf32 ones
@@ -523,6 +523,8 @@ def main():
     ap.add_argument("--layout", default="nhwc", choices=["nhwc", "nchw"],
                     help="internal activation layout of the graph: channels-innermost (TMA im2col kernels) or planar")
     ap.add_argument("--no-fuse", action="store_true", help="keep the shortcut adds as separate kernels")
+    ap.add_argument("--split-1x1", action="store_true", help="bf16x3: 1x1 convolutions read pre-split planes too (their "
+                    "producers then write fp32 rows AND planes)")
     ap.add_argument("--no-split", action="store_true", help="bf16x3: fp32 activations between all layers (no pre-split planes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-images", type=int, default=2)

@@ -446,12 +446,15 @@ class TNNet:
         self.channels_last = bool(on)
         return self
 
-    def setSplitActivations(self, on: bool = True):
+    def setSplitActivations(self, on: bool = True, split_into_1x1: bool = False):
         """BF16x3 graphs: keep every activation that a convolution reads as PRE-SPLIT bf16 planes
         (TNN_LAYOUT_NHWC_SPLIT, include/tensorium_b200.h): the producing epilogue writes hi = bf16(x), lo = bf16(x - hi),
         the consuming convolution's TMA lands them as tensor-core operands and nothing converts — the same products
         and fp32 accumulation as the fp32-input kernel, bit for bit.  fp32 rows are written only where something other
         than a convolution reads the tensor: the operand of a later shortcut, a yolo layer, the graph's last layer.
+        split_into_1x1=False: a 1x1 convolution reads fp32 rows and splits them in shared memory itself — it touches
+        every element once (no 9x redundancy as in a 3x3 layer) and is bound by HBM, while its input is typically a
+        shortcut output that a later shortcut needs as fp32 anyway: the tensor is then written once instead of twice.
         Call after setChannelsLast() and fuseShortcuts()."""
         n = len(self.layers)
         if not on:
@@ -472,7 +475,10 @@ class TNNet:
             l = self.layers[j]
             if isinstance(l, TConvolutionalLayer):
                 if j > 0:
-                    need_split[j - 1] = True
+                    if l.kernelSize == 1 and not split_into_1x1:
+                        need_f32[j - 1] = True
+                    else:
+                        need_split[j - 1] = True
             elif isinstance(l, TShortcutLayer):
                 assert getattr(l, "_fused_into_conv", False), "pre-split graphs need the shortcuts folded into the convolutions"
                 need_f32[l.inputLayers[0]] = True
@@ -489,7 +495,7 @@ class TNNet:
             if isinstance(l, TConvolutionalLayer):
                 t = j + 1 if l._residual is not None else j     # the tensor this convolution writes
                 tgt = self.layers[t].output
-                l.in_split = j > 0
+                l.in_split = j > 0 and (l.kernelSize != 1 or split_into_1x1)
                 l.out_split = need_split[t]
                 # (an image layer too deep for the tensor-core image kernel runs the direct kernel, which writes rows first)
                 l.out_f32 = need_f32[t] or not need_split[t] or (j == 0 and l.c * l.kernelSize ** 2 > 32)
