@@ -1554,7 +1554,7 @@ constexpr int kGemmNotTaken = umma::kNotTaken;
 
 static int gemm_on_conv(tnn_context *ctx, bool tA, bool tB, int64_t M, int64_t N, int64_t K, float alpha, const float *A,
                         int64_t lda, const float *B, int64_t ldb, float beta, float *C, int64_t ldc) {
-  if (!ctx->gemm_nhwc || ctx->capturing || ctx->math_mode == TNN_MATH_FP32) return kGemmNotTaken;
+  if (!ctx->gemm_nhwc || ctx->math_mode == TNN_MATH_FP32) return kGemmNotTaken;
   if (!(beta == 0.0f || beta == 1.0f)) return kGemmNotTaken;
   const int sms = ctx->prop.multiProcessorCount;
   // enough 256 x 256 pair tiles for every TPC and a contraction worth the operand passes
@@ -1571,6 +1571,7 @@ static int gemm_on_conv(tnn_context *ctx, bool tA, bool tB, int64_t M, int64_t N
   const size_t aRows = (tA ? (size_t)M * K : 0), aPlanes = bf ? (size_t)M * K : 0, bRows = bDirect ? 0 : (size_t)N * K;
   const size_t floats = aRows + aPlanes + bRows + (size_t)N + 64;
   if (ctx->gemm_scratch_bytes < floats * sizeof(float)) {
+    if (ctx->capturing) return kGemmNotTaken;   // no allocation inside a capture: the eager warm-up step sized it, or not
     TNN_CUDA(cudaStreamSynchronize(ctx->stream));
     if (ctx->gemm_scratch) {
       int rc = tnn_release_scratch(ctx, ctx->gemm_scratch);
