@@ -324,7 +324,9 @@ TNN_API int32_t tnn_set_weights_static(tnn_context *ctx, const float *weights, i
  * times to kernels with it): 0 none yet, 1 direct fp32 (k_conv_direct), 2 tcgen05 gathering implicit GEMM (k_umma
  * with Im2colPixelLoader), 3 tcgen05 with TMA-fed activations (k_umma with TmaPatchLoader), 4 tcgen05 halo-tile
  * (k_umma_halo), 5 CUDA-core implicit GEMM (simt::k_gemm, TNN_MATH_FP32), 7 tcgen05 with TMA im2col-mode
- * activations on channels-innermost tensors (nhwc::k_conv_nhwc), 8 direct fp32 writing channels-innermost rows. */
+ * activations on channels-innermost tensors (nhwc::k_conv_nhwc, one CTA per tile), 8 direct fp32 writing
+ * channels-innermost rows, 9 the image layer on the tensor cores (nhwc::k_conv_image), 11 the same as 7 on CTA pairs
+ * (nhwc::k_conv_nhwc_pair, tcgen05.mma.cta_group::2). */
 TNN_API int32_t tnn_last_conv_kernel(tnn_context *ctx);
 /* backwardGPU wgrad (nConvolutionLayer.pas:1203-1232): weight_updates += sum_b delta_b * im2col(in_b)^T */
 TNN_API int32_t tnn_conv2d_backward_filter(tnn_context *ctx, const tnn_conv_desc *d, const float *in,

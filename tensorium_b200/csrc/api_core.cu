@@ -92,6 +92,8 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     ctx->nhwc_pair = (np_ && np_[0] == '0') ? 0 : 1;
     const char *gn = getenv("TNN_GEMM_NHWC");
     ctx->gemm_nhwc = (gn && gn[0] == '0') ? 0 : 1;
+    const char *ba = getenv("TNN_NHWC_BN_AUTO");
+    ctx->nhwc_bn_auto = (ba && ba[0] == '0') ? 0 : 1;
     const char *ni = getenv("TNN_NHWC_IMAGE");
     ctx->nhwc_image = (ni && ni[0] == '0') ? 0 : 1;
     const char *nk = getenv("TNN_NHWC_KB");

@@ -967,6 +967,26 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   // a layer with at most 16 channels (the image layer) moves half the zero padding per tap with 16-channel stages
   const int KB = aSplit ? 32 : split ? (ctx->nhwc_kb ? ctx->nhwc_kb : ((bf && g.C > 16) ? 32 : 16)) : 32;
   Plan p = make_plan(ctx, M, N, K, split, false, false);
+  // Wave quantisation: with several filter tiles per pixel tile the width of a tile is a free parameter.  172 tiles of
+  // 256 filters on 74 CTA pairs are 2.3 waves = 3; 215 tiles of 224 filters are 2.9 waves = 3 of cheaper tiles.  A tile's
+  // cost is modelled as 1/4 fixed (activation traffic, epilogue set-up) + 3/4 proportional to its width.
+  if (ctx->nhwc_pair && ctx->nhwc_bn_auto && N > 256 && p.BN == 256) {
+    const int64_t pairs = ctx->prop.multiProcessorCount / 2, mPairs = (p.sched.mTiles + 1) / 2;
+    double best = 0;
+    int bestBN = 256;
+    for (int bn = 256; bn >= 160; bn -= 32) {
+      const int64_t tiles = mPairs * cdiv64(N, bn);
+      if (tiles < pairs) continue;
+      const double cost = (double)cdiv64(tiles, pairs) * (0.25 + 0.75 * bn / 256.0);
+      if (best == 0 || cost < best * 0.97) { best = cost; bestBN = bn; }   // narrower only for a clear (3 %) gain
+    }
+    if (bestBN != 256) {
+      p.BN = bestBN;
+      p.sched.nTiles = (int)cdiv64(N, bestBN);
+      p.sched.numTiles = p.sched.mTiles * p.sched.nTiles * p.sched.kSplits;
+      p.sched.wideTiles = p.sched.numTiles;
+    }
+  }
   // half-width tail tiles: the TMA store writes whole 32-filter boxes, so a half tile must be a multiple of 32 wide
   // CTA pairs (cta_group::2) halve the weight traffic through shared memory — the bound of the single-CTA kernel.
   // Taken when the tile is wide enough to split (each CTA holds BN/2 >= 32 weight rows) and there are pair tiles for
@@ -1020,6 +1040,7 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   }
   if (rc) return rc;
   Geo geo{g.OW, g.OH * g.OW, g.sx, g.sy, g.pw, g.ph, g.dx, g.dy, g.kw, CB * 32 / KB, (int)M};
+  ctx->last_conv_kernel = pairMode ? 11 : 7;
   auto go = [&](auto epi) -> int {
     if (pairMode) {
       const int grid = (int)(2 * (pairTiles < sms / 2 ? pairTiles : sms / 2));

@@ -361,7 +361,8 @@ class TNNCuda:
                     3: "umma::k_umma<TmaPatchLoader> (TMA activations)", 4: "umma::k_umma_halo", 5: "simt::k_gemm",
                     6: "umma::k_umma_pair (gather, CTA pairs)",
                     7: "nhwc::k_conv_nhwc (TMA im2col activations, TMA store)", 8: "direct::k_conv_direct (NHWC out)",
-                    9: "nhwc::k_conv_image (planar image in, tensor cores, TMA store)"}
+                    9: "nhwc::k_conv_image (planar image in, tensor cores, TMA store)",
+                    11: "nhwc::k_conv_nhwc_pair (CTA pairs, TMA im2col activations, TMA store)"}
 
     def setWeightsStatic(self, weights, is_static: bool = True):
         """The backend may keep its re-ordered / TF32-split copy of `weights` across calls (inference)."""
