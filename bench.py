@@ -256,10 +256,12 @@ def run_ours(args, rank, world, local_rank):
     # (tnn_conv2d_forward_nhwc_residual; bit-identical to the separate layers, tests/test_gpu_yolo.py)
     net = build_yolov3(BATCH, SIZE, seed=1234, channels_last=args.layout == "nhwc",
                        fuse_shortcuts=args.layout == "nhwc" and not args.no_fuse)
-    # BF16x3: activations that only convolutions read stay as pre-split bf16 hi/lo planes (tnn_conv2d_forward_split) —
-    # the planes the kernel would otherwise derive in shared memory for every tap; same bits out
+    # BF16x3: activations between convolutions are pre-split bf16 hi/lo planes (tnn_conv2d_forward_split_residual) — the
+    # planes the kernel would otherwise derive in shared memory for every tap; the folded shortcuts read their operand
+    # from its planes (hi + lo = the fp32 value to 2^-18 relative), so every tensor is written once
     can_split = args.layout == "nhwc" and not args.no_fuse and not args.no_split
-    net.setSplitActivations(can_split and args.math == "bf16x3", split_into_1x1=args.split_1x1)
+    net.setSplitActivations(can_split and args.math == "bf16x3", split_into_1x1=args.split_1x1,
+                            planes_only=not args.fp32_shortcuts)
     # shortcut fusion into the conv epilogue: "" (off, default), "gather" or "all".  Measured (B200, batch 64): 27.7 ms
     # un-fused, 28.0 ms with the MMA-bound gathering layers fused, 28.9 ms with all 23 fused — the residual read in
     # the four epilogue warps costs what the separate add kernels cost, so it stays off.
@@ -424,14 +426,16 @@ def run_ours(args, rank, world, local_rank):
             if m == args.math:
                 continue
             cu.set_math_mode(MATH[m])
-            net.setSplitActivations(can_split and m == "bf16x3", split_into_1x1=args.split_1x1)
+            net.setSplitActivations(can_split and m == "bf16x3", split_into_1x1=args.split_1x1,
+                                        planes_only=not args.fp32_shortcuts)
             for _ in range(3):
                 step_resident()
             ms_m = timed(step_resident, 5)
             modes[m] = {"images_per_s": aggregate_images_per_s(world, 5, ms_m), "ms_per_step": ms_m / 5, "steps": 5,
                         "gate": "5e-3" if m == "tf32" else "1e-4"}
         cu.set_math_mode(MATH[args.math])
-        net.setSplitActivations(can_split and args.math == "bf16x3", split_into_1x1=args.split_1x1)
+        net.setSplitActivations(can_split and args.math == "bf16x3", split_into_1x1=args.split_1x1,
+                            planes_only=not args.fp32_shortcuts)
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import cifar_train
         cu.set_math_mode(MATH["3xtf32"])   # the training kernels (wgrad, dgrad, connected layers) are the planar tf32 ones
@@ -471,8 +475,11 @@ def run_ours(args, rank, world, local_rank):
             "config": {"workload": f"YOLOv3-{SIZE} inference, 107 layers (75 conv), BN folded, random-init weights",
                        "per_gpu_batch": BATCH, "global_batch": BATCH * world, "image": SIZE,
                        "math": args.math, "layout": args.layout,
-                       "activations": ("pre-split bf16 hi/lo planes between convolutions (4 B/element, the operands BF16x3 "
-                                       "multiplies); fp32 rows where a shortcut / yolo layer reads"
+                       "activations": (("pre-split bf16 hi/lo planes between convolutions (4 B/element, the operands BF16x3 "
+                                        "multiplies); " + ("fp32 rows where a shortcut / 1x1 convolution / yolo layer reads"
+                                                           if args.fp32_shortcuts else
+                                                           "every tensor written once, the folded shortcuts add hi + lo of "
+                                                           "their operand's planes; fp32 only for the yolo layers"))
                                        if getattr(net, "split_activations", False) else "fp32"),
                        "shortcuts_fused_into_conv": sum(bool(getattr(l, "_fused_into_conv", False)) for l in net.layers),
                        "parallelism": f"batch-sharded x{world}, no collective",
@@ -525,6 +532,8 @@ def main():
     ap.add_argument("--no-fuse", action="store_true", help="keep the shortcut adds as separate kernels")
     ap.add_argument("--split-1x1", action="store_true", help="bf16x3: 1x1 convolutions read pre-split planes too (their "
                     "producers then write fp32 rows AND planes)")
+    ap.add_argument("--fp32-shortcuts", action="store_true", help="bf16x3: keep fp32 rows for the shortcut operands and the "
+                    "1x1 convolutions' inputs (the graph of the first half of round 2) instead of planes everywhere")
     ap.add_argument("--no-split", action="store_true", help="bf16x3: fp32 activations between all layers (no pre-split planes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-images", type=int, default=2)

@@ -419,6 +419,19 @@ TNN_API int32_t tnn_conv2d_forward_split(tnn_context *ctx, const tnn_conv_desc *
                                          float *out, int64_t outOffset, int64_t outPitch, int32_t outLayout,
                                          void *outSplit, int64_t outSplitOffset, int64_t outSplitPitch,
                                          int64_t outSplitPlane);
+/* The same, with the folded shortcut's other operand in either form: residualLayout TNN_LAYOUT_NHWC (fp32 rows,
+ * residualPitch in floats, residualPlane ignored) or TNN_LAYOUT_NHWC_SPLIT (the hi plane; offset, pitch and plane in bf16
+ * elements, multiples of 8; filters a multiple of 8).  From planes the operand is hi + lo — the value the planes hold,
+ * i.e. the fp32 tensor to 2^-18 relative — so a graph can keep EVERY tensor between convolutions as planes only
+ * (written once, 4 bytes per element, no fp32 twin for the shortcuts) and every convolution, 1x1 included, reads its
+ * operands by TMA with no conversion in shared memory. */
+TNN_API int32_t tnn_conv2d_forward_split_residual(tnn_context *ctx, const tnn_conv_desc *d, const void *in, int64_t inOffset,
+                                                  int64_t inPitch, int32_t inLayout, int64_t inPlane, const float *weights,
+                                                  const float *scale, const float *bias, int32_t activation,
+                                                  const void *residual, int64_t residualOffset, int64_t residualPitch,
+                                                  int32_t residualLayout, int64_t residualPlane, float *out,
+                                                  int64_t outOffset, int64_t outPitch, int32_t outLayout, void *outSplit,
+                                                  int64_t outSplitOffset, int64_t outSplitPitch, int64_t outSplitPlane);
 /* fp32 rows of channels <-> the pre-split planes (the way back is hi + lo, exact in fp32); channels a multiple of 8 */
 TNN_API int32_t tnn_nhwc_to_split(tnn_context *ctx, int64_t rows, int64_t channels, const float *in, int64_t inPitch,
                                   void *outSplit, int64_t outPitch, int64_t outPlane);

@@ -125,6 +125,10 @@ struct NhwcEpilogue {
   // value + residual[row][filter], rows of `resPitch` floats — one fp32 add after the activation, like the separate layer
   const float *residual;
   int64_t resPitch;
+  // ... or the same operand as pre-split planes (a graph that keeps every tensor between convolutions only as planes):
+  // residual = hi + lo, the value the planes hold; resSplitPitch / resSplitPlane in bf16 elements
+  const uint16_t *resHi;
+  int64_t resSplitPitch, resSplitPlane;
   // what to write: fp32 rows (tmOut) and / or the pre-split bf16 planes the next convolution's TMA reads directly
   // (tmOutHi / tmOutLo: hi = bf16_rn(v), lo = bf16_rn(v - hi) — the very split the converter warps would derive)
   bool f32Out, splitOut;
@@ -230,14 +234,27 @@ __device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int 
       const int64_t n = n0 + c0;
       // the shortcut's other operand: this thread's 32 consecutive filters of its pixel row, fetched before the staging
       // wait so that the loads are in flight while the scale / bias scratch is filled
-      float4 res[8];
-      const bool addRes = epi.residual != nullptr;
+      // (fp32 rows: res[j] = filters 4j .. 4j+3; planes: res[q] = the hi halves of filters 8q .. 8q+7, res[4 + q] the lo)
+      uint4 res[8];
+      const bool resSplit = epi.resHi != nullptr;
+      const bool addRes = epi.residual != nullptr || resSplit;
       if (addRes) {
         const int64_t row = (int64_t)row0 + lane;
-        const float4 *rq = reinterpret_cast<const float4 *>(epi.residual + (row < epi.rows ? row : 0) * epi.resPitch + n);
+        const bool rowOk = row < epi.rows;
+        if (resSplit) {
+          const uint4 *rh = reinterpret_cast<const uint4 *>(epi.resHi + (rowOk ? row : 0) * epi.resSplitPitch + n);
+          const uint4 *rl = reinterpret_cast<const uint4 *>(epi.resHi + epi.resSplitPlane + (rowOk ? row : 0) * epi.resSplitPitch + n);
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          res[j] = (row < epi.rows && 4 * j < cnt) ? __ldg(rq + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int q = 0; q < 4; ++q) {
+            const bool ok = rowOk && 8 * q < cnt;
+            res[q] = ok ? __ldg(rh + q) : make_uint4(0u, 0u, 0u, 0u);
+            res[4 + q] = ok ? __ldg(rl + q) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        } else {
+          const uint4 *rq = reinterpret_cast<const uint4 *>(epi.residual + (rowOk ? row : 0) * epi.resPitch + n);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) res[j] = (rowOk && 4 * j < cnt) ? __ldg(rq + j) : make_uint4(0u, 0u, 0u, 0u);
+        }
       }
       __syncwarp();
       scratch[lane] = (epi.scale && lane < cnt) ? __ldg(epi.scale + n + lane) : 1.0f;
@@ -268,9 +285,21 @@ __device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int 
             o[4 * h + u] = simple ? fmaxf(v, __fmul_rn(neg, v)) : act_out_of_line(v, epi.act);
           }
           if (addRes) {
-            const float4 rr = res[(j8 >> 2) + h];
-            o[4 * h + 0] = __fadd_rn(o[4 * h + 0], rr.x); o[4 * h + 1] = __fadd_rn(o[4 * h + 1], rr.y);
-            o[4 * h + 2] = __fadd_rn(o[4 * h + 2], rr.z); o[4 * h + 3] = __fadd_rn(o[4 * h + 3], rr.w);
+            float rr[4];
+            if (resSplit) {
+              // two bf16 per word, the even filter in the low half (pack_bf16x2): value = hi + lo, exact in fp32
+              const uint4 qh = res[j8 >> 3], ql = res[4 + (j8 >> 3)];
+              const uint32_t wh0 = h ? qh.z : qh.x, wh1 = h ? qh.w : qh.y, wl0 = h ? ql.z : ql.x, wl1 = h ? ql.w : ql.y;
+              rr[0] = __fadd_rn(__uint_as_float(wh0 << 16), __uint_as_float(wl0 << 16));
+              rr[1] = __fadd_rn(__uint_as_float(wh0 & 0xFFFF0000u), __uint_as_float(wl0 & 0xFFFF0000u));
+              rr[2] = __fadd_rn(__uint_as_float(wh1 << 16), __uint_as_float(wl1 << 16));
+              rr[3] = __fadd_rn(__uint_as_float(wh1 & 0xFFFF0000u), __uint_as_float(wl1 & 0xFFFF0000u));
+            } else {
+              const uint4 q = res[(j8 >> 2) + h];
+              rr[0] = __uint_as_float(q.x); rr[1] = __uint_as_float(q.y); rr[2] = __uint_as_float(q.z); rr[3] = __uint_as_float(q.w);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) o[4 * h + u] = __fadd_rn(o[4 * h + u], rr[u]);
           }
         }
         const float4 oa = make_float4(o[0], o[1], o[2], o[3]), ob = make_float4(o[4], o[5], o[6], o[7]);
@@ -941,7 +970,7 @@ struct SplitRef {
 static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, int64_t inPitch,
                         SplitRef inSplit, const float *weights, const float *scale, const float *bias, int act, float *out,
                         int64_t outPitch, bool outNchw, SplitRef outSplit, const float *residual = nullptr,
-                        int64_t resPitch = 0) {
+                        int64_t resPitch = 0, SplitRef resSplit = SplitRef{nullptr, 0, 0}) {
   const int kk = g.kh * g.kw;
   const bool aSplit = inSplit.hi != nullptr;
   if (aSplit) {
@@ -1083,7 +1112,12 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   if (residual)
     TNN_REQUIRE((resPitch % 4) == 0 && resPitch >= N && (N % 4) == 0 && (((uintptr_t)residual) & 15) == 0,
                 "the residual needs 16-byte aligned rows and a filter count that is a multiple of 4");
-  NhwcEpilogue epi{scale, bias, act, M, N, residual, resPitch, out != nullptr, outSplit.hi != nullptr};
+  if (resSplit.hi)
+    TNN_REQUIRE(residual == nullptr && (resSplit.pitch % 8) == 0 && resSplit.pitch >= N && (resSplit.plane % 8) == 0 &&
+                    (N % 8) == 0 && (((uintptr_t)resSplit.hi) & 15) == 0,
+                "a pre-split residual needs pitch, plane stride and filter count multiples of 8 and a 16-byte aligned base");
+  NhwcEpilogue epi{scale, bias, act, M, N, residual, resPitch, resSplit.hi, resSplit.pitch, resSplit.plane,
+                   out != nullptr, outSplit.hi != nullptr};
   return go(epi);
 }
 
@@ -1403,7 +1437,7 @@ static int conv_image(tnn_context *ctx, const simt::ConvGeom &g, int batch, cons
     if (rc) return rc;
   }
   // rows = 1 / row0 = 0: the 4-D stores clip ragged patches themselves
-  NhwcEpilogue epi{scale, bias, act, 1, N, nullptr, 0, out != nullptr, outSplit.hi != nullptr};
+  NhwcEpilogue epi{scale, bias, act, 1, N, nullptr, 0, nullptr, 0, 0, out != nullptr, outSplit.hi != nullptr};
   const int64_t tiles = (int64_t)batch * ig.tilesX * ig.tilesY;
   TNN_REQUIRE(tiles < (1ll << 30), "too many patches");
   const int numTiles = (int)tiles;
@@ -1704,7 +1738,28 @@ int32_t tnn_conv2d_forward_split(tnn_context *ctx, const tnn_conv_desc *d, const
                                  const float *bias, int32_t activation, const float *residual, int64_t residualOffset,
                                  int64_t residualPitch, float *out, int64_t outOffset, int64_t outPitch, int32_t outLayout,
                                  void *outSplit, int64_t outSplitOffset, int64_t outSplitPitch, int64_t outSplitPlane) {
+  return tnn_conv2d_forward_split_residual(ctx, d, in, inOffset, inPitch, inLayout, inPlane, weights, scale, bias, activation,
+                                           residual, residualOffset, residualPitch, TNN_LAYOUT_NHWC, 0, out, outOffset,
+                                           outPitch, outLayout, outSplit, outSplitOffset, outSplitPitch, outSplitPlane);
+}
+
+int32_t tnn_conv2d_forward_split_residual(tnn_context *ctx, const tnn_conv_desc *d, const void *in, int64_t inOffset,
+                                          int64_t inPitch, int32_t inLayout, int64_t inPlane, const float *weights,
+                                          const float *scale, const float *bias, int32_t activation, const void *residualAny,
+                                          int64_t residualOffset, int64_t residualPitch, int32_t residualLayout,
+                                          int64_t residualPlane, float *out, int64_t outOffset, int64_t outPitch,
+                                          int32_t outLayout, void *outSplit, int64_t outSplitOffset, int64_t outSplitPitch,
+                                          int64_t outSplitPlane) {
   TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(residualLayout == TNN_LAYOUT_NHWC || residualLayout == TNN_LAYOUT_NHWC_SPLIT,
+              "the residual is rows of channels (fp32) or pre-split planes");
+  const float *residual = residualLayout == TNN_LAYOUT_NHWC ? (const float *)residualAny : nullptr;
+  nhwc::SplitRef rs{nullptr, 0, 0};
+  if (residualAny && residualLayout == TNN_LAYOUT_NHWC_SPLIT) {
+    rs = nhwc::SplitRef{(const uint16_t *)residualAny + residualOffset, residualPitch, residualPlane};
+    TNN_REQUIRE(inLayout != TNN_LAYOUT_NCHW && outLayout == TNN_LAYOUT_NHWC,
+                "the residual add is fused for channels-innermost tensors");
+  }
   simt::ConvGeom g;
   int rc = fill_geom_nhwc(d, g);
   if (rc) return rc;
@@ -1741,7 +1796,7 @@ int32_t tnn_conv2d_forward_split(tnn_context *ctx, const tnn_conv_desc *d, const
   if (inLayout == TNN_LAYOUT_NHWC_SPLIT) is = nhwc::SplitRef{(const uint16_t *)in + inOffset, inPitch, inPlane};
   else inf = (const float *)in + inOffset;
   return nhwc::conv_forward(ctx, g, (int)d->batch, inf, inPitch, is, weights, scale, bias, activation, out, outPitch,
-                            outLayout == TNN_LAYOUT_NCHW, os, residual, residualPitch);
+                            outLayout == TNN_LAYOUT_NCHW, os, residual, residualPitch, rs);
 }
 
 int32_t tnn_nhwc_to_split(tnn_context *ctx, int64_t rows, int64_t channels, const float *in, int64_t inPitch, void *outSplit,

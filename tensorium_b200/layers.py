@@ -113,6 +113,7 @@ class TConvolutionalLayer:
         self._in_nhwc = None  # private channels-innermost copy of a planar input the direct kernel cannot take
         self.in_split = self.out_split = False  # pre-split bf16 planes in / out (TNNet.setSplitActivations)
         self.out_f32 = True
+        self.res_split = False  # the folded shortcut's other operand is read from its planes (no fp32 twin exists)
         self._desc = nn.TNNCuda.conv_desc(batch, c, h, w, filters, kernelSize, kernelSize, padding, padding, stride,
                                           stride, dilation, dilation)
 
@@ -187,13 +188,18 @@ class TConvolutionalLayer:
                 else:
                     in_ptr, in_plane = src.devData, 0
                 res = self._residual
-                cu.conv2dForwardSplit(self._desc, in_ptr, 0, in_pitch, in_layout, in_plane, self.weights.devData,
-                                      sc.devData if sc is not None else None, bi.devData, self.ActivationType,
-                                      res.devData if res is not None else None, 0,
-                                      (getattr(res, "pitch", 0) or self.filters) if res is not None else 0,
-                                      tgt.devData if self.out_f32 else None, 0, self.out_pitch or self.filters,
-                                      self.out_layout, tgt.split.devData if self.out_split else None, 0, self.filters,
-                                      tgt.Size())
+                if res is None:
+                    res_ptr, res_pitch, res_layout, res_plane = None, 0, NHWC, 0
+                elif self.res_split:   # the shortcut's other operand exists only as planes: residual = hi + lo
+                    res_ptr, res_pitch, res_layout, res_plane = res.split.devData, self.filters, SPLIT, res.Size()
+                else:
+                    res_ptr, res_pitch, res_layout, res_plane = res.devData, getattr(res, "pitch", 0) or self.filters, NHWC, 0
+                cu.conv2dForwardSplitResidual(self._desc, in_ptr, 0, in_pitch, in_layout, in_plane, self.weights.devData,
+                                              sc.devData if sc is not None else None, bi.devData, self.ActivationType,
+                                              res_ptr, 0, res_pitch, res_layout, res_plane,
+                                              tgt.devData if self.out_f32 else None, 0, self.out_pitch or self.filters,
+                                              self.out_layout, tgt.split.devData if self.out_split else None, 0,
+                                              self.filters, tgt.Size())
                 return
             if self._residual is not None and in_layout == NHWC and self.out_layout == NHWC:
                 # the shortcut that follows, folded into the epilogue (TNNet.fuseShortcuts): writes the shortcut's output

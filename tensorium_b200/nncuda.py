@@ -452,6 +452,16 @@ class TNNCuda:
             _addr(bias), int(activation), _addr(residual), residualOffset, residualPitch, _addr(out), outOffset, outPitch,
             int(outLayout), _addr(outSplit), outSplitOffset, outSplitPitch, outSplitPlane))
 
+    def conv2dForwardSplitResidual(self, desc, in_, inOffset, inPitch, inLayout, inPlane, weights, scale, bias, activation,
+                                   residual, residualOffset, residualPitch, residualLayout, residualPlane, out, outOffset,
+                                   outPitch, outLayout, outSplit, outSplitOffset, outSplitPitch, outSplitPlane):
+        """conv2dForwardSplit with the folded shortcut's other operand as fp32 rows (LAYOUT_NHWC) or as pre-split planes
+        (LAYOUT_NHWC_SPLIT: residual = hi + lo)."""
+        self._ck(self._l.tnn_conv2d_forward_split_residual(
+            self._h, C.byref(desc), _addr(in_), inOffset, inPitch, int(inLayout), inPlane, _addr(weights), _addr(scale),
+            _addr(bias), int(activation), _addr(residual), residualOffset, residualPitch, int(residualLayout), residualPlane,
+            _addr(out), outOffset, outPitch, int(outLayout), _addr(outSplit), outSplitOffset, outSplitPitch, outSplitPlane))
+
     def nhwcToSplit(self, rows, channels, in_, inPitch, outSplit, outPitch, outPlane):
         self._ck(self._l.tnn_nhwc_to_split(self._h, rows, channels, _addr(in_), inPitch, _addr(outSplit), outPitch, outPlane))
 

@@ -446,7 +446,7 @@ class TNNet:
         self.channels_last = bool(on)
         return self
 
-    def setSplitActivations(self, on: bool = True, split_into_1x1: bool = False):
+    def setSplitActivations(self, on: bool = True, split_into_1x1: bool = False, planes_only: bool = False):
         """BF16x3 graphs: keep every activation that a convolution reads as PRE-SPLIT bf16 planes
         (TNN_LAYOUT_NHWC_SPLIT, include/tensorium_b200.h): the producing epilogue writes hi = bf16(x), lo = bf16(x - hi),
         the consuming convolution's TMA lands them as tensor-core operands and nothing converts — the same products
@@ -455,11 +455,16 @@ class TNNet:
         split_into_1x1=False: a 1x1 convolution reads fp32 rows and splits them in shared memory itself — it touches
         every element once (no 9x redundancy as in a 3x3 layer) and is bound by HBM, while its input is typically a
         shortcut output that a later shortcut needs as fp32 anyway: the tensor is then written once instead of twice.
+        planes_only=True: every tensor between convolutions exists ONLY as planes.  The folded shortcuts read their other
+        operand from its planes too (tnn_conv2d_forward_split_residual: residual = hi + lo, the fp32 value to 2^-18
+        relative), so no tensor is written twice AND the 1x1 convolutions take their operands by TMA with no conversion
+        in shared memory.  fp32 is written only for the yolo layers and the graph's last layer.
         Call after setChannelsLast() and fuseShortcuts()."""
         n = len(self.layers)
+        split_into_1x1 = split_into_1x1 or planes_only
         if not on:
             for l in self.layers:
-                for a in ("in_split", "out_split", "split_planes"):
+                for a in ("in_split", "out_split", "split_planes", "res_split"):
                     if hasattr(l, a):
                         setattr(l, a, False)
                 for a in ("out_f32", "f32_rows"):
@@ -481,7 +486,10 @@ class TNNet:
                         need_split[j - 1] = True
             elif isinstance(l, TShortcutLayer):
                 assert getattr(l, "_fused_into_conv", False), "pre-split graphs need the shortcuts folded into the convolutions"
-                need_f32[l.inputLayers[0]] = True
+                if planes_only:
+                    need_split[l.inputLayers[0]] = True
+                else:
+                    need_f32[l.inputLayers[0]] = True
             elif isinstance(l, TConcatLayer):
                 for idx in l.inputLayers:
                     need_split[idx] |= need_split[j]
@@ -497,6 +505,7 @@ class TNNet:
                 tgt = self.layers[t].output
                 l.in_split = j > 0 and (l.kernelSize != 1 or split_into_1x1)
                 l.out_split = need_split[t]
+                l.res_split = planes_only and l._residual is not None
                 # (an image layer too deep for the tensor-core image kernel runs the direct kernel, which writes rows first)
                 l.out_f32 = need_f32[t] or not need_split[t] or (j == 0 and l.c * l.kernelSize ** 2 > 32)
                 assert not (l.out_split and l.out_layout != nn.TNNCuda.LAYOUT_NHWC), "planes are fp32 only"
@@ -664,5 +673,5 @@ def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=12
     if fuse_shortcuts and fused:
         net.fuseShortcuts()
     if split_activations:
-        net.setSplitActivations()
+        net.setSplitActivations(planes_only=split_activations == "planes")
     return net

@@ -265,6 +265,51 @@ def test_conv_forward_presplit(cuda_backend, oracle, geom):
     assert np.array_equal(outs["planes"][1], outs["both"][1])
 
 
+@pytest.mark.parametrize("geom", [g for g in SPLIT_GEOMS if g[8]] + [(3, 64, 26, 26, 32, 1, 0, 1, True)])
+def test_conv_forward_presplit_residual_from_planes(cuda_backend, oracle, geom):
+    """tnn_conv2d_forward_split_residual with the shortcut operand as pre-split planes: the operand the kernel adds is
+    hi + lo, so the result is BIT-IDENTICAL to the fp32-residual form fed hi + lo (both outputs), and within the 1e-4 gate
+    of the oracle computed with the ORIGINAL fp32 operand (the planes hold it to 2^-18 relative)."""
+    cu = cuda_backend
+    B, C, H, W, F, k, p, s, _ = geom
+    rng = np.random.default_rng(sum(geom[:8]) + 23)
+    x, w, b = conv_case(rng, B, C, H, W, F, k)
+    sc = rng.uniform(0.5, 1.5, F).astype(np.float32)
+    want = oracle.conv2d(x, w, p, s, s, 1, k, k)
+    oracle.forward_scale(want, sc, B)
+    oracle.forward_bias(want, b, B)
+    oracle.activate_array(want, oracle.ACT["LEAKY"])
+    OH, OW = want.shape[2], want.shape[3]
+    M = B * OH * OW
+    res = rng.uniform(-1, 1, (B, F, OH, OW)).astype(np.float32)
+    want = want + res
+    dx, dw, db, ds = Dev(cu, to_nhwc(x)), Dev(cu, w), Dev(cu, b), Dev(cu, sc)
+    dres = Dev(cu, to_nhwc(res))
+    dxs, drs, drr = Dev(cu, n=x.size), Dev(cu, n=M * F), Dev(cu, n=M * F)
+    n_in = B * H * W * C
+    cu.nhwcToSplit(B * H * W, C, dx.ptr, C, dxs.ptr, C, n_in)
+    cu.nhwcToSplit(M, F, dres.ptr, F, drs.ptr, F, M * F)
+    cu.splitToNhwc(M, F, drs.ptr, F, M * F, drr.ptr, F)       # hi + lo as fp32 rows
+    desc = cu.conv_desc(B, C, H, W, F, k, k, p, p, s, s)
+    act = oracle.ACT["LEAKY"]
+    outs = {}
+    cu.set_math_mode(BF3)
+    try:
+        for name, (rp, lay, plane) in {"planes": (drs, SPLIT, M * F), "rows": (drr, NHWC, 0)}.items():
+            do, dsp = Dev(cu, n=M * F), Dev(cu, n=M * F)
+            cu.conv2dForwardSplitResidual(desc, dxs.ptr, 0, C, SPLIT, n_in, dw.ptr, ds.ptr, db.ptr, act, rp.ptr, 0, F, lay,
+                                          plane, do.ptr, 0, F, NHWC, dsp.ptr, 0, F, M * F)
+            assert "k_conv_nhwc" in cu.lastConvKernel()
+            outs[name] = (do.read((B, OH, OW, F)), dsp.read().view(np.uint16).reshape(2, M, F))
+    finally:
+        cu.set_math_mode(X3)
+    assert np.array_equal(outs["planes"][0], outs["rows"][0])
+    assert np.array_equal(outs["planes"][1], outs["rows"][1])
+    got = from_nhwc(outs["planes"][0], F)
+    e1, e2 = rel_max(got, want), rel_elem(got, want, floor=1.0)
+    assert e1 < TOL_3XTF32 and e2 < TOL_3XTF32, (e1, e2)
+
+
 # (B, C, H, W, F, k, pad, stride)
 IMAGE_GEOMS = [
     (2, 3, 20, 24, 32, 3, 1, 1),     # the YOLOv3 / CIFAR image layer shape: K = 27

@@ -10,11 +10,14 @@ pytestmark = pytest.mark.gpu
 
 def run_net(cu, size, batch, variant, params, x):
     """variant: fused | unfused | channels_last | split (= channels-last, shortcuts folded into the convolutions,
-    pre-split bf16 activations: the graph bench.py times in its default BF16x3 arithmetic)"""
+    pre-split bf16 activations, fp32 rows where a shortcut or a 1x1 convolution reads) | planes (= split with EVERY
+    tensor between convolutions only as planes, the shortcut operands read as hi + lo: the graph bench.py times in its
+    default BF16x3 arithmetic)"""
     from tensorium_b200.nnet import build_yolov3
     net = build_yolov3(batch, size, params=params, fused=variant != "unfused",
-                       channels_last=variant in ("channels_last", "split"), fuse_shortcuts=variant == "split",
-                       split_activations=variant == "split")
+                       channels_last=variant in ("channels_last", "split", "planes"),
+                       fuse_shortcuts=variant in ("split", "planes"),
+                       split_activations={"split": True, "planes": "planes"}.get(variant, False))
     cu.writeBuffer(net.input.devData, x.nbytes, x)
     net.predict()
     return net
@@ -74,6 +77,9 @@ def check_conv_layers(cu, net, probe, x, batch, tol, expect_kernel=None):
             r = probe[net.layers[tgt].inputLayers[0]]
             r = np.ascontiguousarray(r.transpose(0, 2, 3, 1)) if getattr(l, "in_layout", 0) else r
             cu.writeBuffer(l._residual.devData, r.nbytes, r)
+            if getattr(l, "res_split", False):   # the operand is read from its planes
+                b_, f_, h_, w_ = l._residual.FShape
+                cu.nhwcToSplit(b_ * h_ * w_, f_, l._residual.devData, f_, l._residual.split.devData, f_, b_ * f_ * h_ * w_)
         l.forwardGPU(st)
         if expect_kernel is not None:
             assert expect_kernel(i) in cu.lastConvKernel(), (i, cu.lastConvKernel())
@@ -103,7 +109,9 @@ def check_detections(net, outs, want, batch, thresh, nms=0.45, images=None):
     The GPU outputs differ from the oracle's by d = max|g - r| (measured here), so a score within `margin` = 8d of the
     threshold may legitimately be kept on one side and dropped on the other.  Such a borderline score is the LOWEST of
     its class, so it can be suppressed but never suppresses a non-borderline one (NMS walks scores downward): every
-    score farther than `margin` from the threshold must match one to one; borderline ones may be unmatched."""
+    score farther than `margin` from the threshold must match one to one; borderline ones may be unmatched.  The same
+    margin applies to the ORDER of two mutually suppressing boxes of one class: when their scores differ by less than
+    it, either of the two may be the survivor (seen at 96 x 96: 0.10220449 vs 0.10220415)."""
     from oracle import ref_detect as rd
     d = max(float(np.abs(g - r).max()) for g, r in zip(outs, want))
     margin = 8 * d + 1e-7
@@ -127,7 +135,11 @@ def check_detections(net, outs, want, batch, thresh, nms=0.45, images=None):
         fr = firm(ref)
 
         def twin(e, lst):
-            return any(c == e[0] and abs(p - e[1]) <= margin and rd.box_iou(bx, e[2]) >= 0.99 for c, p, bx in lst)
+            if any(c == e[0] and abs(p - e[1]) <= margin and rd.box_iou(bx, e[2]) >= 0.99 for c, p, bx in lst):
+                return True
+            # near-tie: two boxes of one class that suppress each other (IoU > nms) and whose scores differ by less than
+            # the margin are ordered by the sort either way — one side keeps the first, the other side the second
+            return any(c == e[0] and abs(p - e[1]) <= margin and rd.box_iou(bx, e[2]) > nms for c, p, bx in lst)
         for e in fr:
             assert twin(e, got), ("oracle score without a product twin", e)
         for e in firm(got):
@@ -136,11 +148,11 @@ def check_detections(net, outs, want, batch, thresh, nms=0.45, images=None):
     return total  # class scores that survived NMS (and were compared), over the images
 
 
-@pytest.mark.parametrize("variant", ["fused", "unfused", "channels_last", "split"])
+@pytest.mark.parametrize("variant", ["fused", "unfused", "channels_last", "split", "planes"])
 def test_yolov3_small_against_oracle(cuda_backend, oracle, variant):
     from tensorium_b200.nnet import init_yolov3_params, yolov3_spec
     cu = cuda_backend
-    if variant == "split":
+    if variant in ("split", "planes"):
         cu.set_math_mode(3)
     try:
         _yolov3_small(cu, oracle, variant)
@@ -171,7 +183,7 @@ def _yolov3_small(cu, oracle, variant):
 
 
 @pytest.mark.parametrize("math,tol", [("3xtf32", TOL_3XTF32), ("tf32", 5e-3), ("bf16x3", TOL_3XTF32),
-                                      ("bf16x3-split", TOL_3XTF32)])
+                                      ("bf16x3-split", TOL_3XTF32), ("bf16x3-planes", TOL_3XTF32)])
 def test_yolov3_416_bench_configuration(cuda_backend, oracle, math, tol):
     """The benchmark's own configuration (BASELINE.json configs[3]: 416 x 416, channels-last graph, objectness bias
     -4, detection threshold 0.45) at batch 8: the same kernels bench.py times (the channels-innermost dispatch does
@@ -184,9 +196,9 @@ def test_yolov3_416_bench_configuration(cuda_backend, oracle, math, tol):
     params = init_yolov3_params(spec, seed=1234, objectness_bias=-4.0)
     x = np.random.Generator(np.random.PCG64(1234)).random((batch, 3, size, size), dtype=np.float32)
     want, probe = oracle_forward(oracle, spec, params, x, key=(size, batch, 1234))
-    cu.set_math_mode({"3xtf32": 1, "tf32": 2, "bf16x3": 3, "bf16x3-split": 3}[math])
+    cu.set_math_mode({"3xtf32": 1, "tf32": 2, "bf16x3": 3, "bf16x3-split": 3, "bf16x3-planes": 3}[math])
     try:
-        net = run_net(cu, size, batch, "split" if math.endswith("split") else "channels_last", params, x)
+        net = run_net(cu, size, batch, math.split("-")[1] if "-" in math else "channels_last", params, x)
         worst = check_conv_layers(cu, net, probe, x, batch, tol,
                                   expect_kernel=lambda i: ("direct" if math == "3xtf32" else "k_conv_image") if i == 0 else "k_conv_nhwc")
         print(f"416x416 batch {batch} {math}: worst per-layer rel err {worst:.3e}")

@@ -200,6 +200,8 @@ meth("procedure setWeightsStatic(const weights: TCUMem; const isStatic: boolean)
 meth("procedure setMathMode(const mode: longint)", "tnn_set_math_mode", "mode", False)
 meth("procedure conv2dForwardSplit(const d: TNNConvDesc; const inp: TCUMem; const inOffset, inPitch: SizeInt; const inLayout: longint; const inPlane: SizeInt; const weights, scale, bias: TCUMem; const activation: longint; const residual: TCUMem; const residualOffset, residualPitch: SizeInt; const outp: TCUMem; const outOffset, outPitch: SizeInt; const outLayout: longint; const outSplit: TCUMem; const outSplitOffset, outSplitPitch, outSplitPlane: SizeInt)",
      "tnn_conv2d_forward_split", "@d, inp, inOffset, inPitch, inLayout, inPlane, weights, scale, bias, activation, residual, residualOffset, residualPitch, outp, outOffset, outPitch, outLayout, outSplit, outSplitOffset, outSplitPitch, outSplitPlane")
+meth("procedure conv2dForwardSplitResidual(const d: TNNConvDesc; const inp: TCUMem; const inOffset, inPitch: SizeInt; const inLayout: longint; const inPlane: SizeInt; const weights, scale, bias: TCUMem; const activation: longint; const residual: TCUMem; const residualOffset, residualPitch: SizeInt; const residualLayout: longint; const residualPlane: SizeInt; const outp: TCUMem; const outOffset, outPitch: SizeInt; const outLayout: longint; const outSplit: TCUMem; const outSplitOffset, outSplitPitch, outSplitPlane: SizeInt)",
+     "tnn_conv2d_forward_split_residual", "@d, inp, inOffset, inPitch, inLayout, inPlane, weights, scale, bias, activation, residual, residualOffset, residualPitch, residualLayout, residualPlane, outp, outOffset, outPitch, outLayout, outSplit, outSplitOffset, outSplitPitch, outSplitPlane")
 meth("procedure nhwcToSplit(const rows, channels: SizeInt; const inp: TCUMem; const inPitch: SizeInt; const outSplit: TCUMem; const outPitch, outPlane: SizeInt)",
      "tnn_nhwc_to_split", "rows, channels, inp, inPitch, outSplit, outPitch, outPlane")
 meth("procedure splitToNhwc(const rows, channels: SizeInt; const inSplit: TCUMem; const inPitch, inPlane: SizeInt; const outp: TCUMem; const outPitch: SizeInt)",
