@@ -1275,8 +1275,11 @@ int launch(tnn_context *ctx, const Plan &p, LA la, LB lb, EPI epi, const CUtenso
 }
 
 inline bool gemm_supported(tnn_context *, int64_t M, int64_t N, int64_t K) {
-  // tiny problems are latency bound: leave them to the CUDA-core kernel
-  return M * N * K >= (1ll << 18) && K >= 8;
+  // tiny problems are latency bound: leave them to the CUDA-core kernel.  So are thin ones: with fewer than 16 rows or
+  // columns the 128 x BN tile is more than 7/8 padding, and a contraction shorter than one k-block cannot use the TMA-fed
+  // kernel — the register-staged tensor kernel needed 54 / 60 us for the 10-class connected layer's two backward products
+  // (10 x 1024 x 128 and 128 x 1024 x 10) in the deepCIFAR10 step, the CUDA-core kernel a few us
+  return M * N * K >= (1ll << 18) && K >= BK && M >= 16 && N >= 16;
 }
 
 template <typename LA, typename LB>
