@@ -442,16 +442,27 @@ def run_ours(args, rank, world, local_rank):
         cifar = {"workload": "deepCIFAR10 (nmodels.pas:82-111) training step: host batch in, forward, backward, NCCL "
                              "all-reduce of the update bucket (tnn_allreduce_sum, captured in the step's CUDA graph), SGD; "
                              "synthetic 32x32 images, 3xtf32", "math": "3xtf32"}
+        # (a failure in a secondary object must not cost the headline line: it is recorded in the object instead; every
+        # rank runs the same deterministic code, so all ranks fail or none does and nobody waits in a collective)
+        def secondary(name, fn):
+            try:
+                cifar[name] = fn()
+            except Exception as e:  # noqa: BLE001
+                cifar[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
         if world == 1:
-            cifar["batch128"] = cifar_train.train_throughput(cu, stream, 128, 100, 5, rank, world)
+            secondary("batch128", lambda: cifar_train.train_throughput(cu, stream, 128, 100, 5, rank, world))
         else:
-            cifar["global_batch_128_split"] = cifar_train.train_throughput(cu, stream, max(128 // world, 1), 100, 5, rank, world)
-            cifar["batch128_per_gpu"] = cifar_train.train_throughput(cu, stream, 128, 100, 5, rank, world)
-            cifar["global_batch_128_split_syncbn"] = cifar_train.train_throughput(cu, stream, max(128 // world, 1), 100, 5,
-                                                                                 rank, world, sync_bn=True)
+            per = max(128 // world, 1)
+            secondary("global_batch_128_split", lambda: cifar_train.train_throughput(cu, stream, per, 100, 5, rank, world))
+            secondary("batch128_per_gpu", lambda: cifar_train.train_throughput(cu, stream, 128, 100, 5, rank, world))
+            secondary("global_batch_128_split_syncbn",
+                      lambda: cifar_train.train_throughput(cu, stream, per, 100, 5, rank, world, sync_bn=True))
         cu.set_math_mode(MATH[args.math])
         if rank == 0:
-            membound = membound_roofline(cu, stream, float(peaks["hbm_gbs"]))
+            try:
+                membound = membound_roofline(cu, stream, float(peaks["hbm_gbs"]))
+            except Exception as e:  # noqa: BLE001
+                membound = {"error": f"{type(e).__name__}: {e}"[:300]}
 
     if rank == 0:
         if args.layers_out:
