@@ -371,6 +371,17 @@ TNN_API int32_t tnn_sgd_update_multi(tnn_context *ctx, int32_t count, float *con
  * mapped v*scale_xy + 0.5*(1-scale_xy) when scale_xy != 1. */
 TNN_API int32_t tnn_yolo_activate(tnn_context *ctx, int64_t batch, int64_t n, int64_t classes, int64_t wh,
                                   float *out, float scale_xy);
+/* The candidate test of TYoloLayer.getDetections (nyololayer.pas:414-418, `if objectness > thresh`) on the device, so
+ * that the host reads a short list instead of the whole output tensor: every (image, anchor, cell) of the ACTIVATED
+ * output out[batch][n*(5+classes)][wh] whose objectness exceeds thresh appends one record to `cand`:
+ *   cand[0]                       uint32 count of candidates found (zero it before the first call of a step; it keeps
+ *                                 counting past maxCand, the list then holds the first maxCand to arrive -> read the
+ *                                 full output instead)
+ *   cand + 4 + r*(classes + 9)    record r: int32 {tag, image, anchor, cell}, then the classes + 5 entries of the cell
+ * Several layers may append to one list (tag tells them apart).  Record order is arrival order: sort by
+ * (tag, image, cell, anchor) to get the order in which the reference's loops visit them. */
+TNN_API int32_t tnn_yolo_candidates(tnn_context *ctx, int64_t batch, int64_t n, int64_t classes, int64_t wh,
+                                    const float *out, float thresh, int32_t tag, int64_t maxCand, float *cand);
 /* out[b][cOff..cOff+c] = in  — per-image channel concat used by route layers */
 TNN_API int32_t tnn_concat_channels(tnn_context *ctx, int64_t batch, int64_t c, int64_t blockSize, const float *in,
                                     int64_t outChannels, int64_t cOffset, float *out);

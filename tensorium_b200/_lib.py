@@ -116,6 +116,7 @@ SIGNATURES = {
     "tnn_sgd_update": (i32, [ctxp, i64, fptr, fptr, f32, f32, f32]),
     "tnn_sgd_update_multi": (i32, [ctxp, i32, vp, vp, vp, vp, vp, f32]),
     "tnn_yolo_activate": (i32, [ctxp, i64, i64, i64, i64, fptr, f32]),
+    "tnn_yolo_candidates": (i32, [ctxp, i64, i64, i64, i64, fptr, f32, i32, i64, fptr]),
     "tnn_concat_channels": (i32, [ctxp, i64, i64, i64, fptr, i64, i64, fptr]),
     "tnn_conv2d_forward_nhwc": (i32, [ctxp, C.POINTER(ConvDesc), fptr, i64, i64, i32, fptr, fptr, fptr, i32, fptr, i64,
                                       i64, i32]),

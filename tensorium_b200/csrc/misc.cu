@@ -174,6 +174,32 @@ __global__ void __launch_bounds__(kT) k_concat4(int64_t total4, int64_t cb4, int
   }
 }
 
+// ---- TYoloLayer.getDetections' candidate test (nyololayer.pas:414-418: `if objectness > thresh`) on the device: one thread
+// per (image, anchor, cell) reads the objectness plane; a candidate's (classes + 5) entries (stride wh in the planar
+// output) are appended to a compact record list.  The host decodes the records exactly as it decodes the full output
+// (same floats), so only a few KB instead of the whole output tensor cross PCIe.
+//   cand[0] = number of candidates found (may exceed maxCand: the list then holds the first maxCand to arrive)
+//   record r at cand + 4 + r*(classes + 9): {tag, image, anchor, cell} as int32, then the classes + 5 entries
+__global__ void __launch_bounds__(256) k_yolo_candidates(int64_t total, int n, int entries, int wh, const float *__restrict__ out,
+                                                         float thresh, int tag, int maxCand, float *__restrict__ cand) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(t % wh);
+    const int64_t ba = t / wh;   // image * n + anchor
+    const float *p = out + ba * entries * wh + i;
+    const float obj = __ldg(p + 4 * (int64_t)wh);
+    if (!(obj > thresh)) continue;
+    const unsigned slot = atomicAdd(reinterpret_cast<unsigned *>(cand), 1u);
+    if (slot >= (unsigned)maxCand) continue;
+    float *r = cand + 4 + (int64_t)slot * (entries + 4);
+    reinterpret_cast<int *>(r)[0] = tag;
+    reinterpret_cast<int *>(r)[1] = (int)(ba / n);
+    reinterpret_cast<int *>(r)[2] = (int)(ba % n);
+    reinterpret_cast<int *>(r)[3] = i;
+    for (int e = 0; e < entries; ++e) r[4 + e] = __ldg(p + (int64_t)e * wh);
+  }
+}
+
+
 extern "C" {
 
 int32_t tnn_im2col(tnn_context *ctx, int64_t C, int64_t H, int64_t W, int64_t kh, int64_t kw, int64_t ph, int64_t pw,
@@ -275,6 +301,19 @@ int32_t tnn_concat_channels(tnn_context *ctx, int64_t batch, int64_t c, int64_t 
                                                         (float4 *)out);
   else
     k_concat<<<grid1d(total), kT, 0, ctx->stream>>>(total, cb, outCb, offCb, in, out);
+  TNN_LAUNCHED(ctx);
+  return 0;
+}
+
+int32_t tnn_yolo_candidates(tnn_context *ctx, int64_t batch, int64_t n, int64_t classes, int64_t wh, const float *out,
+                            float thresh, int32_t tag, int64_t maxCand, float *cand) {
+  TNN_CHECK_CTX(ctx);
+  TNN_REQUIRE(out != nullptr && cand != nullptr && maxCand > 0 && maxCand < (1ll << 30) && wh < (1ll << 31) && n > 0,
+              "bad candidate list arguments");
+  const int64_t total = batch * n * wh;
+  if (total <= 0) return 0;
+  k_yolo_candidates<<<grid1d(total), kT, 0, ctx->stream>>>(total, (int)n, (int)(classes + 5), (int)wh, out, thresh, tag,
+                                                          (int)maxCand, cand);
   TNN_LAUNCHED(ctx);
   return 0;
 }

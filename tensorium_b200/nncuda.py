@@ -423,6 +423,11 @@ class TNNCuda:
     def yoloActivate(self, batch, n, classes, wh, out, scale_xy=1.0):
         self._ck(self._l.tnn_yolo_activate(self._h, batch, n, classes, wh, _addr(out), scale_xy))
 
+    def yoloCandidates(self, batch, n, classes, wh, out, thresh, tag, maxCand, cand):
+        """The `objectness > thresh` test of TYoloLayer.getDetections on the device: appends compact records to `cand`."""
+        self._ck(self._l.tnn_yolo_candidates(self._h, batch, n, classes, wh, _addr(out), float(thresh), int(tag), maxCand,
+                                             _addr(cand)))
+
     def concatChannels(self, batch, c, blockSize, in_, outChannels, cOffset, out):
         self._ck(self._l.tnn_concat_channels(self._h, batch, c, blockSize, _addr(in_), outChannels, cOffset,
                                              _addr(out)))

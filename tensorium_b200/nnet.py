@@ -145,22 +145,31 @@ class TYoloLayer:
         Detections(img.w, img.h, thresh, relative=true, letter=false), MSCOCOYolo.pas:364)."""
         wh = self.w * self.h
         p = pred[abatch].reshape(self.n, self.classes + 5, wh)
-        boxes, objs, probs = [], [], []
+        cells = []
         for i in range(wh):
-            row, col = divmod(i, self.w)
             for _n in range(self.n):
-                objectness = p[_n, 4, i]
-                if objectness > thresh:
-                    a = self.mask[_n]
-                    bx = (col + p[_n, 0, i]) / self.w
-                    by = (row + p[_n, 1, i]) / self.h
-                    bw = np.exp(p[_n, 2, i]) * self.biases[2 * a] / netw
-                    bh = np.exp(p[_n, 3, i]) * self.biases[2 * a + 1] / neth
-                    pr = objectness * p[_n, 5:, i]
-                    pr = np.where(pr > thresh, pr, 0).astype(np.float32)
-                    boxes.append((bx, by, bw, bh))
-                    objs.append(objectness)
-                    probs.append(pr)
+                if p[_n, 4, i] > thresh:
+                    cells.append((i, _n, p[_n, :, i]))
+        return self.decodeCells(cells, netw, neth, thresh, img_w, img_h, relative, letter)
+
+    def decodeCells(self, cells, netw, neth, thresh, img_w=None, img_h=None, relative=True, letter=False):
+        """The body of getDetections' loop for the cells that passed `objectness > thresh`, in the reference's visiting
+        order: cells = [(cell index, anchor, the classes + 5 entries of that cell)] — from the full output
+        (getDetections) or from the device-side candidate list (tnn_yolo_candidates, TNNet.collectCandidates)."""
+        boxes, objs, probs = [], [], []
+        for i, _n, e in cells:
+            row, col = divmod(i, self.w)
+            objectness = e[4]
+            a = self.mask[_n]
+            bx = (col + e[0]) / self.w
+            by = (row + e[1]) / self.h
+            bw = np.exp(e[2]) * self.biases[2 * a] / netw
+            bh = np.exp(e[3]) * self.biases[2 * a + 1] / neth
+            pr = objectness * e[5:]
+            pr = np.where(pr > thresh, pr, 0).astype(np.float32)
+            boxes.append((bx, by, bw, bh))
+            objs.append(objectness)
+            probs.append(pr)
         if not boxes:
             return np.zeros((0, 4), np.float32), np.zeros(0, np.float32), np.zeros((0, self.classes), np.float32)
         boxes = correctBoxes(np.asarray(boxes, np.float32), img_w or netw, img_h or neth, netw, neth, relative, letter)
@@ -555,6 +564,47 @@ class TNNet:
         for li, l in enumerate(self.yolo_layers()):
             pred = host_outputs[li] if host_outputs is not None else l.output.pullFromDevice()
             b, o, p = l.getDetections(pred, self.w, self.h, thresh, abatch, img_w, img_h, relative, letter)
+            bs.append(b), os_.append(o), ps.append(p)
+        boxes, objs, probs = np.concatenate(bs), np.concatenate(os_), np.concatenate(ps)
+        return doNMSSort(boxes, objs, probs, nms)
+
+
+    # ---- device-side candidate test (tnn_yolo_candidates): the host reads a short list, not the output tensors
+    def collectCandidates(self, thresh=0.45, max_cand=8192, cand: TSingleTensor | None = None) -> TSingleTensor:
+        """After predict(): every (image, anchor, cell) of the yolo layers whose objectness exceeds `thresh` is appended
+        to one compact list on the device (layer = tag).  Returns the device tensor: [count, -, -, -] then records of
+        4 + classes + 5 floats."""
+        yl = self.yolo_layers()
+        rec = yl[0].classes + 9
+        if cand is None:
+            cand = getattr(self, "_cand", None)
+            if cand is None or cand.Size() != 4 + max_cand * rec:
+                cand = self._cand = TSingleTensor((4 + max_cand * rec,), groups=1, host=False)
+        cu = cuda()
+        cand.setCUDA()
+        cu.fill(4, cand.devData, 0, 0.0, 1)
+        for tag, l in enumerate(yl):
+            cu.yoloCandidates(l.batch, l.n, l.classes, l.w * l.h, l.output.devData, thresh, tag, max_cand, cand.devData)
+        return cand
+
+    def DetectionsFromCandidates(self, cand_host: np.ndarray, thresh=0.45, nms=0.45, abatch=0, img_w=None, img_h=None,
+                                 relative=True, letter=False):
+        """Detections() from the host copy of collectCandidates()' list: the records of image `abatch` are put back into
+        the order in which getDetections visits them (layer, cell, anchor) and decoded by the same code."""
+        yl = self.yolo_layers()
+        rec = yl[0].classes + 9
+        count = int(cand_host[:1].view(np.uint32)[0])
+        cap = (cand_host.size - 4) // rec
+        if count > cap:
+            raise OverflowError(f"{count} candidates, the list holds {cap}: read the full outputs (Detections)")
+        r = cand_host[4:4 + count * rec].reshape(count, rec)
+        key = r[:, :4].view(np.int32)
+        bs, os_, ps = [], [], []
+        for tag, l in enumerate(yl):
+            sel = np.nonzero((key[:, 0] == tag) & (key[:, 1] == abatch))[0]
+            sel = sel[np.lexsort((key[sel, 2], key[sel, 3]))]   # by cell, then anchor
+            cells = [(int(key[j, 3]), int(key[j, 2]), r[j, 4:]) for j in sel]
+            b, o, p = l.decodeCells(cells, self.w, self.h, thresh, img_w, img_h, relative, letter)
             bs.append(b), os_.append(o), ps.append(p)
         boxes, objs, probs = np.concatenate(bs), np.concatenate(os_), np.concatenate(ps)
         return doNMSSort(boxes, objs, probs, nms)

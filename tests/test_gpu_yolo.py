@@ -179,7 +179,17 @@ def _yolov3_small(cu, oracle, variant):
     for g, r in zip(outs, want):
         assert rel_max(g, r) < 2e-3
     # (3) detections + NMS: product on GPU outputs vs the oracle's restatement on oracle outputs
-    assert check_detections(net, outs, want, batch, pick_threshold(want, batch, q=0.99)) > 0  # not vacuous
+    thresh = pick_threshold(want, batch, q=0.99)
+    assert check_detections(net, outs, want, batch, thresh) > 0  # not vacuous
+    # (4) the device-side candidate list (tnn_yolo_candidates) gives the host exactly what the full outputs give it
+    ch = net.collectCandidates(thresh).pullFromDevice()
+    assert 0 < int(ch[:1].view(np.uint32)[0]) <= 8192
+    for b in range(batch):
+        full, comp = net.Detections(thresh, 0.45, b, host_outputs=outs), net.DetectionsFromCandidates(ch, thresh, 0.45, b)
+        for u, v in zip(full, comp):
+            assert u.shape == v.shape and np.array_equal(u, v)
+    with pytest.raises(OverflowError):
+        net.DetectionsFromCandidates(net.collectCandidates(thresh, max_cand=4).pullFromDevice(), thresh, 0.45, 0)
 
 
 @pytest.mark.parametrize("math,tol", [("3xtf32", TOL_3XTF32), ("tf32", 5e-3), ("bf16x3", TOL_3XTF32),

@@ -194,6 +194,8 @@ meth("procedure sgdUpdateMulti(const count: longint; const params, updates: PPoi
      "tnn_sgd_update_multi", "count, params, updates, sizes, rates, decayTerms, momentum")
 meth("procedure yoloActivate(const batch, n, classes, wh: SizeInt; const outp: TCUMem; const scaleXY: T)",
      "tnn_yolo_activate", "batch, n, classes, wh, outp, scaleXY")
+meth("procedure yoloCandidates(const batch, n, classes, wh: SizeInt; const outp: TCUMem; const thresh: T; const tag: longint; const maxCand: SizeInt; const cand: TCUMem)",
+     "tnn_yolo_candidates", "batch, n, classes, wh, outp, thresh, tag, maxCand, cand")
 meth("procedure concatChannels(const batch, c, blockSize: SizeInt; const inp: TCUMem; const outChannels, cOffset: SizeInt; const outp: TCUMem)",
      "tnn_concat_channels", "batch, c, blockSize, inp, outChannels, cOffset, outp")
 meth("procedure setWeightsStatic(const weights: TCUMem; const isStatic: boolean)", "tnn_set_weights_static", "weights, ord(isStatic)", False)
