@@ -96,6 +96,8 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     ctx->nhwc_bn_auto = (ba && ba[0] == '0') ? 0 : 1;
     const char *ni = getenv("TNN_NHWC_IMAGE");
     ctx->nhwc_image = (ni && ni[0] == '0') ? 0 : 1;
+    const char *pd = getenv("TNN_PDL");
+    ctx->pdl = (pd && pd[0] == '0') ? 0 : 1;
     const char *nk = getenv("TNN_NHWC_KB");
     ctx->nhwc_kb = (nk && atoi(nk) == 32) ? 32 : (nk && atoi(nk) == 16) ? 16 : 0;
   }

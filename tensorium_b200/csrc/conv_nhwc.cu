@@ -348,6 +348,14 @@ __device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int 
   }
 }
 
+// Programmatic dependent launch: a kernel launched with programmatic stream serialization may start while the previous
+// kernel of the stream is still running; `pdl_wait` blocks until that kernel has completed and its writes are visible.
+// Everything before it (barrier initialisation, TMEM allocation, descriptor prefetch, the cluster rendezvous) overlaps
+// the previous layer's last, partly filled wave.  `pdl_trigger` lets the NEXT kernel's CTAs be scheduled as soon as SMs
+// free up.  Both are no-ops for a kernel launched the ordinary way.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ASPLIT (BF16x3 only): the activations arrive PRE-SPLIT — two bf16 planes (hi, lo) written by the producing layer's
 // epilogue — so both A tiles land by TMA in the tensor-core layout and nobody converts: the TF32-mode pipeline
 // (TMA -> mbarrier -> MMA) with the BF16x3 arithmetic.  tmA = hi plane, tmA2 = lo plane.
@@ -400,6 +408,8 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_trigger();
+  pdl_wait();   // nothing above reads or writes global memory
   const uint32_t tmem_base = ctl.tmem_base;
 
   if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
@@ -695,6 +705,8 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
   __syncthreads();
   cluster_sync_all();  // both CTAs' barriers exist before anyone signals across the pair
   tc_fence_after();
+  pdl_trigger();
+  pdl_wait();   // nothing above reads or writes global memory
   const uint32_t tmem_base = ctl.tmem_base;
 
   if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
@@ -938,12 +950,29 @@ struct Maps {
   alignas(64) CUtensorMap a, a2, bhi, blo, out, outHi, outLo;
 };
 
+// launch configuration with programmatic stream serialization (see pdl_wait) unless TNN_PDL=0
+static cudaLaunchConfig_t pdl_config(tnn_context *ctx, int grid, int threads, size_t smemBytes, cudaLaunchAttribute *at) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)threads);
+  cfg.dynamicSmemBytes = smemBytes;
+  cfg.stream = ctx->stream;
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = ctx->pdl ? 1 : 0;
+  return cfg;
+}
+
 template <int MODE, int KB, bool ASPLIT, typename EPI>
 static int launch_nhwc(tnn_context *ctx, const Plan &p, const Geo &geo, EPI epi, const Maps &m) {
   auto kern = k_conv_nhwc<MODE, KB, ASPLIT, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
-  kern<<<p.grid, kThreads, p.smemBytes, ctx->stream>>>(epi, p.sched, geo, p.BN, p.stages, p.accCols, m.a, m.a2, m.bhi, m.blo,
-                                                       m.out, m.outHi, m.outLo);
+  cudaLaunchAttribute at[1];
+  cudaLaunchConfig_t cfg = pdl_config(ctx, p.grid, kThreads, p.smemBytes, at);
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, epi, p.sched, geo, p.BN, p.stages, p.accCols, m.a, m.a2, m.bhi, m.blo, m.out, m.outHi,
+                              m.outLo));
   TNN_LAUNCHED(ctx);
   return 0;
 }
@@ -953,8 +982,10 @@ static int launch_nhwc_pair(tnn_context *ctx, int grid, size_t smemBytes, int mT
                             int BN, int stages, EPI epi, const Maps &m) {
   auto kern = k_conv_nhwc_pair<MODE, KB, ASPLIT, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
-  kern<<<grid, kThreads, smemBytes, ctx->stream>>>(epi, mTiles, nTiles, kBlocks, geo, BN, stages, m.a, m.a2, m.bhi, m.blo,
-                                                   m.out, m.outHi, m.outLo);
+  cudaLaunchAttribute at[1];
+  cudaLaunchConfig_t cfg = pdl_config(ctx, grid, kThreads, smemBytes, at);
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, epi, mTiles, nTiles, kBlocks, geo, BN, stages, m.a, m.a2, m.bhi, m.blo, m.out, m.outHi,
+                              m.outLo));
   TNN_LAUNCHED(ctx);
   return 0;
 }
