@@ -10,7 +10,8 @@ from util import Dev
 
 MATH = {"fp32": 0, "3xtf32": 1, "tf32": 2, "bf16x3": 3}
 NHWC = os.environ.get("TNN_NHWC", "0") == "1"
-SPLIT = os.environ.get("TNN_SPLIT", "0") == "1"   # pre-split bf16 planes in and out (tnn_conv2d_forward_split, bf16x3 only)
+SPLIT = os.environ.get("TNN_SPLIT", "0") in ("1", "2")   # pre-split bf16 planes in and out (tnn_conv2d_forward_split, bf16x3 only)
+SPLIT_RES = os.environ.get("TNN_SPLIT", "0") == "2"       # ... plus the folded shortcut's operand read from planes
 math = sys.argv[1] if len(sys.argv) > 1 else "3xtf32"
 cfgs = [tuple(int(v) for v in a.split(",")) for a in sys.argv[2:]] or [(64, 256, 26, 512, 3, 1)]
 cu = tensor.initCUDART(0)
@@ -27,8 +28,14 @@ for (B, C, H, F, k, s) in cfgs:
     if SPLIT:
         dxs, dos = Dev(cu, n=x.size), Dev(cu, n=B * F * oh * oh)
         cu.nhwcToSplit(B * H * H, C, dx.ptr, C, dxs.ptr, C, x.size)
-        run = lambda: cu.conv2dForwardSplit(desc, dxs.ptr, 0, C, 2, x.size, dw.ptr, None, db.ptr, 9, None, 0, 0, None, 0, F, 1,
-                                            dos.ptr, 0, F, B * F * oh * oh)
+        nout = B * F * oh * oh
+        if SPLIT_RES:
+            drs = Dev(cu, rng.random(nout, dtype=np.float32))   # any bits will do as hi / lo planes for timing
+            run = lambda: cu.conv2dForwardSplitResidual(desc, dxs.ptr, 0, C, 2, x.size, dw.ptr, None, db.ptr, 9, drs.ptr, 0, F,
+                                                        2, nout, None, 0, F, 1, dos.ptr, 0, F, nout)
+        else:
+            run = lambda: cu.conv2dForwardSplit(desc, dxs.ptr, 0, C, 2, x.size, dw.ptr, None, db.ptr, 9, None, 0, 0, None, 0, F,
+                                                1, dos.ptr, 0, F, nout)
     elif NHWC:
         run = lambda: cu.conv2dForwardNhwc(desc, dx.ptr, 0, C, 1, dw.ptr, None, db.ptr, 9, do.ptr, 0, F, 1)
     else:

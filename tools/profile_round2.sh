@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-2 profile capture (run on the GPU box through gpurun; ONE ncu-using call per part).  Every ncu pass repeats a
 # command that has just exited 0 without ncu; numbers printed under ncu are never used as bench values.
-# usage: profile_round2.sh yolo | conv | split | membound
+# usage: profile_round2.sh yolo | conv | split | planes | membound
 set -u
 O=gpurun_out/prof2
 mkdir -p $O
@@ -31,6 +31,16 @@ split)
   python tools/image_one.py bf16x3 planes > $O/one_image.log 2>&1 && \
   ncu --set full --clock-control none --import-source on -k regex:k_conv_image -c 1 -s 2 -o $O/r02_image_c3f32_bf16x3 \
       python tools/image_one.py bf16x3 planes > $O/ncu_image.log 2>&1
+  ;;
+planes)
+  # the benchmark's default graph since the second half of round 2: every tensor only as planes.  (1) a wide 3x3 layer with
+  # the folded shortcut's operand read from planes, (2) a 1x1 layer on planes (no converter warps)
+  TNN_SPLIT=2 python tools/conv_one.py bf16x3 64,256,26,512,3,1 > $O/one_planes_res.log 2>&1 && \
+  TNN_SPLIT=2 ncu --set full --clock-control none --import-source on -k regex:k_conv_nhwc -c 1 -s 3 -o $O/r02_nhwc_pair_planes_res_c256f512_bf16x3 \
+      python tools/conv_one.py bf16x3 64,256,26,512,3,1 > $O/ncu_planes_res.log 2>&1
+  TNN_SPLIT=1 python tools/conv_one.py bf16x3 64,256,52,128,1,1 > $O/one_planes_1x1.log 2>&1 && \
+  TNN_SPLIT=1 ncu --set full --clock-control none --import-source on -k regex:k_conv_nhwc -c 1 -s 3 -o $O/r02_nhwc_pair_planes_1x1_c256f128_bf16x3 \
+      python tools/conv_one.py bf16x3 64,256,52,128,1,1 > $O/ncu_planes_1x1.log 2>&1
   ;;
 membound)
   python tools/membound_driver.py > $O/membound_plain.log 2>&1 && \
