@@ -96,6 +96,9 @@ int32_t tnn_create(int32_t device_index, tnn_context **out) {
     ctx->nhwc_bn_auto = (ba && ba[0] == '0') ? 0 : 1;
     const char *ni = getenv("TNN_NHWC_IMAGE");
     ctx->nhwc_image = (ni && ni[0] == '0') ? 0 : 1;
+    const char *es = getenv("TNN_NHWC_EPI_SETS");
+    ctx->nhwc_epi_sets = es ? atoi(es) : 0;
+    if (ctx->nhwc_epi_sets < 0 || ctx->nhwc_epi_sets > 2) ctx->nhwc_epi_sets = 0;
     const char *pd = getenv("TNN_PDL");
     ctx->pdl = (pd && pd[0] == '0') ? 0 : 1;
     const char *nk = getenv("TNN_NHWC_KB");

@@ -22,6 +22,7 @@ struct tnn_context {
   int nhwc_kb;          // channels per pipeline stage of the NHWC convolution in 3xTF32 mode: 0 = default (16), 16 or 32 (TNN_NHWC_KB)
   int nhwc_bn_auto;     // 1: with several filter tiles per pixel tile, the tile width (256 / 224 / 192 / 160) that minimises the wave count x tile cost (default; TNN_NHWC_BN_AUTO=0: always 256)
   int pdl;              // 1: the channels-innermost convolutions launch with programmatic stream serialization (their prologue overlaps the previous kernel's tail); TNN_PDL=0 off
+  int nhwc_epi_sets;    // 0: automatic; 1 / 2: sets of epilogue warps in the CTA-pair channels-innermost kernel (TNN_NHWC_EPI_SETS)
   int nhwc_image;       // 1: the image layer of a channels-innermost graph runs on the tensor cores (BF16x3 / TF32 modes); TNN_NHWC_IMAGE=0: direct kernel
   int last_conv_kernel; // which kernel the last tnn_conv2d_forward took (TNN_CONV_KERNEL_*), for measurement tools
   int64_t launches;

@@ -145,7 +145,7 @@ struct Ctl {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
-  alignas(16) float epi_sb[kEpilogueWarps][64];
+  alignas(16) float epi_sb[kEpilogueWarps][64];   // (a second set of epilogue warps keeps its scratch behind its staging tiles)
 };
 
 // The eight converter warps work as kConvGroups independent groups, group g taking k-blocks g, g + kConvGroups, ...:
@@ -212,18 +212,27 @@ struct StoreRows {   // the default store: 32 consecutive pixel rows of the 2-D 
 template <typename EPI, typename RELEASE, typename STORE>
 __device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int bn, int64_t n0, int row0, float *scratch,
                                            uint8_t *stg, int &sbuf, const CUtensorMap *tmOut, const CUtensorMap *tmOutHi,
-                                           const CUtensorMap *tmOutLo, RELEASE release, STORE store) {
+                                           const CUtensorMap *tmOutLo, RELEASE release, STORE store, int ci0 = 0,
+                                           int ciStep = 1) {
+  // ci0 / ciStep: the warp drains chunks ci0, ci0 + ciStep, ... of the tile (two sets of epilogue warps share a tile
+  // chunk by chunk); `release` follows the warp's LAST TMEM read — at once if it has no chunk in this tile
   const int lane = threadIdx.x & 31;
   const int nChunks = (bn + 31) >> 5;
+  if (ci0 >= nChunks) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) release();
+    return;
+  }
   if constexpr (EPI::kTmaStore) {
     const bool leaky = epi.act == TNN_ACT_LEAKY || epi.act == TNN_ACT_REVLEAKY;
     const bool simple = leaky || epi.act == TNN_ACT_LINEAR;
     const float neg = leaky ? 0.1f : 1.0f;
-    for (int ci = 0; ci < nChunks; ++ci) {
+    for (int ci = ci0; ci < nChunks; ci += ciStep) {
       const int c0 = ci * 32;
       uint32_t r[32];
       tmem_ld32(tmem_d + (uint32_t)c0, r);
-      if (ci == nChunks - 1) {
+      if (ci + ciStep >= nChunks) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) release();
@@ -332,11 +341,11 @@ __device__ __forceinline__ void drain_tile(const EPI &epi, uint32_t tmem_d, int 
     const int64_t m = (int64_t)row0 + lane;
     bool mvalid;
     typename EPI::Row rc = epi.row(m, mvalid);
-    for (int ci = 0; ci < nChunks; ++ci) {
+    for (int ci = ci0; ci < nChunks; ci += ciStep) {
       const int c0 = ci * 32;
       uint32_t r[32];
       tmem_ld32(tmem_d + (uint32_t)c0, r);
-      if (ci == nChunks - 1) {
+      if (ci + ciStep >= nChunks) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) release();
@@ -656,7 +665,7 @@ __device__ __forceinline__ void tma2_load_im2col(uint32_t dst_smem, const CUtens
 // BN = filters per pair tile (multiple of 32, <= 256): each CTA holds BN/2 weight rows.  mTiles counts 128-pixel tiles.
 template <int MODE, int KB, bool ASPLIT, typename EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
-k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, int stages,
+k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, int stages, int epiSets,
                  const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
                  const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutHi,
@@ -689,7 +698,7 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&ctl.tmem_full[s], 1);
-      mbar_init(&ctl.tmem_empty[s], 2 * kEpilogueWarps);
+      mbar_init(&ctl.tmem_empty[s], 2 * kEpilogueWarps * epiSets);
     }
     fence_barrier_init();
   }
@@ -709,7 +718,12 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
   pdl_wait();   // nothing above reads or writes global memory
   const uint32_t tmem_base = ctl.tmem_base;
 
-  if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
+  // TMA-only modes leave warps 4-11 without work: with epiSets == 2 warps 4-7 (TMEM lane quadrants 0-3 again) form a
+  // second set of epilogue warps and the two sets drain a tile's 32-filter chunks alternately.  The four epilogue warps
+  // are one warp per scheduler, so every latency of a chunk's chain is exposed: on a 1x1 layer on planes ncu showed them
+  // in the chunk body 84 % of the time at ~0.2 instructions per cycle — layers with short main loops are epilogue-bound.
+  const bool secondEpi = !CONVERT && epiSets == 2 && warp >= kEpilogueWarps && warp < 2 * kEpilogueWarps;
+  if (warp >= kFirstProducerWarp && warp < kMmaWarp && !secondEpi) {
     // ===================== split modes on fp32 activations: second plane(s) of this CTA's A tile =====================
     if (CONVERT) {
       constexpr int kConvGroups = ConvGroups<MODE>::kGroups, kConvGroupWarps = ConvGroups<MODE>::kWarps;
@@ -833,11 +847,13 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
     }
   } else {
     // ===================== epilogue: each CTA drains its own 128 TMEM lanes =====================
-    const int quad = warp;
+    const int quad = warp & 3, set = warp >> 2;
     int it = 0;
-    uint8_t *stg = smem + (size_t)stages * stageBytes + (size_t)quad * (kStageBufs * kStageTile);
+    uint8_t *stg = smem + (size_t)stages * stageBytes + (size_t)warp * (kStageBufs * kStageTile);
     int sbuf = 0;
-    float *scratch = ctl.epi_sb[quad];
+    float *scratch = set == 0 ? ctl.epi_sb[quad]
+                              : reinterpret_cast<float *>(smem + (size_t)stages * stageBytes +
+                                                          (size_t)2 * kEpilogueWarps * (kStageBufs * kStageTile)) + quad * 64;
     for (int t = pair; t < numTiles; t += numPairs, ++it) {
       const int mp = t % mPairs, nt = t / mPairs;
       const int as = it & 1;
@@ -850,7 +866,7 @@ k_conv_nhwc_pair(EPI epi, int mTiles, int nTiles, int kBlocks, Geo g, int BN, in
       drain_tile(epi, tmem_d, BN, n0, row0, scratch, stg, sbuf, &tmOut, &tmOutHi, &tmOutLo, [&] {
         if (rank == 0) mbar_arrive(&ctl.tmem_empty[as]);
         else mbar_arrive_cluster(&ctl.tmem_empty[as], 0);
-      }, StoreRows{row0});
+      }, StoreRows{row0}, set, epiSets);
     }
     if (EPI::kTmaStore && lane == 0) bulk_wait_all();
   }
@@ -979,13 +995,13 @@ static int launch_nhwc(tnn_context *ctx, const Plan &p, const Geo &geo, EPI epi,
 
 template <int MODE, int KB, bool ASPLIT, typename EPI>
 static int launch_nhwc_pair(tnn_context *ctx, int grid, size_t smemBytes, int mTiles, int nTiles, int kBlocks, const Geo &geo,
-                            int BN, int stages, EPI epi, const Maps &m) {
+                            int BN, int stages, int epiSets, EPI epi, const Maps &m) {
   auto kern = k_conv_nhwc_pair<MODE, KB, ASPLIT, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes));
   cudaLaunchAttribute at[1];
   cudaLaunchConfig_t cfg = pdl_config(ctx, grid, kThreads, smemBytes, at);
-  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, epi, mTiles, nTiles, kBlocks, geo, BN, stages, m.a, m.a2, m.bhi, m.blo, m.out, m.outHi,
-                              m.outLo));
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, epi, mTiles, nTiles, kBlocks, geo, BN, stages, epiSets, m.a, m.a2, m.bhi, m.blo, m.out,
+                              m.outHi, m.outLo));
   TNN_LAUNCHED(ctx);
   return 0;
 }
@@ -1058,8 +1074,14 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   if (!pairMode && (outNchw || (p.BN % 64) == 0)) split_tail_wave(ctx, p);
   const size_t stageBytes = bf ? (size_t)BM * KB * (aSplit ? 4 : 8) + (size_t)bnCta * KB * 4
                                : (size_t)(BM + bnCta) * KB * 4 * (split ? 2 : 1);
-  const size_t epiBytes = outNchw ? 0 : (size_t)kEpilogueWarps * kStageBufs * kStageTile;
-  int st = (int)((225 * 1024 - epiBytes) / stageBytes);
+  // Two sets of epilogue warps (CTA pairs, TMA-only modes): layers whose main loop per tile is short against the drain
+  // of its chunks — every 1x1 layer and the 3x3 layers up to 64 channels (K <= 1024) — are paced by the epilogue.
+  // The second set costs 32 KB of staging: one pipeline stage of the widest tiles.  TNN_NHWC_EPI_SETS=1/2 forces it.
+  const bool convert = split && !aSplit;
+  int epiSets = 1;
+  if (pairMode && !convert && !outNchw) epiSets = ctx->nhwc_epi_sets ? ctx->nhwc_epi_sets : (K <= 1024 ? 2 : 1);
+  const size_t epiBytes = outNchw ? 0 : (size_t)epiSets * kEpilogueWarps * kStageBufs * kStageTile + (epiSets == 2 ? 1024 : 0);
+  int st = (int)((224 * 1024 - epiBytes) / stageBytes);   // stages + staging + 1 KB of alignment slack = at most 225 KB
   p.stages = st > kMaxStages ? kMaxStages : st;
   TNN_REQUIRE(p.stages >= 2, "tile does not fit shared memory");
   p.smemBytes = stageBytes * p.stages + epiBytes + 1024;
@@ -1106,7 +1128,7 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
       const int grid = (int)(2 * (pairTiles < sms / 2 ? pairTiles : sms / 2));
       const int kBlocks = (int)(K / KB);
 #define TNN_PAIR_GO(MODE, KBV, AS) \
-  launch_nhwc_pair<MODE, KBV, AS>(ctx, grid, p.smemBytes, p.sched.mTiles, p.sched.nTiles, kBlocks, geo, p.BN, p.stages, epi, m)
+  launch_nhwc_pair<MODE, KBV, AS>(ctx, grid, p.smemBytes, p.sched.mTiles, p.sched.nTiles, kBlocks, geo, p.BN, p.stages, epiSets, epi, m)
       if (aSplit) return TNN_PAIR_GO(MODE_BF16X3, 32, true);
       if (bf) return KB == 16 ? TNN_PAIR_GO(MODE_BF16X3, 16, false) : TNN_PAIR_GO(MODE_BF16X3, 32, false);
       if (!split) return TNN_PAIR_GO(MODE_TF32, 32, false);

@@ -4,7 +4,7 @@
 var=$1; rounds=${2:-2}; shift 2
 mkdir -p gpurun_out/ab
 for r in $(seq $rounds); do
-  for v in 0 1; do
+  for v in ${VALS:-0 1}; do
     env $var=$v timeout 300 python bench.py --no-secondary --no-cpu --steps 10 "$@" --layers-out gpurun_out/ab/layers_$var$v.json > gpurun_out/ab/bench_$var$v.json 2> gpurun_out/ab/bench_$var$v.err
     python - <<P
 import json
