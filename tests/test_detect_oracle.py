@@ -145,3 +145,49 @@ def test_product_decode_and_nms_match_the_oracle(letter, relative):
         for (c1, p1, b1), (c2, p2, b2) in zip(want, got):
             assert c1 == c2 and p1 == pytest.approx(p2, rel=1e-6)
             assert rd.box_iou(b1, b2) >= 0.99
+
+
+def test_candidate_list_decodes_like_the_full_outputs():
+    """TNNet.DetectionsFromCandidates (host side of tnn_yolo_candidates): a candidate list assembled here the way the
+    kernel writes it — [count, -, -, -] then records {tag, image, anchor, cell | classes + 5 entries}, in ARBITRARY
+    arrival order — must give exactly the boxes / objectness / class scores that the full outputs give; a count beyond
+    the list's capacity must raise."""
+    rng = np.random.default_rng(11)
+    anchors = np.asarray(nnet.YOLOV3_ANCHORS, np.float32)
+    net = nnet.TNNet.__new__(nnet.TNNet)
+    net.w, net.h = 160, 128
+    layers, outs = [], []
+    n, classes, batch, thresh = 3, 6, 2, 0.6
+    for (h, w, mask) in ((4, 5, [6, 7, 8]), (8, 10, [3, 4, 5])):
+        out = rng.uniform(0, 1, (batch, n * (classes + 5), h, w)).astype(np.float32)
+        yl = nnet.TYoloLayer.__new__(nnet.TYoloLayer)
+        yl.w, yl.h, yl.n, yl.classes, yl.mask, yl.biases, yl.batch = w, h, n, classes, mask, anchors, batch
+        layers.append(yl)
+        outs.append(out)
+    net.yolo_layers = lambda: layers
+    rec = classes + 9
+    records = []
+    for tag, (yl, out) in enumerate(zip(layers, outs)):
+        p = out.reshape(batch, n, classes + 5, yl.w * yl.h)
+        for b in range(batch):
+            for a in range(n):
+                for i in range(yl.w * yl.h):
+                    if p[b, a, 4, i] > thresh:
+                        r = np.empty(rec, np.float32)
+                        r[:4].view(np.int32)[:] = (tag, b, a, i)
+                        r[4:] = p[b, a, :, i]
+                        records.append(r)
+    assert len(records) > 40
+    order = rng.permutation(len(records))                       # atomics: arrival order is arbitrary
+    cap = len(records) + 5
+    cand = np.zeros(4 + cap * rec, np.float32)
+    cand[:1].view(np.uint32)[0] = len(records)
+    cand[4:4 + len(records) * rec] = np.concatenate([records[j] for j in order])
+    for b in range(batch):
+        full = net.Detections(thresh, 0.45, b, host_outputs=outs, img_w=300, img_h=200, relative=True, letter=True)
+        comp = net.DetectionsFromCandidates(cand, thresh, 0.45, b, img_w=300, img_h=200, relative=True, letter=True)
+        for u, v in zip(full, comp):
+            assert u.shape == v.shape and np.array_equal(u, v)
+    cand[:1].view(np.uint32)[0] = cap + 1
+    with pytest.raises(OverflowError):
+        net.DetectionsFromCandidates(cand, thresh, 0.45, 0)

@@ -6,7 +6,7 @@ mkdir -p gpurun_out/ab
 for r in $(seq $rounds); do
   for v in $names; do
     if [ $v = tree ]; then unset TNN_LIB; else export TNN_LIB=$PWD/ab/$v.so; fi
-    python bench.py --no-secondary --no-cpu --steps 10 "$@" --layers-out gpurun_out/ab/layers_$v.json > gpurun_out/ab/bench_$v.json 2> gpurun_out/ab/bench_$v.err
+    python bench.py --no-secondary --no-cpu --steps ${STEPS:-10} "$@" --layers-out gpurun_out/ab/layers_$v.json > gpurun_out/ab/bench_$v.json 2> gpurun_out/ab/bench_$v.err
     python - <<P
 import json
 d = json.loads(open("gpurun_out/ab/bench_$v.json").read())
