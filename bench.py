@@ -255,7 +255,8 @@ def run_ours(args, rank, world, local_rank):
     # channels-innermost graph: the 23 shortcut adds are folded into the preceding convolution's epilogue
     # (tnn_conv2d_forward_nhwc_residual; bit-identical to the separate layers, tests/test_gpu_yolo.py)
     net = build_yolov3(BATCH, SIZE, seed=1234, channels_last=args.layout == "nhwc",
-                       fuse_shortcuts=args.layout == "nhwc" and not args.no_fuse)
+                       fuse_shortcuts=args.layout == "nhwc" and not args.no_fuse,
+                       fuse_yolo=args.layout == "nhwc" and not args.no_fuse)   # yolo activation in the heads' epilogues
     # BF16x3: activations between convolutions are pre-split bf16 hi/lo planes (tnn_conv2d_forward_split_residual) — the
     # planes the kernel would otherwise derive in shared memory for every tap; the folded shortcuts read their operand
     # from its planes (hi + lo = the fp32 value to 2^-18 relative), so every tensor is written once
@@ -514,7 +515,9 @@ def run_ours(args, rank, world, local_rank):
                                                            "every tensor written once, the folded shortcuts add hi + lo of "
                                                            "their operand's planes; fp32 only for the yolo layers"))
                                        if getattr(net, "split_activations", False) else "fp32"),
-                       "shortcuts_fused_into_conv": sum(bool(getattr(l, "_fused_into_conv", False)) for l in net.layers),
+                       "shortcuts_fused_into_conv": sum(bool(getattr(l, "_fused_into_conv", False)) and l.layerType != "yolo"
+                                                        for l in net.layers),
+                       "yolo_layers_fused_into_heads": sum(getattr(l, "_yolo", None) is not None for l in net.layers),
                        "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "activations streamed per step = 14.6 GB per GPU, far larger than the 126 MB L2 (no flush needed)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes_in,

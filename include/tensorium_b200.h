@@ -443,6 +443,14 @@ TNN_API int32_t tnn_conv2d_forward_split_residual(tnn_context *ctx, const tnn_co
                                                   int32_t residualLayout, int64_t residualPlane, float *out,
                                                   int64_t outOffset, int64_t outPitch, int32_t outLayout, void *outSplit,
                                                   int64_t outSplitOffset, int64_t outSplitPitch, int64_t outSplitPlane);
+/* A yolo head: the linear 1x1 convolution in front of a yolo layer WITH that layer's activation folded into its epilogue
+ * (TYoloLayer.forwardGPU nyololayer.pas:1068-1112: copy + logistic on x, y, objectness and class entries, x / y mapped
+ * v*scale_xy + 0.5*(1 - scale_xy)) — out is the yolo layer's output [batch][anchors*(classes+5)][OH*OW] (planes), the
+ * copy and the activation pass over it disappear.  Same expressions as tnn_yolo_activate, same bits. */
+TNN_API int32_t tnn_conv2d_forward_yolo_head(tnn_context *ctx, const tnn_conv_desc *d, const void *in, int64_t inOffset,
+                                             int64_t inPitch, int32_t inLayout, int64_t inPlane, const float *weights,
+                                             const float *scale, const float *bias, float *out, int64_t outOffset,
+                                             int64_t classes, float scale_xy);
 /* fp32 rows of channels <-> the pre-split planes (the way back is hi + lo, exact in fp32); channels a multiple of 8 */
 TNN_API int32_t tnn_nhwc_to_split(tnn_context *ctx, int64_t rows, int64_t channels, const float *in, int64_t inPitch,
                                   void *outSplit, int64_t outPitch, int64_t outPlane);

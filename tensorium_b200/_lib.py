@@ -126,6 +126,8 @@ SIGNATURES = {
                                        i64, fptr, i64, i64, i32, fptr, i64, i64, i64]),
     "tnn_conv2d_forward_split_residual": (i32, [ctxp, C.POINTER(ConvDesc), fptr, i64, i64, i32, i64, fptr, fptr, fptr, i32,
                                                 fptr, i64, i64, i32, i64, fptr, i64, i64, i32, fptr, i64, i64, i64]),
+    "tnn_conv2d_forward_yolo_head": (i32, [ctxp, C.POINTER(ConvDesc), fptr, i64, i64, i32, i64, fptr, fptr, fptr, fptr, i64,
+                                           i64, f32]),
     "tnn_nhwc_to_split": (i32, [ctxp, i64, i64, fptr, i64, fptr, i64, i64]),
     "tnn_split_to_nhwc": (i32, [ctxp, i64, i64, fptr, i64, i64, fptr, i64]),
     "tnn_nchw_to_nhwc": (i32, [ctxp, i64, i64, i64, fptr, fptr, i64]),

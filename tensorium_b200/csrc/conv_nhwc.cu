@@ -136,6 +136,36 @@ struct NhwcEpilogue {
 // NCHW planes (head layers): the epilogue of the NCHW kernels
 struct NchwEpilogue : ConvEpilogueT<false> {
   static constexpr bool kTmaStore = false;
+  // yoloEntries > 0: the yolo layer that follows a head convolution, folded in (TYoloLayer.forwardGPU
+  // nyololayer.pas:1081-1099 = tnn_yolo_activate): filter f is entry e = f % yoloEntries of its anchor; logistic on
+  // every entry but the raw w / h (e = 2, 3), x / y then mapped v*yoloA + yoloB — the same expressions, so the same bits
+  int yoloEntries;
+  float yoloA, yoloB;
+  __device__ __forceinline__ void store_chunk(const Row &r, int64_t n, const uint32_t (&acc)[32], int cnt, bool rowvalid,
+                                              float *scratch) const {
+    if (yoloEntries <= 0) {
+      ConvEpilogueT<false>::store_chunk(r, n, acc, cnt, rowvalid, scratch);
+      return;
+    }
+    const int lane = threadIdx.x & 31;
+    __syncwarp();
+    scratch[lane] = (scale && lane < cnt) ? __ldg(scale + n + lane) : 1.0f;
+    scratch[32 + lane] = (bias && lane < cnt) ? __ldg(bias + n + lane) : 0.0f;
+    __syncwarp();
+    float *q = r.q + n * P;
+    int e = (int)(n % yoloEntries);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float v = __fadd_rn(__fmul_rn(__uint_as_float(acc[j]), scratch[j]), scratch[32 + j]);   // (linear head convolution)
+      if (e != 2 && e != 3) {
+        float t = 1.0f / (1.0f + expf(-v));
+        if (e < 2 && yoloA != 1.0f) t = __fadd_rn(__fmul_rn(t, yoloA), yoloB);
+        v = t;
+      }
+      if (rowvalid && j < cnt) q[(int64_t)j * P] = v;
+      if (++e == yoloEntries) e = 0;
+    }
+  }
 };
 
 struct Ctl {
@@ -1017,7 +1047,8 @@ struct SplitRef {
 static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, const float *in, int64_t inPitch,
                         SplitRef inSplit, const float *weights, const float *scale, const float *bias, int act, float *out,
                         int64_t outPitch, bool outNchw, SplitRef outSplit, const float *residual = nullptr,
-                        int64_t resPitch = 0, SplitRef resSplit = SplitRef{nullptr, 0, 0}) {
+                        int64_t resPitch = 0, SplitRef resSplit = SplitRef{nullptr, 0, 0}, int yoloEntries = 0,
+                        float yoloScaleXY = 1.0f) {
   const int kk = g.kh * g.kw;
   const bool aSplit = inSplit.hi != nullptr;
   if (aSplit) {
@@ -1145,7 +1176,8 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   };
   if (outNchw) {
     TNN_REQUIRE(out != nullptr && outSplit.hi == nullptr, "planar output is fp32 only");
-    NchwEpilogue epi{{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, nullptr}};
+    NchwEpilogue epi{{out, scale, bias, g.OH * g.OW, g.outImg, act, M, N, false, 0, 0, 0, 0, 0, 0, 0, 0, nullptr},
+                     yoloEntries, yoloScaleXY, 0.5f * (1.0f - yoloScaleXY)};
     return go(epi);
   }
   TNN_REQUIRE(out != nullptr || outSplit.hi != nullptr, "no output tensor");
@@ -1852,6 +1884,28 @@ int32_t tnn_conv2d_forward_split_residual(tnn_context *ctx, const tnn_conv_desc 
   else inf = (const float *)in + inOffset;
   return nhwc::conv_forward(ctx, g, (int)d->batch, inf, inPitch, is, weights, scale, bias, activation, out, outPitch,
                             outLayout == TNN_LAYOUT_NCHW, os, residual, residualPitch, rs);
+}
+
+int32_t tnn_conv2d_forward_yolo_head(tnn_context *ctx, const tnn_conv_desc *d, const void *in, int64_t inOffset,
+                                     int64_t inPitch, int32_t inLayout, int64_t inPlane, const float *weights,
+                                     const float *scale, const float *bias, float *out, int64_t outOffset, int64_t classes,
+                                     float scale_xy) {
+  TNN_CHECK_CTX(ctx);
+  simt::ConvGeom g;
+  int rc = fill_geom_nhwc(d, g);
+  if (rc) return rc;
+  TNN_REQUIRE(inLayout == TNN_LAYOUT_NHWC || inLayout == TNN_LAYOUT_NHWC_SPLIT, "the head reads channels-innermost activations");
+  TNN_REQUIRE(ctx->math_mode != TNN_MATH_FP32, "the channels-innermost path runs on the tensor cores");
+  TNN_REQUIRE(in != nullptr && out != nullptr && classes > 0 && (g.F % (classes + 5)) == 0,
+              "a yolo head has anchors * (classes + 5) filters");
+  ctx->last_conv_kernel = 7;
+  nhwc::SplitRef is{nullptr, 0, 0};
+  const float *inf = nullptr;
+  if (inLayout == TNN_LAYOUT_NHWC_SPLIT) is = nhwc::SplitRef{(const uint16_t *)in + inOffset, inPitch, inPlane};
+  else inf = (const float *)in + inOffset;
+  return nhwc::conv_forward(ctx, g, (int)d->batch, inf, inPitch, is, weights, scale, bias, TNN_ACT_LINEAR, out + outOffset, 0,
+                            true, nhwc::SplitRef{nullptr, 0, 0}, nullptr, 0, nhwc::SplitRef{nullptr, 0, 0},
+                            (int)(classes + 5), scale_xy);
 }
 
 int32_t tnn_nhwc_to_split(tnn_context *ctx, int64_t rows, int64_t channels, const float *in, int64_t inPitch, void *outSplit,

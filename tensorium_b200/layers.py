@@ -114,6 +114,7 @@ class TConvolutionalLayer:
         self.in_split = self.out_split = False  # pre-split bf16 planes in / out (TNNet.setSplitActivations)
         self.out_f32 = True
         self.res_split = False  # the folded shortcut's other operand is read from its planes (no fp32 twin exists)
+        self._yolo = None       # the yolo layer folded into this (head) convolution's epilogue (TNNet.fuseYoloHeads)
         self._desc = nn.TNNCuda.conv_desc(batch, c, h, w, filters, kernelSize, kernelSize, padding, padding, stride,
                                           stride, dilation, dilation)
 
@@ -177,6 +178,18 @@ class TConvolutionalLayer:
                     self._in_nhwc.pitch = pitch
                 cu.nchwToNhwc(self.batch, self.c, self.h * self.w, src.devData, self._in_nhwc.devData, self._in_nhwc.pitch)
                 src, in_layout, in_pitch = self._in_nhwc, NHWC, self._in_nhwc.pitch
+            if self._yolo is not None and in_layout == NHWC:
+                # the yolo layer that follows, folded into this head's epilogue (TNNet.fuseYoloHeads): writes ITS output
+                yl = self._yolo
+                yl.output.setCUDA()
+                if self.in_split:
+                    in_ptr, lay, pitch, plane = src.split.devData, nn.TNNCuda.LAYOUT_NHWC_SPLIT, self.c, src.Size()
+                else:
+                    in_ptr, lay, pitch, plane = src.devData, NHWC, in_pitch, 0
+                cu.conv2dForwardYoloHead(self._desc, in_ptr, 0, pitch, lay, plane, self.weights.devData,
+                                         sc.devData if sc is not None else None, bi.devData, yl.output.devData, 0,
+                                         yl.classes, yl.scaleXY)
+                return
             if self.in_split or self.out_split:
                 # pre-split (bf16 hi / lo planes) activations in and / or out (TNNet.setSplitActivations; BF16x3 mode)
                 SPLIT = nn.TNNCuda.LAYOUT_NHWC_SPLIT

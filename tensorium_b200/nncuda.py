@@ -467,6 +467,14 @@ class TNNCuda:
             _addr(bias), int(activation), _addr(residual), residualOffset, residualPitch, int(residualLayout), residualPlane,
             _addr(out), outOffset, outPitch, int(outLayout), _addr(outSplit), outSplitOffset, outSplitPitch, outSplitPlane))
 
+    def conv2dForwardYoloHead(self, desc, in_, inOffset, inPitch, inLayout, inPlane, weights, scale, bias, out, outOffset,
+                              classes, scaleXY):
+        """The linear 1x1 head convolution with the following yolo layer's activation folded into its epilogue; `out` is
+        the yolo layer's (planar) output."""
+        self._ck(self._l.tnn_conv2d_forward_yolo_head(
+            self._h, C.byref(desc), _addr(in_), inOffset, inPitch, int(inLayout), inPlane, _addr(weights), _addr(scale),
+            _addr(bias), _addr(out), outOffset, classes, float(scaleXY)))
+
     def nhwcToSplit(self, rows, channels, in_, inPitch, outSplit, outPitch, outPlane):
         self._ck(self._l.tnn_nhwc_to_split(self._h, rows, channels, _addr(in_), inPitch, _addr(outSplit), outPitch, outPlane))
 

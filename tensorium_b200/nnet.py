@@ -123,6 +123,8 @@ class TYoloLayer:
     def forwardGPU(self, state: TNNetState, net: "TNNet"):
         cu = cuda()
         self.output.setCUDA()
+        if getattr(self, "_fused_into_conv", False):
+            return  # the head convolution's epilogue already wrote the activated output here (TNNet.fuseYoloHeads)
         wh = self.w * self.h
         cu.copy(state.input.Size(), state.input.devData, 0, 1, self.output.devData, 0, 1)
         if self.fused:
@@ -430,6 +432,26 @@ class TNNet:
                 n += 1
         return n
 
+    def fuseYoloHeads(self):
+        """Channels-innermost inference graph: a linear head convolution whose output feeds ONLY the yolo layer that
+        follows applies that layer's activation in its epilogue (tnn_conv2d_forward_yolo_head) and writes the yolo
+        layer's output directly — the copy and the activation pass of TYoloLayer.forwardGPU (nyololayer.pas:1068-1112)
+        disappear.  The head convolution's own output tensor is then never written.  Same expressions, same bits
+        (tests/test_gpu_yolo.py).  Call after setChannelsLast(); returns the number of fused heads."""
+        assert getattr(self, "channels_last", False), "yolo heads are folded in the channels-innermost graph"
+        used = set()
+        for l in self.layers:
+            used.update(getattr(l, "inputLayers", []))
+        n = 0
+        for i in range(len(self.layers) - 1):
+            c, y = self.layers[i], self.layers[i + 1]
+            if (isinstance(c, TConvolutionalLayer) and isinstance(y, TYoloLayer) and c.fused and y.fused and i not in used
+                    and c.ActivationType == nn.acLINEAR and not c.isBatchNormalized and c._residual is None):
+                c._yolo = y
+                y._fused_into_conv = True
+                n += 1
+        return n
+
     def setChannelsLast(self, on: bool = True):
         """Inference graph with channels-innermost (NHWC) INTERNAL activations (include/tensorium_b200.h, last section):
         the first convolution reads the planar image, every convolution that feeds a yolo layer writes planes, and all
@@ -683,7 +705,7 @@ def init_yolov3_params(spec, c_in=3, seed=1234, objectness_bias=-4.0):
 
 
 def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=1234, fuse_shortcuts=False,
-                 channels_last=False, split_activations=False):
+                 channels_last=False, split_activations=False, fuse_yolo=False):
     """Builds the 107-layer net on the current `cuda` backend.  fuse_bn=True mirrors MSCOCOYolo.pas:327-340
     (Neural.fuseBatchNorm before predict)."""
     spec = yolov3_spec()
@@ -724,4 +746,6 @@ def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=12
         net.fuseShortcuts()
     if split_activations:
         net.setSplitActivations(planes_only=split_activations == "planes")
+    if fuse_yolo:
+        net.fuseYoloHeads()
     return net

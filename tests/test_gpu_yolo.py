@@ -12,12 +12,13 @@ def run_net(cu, size, batch, variant, params, x):
     """variant: fused | unfused | channels_last | split (= channels-last, shortcuts folded into the convolutions,
     pre-split bf16 activations, fp32 rows where a shortcut or a 1x1 convolution reads) | planes (= split with EVERY
     tensor between convolutions only as planes, the shortcut operands read as hi + lo: the graph bench.py times in its
-    default BF16x3 arithmetic)"""
+    default BF16x3 arithmetic, with the yolo layers' activation folded into the head convolutions)"""
     from tensorium_b200.nnet import build_yolov3
     net = build_yolov3(batch, size, params=params, fused=variant != "unfused",
                        channels_last=variant in ("channels_last", "split", "planes"),
                        fuse_shortcuts=variant in ("split", "planes"),
-                       split_activations={"split": True, "planes": "planes"}.get(variant, False))
+                       split_activations={"split": True, "planes": "planes"}.get(variant, False),
+                       fuse_yolo=variant == "planes")
     cu.writeBuffer(net.input.devData, x.nbytes, x)
     net.predict()
     return net
@@ -80,6 +81,8 @@ def check_conv_layers(cu, net, probe, x, batch, tol, expect_kernel=None):
             if getattr(l, "res_split", False):   # the operand is read from its planes
                 b_, f_, h_, w_ = l._residual.FShape
                 cu.nhwcToSplit(b_ * h_ * w_, f_, l._residual.devData, f_, l._residual.split.devData, f_, b_ * f_ * h_ * w_)
+        if getattr(l, "_yolo", None) is not None:
+            tgt = i + 1   # the yolo layer is folded into this head: compare with the oracle's yolo output
         l.forwardGPU(st)
         if expect_kernel is not None:
             assert expect_kernel(i) in cu.lastConvKernel(), (i, cu.lastConvKernel())
@@ -173,6 +176,8 @@ def _yolov3_small(cu, oracle, variant):
     # (2) end to end: 75 convolutions of drift stay well inside the detection tolerance
     net.predict()
     for i in (4, 36, 61, 79, 85, 86, 97, 98, 105):
+        if getattr(net.layers[i], "_yolo", None) is not None:
+            continue   # a head with the yolo layer folded in writes only the yolo output (compared below)
         got = net.output_nchw(i)
         assert got.shape == probe[i].shape and rel_max(got, probe[i]) < 2e-3, (i, rel_max(got, probe[i]))
     outs = [l.output.pullFromDevice() for l in net.yolo_layers()]
@@ -251,6 +256,32 @@ def test_shortcut_fusion_is_bit_identical(cuda_backend, channels_last):
                     [l.output.pullFromDevice().copy() for l in net.yolo_layers()])
     for a, b in zip(*outs):
         assert np.array_equal(a, b)
+
+
+def test_yolo_head_fusion_is_bit_identical(cuda_backend):
+    """tnn_conv2d_forward_yolo_head: head convolution + the yolo layer's copy / logistic pass == the separate layers, bit
+    for bit, in the channels-innermost graph with fp32 rows (3xTF32) and with planes (BF16x3)."""
+    from tensorium_b200.nnet import build_yolov3, init_yolov3_params, yolov3_spec
+    cu = cuda_backend
+    size, batch = 64, 2
+    params = init_yolov3_params(yolov3_spec(), seed=8, objectness_bias=-1.0)
+    x = np.random.default_rng(2).random((batch, 3, size, size), dtype=np.float32)
+    for mode, split in ((1, False), (3, "planes")):
+        cu.set_math_mode(mode)
+        try:
+            outs = []
+            for fuse in (False, True):
+                net = build_yolov3(batch, size, params=params, fuse_shortcuts=True, channels_last=True,
+                                   split_activations=split, fuse_yolo=fuse)
+                if fuse:
+                    assert sum(getattr(l, "_yolo", None) is not None for l in net.layers) == 3
+                cu.writeBuffer(net.input.devData, x.nbytes, x)
+                net.predict()
+                outs.append([l.output.pullFromDevice().copy() for l in net.yolo_layers()])
+        finally:
+            cu.set_math_mode(1)
+        for a, b in zip(*outs):
+            assert np.array_equal(a, b)
 
 
 def test_cfg_and_weights_file_build_the_same_net(cuda_backend, tmp_path):

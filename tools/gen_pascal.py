@@ -204,6 +204,8 @@ meth("procedure conv2dForwardSplit(const d: TNNConvDesc; const inp: TCUMem; cons
      "tnn_conv2d_forward_split", "@d, inp, inOffset, inPitch, inLayout, inPlane, weights, scale, bias, activation, residual, residualOffset, residualPitch, outp, outOffset, outPitch, outLayout, outSplit, outSplitOffset, outSplitPitch, outSplitPlane")
 meth("procedure conv2dForwardSplitResidual(const d: TNNConvDesc; const inp: TCUMem; const inOffset, inPitch: SizeInt; const inLayout: longint; const inPlane: SizeInt; const weights, scale, bias: TCUMem; const activation: longint; const residual: TCUMem; const residualOffset, residualPitch: SizeInt; const residualLayout: longint; const residualPlane: SizeInt; const outp: TCUMem; const outOffset, outPitch: SizeInt; const outLayout: longint; const outSplit: TCUMem; const outSplitOffset, outSplitPitch, outSplitPlane: SizeInt)",
      "tnn_conv2d_forward_split_residual", "@d, inp, inOffset, inPitch, inLayout, inPlane, weights, scale, bias, activation, residual, residualOffset, residualPitch, residualLayout, residualPlane, outp, outOffset, outPitch, outLayout, outSplit, outSplitOffset, outSplitPitch, outSplitPlane")
+meth("procedure conv2dForwardYoloHead(const d: TNNConvDesc; const inp: TCUMem; const inOffset, inPitch: SizeInt; const inLayout: longint; const inPlane: SizeInt; const weights, scale, bias, outp: TCUMem; const outOffset, classes: SizeInt; const scaleXY: T)",
+     "tnn_conv2d_forward_yolo_head", "@d, inp, inOffset, inPitch, inLayout, inPlane, weights, scale, bias, outp, outOffset, classes, scaleXY")
 meth("procedure nhwcToSplit(const rows, channels: SizeInt; const inp: TCUMem; const inPitch: SizeInt; const outSplit: TCUMem; const outPitch, outPlane: SizeInt)",
      "tnn_nhwc_to_split", "rows, channels, inp, inPitch, outSplit, outPitch, outPlane")
 meth("procedure splitToNhwc(const rows, channels: SizeInt; const inSplit: TCUMem; const inPitch, inPlane: SizeInt; const outp: TCUMem; const outPitch: SizeInt)",
