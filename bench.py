@@ -263,6 +263,9 @@ def run_ours(args, rank, world, local_rank):
     can_split = args.layout == "nhwc" and not args.no_fuse and not args.no_split
     net.setSplitActivations(can_split and args.math == "bf16x3", split_into_1x1=args.split_1x1,
                             planes_only=not args.fp32_shortcuts)
+    def elide(m):   # planes-only graph: sources written straight into the route buffers, single-source routes aliased
+        return net.elideRoutes() if can_split and m == "bf16x3" and not args.fp32_shortcuts and not args.no_elide else 0
+    routes_elided = elide(args.math)
     # shortcut fusion into the conv epilogue: "" (off, default), "gather" or "all".  Measured (B200, batch 64): 27.7 ms
     # un-fused, 28.0 ms with the MMA-bound gathering layers fused, 28.9 ms with all 23 fused — the residual read in
     # the four epilogue warps costs what the separate add kernels cost, so it stays off.
@@ -451,6 +454,7 @@ def run_ours(args, rank, world, local_rank):
             cu.set_math_mode(MATH[m])
             net.setSplitActivations(can_split and m == "bf16x3", split_into_1x1=args.split_1x1,
                                         planes_only=not args.fp32_shortcuts)
+            elide(m)
             for _ in range(3):
                 step_resident()
             ms_m = timed(step_resident, 5)
@@ -459,6 +463,7 @@ def run_ours(args, rank, world, local_rank):
         cu.set_math_mode(MATH[args.math])
         net.setSplitActivations(can_split and args.math == "bf16x3", split_into_1x1=args.split_1x1,
                             planes_only=not args.fp32_shortcuts)
+        elide(args.math)
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import cifar_train
         cu.set_math_mode(MATH["3xtf32"])   # the training kernels (wgrad, dgrad, connected layers) are the planar tf32 ones
@@ -517,6 +522,7 @@ def run_ours(args, rank, world, local_rank):
                                        if getattr(net, "split_activations", False) else "fp32"),
                        "shortcuts_fused_into_conv": sum(bool(getattr(l, "_fused_into_conv", False)) and l.layerType != "yolo"
                                                         for l in net.layers),
+                       "routes_elided": routes_elided,
                        "yolo_layers_fused_into_heads": sum(getattr(l, "_yolo", None) is not None for l in net.layers),
                        "parallelism": f"batch-sharded x{world}, no collective",
                        "l2": "activations streamed per step = 14.6 GB per GPU, far larger than the 126 MB L2 (no flush needed)"},
@@ -577,6 +583,7 @@ def main():
                     "producers then write fp32 rows AND planes)")
     ap.add_argument("--fp32-shortcuts", action="store_true", help="bf16x3: keep fp32 rows for the shortcut operands and the "
                     "1x1 convolutions' inputs (the graph of the first half of round 2) instead of planes everywhere")
+    ap.add_argument("--no-elide", action="store_true", help="bf16x3 planes-only graph: keep the copying route layers")
     ap.add_argument("--no-split", action="store_true", help="bf16x3: fp32 activations between all layers (no pre-split planes)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-images", type=int, default=2)

@@ -16,7 +16,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 from . import nncuda as nn
-from .tensor import TSingleTensor, cuda
+from .tensor import TSingleTensor, cuda, split_view
 
 ltCONVOLUTIONAL, ltBATCHNORM = "convolutional", "batchnorm"
 
@@ -183,7 +183,8 @@ class TConvolutionalLayer:
                 yl = self._yolo
                 yl.output.setCUDA()
                 if self.in_split:
-                    in_ptr, lay, pitch, plane = src.split.devData, nn.TNNCuda.LAYOUT_NHWC_SPLIT, self.c, src.Size()
+                    in_ptr, pitch, plane = split_view(src)
+                    lay = nn.TNNCuda.LAYOUT_NHWC_SPLIT
                 else:
                     in_ptr, lay, pitch, plane = src.devData, NHWC, in_pitch, 0
                 cu.conv2dForwardYoloHead(self._desc, in_ptr, 0, pitch, lay, plane, self.weights.devData,
@@ -196,23 +197,24 @@ class TConvolutionalLayer:
                 tgt = self._fused_out if self._residual is not None else self.output
                 tgt.setCUDA()
                 if self.in_split:
-                    n_in = self.batch * self.h * self.w * self.c
-                    in_ptr, in_layout, in_pitch, in_plane = src.split.devData, SPLIT, self.c, n_in
+                    in_ptr, in_pitch, in_plane = split_view(src)
+                    in_layout = SPLIT
                 else:
                     in_ptr, in_plane = src.devData, 0
                 res = self._residual
                 if res is None:
                     res_ptr, res_pitch, res_layout, res_plane = None, 0, NHWC, 0
                 elif self.res_split:   # the shortcut's other operand exists only as planes: residual = hi + lo
-                    res_ptr, res_pitch, res_layout, res_plane = res.split.devData, self.filters, SPLIT, res.Size()
+                    res_ptr, res_pitch, res_plane = split_view(res)
+                    res_layout = SPLIT
                 else:
                     res_ptr, res_pitch, res_layout, res_plane = res.devData, getattr(res, "pitch", 0) or self.filters, NHWC, 0
+                out_ptr, out_pitch, out_plane = split_view(tgt) if self.out_split else (None, self.filters, tgt.Size())
                 cu.conv2dForwardSplitResidual(self._desc, in_ptr, 0, in_pitch, in_layout, in_plane, self.weights.devData,
                                               sc.devData if sc is not None else None, bi.devData, self.ActivationType,
                                               res_ptr, 0, res_pitch, res_layout, res_plane,
                                               tgt.devData if self.out_f32 else None, 0, self.out_pitch or self.filters,
-                                              self.out_layout, tgt.split.devData if self.out_split else None, 0,
-                                              self.filters, tgt.Size())
+                                              self.out_layout, out_ptr, 0, out_pitch, out_plane)
                 return
             if self._residual is not None and in_layout == NHWC and self.out_layout == NHWC:
                 # the shortcut that follows, folded into the epilogue (TNNet.fuseShortcuts): writes the shortcut's output

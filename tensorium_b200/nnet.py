@@ -9,7 +9,7 @@ import numpy as np
 
 from . import nncuda as nn
 from .layers import TConvolutionalLayer, TNNetState, TUpdateArgs
-from .tensor import TSingleTensor, cuda
+from .tensor import TSingleTensor, cuda, split_view
 
 
 class TShortcutLayer:
@@ -52,6 +52,8 @@ class TConcatLayer:
     def forwardGPU(self, state: TNNetState, net: "TNNet"):
         cu = cuda()
         self.output.setCUDA()
+        if getattr(self, "_elided", False):
+            return  # the sources already live in this buffer (TNNet.elideRoutes)
         off = 0
         for li, c in zip(self.inputLayers, self._cs):
             src = net.layers[li].output
@@ -63,8 +65,9 @@ class TConcatLayer:
                 if getattr(self, "split_planes", False):
                     # pre-split tensors (TNNet.setSplitActivations): the same slice copy on the hi and the lo plane —
                     # rows of c bf16 = c/2 floats, planes rows*C bf16 elements apart
+                    sp, spitch, splane = split_view(src)
                     for plane in (0, 1):
-                        cu.rowsCopy(rows, c // 2, src.split.devData + 2 * plane * rows * c, c // 2,
+                        cu.rowsCopy(rows, c // 2, sp + 2 * plane * splane, spitch // 2,
                                     self.output.split.devData + 2 * (plane * rows * self.outC + off), self.outC // 2)
             elif self.batch == 1 or len(self.inputLayers) == 1:
                 cu.copy(src.Size(), src.devData, 0, 1, self.output.devData, off * self.h * self.w, 1)
@@ -90,11 +93,11 @@ class TUpsampleLayer:
                                     getattr(state.input, "pitch", 0) or self.c, self.output.devData, self.c)
             if getattr(self, "split_planes", False):
                 assert self.scale == 1.0, "pre-split planes are repeated, not rescaled"
-                n_in, n_out = self.batch * self.h * self.w * self.c, self.output.Size()
+                ip, ipitch, iplane = split_view(state.input)
+                op, opitch, oplane = split_view(self.output)   # (its own planes, or a slice of an elided route's buffer)
                 for plane in (0, 1):  # bf16 rows seen as rows of c/2 floats
                     cuda().upSampleNhwc(self.batch, self.c // 2, self.h, self.w, self.stride, 1.0,
-                                        state.input.split.devData + 2 * plane * n_in, self.c // 2,
-                                        self.output.split.devData + 2 * plane * n_out, self.c // 2)
+                                        ip + 2 * plane * iplane, ipitch // 2, op + 2 * plane * oplane, opitch // 2)
             return
         cuda().upSample(self.batch, self.c, self.h, self.w, state.input.devData, self.stride, 1, self.scale,
                         self.output.devData)
@@ -432,6 +435,43 @@ class TNNet:
                 n += 1
         return n
 
+    def elideRoutes(self, on: bool = True):
+        """Planes-only inference graph (after setSplitActivations(planes_only=True)): route layers stop copying.
+        A single-source route is an alias of its source.  A concatenating route becomes the OWNER of the tensor: every
+        source's planes are a column slice of the route's buffer (tensor.split_view: pitch = the route's channels), so the
+        producing epilogue / upsample writes there and every other reader of the source reads there — the pitch and
+        offset arguments of the C ABI do the rest.  Returns the number of elided routes.  on=False puts the copying
+        routes back (setSplitActivations does so before it re-assigns the tensor forms)."""
+        if not on:
+            for l in self.layers:
+                if isinstance(l, TConcatLayer) and getattr(l, "_elided", False):
+                    l.output = l._own_output
+                    for i in l.inputLayers:
+                        if getattr(self.layers[i].output, "split_at", None) is not None:
+                            self.layers[i].output.split_at = None
+                    l._elided = False
+            return 0
+        assert getattr(self, "split_activations", False), "routes are elided in the pre-split graph"
+        n = 0
+        for j, l in enumerate(self.layers):
+            if not isinstance(l, TConcatLayer) or not getattr(l, "split_planes", False) or getattr(l, "f32_rows", True):
+                continue
+            srcs = [self.layers[i].output for i in l.inputLayers]
+            if any(getattr(t, "split_at", None) is not None or getattr(t, "f32_valid", False) for t in srcs):
+                continue   # a source that already lives in another route's buffer, or that something reads as fp32
+            l._own_output = l.output
+            if len(srcs) == 1:
+                l.output = srcs[0]
+            else:
+                rows = self.batch * l.h * l.w
+                off = 0
+                for t, c in zip(srcs, l._cs):
+                    t.split_at = (l.output.split, off, l.outC, rows * l.outC)
+                    off += c
+            l._elided = True
+            n += 1
+        return n
+
     def fuseYoloHeads(self):
         """Channels-innermost inference graph: a linear head convolution whose output feeds ONLY the yolo layer that
         follows applies that layer's activation in its epilogue (tnn_conv2d_forward_yolo_head) and writes the yolo
@@ -493,6 +533,7 @@ class TNNet:
         Call after setChannelsLast() and fuseShortcuts()."""
         n = len(self.layers)
         split_into_1x1 = split_into_1x1 or planes_only
+        self.elideRoutes(False)
         if not on:
             for l in self.layers:
                 for a in ("in_split", "out_split", "split_planes", "res_split"):
@@ -559,7 +600,8 @@ class TNNet:
         if not getattr(l.output, "f32_valid", True):
             # only the pre-split planes were written: fp32 = hi + lo (exact) into the tensor's idle fp32 twin
             b, c, h, w = l.output.FShape
-            cuda().splitToNhwc(b * h * w, c, l.output.split.devData, c, b * h * w * c, l.output.devData, c)
+            sp, spitch, splane = split_view(l.output)
+            cuda().splitToNhwc(b * h * w, c, sp, spitch, splane, l.output.devData, c)
         data = l.output.pullFromDevice()
         l.output.setCUDA()
         if getattr(l.output, "layout", "NCHW") == "NHWC":
@@ -705,7 +747,7 @@ def init_yolov3_params(spec, c_in=3, seed=1234, objectness_bias=-4.0):
 
 
 def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=1234, fuse_shortcuts=False,
-                 channels_last=False, split_activations=False, fuse_yolo=False):
+                 channels_last=False, split_activations=False, fuse_yolo=False, elide_routes=False):
     """Builds the 107-layer net on the current `cuda` backend.  fuse_bn=True mirrors MSCOCOYolo.pas:327-340
     (Neural.fuseBatchNorm before predict)."""
     spec = yolov3_spec()
@@ -748,4 +790,6 @@ def build_yolov3(batch, size=416, params=None, fuse_bn=True, fused=True, seed=12
         net.setSplitActivations(planes_only=split_activations == "planes")
     if fuse_yolo:
         net.fuseYoloHeads()
+    if elide_routes:
+        net.elideRoutes()
     return net

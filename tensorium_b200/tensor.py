@@ -29,6 +29,17 @@ def cuda():
     return _cuda
 
 
+def split_view(t):
+    """Where tensor t's pre-split bf16 planes live (TNNet.setSplitActivations): (device address of the hi plane's first
+    element, pixel pitch, plane stride), pitch and stride in bf16 elements.  Normally its own `split` buffer with
+    pitch = channels; a source of an elided route layer (TNNet.elideRoutes) is a column slice of the route's buffer."""
+    v = getattr(t, "split_at", None)
+    if v is not None:
+        base, off, pitch, plane = v
+        return base.devData + 2 * off, pitch, plane
+    return t.split.devData, t.FShape[1], t.Size()
+
+
 class TSingleTensor:
     def __init__(self, shape, groups: int | None = None, data=None, device: bool = True, host: bool = True,
                  devptr: int = 0, dtype=np.float32):

@@ -12,13 +12,14 @@ def run_net(cu, size, batch, variant, params, x):
     """variant: fused | unfused | channels_last | split (= channels-last, shortcuts folded into the convolutions,
     pre-split bf16 activations, fp32 rows where a shortcut or a 1x1 convolution reads) | planes (= split with EVERY
     tensor between convolutions only as planes, the shortcut operands read as hi + lo: the graph bench.py times in its
-    default BF16x3 arithmetic, with the yolo layers' activation folded into the head convolutions)"""
+    default BF16x3 arithmetic, with the yolo layers' activation folded into the head convolutions and the route layers
+    elided)"""
     from tensorium_b200.nnet import build_yolov3
     net = build_yolov3(batch, size, params=params, fused=variant != "unfused",
                        channels_last=variant in ("channels_last", "split", "planes"),
                        fuse_shortcuts=variant in ("split", "planes"),
                        split_activations={"split": True, "planes": "planes"}.get(variant, False),
-                       fuse_yolo=variant == "planes")
+                       fuse_yolo=variant == "planes", elide_routes=variant == "planes")
     cu.writeBuffer(net.input.devData, x.nbytes, x)
     net.predict()
     return net
@@ -282,6 +283,32 @@ def test_yolo_head_fusion_is_bit_identical(cuda_backend):
             cu.set_math_mode(1)
         for a, b in zip(*outs):
             assert np.array_equal(a, b)
+
+
+def test_route_elision_is_bit_identical(cuda_backend):
+    """TNNet.elideRoutes: sources written straight into the route's buffer (pitch / offset arguments of the C ABI) ==
+    the copying route layers, bit for bit: every yolo output and the tensors around both concatenations."""
+    from tensorium_b200.nnet import build_yolov3, init_yolov3_params, yolov3_spec
+    cu = cuda_backend
+    size, batch = 64, 2
+    params = init_yolov3_params(yolov3_spec(), seed=8, objectness_bias=-1.0)
+    x = np.random.default_rng(2).random((batch, 3, size, size), dtype=np.float32)
+    cu.set_math_mode(3)
+    try:
+        outs = []
+        for elide in (False, True):
+            net = build_yolov3(batch, size, params=params, fuse_shortcuts=True, channels_last=True,
+                               split_activations="planes", elide_routes=elide)
+            if elide:
+                assert sum(getattr(l, "_elided", False) for l in net.layers) == 4
+            cu.writeBuffer(net.input.devData, x.nbytes, x)
+            net.predict()
+            outs.append([net.output_nchw(i) for i in (36, 61, 83, 85, 86, 87, 95, 97, 98, 99)] +
+                        [l.output.pullFromDevice().copy() for l in net.yolo_layers()])
+    finally:
+        cu.set_math_mode(1)
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
 
 
 def test_cfg_and_weights_file_build_the_same_net(cuda_backend, tmp_path):
