@@ -400,7 +400,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // (TMA -> mbarrier -> MMA) with the BF16x3 arithmetic.  tmA = hi plane, tmA2 = lo plane.
 template <int MODE, int KB, bool ASPLIT, typename EPI>
 __global__ void __launch_bounds__(kThreads, 1)
-k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCols,
+k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCols, int epiSets,
             const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
             const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOutHi,
@@ -451,7 +451,11 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
   pdl_wait();   // nothing above reads or writes global memory
   const uint32_t tmem_base = ctl.tmem_base;
 
-  if (warp >= kFirstProducerWarp && warp < kMmaWarp) {
+  // epiSets == 2 (TMA-only modes, narrow tiles): warps 4-7 are a second set of epilogue warps; here the two sets take
+  // ALTERNATE TILES — set s drains accumulator s — because a narrow tile has a single 32-filter chunk to drain
+  // (the CTA-pair kernel's sets alternate chunks within a tile)
+  const bool secondEpi = !CONVERT && epiSets == 2 && warp >= kEpilogueWarps && warp < 2 * kEpilogueWarps;
+  if (warp >= kFirstProducerWarp && warp < kMmaWarp && !secondEpi) {
     // ===================== split modes on fp32 activations: second plane(s) of the landed A tile =====================
     if (CONVERT) {
       constexpr int kConvGroups = ConvGroups<MODE>::kGroups, kConvGroupWarps = ConvGroups<MODE>::kWarps;
@@ -576,13 +580,16 @@ k_conv_nhwc(EPI epi, TileSched sched, Geo g, int BN, int stages, uint32_t accCol
       }
     }
   } else {
-    // ===================== epilogue warps 0-3 =====================
-    const int quad = warp;
+    // ===================== epilogue warps 0-3 (and 4-7 as a second set) =====================
+    const int quad = warp & 3, set = warp >> 2;
     int it = 0;
-    uint8_t *stg = smem + (size_t)stages * stageBytes + (size_t)quad * (kStageBufs * kStageTile);
+    uint8_t *stg = smem + (size_t)stages * stageBytes + (size_t)warp * (kStageBufs * kStageTile);
     int sbuf = 0;
-    float *scratch = ctl.epi_sb[quad];
+    float *scratch = set == 0 ? ctl.epi_sb[quad]
+                              : reinterpret_cast<float *>(smem + (size_t)stages * stageBytes +
+                                                          (size_t)2 * kEpilogueWarps * (kStageBufs * kStageTile)) + quad * 64;
     for (int t = blockIdx.x; t < sched.numTiles; t += gridDim.x, ++it) {
+      if (epiSets == 2 && (it & 1) != set) continue;   // the other set's accumulator
       int mt, nt, kb0, kb1;
       sched.decode(t, mt, nt, kb0, kb1);
       const int as = (int)(it & 1);
@@ -1012,13 +1019,13 @@ static cudaLaunchConfig_t pdl_config(tnn_context *ctx, int grid, int threads, si
 }
 
 template <int MODE, int KB, bool ASPLIT, typename EPI>
-static int launch_nhwc(tnn_context *ctx, const Plan &p, const Geo &geo, EPI epi, const Maps &m) {
+static int launch_nhwc(tnn_context *ctx, const Plan &p, const Geo &geo, int epiSets, EPI epi, const Maps &m) {
   auto kern = k_conv_nhwc<MODE, KB, ASPLIT, EPI>;
   TNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smemBytes));
   cudaLaunchAttribute at[1];
   cudaLaunchConfig_t cfg = pdl_config(ctx, p.grid, kThreads, p.smemBytes, at);
-  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, epi, p.sched, geo, p.BN, p.stages, p.accCols, m.a, m.a2, m.bhi, m.blo, m.out, m.outHi,
-                              m.outLo));
+  TNN_CUDA(cudaLaunchKernelEx(&cfg, kern, epi, p.sched, geo, p.BN, p.stages, p.accCols, epiSets, m.a, m.a2, m.bhi, m.blo, m.out,
+                              m.outHi, m.outLo));
   TNN_LAUNCHED(ctx);
   return 0;
 }
@@ -1113,6 +1120,9 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
   // (stride-2 layers are paced by their input traffic, not by the drain: measured 1-6 % slower with two sets)
   if (pairMode && !convert && !outNchw)
     epiSets = ctx->nhwc_epi_sets ? ctx->nhwc_epi_sets : ((K <= 1024 && g.sx == 1 && g.sy == 1) ? 2 : 1);
+  // the single-CTA kernel (tiles too narrow for a pair: 64 -> 32 @208^2) alternates TILES between its two sets
+  if (!pairMode && !convert && !outNchw && p.BN <= 64 && p.sched.kSplits == 1)
+    epiSets = ctx->nhwc_epi_sets ? ctx->nhwc_epi_sets : 2;
   const size_t epiBytes = outNchw ? 0 : (size_t)epiSets * kEpilogueWarps * kStageBufs * kStageTile + (epiSets == 2 ? 1024 : 0);
   int st = (int)((224 * 1024 - epiBytes) / stageBytes);   // stages + staging + 1 KB of alignment slack = at most 225 KB
   p.stages = st > kMaxStages ? kMaxStages : st;
@@ -1168,11 +1178,11 @@ static int conv_forward(tnn_context *ctx, const simt::ConvGeom &g, int batch, co
       return KB == 16 ? TNN_PAIR_GO(MODE_3X, 16, false) : TNN_PAIR_GO(MODE_3X, 32, false);
 #undef TNN_PAIR_GO
     }
-    if (aSplit) return launch_nhwc<MODE_BF16X3, 32, true>(ctx, p, geo, epi, m);
-    if (bf) return KB == 16 ? launch_nhwc<MODE_BF16X3, 16, false>(ctx, p, geo, epi, m)
-                            : launch_nhwc<MODE_BF16X3, 32, false>(ctx, p, geo, epi, m);
-    if (!split) return launch_nhwc<MODE_TF32, 32, false>(ctx, p, geo, epi, m);
-    return KB == 16 ? launch_nhwc<MODE_3X, 16, false>(ctx, p, geo, epi, m) : launch_nhwc<MODE_3X, 32, false>(ctx, p, geo, epi, m);
+    if (aSplit) return launch_nhwc<MODE_BF16X3, 32, true>(ctx, p, geo, epiSets, epi, m);
+    if (bf) return KB == 16 ? launch_nhwc<MODE_BF16X3, 16, false>(ctx, p, geo, epiSets, epi, m)
+                            : launch_nhwc<MODE_BF16X3, 32, false>(ctx, p, geo, epiSets, epi, m);
+    if (!split) return launch_nhwc<MODE_TF32, 32, false>(ctx, p, geo, epiSets, epi, m);
+    return KB == 16 ? launch_nhwc<MODE_3X, 16, false>(ctx, p, geo, epiSets, epi, m) : launch_nhwc<MODE_3X, 32, false>(ctx, p, geo, epiSets, epi, m);
   };
   if (outNchw) {
     TNN_REQUIRE(out != nullptr && outSplit.hi == nullptr, "planar output is fp32 only");
