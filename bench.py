@@ -528,6 +528,9 @@ def run_ours(args, rank, world, local_rank):
                        "l2": "activations streamed per step = 14.6 GB per GPU, far larger than the 126 MB L2 (no flush needed)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes_in,
                     "d2h_bytes_per_step": nbytes_cand, "ms_per_step": ms_e2e / args.steps,
+                    "note": "H2D of batch i+1 and D2H of result i run on a second stream and overlap the compute of batch i, "
+                            "so the region costs what the compute costs; it is timed after the resident region and may come "
+                            "out a percent faster or slower with the clock the power cap allows at that moment",
                     "result": f"detection candidates (objectness > {THRESH}, TYoloLayer.getDetections' test run on the "
                               f"device by tnn_yolo_candidates): count + up to {MAX_CAND} records of 89 floats, read back "
                               f"every step; {n_cand} candidates in the last step (random-init heads, objectness bias -4)",
