@@ -129,3 +129,43 @@ def test_fp32_shortcut_graph_reads_rows(backend):
     assert len(with_res) == 23 and all(c[1][13] == nn.TNNCuda.LAYOUT_NHWC for c in with_res)
     names = [c[0] for c in backend.calls]
     assert names.count("yoloActivate") == 3 and names.count("rowsCopy") > 0
+
+
+def test_deepcifar10_training_step_call_sequence(backend):
+    """One fused training step of deepCIFAR10 (models.py; nmodels.pas:82-111) as the backend sees it: six convolutions
+    with training batch norm forward, the mirrored backward (batch-norm backward, wgrad, dgrad except into the image),
+    ONE multi-tensor SGD launch — and, data parallel, ONE all-reduce of the update bucket between the last backward
+    call and the update (dataparallel.NativeBucket; nnet.pas:378-403)."""
+    from tensorium_b200 import dataparallel, models
+    net = models.deepCIFAR10(8, fused=True, seed=0, learningRate=0.01)
+    # a 2-replica bucket without a process group: the native bucket only needs a communicator handle and a world size
+    grads = net.gradients()
+    bucket = dataparallel.NativeBucket(backend, [g.Size() for g in grads], comm=object(), world=2)
+    for i, g in enumerate(grads):
+        g.rebind(bucket.ptr(i))
+        g.setCUDA()
+    net.bucket, net.replicas = bucket, 2
+    x = np.zeros((8, 3, 32, 32), np.float32)
+    t = np.zeros((8, 10), np.float32)
+    t[:, 0] = 1
+    net.input.Data[...] = x
+    net.input.setCPU()
+    net.truth = tensor.TSingleTensor(net.layers[-1].output.FShape, groups=8)
+    net.truth.Data[...] = t
+    backend.calls.clear()
+    net.Propagate()
+    net.update()
+    names = [c[0] for c in backend.calls]
+    assert names.count("conv2dForward") == 6 and names.count("batchNormForwardTraining") == 6
+    assert names.count("batchNormBackward") == 6 and names.count("conv2dBackwardFilter") == 6
+    assert names.count("conv2dBackwardData") == 5          # nothing is back-propagated into the image
+    assert names.count("sgdUpdateMulti") == 1 and names.count("sgdUpdate") == 0
+    assert names.count("allreduceSum") == 1
+    ar, sgd = names.index("allreduceSum"), names.index("sgdUpdateMulti")
+    last_bwd = max(i for i, n in enumerate(names) if n.startswith("conv2dBackward") or n == "batchNormBackward")
+    assert last_bwd < ar < sgd
+    _, (comm, base, off, n) = backend.calls[ar]
+    assert base == bucket.base and off == 0 and n == bucket.total
+    # every replica keeps momentum / replicas in its buffer: the SUM of the next step restores momentum * summed update
+    items, mom = backend.calls[sgd][1]
+    assert mom == pytest.approx(net.momentum / 2) and len(items) == len(grads)
